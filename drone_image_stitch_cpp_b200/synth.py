@@ -1,0 +1,105 @@
+"""Synthetic survey generator: a procedural orthophoto and drone frames cut from
+it through known affine transforms, so overlaps are photometrically consistent.
+
+Used by tests/ and bench.py only to make inputs; torch is plumbing here (runs on CPU or on the GPU).
+Cameras follow what cv::Stitcher holds in SCANS mode (reference: src/stitch_app.cpp:208, :259):
+K = diag(a, a, 1) float32, R = 3x3 float32 affine, warp scale = a (a = 1/work_scale).
+"""
+import math
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+MASTER_SEED = 20261018
+
+
+def orthophoto(h, w, seed=MASTER_SEED, device="cpu"):
+    """fBm value noise + a few flat shapes, uint8 BGR (h, w, 3), mean ~110, sigma ~50."""
+    g = torch.Generator(device="cpu").manual_seed(int(seed))
+    img = torch.zeros(1, 3, h, w, device=device)
+    amp, tot = 1.0, 0.0
+    for octave in range(7):
+        gh = max(2, math.ceil(h / (512 >> octave)) + 2)
+        gw = max(2, math.ceil(w / (512 >> octave)) + 2)
+        n = torch.rand(1, 3, gh, gw, generator=g).to(device)
+        img += amp * F.interpolate(n, size=(h, w), mode="bicubic", align_corners=True)
+        tot += amp
+        amp *= 0.6
+    img = (img / tot - 0.5) * 2.0 + 0.43
+    # flat shapes (fields / roofs): axis-aligned rectangles with random tint
+    nshape = max(4, (h * w) // 400_000)
+    ys = torch.randint(0, h, (nshape,), generator=g).tolist()
+    xs = torch.randint(0, w, (nshape,), generator=g).tolist()
+    hs = torch.randint(20, max(21, min(h, 600)), (nshape,), generator=g).tolist()
+    ws = torch.randint(20, max(21, min(w, 600)), (nshape,), generator=g).tolist()
+    tint = (torch.rand(nshape, 3, generator=g) * 0.5 - 0.25).to(device)
+    for i in range(nshape):
+        img[0, :, ys[i]:ys[i] + hs[i], xs[i]:xs[i] + ws[i]] += tint[i].view(3, 1, 1)
+    fine = torch.rand(1, 1, h, w, generator=g).to(device) * 0.08 - 0.04
+    img = (img + fine).clamp_(0.0, 1.0)
+    return (img[0].permute(1, 2, 0) * 255.0).round_().to(torch.uint8).contiguous()
+
+
+@dataclass
+class Survey:
+    frames: List[np.ndarray]            # HxWx3 uint8 BGR
+    Ks: List[np.ndarray]                # 3x3 float32
+    Rs: List[np.ndarray]                # 3x3 float32 affine
+    scale: float
+    A: List[np.ndarray] = field(default_factory=list)   # 2x3 float64 frame px -> ortho px (ground truth)
+
+
+def cut_frame(ortho_chw, A, fw, fh):
+    """Sample the orthophoto (1,3,H,W float) at A*(x,y,1) for every frame pixel, bilinear."""
+    H, W = ortho_chw.shape[-2:]
+    dev = ortho_chw.device
+    ys, xs = torch.meshgrid(torch.arange(fh, device=dev, dtype=torch.float32),
+                            torch.arange(fw, device=dev, dtype=torch.float32), indexing="ij")
+    ox = A[0, 0] * xs + A[0, 1] * ys + A[0, 2]
+    oy = A[1, 0] * xs + A[1, 1] * ys + A[1, 2]
+    grid = torch.stack([(ox + 0.5) / W * 2 - 1, (oy + 0.5) / H * 2 - 1], dim=-1)[None]
+    out = F.grid_sample(ortho_chw, grid, mode="bilinear", padding_mode="reflection", align_corners=False)
+    return out[0].permute(1, 2, 0).round_().clamp_(0, 255).to(torch.uint8).contiguous()
+
+
+def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scale_jit=0.02, trans_jit=20.0,
+                work_scale=1.0, device="cpu", serpentine=True, side_overlap=None):
+    """nx x ny frames of fw x fh, step = (1-overlap) of the frame size, with jitter.
+    work_scale != 1 exercises the K = diag(1/ws), scale = 1/ws camera convention."""
+    rng = np.random.default_rng(seed)
+    so = overlap if side_overlap is None else side_overlap
+    stepx, stepy = fw * (1.0 - overlap), fh * (1.0 - so)
+    margin = int(0.15 * max(fw, fh)) + 64
+    W = int(stepx * (nx - 1) + fw) + 2 * margin
+    H = int(stepy * (ny - 1) + fh) + 2 * margin
+    ortho = orthophoto(H, W, seed, device)
+    ortho_f = ortho.permute(2, 0, 1)[None].float()
+    a = np.float32(1.0 / work_scale)
+    frames, Ks, Rs, As = [], [], [], []
+    for j in range(ny):
+        cols = range(nx) if (not serpentine or j % 2 == 0) else range(nx - 1, -1, -1)
+        for i in cols:
+            th = math.radians(rng.uniform(-rot_deg, rot_deg))
+            s = rng.uniform(1 - scale_jit, 1 + scale_jit)
+            tx = margin + i * stepx + rng.uniform(-trans_jit, trans_jit)
+            ty = margin + j * stepy + rng.uniform(-trans_jit, trans_jit)
+            cx, cy = fw / 2.0, fh / 2.0
+            # rotate/scale about the frame centre, then translate
+            r00, r01, r10, r11 = s * math.cos(th), -s * math.sin(th), s * math.sin(th), s * math.cos(th)
+            A = np.array([[r00, r01, tx + cx - (r00 * cx + r01 * cy)],
+                          [r10, r11, ty + cy - (r10 * cx + r11 * cy)]], np.float64)
+            fr = cut_frame(ortho_f, torch.tensor(A, dtype=torch.float32), fw, fh)
+            frames.append(fr.cpu().numpy())
+            As.append(A)
+            Ks.append(np.array([[a, 0, 0], [0, a, 0], [0, 0, 1]], np.float32))
+            # AffineWarper's backward map is x_src = a * L * (u/a + L^T T0) with R = [L | T0] (OpenCV
+            # PlaneProjector::mapBackward after getRTfromHomogeneous), i.e. R holds the canvas->frame
+            # map in work-scale units. Solve L, T0 so that it equals the inverse of A.
+            Bl = np.linalg.inv(A[:, :2])
+            Bt = -Bl @ A[:, 2]
+            T0 = np.linalg.solve(Bl @ Bl.T, Bt) / float(a)
+            Rs.append(np.array([[Bl[0, 0], Bl[0, 1], T0[0]], [Bl[1, 0], Bl[1, 1], T0[1]], [0, 0, 1]], np.float32))
+    return Survey(frames, Ks, Rs, float(a), As)
