@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's compose step over the C ABI.
+
+`compose_panorama` takes what the reference has in hand right after
+`stitcher->estimateTransform(images)` (/root/reference/src/stitch_robust.cpp:251) — the frames, the
+per-camera K / R (float32 3x3) and the warp scale — and does what `stitcher->composePanorama(output)`
+(:256) does with the components the reference configures (:203-213): AffineWarper placement,
+LINEAR/REFLECT image warp, NEAREST/CONSTANT mask warp, MultiBandBlender(bands) (or
+FeatherBlender(0.02) for BASELINE config 1), ->8U. All pixel work happens in libdronestitch_cuda.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def plane_transform(K, R, scale, affine=True, border=L.DS_BORDER_REFLECT):
+    t = L.ds_transform()
+    t.kind = L.DS_XF_PLANE_F32
+    t.affine_warper = 1 if affine else 0
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    R = np.ascontiguousarray(R, np.float32).reshape(9)
+    for i in range(9):
+        t.K[i] = float(K[i])
+        t.R[i] = float(R[i])
+    t.scale = float(np.float32(scale))
+    t.border = border
+    return t
+
+
+def affine_transform(M, corner, size, border=L.DS_BORDER_CONSTANT):
+    """cv::warpAffine semantics: forward 2x3 double M (source px -> px of the frame's own bbox)."""
+    t = L.ds_transform()
+    t.kind = L.DS_XF_AFFINE_F64
+    M = np.ascontiguousarray(M, np.float64).reshape(-1)
+    for i in range(6):
+        t.M[i] = float(M[i])
+    t.M[6], t.M[7], t.M[8] = 0.0, 0.0, 1.0
+    t.corner_x, t.corner_y = int(corner[0]), int(corner[1])
+    t.width, t.height = int(size[0]), int(size[1])
+    t.border = border
+    return t
+
+
+def homography_transform(H, corner, size, border=L.DS_BORDER_CONSTANT):
+    """cv::warpPerspective semantics: forward 3x3 double H."""
+    t = L.ds_transform()
+    t.kind = L.DS_XF_HOMOGRAPHY_F64
+    H = np.ascontiguousarray(H, np.float64).reshape(9)
+    for i in range(9):
+        t.M[i] = float(H[i])
+    t.corner_x, t.corner_y = int(corner[0]), int(corner[1])
+    t.width, t.height = int(size[0]), int(size[1])
+    t.border = border
+    return t
+
+
+def warp_roi(xf, w, h, lib=None):
+    lib = lib or L.default_library()
+    out = (C.c_int32 * 4)()
+    lib.check(lib.dll.ds_warp_roi(C.byref(xf), int(w), int(h), out))
+    return tuple(out)
+
+
+def result_roi(rois):
+    """cv::detail::resultRoi(corners, sizes) over (x, y, w, h) tuples."""
+    x0 = min(r[0] for r in rois)
+    y0 = min(r[1] for r in rois)
+    x1 = max(r[0] + r[2] for r in rois)
+    y1 = max(r[1] + r[3] for r in rois)
+    return (x0, y0, x1 - x0, y1 - y0)
+
+
+class Canvas:
+    """One ds_canvas handle (one GPU, one row band)."""
+
+    def __init__(self, roi, blend="multiband", bands=5, sharpness=0.02, out_format="bgr", device=0, band=None,
+                 stream=None, lib=None):
+        self.lib = lib or L.default_library()
+        d = L.ds_canvas_desc()
+        d.x, d.y, d.width, d.height = [int(v) for v in roi]
+        d.blend_mode = L.DS_BLEND_MULTIBAND if blend == "multiband" else L.DS_BLEND_FEATHER
+        d.num_bands = int(bands)
+        d.sharpness = float(sharpness)
+        d.out_format = L.DS_OUT_BGRA8 if out_format == "bgra" else L.DS_OUT_BGR8
+        d.device = int(device)
+        if band is not None:
+            d.band_y0, d.band_y1 = int(band[0]), int(band[1])
+        d.stream = C.c_void_p(stream) if stream else None
+        self.desc = d
+        self.roi = tuple(int(v) for v in roi)
+        self.bpp = 4 if out_format == "bgra" else 3
+        self._h = C.c_void_p()
+        self.lib.check(self.lib.dll.ds_create_canvas(C.byref(d), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self.lib.dll.ds_destroy_canvas(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def touches(self, frame_roi):
+        arr = (C.c_int32 * 4)(*[int(v) for v in frame_roi])
+        return bool(self.lib.dll.ds_frame_touches_band(C.byref(self.desc), arr))
+
+    def upload(self, idx, img, xf, seam_mask=None, channel_gain=None):
+        """img: HxWx3 uint8 (numpy; any row stride) or a (ptr, w, h, stride) tuple."""
+        opts = None
+        keep = []
+        if seam_mask is not None or channel_gain is not None:
+            opts = L.ds_frame_opts()
+            if seam_mask is not None:
+                sm = np.ascontiguousarray(seam_mask, np.uint8)
+                keep.append(sm)
+                opts.seam_mask = sm.ctypes.data
+                opts.seam_mask_stride = sm.strides[0]
+            if channel_gain is not None:
+                g = (C.c_float * 3)(*[float(v) for v in channel_gain])
+                keep.append(g)
+                opts.channel_gain = C.cast(g, C.POINTER(C.c_float))
+        if isinstance(img, tuple):
+            ptr, w, h, stride = img
+        else:
+            assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3 and img.strides[2] == 1 and img.strides[1] == 3
+            ptr, w, h, stride = img.ctypes.data, img.shape[1], img.shape[0], img.strides[0]
+        self.lib.check(self.lib.dll.ds_upload_frame(self._h, int(idx), C.c_void_p(ptr), int(w), int(h), int(stride),
+                                                    C.byref(xf), C.byref(opts) if opts is not None else None))
+
+    def upload_device(self, idx, dev_ptr, w, h, stride, xf):
+        self.lib.check(self.lib.dll.ds_upload_frame_device(self._h, int(idx), C.c_void_p(dev_ptr), int(w), int(h),
+                                                           int(stride), C.byref(xf), None))
+
+    def composite(self):
+        self.lib.check(self.lib.dll.ds_composite(self._h))
+
+    def composite_async(self):
+        self.lib.check(self.lib.dll.ds_composite_async(self._h))
+
+    def synchronize(self):
+        self.lib.check(self.lib.dll.ds_synchronize(self._h))
+
+    def info(self):
+        i = L.ds_canvas_info()
+        self.lib.check(self.lib.dll.ds_get_info(self._h, C.byref(i)))
+        return i
+
+    def download(self, x=0, y=None, w=None, h=None, want_mask=True, out=None):
+        i = self.info()
+        y0 = i.band_y0 if y is None else y
+        y1 = min(i.band_y1, self.roi[3])
+        w = self.roi[2] - x if w is None else w
+        h = y1 - y0 if h is None else h
+        if out is None:
+            out = np.empty((h, w, self.bpp), np.uint8)
+        mask = None
+        if want_mask and self.bpp == 3:
+            mask = np.empty((h, w), np.uint8)
+        self.lib.check(self.lib.dll.ds_download_tile(self._h, int(x), int(y0), int(w), int(h), out.ctypes.data,
+                                                     out.strides[0], mask.ctypes.data if mask is not None else None,
+                                                     mask.strides[0] if mask is not None else 0))
+        return out, mask
+
+    def set_profiling(self, on=True):
+        self.lib.check(self.lib.dll.ds_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """-> list of dict(name, level, ms, algorithmic_bytes) for the last profiled composite."""
+        n = C.c_int()
+        arr = (L.ds_kernel_time * 256)()
+        self.lib.check(self.lib.dll.ds_get_kernel_times(self._h, arr, 256, C.byref(n)))
+        return [dict(name=arr[i].name.decode(), level=arr[i].level, ms=arr[i].ms, algorithmic_bytes=arr[i].algorithmic_bytes)
+                for i in range(min(n.value, 256))]
+
+    # ---- debug taps
+    def placement(self, idx):
+        o = (C.c_int32 * 4)()
+        self.lib.check(self.lib.dll.ds_debug_get_placement(self._h, int(idx), o))
+        return tuple(o)
+
+    def maps(self, idx):
+        x, y, w, h = self.placement(idx)
+        xy = np.empty((h, w, 2), np.int16)
+        a = np.empty((h, w), np.uint16)
+        self.lib.check(self.lib.dll.ds_debug_get_maps(self._h, int(idx), xy.ctypes.data, a.ctypes.data))
+        return xy, a
+
+    def warped(self, idx):
+        x, y, w, h = self.placement(idx)
+        img = np.empty((h, w, 3), np.uint8)
+        m = np.empty((h, w), np.uint8)
+        self.lib.check(self.lib.dll.ds_debug_get_warped(self._h, int(idx), img.ctypes.data, m.ctypes.data))
+        return img, m
+
+    def frame_level(self, idx, level):
+        dims = (C.c_int32 * 4)()
+        self.lib.check(self.lib.dll.ds_debug_get_frame_level(self._h, int(idx), int(level), None, None, dims))
+        g = np.empty((dims[3], dims[2], 3), np.int16)
+        w = np.empty((dims[3], dims[2]), np.float32)
+        self.lib.check(self.lib.dll.ds_debug_get_frame_level(self._h, int(idx), int(level), g.ctypes.data, w.ctypes.data, dims))
+        return g, w, tuple(dims)
+
+
+def compose_panorama(images, Ks, Rs, scale, blend="multiband", bands=5, sharpness=0.02, affine=True,
+                     out_format="bgr", device=0, lib=None, return_canvas=False):
+    """The compose half of stitchWithMode (/root/reference/src/stitch_robust.cpp:255-256).
+    Returns (pano HxWx3 uint8, result_mask HxW uint8, roi (x, y, w, h))."""
+    lib = lib or L.default_library()
+    xfs = [plane_transform(K, R, scale, affine) for K, R in zip(Ks, Rs)]
+    rois = [warp_roi(xf, im.shape[1], im.shape[0], lib) for xf, im in zip(xfs, images)]
+    roi = result_roi(rois)
+    cv = Canvas(roi, blend, bands, sharpness, out_format, device, lib=lib)
+    for i, (im, xf) in enumerate(zip(images, xfs)):
+        cv.upload(i, im, xf)
+    cv.composite()
+    pano, mask = cv.download()
+    if return_canvas:
+        return pano, mask, roi, cv
+    cv.close()
+    return pano, mask, roi

@@ -1,0 +1,765 @@
+// ds_kernels.h — kernel bodies of libdronestitch_cuda.
+//
+// Every body is `template <int NT> run(P, block, tid, smem)`: phases are strided loops
+// `for (i = tid; i < n; i += NT)` separated by DS_SYNC(). Compiled by nvcc for sm_100a they are the
+// product kernels; compiled with DS_EMU and NT = 1 they are the CPU emulation the non-GPU tests use
+// to check tile / halo / border logic against the oracle (tests/emu, never shipped).
+//
+// Arithmetic follows SURVEY.md Appendix A (OpenCV 4.13 semantics the reference relies on):
+//   A2/A3 plane backward map + INTER_BITS tables, A4 15-bit bilinear, A5 nearest mask,
+//   A6/A7 warpAffine / warpPerspective coordinates, A8 pyrDown 16S, A9 pyrDown f32 (op order),
+//   A10 pyrUp 16S, A11 MultiBandBlender feed / blend, A12 FeatherBlender.
+#pragma once
+#include "ds_types.h"
+
+// ---------------------------------------------------------------------------------------------
+// exact helpers
+
+// cv::borderInterpolate for REFLECT (type 1) / REFLECT_101 (type 2); p may be any int.
+DS_D int refl(int p, int len, int type) {
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    const int delta = (type == BORDER_REFL101);
+    do {
+        if (p < 0) p = -p - 1 + delta;
+        else p = len - 1 - (p - len) - delta;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+DS_D int refl101(int p, int len) { return refl(p, len, BORDER_REFL101); }
+
+// pyrUp neighbour rules (A10): index -1 -> 1 (or 0 when n == 1); index n -> n-1.
+DS_D int up_l(int i, int n) { return i > 0 ? i - 1 : (n > 1 ? 1 : 0); }
+DS_D int up_r(int i, int n) { return i < n - 1 ? i + 1 : n - 1; }
+
+// Source coordinate of bbox pixel (u, v) in [0,w) x [0,h) — fixed-point tables + nearest mask.
+DS_D Coord eval_coord(const FrameDev& F, int u, int v) {
+    Coord c;
+    if (F.kind == XF_PLANE) {
+        float U = (float)(F.tlx + u), V = (float)(F.tly + v);
+        if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+        const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+        float x = f_add(f_add(f_mul(F.k[0], up), f_mul(F.k[1], vp)), F.k2one);
+        float y = f_add(f_add(f_mul(F.k[3], up), f_mul(F.k[4], vp)), F.k5one);
+        const float z = f_add(f_add(f_mul(F.k[6], up), f_mul(F.k[7], vp)), F.k8one);
+        if (z != 1.f) { x = f_div(x, z); y = f_div(y, z); }
+        const int ix = f2i_rn(f_mul(x, 32.f)), iy = f2i_rn(f_mul(y, 32.f));
+        c.sx = sat16i(ix >> 5); c.sy = sat16i(iy >> 5);
+        c.ax = ix & 31; c.ay = iy & 31;
+        const int nx = sat16i(f2i_rn(x)), ny = sat16i(f2i_rn(y));
+        c.m = ((unsigned)nx < (unsigned)F.src_w && (unsigned)ny < (unsigned)F.src_h) ? 255 : 0;
+    } else if (F.kind == XF_AFFINE) {
+        const double m0 = F.inv[0], m1 = F.inv[1], b1 = F.inv[2], m3 = F.inv[3], m4 = F.inv[4], b2 = F.inv[5];
+        const int ad = d2i_rn(d_mul(d_mul(m0, (double)u), 1024.0));
+        const int bd = d2i_rn(d_mul(d_mul(m3, (double)u), 1024.0));
+        const int xr = d2i_rn(d_mul(d_add(d_mul(m1, (double)v), b1), 1024.0));
+        const int yr = d2i_rn(d_mul(d_add(d_mul(m4, (double)v), b2), 1024.0));
+        const int X = (xr + 16 + ad) >> 5, Y = (yr + 16 + bd) >> 5;
+        c.sx = sat16i(X >> 5); c.sy = sat16i(Y >> 5);
+        c.ax = X & 31; c.ay = Y & 31;
+        const int nx = sat16i((xr + 512 + ad) >> 10), ny = sat16i((yr + 512 + bd) >> 10);
+        c.m = ((unsigned)nx < (unsigned)F.src_w && (unsigned)ny < (unsigned)F.src_h) ? 255 : 0;
+    } else {
+        const double* I = F.inv;
+        const double X0 = d_add(d_add(d_mul(I[0], (double)u), d_mul(I[1], (double)v)), I[2]);
+        const double Y0 = d_add(d_add(d_mul(I[3], (double)u), d_mul(I[4], (double)v)), I[5]);
+        double Wd = d_add(d_add(d_mul(I[6], (double)u), d_mul(I[7], (double)v)), I[8]);
+        const double W32 = Wd != 0.0 ? d_div(32.0, Wd) : 0.0;
+        const double W1 = Wd != 0.0 ? d_div(1.0, Wd) : 0.0;
+        const double lo = -2147483648.0, hi = 2147483647.0;
+        double fx = d_mul(X0, W32), fy = d_mul(Y0, W32);
+        fx = fx < lo ? lo : (fx > hi ? hi : fx);
+        fy = fy < lo ? lo : (fy > hi ? hi : fy);
+        const int X = d2i_rn(fx), Y = d2i_rn(fy);
+        c.sx = sat16i(X >> 5); c.sy = sat16i(Y >> 5);
+        c.ax = X & 31; c.ay = Y & 31;
+        double gx = d_mul(X0, W1), gy = d_mul(Y0, W1);
+        gx = gx < lo ? lo : (gx > hi ? hi : gx);
+        gy = gy < lo ? lo : (gy > hi ? hi : gy);
+        const int nx = sat16i(d2i_rn(gx)), ny = sat16i(d2i_rn(gy));
+        c.m = ((unsigned)nx < (unsigned)F.src_w && (unsigned)ny < (unsigned)F.src_h) ? 255 : 0;
+    }
+    return c;
+}
+
+DS_D uint32_t src_tap(const FrameDev& F, int x, int y) {
+    // x, y already border-resolved; negative = outside with BORDER_CONSTANT -> 0
+    if ((x | y) < 0) return 0u;
+    return ld_ro(F.src + (size_t)y * F.src_pitch + x);
+}
+
+// A4: cv::remap INTER_LINEAR 8UC3 on the fixed-point coordinate, then the optional channel gain.
+DS_D px8 sample_bilinear(const FrameDev& F, const Coord& c) {
+    uint32_t p00, p01, p10, p11;
+    if ((unsigned)c.sx < (unsigned)(F.src_w - 1) && (unsigned)c.sy < (unsigned)(F.src_h - 1)) {
+        const uint32_t* r0 = F.src + (size_t)c.sy * F.src_pitch + c.sx;
+        p00 = ld_ro(r0); p01 = ld_ro(r0 + 1);
+        p10 = ld_ro(r0 + F.src_pitch); p11 = ld_ro(r0 + F.src_pitch + 1);
+    } else if (F.border == BORDER_CONST) {
+        const int x0 = (unsigned)c.sx < (unsigned)F.src_w ? c.sx : -1;
+        const int x1 = (unsigned)(c.sx + 1) < (unsigned)F.src_w ? c.sx + 1 : -1;
+        const int y0 = (unsigned)c.sy < (unsigned)F.src_h ? c.sy : -1;
+        const int y1 = (unsigned)(c.sy + 1) < (unsigned)F.src_h ? c.sy + 1 : -1;
+        p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
+        p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
+    } else {
+        const int x0 = refl(c.sx, F.src_w, BORDER_REFL), x1 = refl(c.sx + 1, F.src_w, BORDER_REFL);
+        const int y0 = refl(c.sy, F.src_h, BORDER_REFL), y1 = refl(c.sy + 1, F.src_h, BORDER_REFL);
+        p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
+        p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
+    }
+    // weights (32-ax)(32-ay)*32 ... sum to 2^15; (sum + 2^14) >> 15 == (hv + 512) >> 10
+    const int wx1 = c.ax, wx0 = 32 - c.ax, wy1 = c.ay, wy0 = 32 - c.ay;
+    int out[3];
+    DS_UNROLL
+    for (int ch = 0; ch < 3; ch++) {
+        const int sh = 8 * ch;
+        const int a = (int)((p00 >> sh) & 255u), b = (int)((p01 >> sh) & 255u);
+        const int d = (int)((p10 >> sh) & 255u), e = (int)((p11 >> sh) & 255u);
+        const int hv = (a * wx0 + b * wx1) * wy0 + (d * wx0 + e * wx1) * wy1;
+        out[ch] = (hv + 512) >> 10;
+    }
+    if (F.has_gain) {
+        for (int ch = 0; ch < 3; ch++) out[ch] = sat8i(f2i_rn(f_mul((float)out[ch], F.gain[ch])));
+    }
+    px8 r;
+    r.b = (unsigned char)out[0]; r.g = (unsigned char)out[1]; r.r = (unsigned char)out[2]; r.a = 0;
+    return r;
+}
+
+// Warped mask value of bbox pixel (u, v): nearest-warped 255s ANDed with the optional seam mask.
+DS_D int mask_value(const FrameDev& F, const Coord& c, int u, int v) {
+    int m = c.m;
+    if (F.seam) m &= (int)ld_ro(F.seam + (size_t)v * F.seam_pitch + u);
+    return m;
+}
+
+// A9: float pyrDown taps in the op order of the declared oracle build.
+DS_D float pd_scalar(float s0, float s1, float s2, float s3, float s4) {
+    // s2*6 + (s1+s3)*4 + s0 + s4, left to right
+    return f_add(f_add(f_add(f_mul(s2, 6.f), f_mul(f_add(s1, s3), 4.f)), s0), s4);
+}
+DS_D float pd_h_simd(float r0, float r1, float r2, float r3, float r4) {
+    // r2*6 + ((r1+r3)*4 + (r0+r4))
+    return f_add(f_mul(r2, 6.f), f_add(f_mul(f_add(r1, r3), 4.f), f_add(r0, r4)));
+}
+DS_D float pd_v_simd(float r0, float r1, float r2, float r3, float r4) {
+    // ((r1+r3)+r2)*4 + ((r0+r4)+(r2+r2))
+    return f_add(f_mul(f_add(f_add(r1, r3), r2), 4.f), f_add(f_add(r0, r4), f_add(r2, r2)));
+}
+// Horizontal class of output column j for a source row of width w (dw = (w+1)/2).
+DS_D bool pd_h_is_simd(int j, int w, int dw) {
+    int width0 = (w - 3) / 2 + 1;  // C division (truncates toward zero), as cv::pyrDown_
+    if (width0 > dw) width0 = dw;
+    const int n = width0 - 1;       // columns handed to the vector loop, starting at x = 1
+    return j >= 1 && j < 1 + (n > 0 ? (n & ~3) : 0);
+}
+DS_D bool pd_v_is_simd(int j, int dw) { return j < (dw & ~3); }
+
+// ---------------------------------------------------------------------------------------------
+// generic launch plumbing
+
+#if DS_CUDA
+template <class Body, int NT, class P>
+__global__ void __launch_bounds__(NT) ds_kernel(const P p) {
+    extern __shared__ __align__(16) unsigned char ds_smem[];
+    Body::template run<NT>(p, (int)blockIdx.x, (int)threadIdx.x, ds_smem);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// BGR (3 B/px, arbitrary stride) -> BGRX (4 B/px) expansion done once at upload.
+
+struct ExpandParams {
+    const uint8_t* src; size_t src_stride;
+    uint32_t* dst; int dst_pitch;
+    int w, h;
+};
+struct ExpandBody {
+    static constexpr int PER_BLOCK = 2048;
+    static int smem_bytes() { return 0; }
+    static long long blocks(const ExpandParams& p) { return ((long long)p.w * p.h + PER_BLOCK - 1) / PER_BLOCK; }
+    template <int NT>
+    DS_DM void run(const ExpandParams& p, int block, int tid, unsigned char*) {
+        const long long n = (long long)p.w * p.h;
+        for (int i = tid; i < PER_BLOCK; i += NT) {
+            const long long idx = (long long)block * PER_BLOCK + i;
+            if (idx >= n) break;
+            const int y = (int)(idx / p.w), x = (int)(idx - (long long)y * p.w);
+            const uint8_t* s = p.src + (size_t)y * p.src_stride + (size_t)x * 3;
+            p.dst[(size_t)y * p.dst_pitch + x] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Debug taps: fixed-point tables and the warped bbox of one frame.
+
+struct TapParams {
+    const FrameDev* frames; int frame;
+    int16_t* xy; uint16_t* a;      // tables (either both or none)
+    uint8_t* bgr; uint8_t* mask;   // warped image / mask (either both or none)
+};
+struct TapBody {
+    static constexpr int PER_BLOCK = 1024;
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const TapParams& p, int block, int tid, unsigned char*) {
+        const FrameDev& F = p.frames[p.frame];
+        const long long n = (long long)F.w * F.h;
+        for (int i = tid; i < PER_BLOCK; i += NT) {
+            const long long idx = (long long)block * PER_BLOCK + i;
+            if (idx >= n) break;
+            const int v = (int)(idx / F.w), u = (int)(idx - (long long)v * F.w);
+            const Coord c = eval_coord(F, u, v);
+            if (p.xy) {
+                p.xy[2 * idx] = (int16_t)c.sx; p.xy[2 * idx + 1] = (int16_t)c.sy;
+                p.a[idx] = (uint16_t)(c.ay * 32 + c.ax);
+            }
+            if (p.bgr) {
+                const px8 s = sample_bilinear(F, c);
+                p.bgr[3 * idx] = s.b; p.bgr[3 * idx + 1] = s.g; p.bgr[3 * idx + 2] = s.r;
+                p.mask[idx] = (uint8_t)mask_value(F, c, u, v);
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FEATHER step 1: nearest-warped mask of a frame's bbox as a bit plane (1 = non-zero mask).
+// One warp packs 32 pixels with a ballot; tail bits (u >= w) are set so they never act as zeros.
+
+struct MaskBitsParams {
+    const FrameDev* frames; int frame;
+    uint32_t* bits;  // == frames[frame].mbits (non-const view)
+};
+struct MaskBitsBody {
+    static constexpr int WORDS_PER_BLOCK = 8;  // 256 threads = 8 warps = 8 words
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const MaskBitsParams& p, int block, int tid, unsigned char*) {
+        const FrameDev& F = p.frames[p.frame];
+        const long long nwords = (long long)F.mbits_pitch * F.h;
+#if DS_CUDA
+        const long long word = (long long)block * WORDS_PER_BLOCK + (tid >> 5);
+        const int lane = tid & 31;
+        bool bit = true;
+        int v = 0, k = 0;
+        if (word < nwords) {
+            v = (int)(word / F.mbits_pitch); k = (int)(word - (long long)v * F.mbits_pitch);
+            const int u = k * 32 + lane;
+            if (u < F.w) {
+                const Coord c = eval_coord(F, u, v);
+                bit = mask_value(F, c, u, v) != 0;
+            }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, bit);
+        if (word < nwords && lane == 0) p.bits[word] = b;
+#else
+        (void)tid;
+        for (int wi = 0; wi < WORDS_PER_BLOCK; wi++) {
+            const long long word = (long long)block * WORDS_PER_BLOCK + wi;
+            if (word >= nwords) break;
+            const int v = (int)(word / F.mbits_pitch), k = (int)(word - (long long)v * F.mbits_pitch);
+            uint32_t b = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                const int u = k * 32 + lane;
+                bool bit = true;
+                if (u < F.w) {
+                    const Coord c = eval_coord(F, u, v);
+                    bit = mask_value(F, c, u, v) != 0;
+                }
+                b |= (bit ? 1u : 0u) << lane;
+            }
+            p.bits[word] = b;
+        }
+#endif
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FEATHER step 2: one canvas tile gathers every frame that covers it, in feed order:
+//   w = min(L1dist(mask) * sharpness, 1); acc += trunc(pix * w); wsum += w
+// then out = trunc(acc / (wsum + 1e-5)), mask = wsum > 1e-5 (A12). The L1 distance is exact for
+// d < R (R*sharpness >= 1) and only evaluated when the tile's R-window holds a zero mask pixel.
+
+struct OutParams {
+    uint8_t* out; size_t out_pitch;    // BGR8 or BGRA8 rows
+    uint8_t* mask; size_t mask_pitch;  // BGR8 only (BGRA8 carries it in alpha)
+    int fmt;                            // 0 BGR8, 1 BGRA8
+    int w, h;                           // unpadded canvas
+};
+
+struct FeatherParams {
+    const FrameDev* frames;
+    const int* tile_off; const int* tile_frames;
+    const int* tile_ids;  // tiles this launch processes (NULL: block == tile)
+    int tiles_x;
+    float sharpness; int R;
+    int row0, row1;       // canvas rows this handle's band owns
+    OutParams o;
+};
+
+struct FeatherBody {
+    static constexpr int TW = 64, TH = 32, RMAX = 64;
+    static int smem_bytes() { return (TW + 2 * RMAX) * (TH + 2 * RMAX) + 16; }
+    template <int NT>
+    DS_DM void run(const FeatherParams& p, int block, int tid, unsigned char* smem) {
+        constexpr int PPT = TW * TH / NT;
+        const int tile = p.tile_ids ? p.tile_ids[block] : block;
+        unsigned char* s_d = smem + 16;
+        int* s_flag = (int*)smem;
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int X0 = tx * TW, Y0 = ty * TH;
+        const int R = p.R;
+        const int ww = TW + 2 * R, wh = TH + 2 * R;
+        int acc[PPT][3];
+        float ws[PPT];
+        DS_UNROLL
+        for (int k = 0; k < PPT; k++) { acc[k][0] = acc[k][1] = acc[k][2] = 0; ws[k] = 0.f; }
+
+        for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
+            const FrameDev& F = p.frames[p.tile_frames[fi]];
+            // window in bbox coordinates
+            const int wu0 = X0 - R - F.cx, wv0 = Y0 - R - F.cy;
+            if (tid == 0) *s_flag = 0;
+            DS_SYNC();
+            // 1) any zero bit inside window ∩ bbox ?
+            {
+                const int u_lo = imax(wu0, 0), u_hi = imin(wu0 + ww, F.w);  // [u_lo, u_hi)
+                const int v_lo = imax(wv0, 0), v_hi = imin(wv0 + wh, F.h);
+                if (u_lo < u_hi && v_lo < v_hi) {
+                    const int k_lo = u_lo >> 5, k_hi = (u_hi - 1) >> 5;
+                    const int nk = k_hi - k_lo + 1;
+                    const int n = nk * (v_hi - v_lo);
+                    int found = 0;
+                    for (int i = tid; i < n; i += NT) {
+                        const int v = v_lo + i / nk, k = k_lo + i % nk;
+                        uint32_t wd = ld_ro(F.mbits + (size_t)v * F.mbits_pitch + k);
+                        uint32_t sel = 0xffffffffu;
+                        if (k == k_lo) sel &= 0xffffffffu << (u_lo & 31);
+                        if (k == k_hi) sel &= 0xffffffffu >> (31 - ((u_hi - 1) & 31));
+                        if ((~wd) & sel) found = 1;
+                    }
+                    if (found) *s_flag = 1;  // benign race: all writers store 1
+                }
+            }
+            DS_SYNC();
+            const int has_zero = *s_flag;
+            if (has_zero) {
+                // 2) expand to bytes: 0 at zero mask pixels, 255 elsewhere (outside bbox = not a source)
+                for (int i = tid; i < ww * wh; i += NT) {
+                    const int yy = i / ww, xx = i - yy * ww;
+                    const int u = wu0 + xx, v = wv0 + yy;
+                    unsigned char d = 255;
+                    if ((unsigned)u < (unsigned)F.w && (unsigned)v < (unsigned)F.h) {
+                        const uint32_t wd = ld_ro(F.mbits + (size_t)v * F.mbits_pitch + (u >> 5));
+                        d = ((wd >> (u & 31)) & 1u) ? 255 : 0;
+                    }
+                    s_d[i] = d;
+                }
+                DS_SYNC();
+                // horizontal min-plus sweeps, one row per thread
+                for (int yy = tid; yy < wh; yy += NT) {
+                    unsigned char* row = s_d + yy * ww;
+                    int d = 255;
+                    for (int xx = 0; xx < ww; xx++) { d = row[xx] == 0 ? 0 : imin(d + 1, 255); row[xx] = (unsigned char)d; }
+                    d = 255;
+                    for (int xx = ww - 1; xx >= 0; xx--) {
+                        d = row[xx] == 0 ? 0 : imin(d + 1, 255);
+                        if (d < row[xx]) row[xx] = (unsigned char)d;
+                    }
+                }
+                DS_SYNC();
+                // vertical sweeps over the tile's own columns
+                for (int xx = R + tid; xx < R + TW; xx += NT) {
+                    int d = 255;
+                    for (int yy = 0; yy < wh; yy++) {
+                        d = imin(d + 1, 255);
+                        const int g = s_d[yy * ww + xx];
+                        if (g < d) d = g;
+                        s_d[yy * ww + xx] = (unsigned char)d;
+                    }
+                    d = 255;
+                    for (int yy = wh - 1; yy >= 0; yy--) {
+                        d = imin(d + 1, 255);
+                        const int g = s_d[yy * ww + xx];
+                        if (g < d) d = g;
+                        s_d[yy * ww + xx] = (unsigned char)d;
+                    }
+                }
+                DS_SYNC();
+            }
+            // 3) sample + accumulate
+            DS_UNROLL
+            for (int k = 0; k < PPT; k++) {
+                const int pidx = tid + k * NT;
+                const int yy = pidx / TW, xx = pidx - yy * TW;
+                const int u = X0 + xx - F.cx, v = Y0 + yy - F.cy;
+                if ((unsigned)u >= (unsigned)F.w || (unsigned)v >= (unsigned)F.h) continue;
+                float wgt = 1.f;
+                if (has_zero) {
+                    const int d = s_d[(yy + R) * ww + (xx + R)];
+                    if (d == 0) continue;
+                    if (d < R) { wgt = f_mul((float)d, p.sharpness); if (wgt > 1.f) wgt = 1.f; }
+                }
+                const Coord c = eval_coord(F, u, v);
+                const px8 s = sample_bilinear(F, c);
+                acc[k][0] += (int)(short)f2i_rz(f_mul((float)s.b, wgt));
+                acc[k][1] += (int)(short)f2i_rz(f_mul((float)s.g, wgt));
+                acc[k][2] += (int)(short)f2i_rz(f_mul((float)s.r, wgt));
+                ws[k] = f_add(ws[k], wgt);
+            }
+            DS_SYNC();
+        }
+        // normalise + store
+        DS_UNROLL
+        for (int k = 0; k < PPT; k++) {
+            const int pidx = tid + k * NT;
+            const int yy = pidx / TW, xx = pidx - yy * TW;
+            const int X = X0 + xx, Y = Y0 + yy;
+            if (X >= p.o.w || Y >= p.o.h || Y < p.row0 || Y >= p.row1) continue;
+            const float den = f_add(ws[k], 1e-5f);
+            const int m = ws[k] > 1e-5f;
+            int o[3];
+            for (int ch = 0; ch < 3; ch++) {
+                const int v16 = (int)(short)f2i_rz(f_div((float)(short)acc[k][ch], den));
+                o[ch] = m ? sat8i(v16) : 0;
+            }
+            if (p.o.fmt == 1) {
+                uint32_t pk = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | (m ? 0xff000000u : 0u);
+                *(uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 4) = pk;
+            } else {
+                uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 3;
+                q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
+                p.o.mask[(size_t)Y * p.o.mask_pitch + X] = m ? 255 : 0;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MULTIBAND feed, one pyramid level per launch, gather formulation (A11).
+// A canvas tile of level l walks the frames whose feed ROI touches it, in feed order. Per frame:
+//   phase 1  G_l over the tile + halo into shared memory (level 0: inverse warp of the source,
+//            copyMakeBorder(REFLECT) and the warped mask folded in; l >= 1: read the frame's G_l, W_l)
+//   phase 2  G_{l+1} = pyrDown16S (tile/2 + 1 ring, own part written to the frame's pyramid),
+//            W_{l+1} = pyrDownF32 (own part written)
+//   phase 3  lap = sat(G_l - pyrUp(G_{l+1})); acc += trunc(lap * W_l) (int16 wrap); wsum += W_l
+// After the last frame: dst_l = trunc(acc / (wsum + 1e-5)), flag = wsum > 1e-5.
+// The top level (l == L) accumulates G_L itself.
+
+struct MBParams {
+    const FrameDev* frames;
+    const int* tile_off; const int* tile_frames;  // CSR: frames per tile of this level
+    const int* tile_ids;                           // tiles this launch processes (NULL: block == tile)
+    int tiles_x;
+    int level, L;
+    px16* dst; int dst_w, dst_h;  // normalised Laplacian level of the padded canvas
+    int acc_y0, acc_y1;           // rows of this level whose dst the band's collapse reads (dst written only there)
+    int own_y0, own_y1;           // even-aligned rows of this level the handle processes at all
+};
+
+template <int T, bool LEVEL0>
+struct MBBody {
+    static constexpr int PW = T + 7, GW = T / 2 + 2, JW = T / 2;
+    static constexpr int G_BYTES = PW * PW * (LEVEL0 ? 4 : 8);
+    static constexpr int W_BYTES = LEVEL0 ? 0 : PW * PW * 4;
+    static constexpr int G1_BYTES = GW * GW * 8;
+    static constexpr int H_BYTES = PW * JW * 4;
+    static constexpr int ACC_BYTES = T * T * 8, WS_BYTES = T * T * 4;
+    static int smem_bytes() { return G_BYTES + W_BYTES + G1_BYTES + H_BYTES + ACC_BYTES + WS_BYTES; }
+
+    template <int NT>
+    DS_DM void run(const MBParams& p, int block, int tid, unsigned char* smem) {
+        px8* s_g8 = (px8*)smem;
+        px16* s_g16 = (px16*)smem;
+        float* s_w = (float*)(smem + G_BYTES);
+        px16* s_g1 = (px16*)(smem + G_BYTES + W_BYTES);
+        float* s_h = (float*)(smem + G_BYTES + W_BYTES + G1_BYTES);
+        px16* s_acc = (px16*)(smem + G_BYTES + W_BYTES + G1_BYTES + H_BYTES);
+        float* s_ws = (float*)(smem + G_BYTES + W_BYTES + G1_BYTES + H_BYTES + ACC_BYTES);
+
+        const int tile = p.tile_ids ? p.tile_ids[block] : block;
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int X0 = tx * T, Y0 = ty * T;
+        const int l = p.level;
+        const bool top = (l == p.L);
+
+        for (int i = tid; i < T * T; i += NT) { px16 z; z.b = z.g = z.r = z.a = 0; s_acc[i] = z; s_ws[i] = 0.f; }
+        DS_SYNC();
+
+        for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
+            const FrameDev& F = p.frames[p.tile_frames[fi]];
+            const int rx = F.rx >> l, ry = F.ry >> l, rw = F.rw >> l, rh = F.rh >> l;
+            const int ax0 = imax(X0, rx), ax1 = imin(X0 + T, rx + rw);
+            const int ay0 = imax(imax(Y0, ry), p.own_y0), ay1 = imin(imin(Y0 + T, ry + rh), p.own_y1);
+            if (ax0 >= ax1 || ay0 >= ay1) continue;  // block-uniform
+            const int ox0 = ax0 - rx, ox1 = ax1 - rx, oy0 = ay0 - ry, oy1 = ay1 - ry;  // own, ROI-relative
+            int n1x = 0, n1y = 0, jx0 = 0, jx1 = 0, jy0 = 0, jy1 = 0, gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0;
+            int px0 = ox0, px1 = ox1 - 1, py0 = oy0, py1 = oy1 - 1;
+            if (!top) {
+                n1x = rw >> 1; n1y = rh >> 1;
+                jx0 = ox0 >> 1; jx1 = (ox1 + 1) >> 1; jy0 = oy0 >> 1; jy1 = (oy1 + 1) >> 1;
+                gx0 = imax(jx0 - 1, 0); gx1 = imin(jx1, n1x - 1);
+                gy0 = imax(jy0 - 1, 0); gy1 = imin(jy1, n1y - 1);
+                px0 = imax(2 * gx0 - 2, 0); px1 = imin(2 * gx1 + 2, rw - 1);
+                py0 = imax(2 * gy0 - 2, 0); py1 = imin(2 * gy1 + 2, rh - 1);
+            }
+            const int pw = px1 - px0 + 1, ph = py1 - py0 + 1;
+
+            // ---- phase 1: G_l (+ W_l) over [px0..px1] x [py0..py1]
+            for (int i = tid; i < pw * ph; i += NT) {
+                const int yy = i / pw, xx = i - yy * pw;
+                const int px = px0 + xx, py = py0 + yy;
+                if (LEVEL0) {
+                    const int u = F.rx + px - F.cx, v = F.ry + py - F.cy;
+                    const bool inside = (unsigned)u < (unsigned)F.w && (unsigned)v < (unsigned)F.h;
+                    const int ur = refl(u, F.w, BORDER_REFL), vr = refl(v, F.h, BORDER_REFL);
+                    const Coord c = eval_coord(F, ur, vr);
+                    px8 s = sample_bilinear(F, c);
+                    s.a = (unsigned char)(inside ? mask_value(F, c, u, v) : 0);
+                    s_g8[i] = s;
+                } else {
+                    const size_t gi = (size_t)py * rw + px;
+                    s_g16[i] = F.G[l][gi];
+                    s_w[i] = F.W[l][gi];
+                }
+            }
+            DS_SYNC();
+
+            if (!top) {
+                const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
+                // ---- phase 2a: G_{l+1} = pyrDown16S over the g-range
+                for (int i = tid; i < gw * gh; i += NT) {
+                    const int gyy = i / gw, gxx = i - gyy * gw;
+                    const int gx = gx0 + gxx, gy = gy0 + gyy;
+                    int cxi[5], sb = 0, sg = 0, sr = 0;
+                    for (int k = 0; k < 5; k++) cxi[k] = refl101(2 * gx + k - 2, rw) - px0;
+                    for (int ky = 0; ky < 5; ky++) {
+                        const int sy = refl101(2 * gy + ky - 2, rh) - py0;
+                        const int kwy = (ky == 0 || ky == 4) ? 1 : ((ky == 2) ? 6 : 4);
+                        int rb = 0, rg = 0, rr = 0;
+                        for (int kx = 0; kx < 5; kx++) {
+                            const int kwx = (kx == 0 || kx == 4) ? 1 : ((kx == 2) ? 6 : 4);
+                            const int si = sy * pw + cxi[kx];
+                            int vb, vg, vr;
+                            if (LEVEL0) { const px8 q = s_g8[si]; vb = q.b; vg = q.g; vr = q.r; }
+                            else { const px16 q = s_g16[si]; vb = q.b; vg = q.g; vr = q.r; }
+                            rb += kwx * vb; rg += kwx * vg; rr += kwx * vr;
+                        }
+                        sb += kwy * rb; sg += kwy * rg; sr += kwy * rr;
+                    }
+                    px16 o;
+                    o.b = (short)((sb + 128) >> 8); o.g = (short)((sg + 128) >> 8); o.r = (short)((sr + 128) >> 8); o.a = 0;
+                    s_g1[i] = o;
+                    if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1) F.G[l + 1][(size_t)gy * n1x + gx] = o;
+                }
+                // ---- phase 2b: horizontal pass of the weight pyrDown, rows hr0..hr1, own columns
+                const int jw = jx1 - jx0;
+                const int hr0 = imax(2 * jy0 - 2, 0), hr1 = imin(2 * jy1, rh - 1);
+                const int hn = hr1 - hr0 + 1;
+                for (int i = tid; i < hn * jw; i += NT) {
+                    const int rr_ = i / jw, jj = i - rr_ * jw;
+                    const int row = hr0 + rr_, j = jx0 + jj;
+                    float t[5];
+                    for (int k = 0; k < 5; k++) {
+                        const int si = (row - py0) * pw + (refl101(2 * j + k - 2, rw) - px0);
+                        t[k] = LEVEL0 ? f_mul((float)s_g8[si].a, 1.f / 255.f) : s_w[si];
+                    }
+                    s_h[i] = pd_h_is_simd(j, rw, n1x) ? pd_h_simd(t[0], t[1], t[2], t[3], t[4])
+                                                       : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
+                }
+                DS_SYNC();
+                // ---- phase 2c: vertical pass, own (jy, j) -> W_{l+1}
+                for (int i = tid; i < (jy1 - jy0) * jw; i += NT) {
+                    const int jyy = i / jw, jj = i - jyy * jw;
+                    const int jy = jy0 + jyy, j = jx0 + jj;
+                    float t[5];
+                    for (int k = 0; k < 5; k++) t[k] = s_h[(refl101(2 * jy + k - 2, rh) - hr0) * jw + jj];
+                    const float v = pd_v_is_simd(j, n1x) ? pd_v_simd(t[0], t[1], t[2], t[3], t[4])
+                                                         : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
+                    F.W[l + 1][(size_t)jy * n1x + j] = f_mul(v, 1.f / 256.f);
+                }
+                // ---- phase 3: Laplacian + weighted accumulate over the own pixels
+                const int ow = ox1 - ox0, oh = oy1 - oy0;
+                for (int i = tid; i < ow * oh; i += NT) {
+                    const int yy = i / ow, xx = i - yy * ow;
+                    const int ox = ox0 + xx, oy = oy0 + yy;
+                    const int c1x = ox >> 1, c1y = oy >> 1;
+                    const int ixl = up_l(c1x, n1x) - gx0, ixc = c1x - gx0, ixr = up_r(c1x, n1x) - gx0;
+                    const int iyl = up_l(c1y, n1y) - gy0, iyc = c1y - gy0, iyr = up_r(c1y, n1y) - gy0;
+                    int up[3];
+                    {
+                        // horizontal on the three source rows, then vertical (A10)
+                        int hl[3], hc[3], hrr[3];
+                        const px16 a0 = s_g1[iyl * gw + ixl], a1 = s_g1[iyl * gw + ixc], a2 = s_g1[iyl * gw + ixr];
+                        const px16 b0 = s_g1[iyc * gw + ixl], b1 = s_g1[iyc * gw + ixc], b2 = s_g1[iyc * gw + ixr];
+                        const px16 c0 = s_g1[iyr * gw + ixl], c1 = s_g1[iyr * gw + ixc], c2 = s_g1[iyr * gw + ixr];
+                        if (ox & 1) {
+                            hl[0] = 4 * (a1.b + a2.b); hl[1] = 4 * (a1.g + a2.g); hl[2] = 4 * (a1.r + a2.r);
+                            hc[0] = 4 * (b1.b + b2.b); hc[1] = 4 * (b1.g + b2.g); hc[2] = 4 * (b1.r + b2.r);
+                            hrr[0] = 4 * (c1.b + c2.b); hrr[1] = 4 * (c1.g + c2.g); hrr[2] = 4 * (c1.r + c2.r);
+                        } else {
+                            hl[0] = a0.b + 6 * a1.b + a2.b; hl[1] = a0.g + 6 * a1.g + a2.g; hl[2] = a0.r + 6 * a1.r + a2.r;
+                            hc[0] = b0.b + 6 * b1.b + b2.b; hc[1] = b0.g + 6 * b1.g + b2.g; hc[2] = b0.r + 6 * b1.r + b2.r;
+                            hrr[0] = c0.b + 6 * c1.b + c2.b; hrr[1] = c0.g + 6 * c1.g + c2.g; hrr[2] = c0.r + 6 * c1.r + c2.r;
+                        }
+                        for (int ch = 0; ch < 3; ch++) {
+                            const int vv = (oy & 1) ? 4 * (hc[ch] + hrr[ch]) : (hl[ch] + 6 * hc[ch] + hrr[ch]);
+                            up[ch] = (int)(short)((vv + 32) >> 6);
+                        }
+                    }
+                    const int si = (oy - py0) * pw + (ox - px0);
+                    int gb, gg, gr; float wv;
+                    if (LEVEL0) { const px8 q = s_g8[si]; gb = q.b; gg = q.g; gr = q.r; wv = f_mul((float)q.a, 1.f / 255.f); }
+                    else { const px16 q = s_g16[si]; gb = q.b; gg = q.g; gr = q.r; wv = s_w[si]; }
+                    const int ti = (ay0 + yy - Y0) * T + (ax0 + xx - X0);
+                    px16 a = s_acc[ti];
+                    a.b = (short)(a.b + (short)f2i_rz(f_mul((float)sat16i(gb - up[0]), wv)));
+                    a.g = (short)(a.g + (short)f2i_rz(f_mul((float)sat16i(gg - up[1]), wv)));
+                    a.r = (short)(a.r + (short)f2i_rz(f_mul((float)sat16i(gr - up[2]), wv)));
+                    s_acc[ti] = a;
+                    s_ws[ti] = f_add(s_ws[ti], wv);
+                }
+            } else {
+                const int ow = ox1 - ox0, oh = oy1 - oy0;
+                for (int i = tid; i < ow * oh; i += NT) {
+                    const int yy = i / ow, xx = i - yy * ow;
+                    const int si = yy * pw + xx;
+                    int gb, gg, gr; float wv;
+                    if (LEVEL0) { const px8 q = s_g8[si]; gb = q.b; gg = q.g; gr = q.r; wv = f_mul((float)q.a, 1.f / 255.f); }
+                    else { const px16 q = s_g16[si]; gb = q.b; gg = q.g; gr = q.r; wv = s_w[si]; }
+                    const int ti = (ay0 + yy - Y0) * T + (ax0 + xx - X0);
+                    px16 a = s_acc[ti];
+                    a.b = (short)(a.b + (short)f2i_rz(f_mul((float)gb, wv)));
+                    a.g = (short)(a.g + (short)f2i_rz(f_mul((float)gg, wv)));
+                    a.r = (short)(a.r + (short)f2i_rz(f_mul((float)gr, wv)));
+                    s_acc[ti] = a;
+                    s_ws[ti] = f_add(s_ws[ti], wv);
+                }
+            }
+            DS_SYNC();
+        }
+
+        // ---- normalise and store the dst level (only rows the band owns)
+        for (int i = tid; i < T * T; i += NT) {
+            const int yy = i / T, xx = i - yy * T;
+            const int X = X0 + xx, Y = Y0 + yy;
+            if (X >= p.dst_w || Y >= p.dst_h || Y < p.acc_y0 || Y >= p.acc_y1) continue;
+            const px16 a = s_acc[i];
+            const float wsum = s_ws[i];
+            const float den = f_add(wsum, 1e-5f);
+            px16 o;
+            o.b = (short)f2i_rz(f_div((float)a.b, den));
+            o.g = (short)f2i_rz(f_div((float)a.g, den));
+            o.r = (short)f2i_rz(f_div((float)a.r, den));
+            o.a = (short)(wsum > 1e-5f ? 1 : 0);
+            p.dst[(size_t)Y * p.dst_w + X] = o;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MULTIBAND collapse of one level: fine = sat(pyrUp(coarse) + fine). The last step (fine = level 0)
+// also crops to the unpadded canvas, applies the result mask and saturates to 8U (A11 blend).
+// Each work item is 4 horizontally adjacent fine pixels.
+
+struct CollapseParams {
+    const px16* coarse; int cw, ch;
+    px16* fine; int fw, fh;
+    int y0, y1;   // fine rows to process
+    int final;    // 1: write `o` instead of updating `fine`
+    OutParams o;
+};
+struct CollapseBody {
+    static constexpr int PER_BLOCK = 512;  // items (quads) per block
+    static int smem_bytes() { return 0; }
+    static long long items(const CollapseParams& p) { return (long long)((p.fw + 3) / 4) * (p.y1 - p.y0); }
+    template <int NT>
+    DS_DM void run(const CollapseParams& p, int block, int tid, unsigned char*) {
+        const int qw = (p.fw + 3) / 4;
+        const long long n = (long long)qw * (p.y1 - p.y0);
+        for (int it = tid; it < PER_BLOCK; it += NT) {
+            const long long idx = (long long)block * PER_BLOCK + it;
+            if (idx >= n) break;
+            const int Y = p.y0 + (int)(idx / qw), Xq = (int)(idx % qw) * 4;
+            const int c1y = Y >> 1;
+            const int ryl = up_l(c1y, p.ch), ryr = up_r(c1y, p.ch);
+            for (int k = 0; k < 4; k++) {
+                const int X = Xq + k;
+                if (X >= p.fw) break;
+                const int c1x = X >> 1;
+                const int rxl = up_l(c1x, p.cw), rxr = up_r(c1x, p.cw);
+                int hl[3], hc[3], hr[3];
+                const px16 a1 = p.coarse[(size_t)ryl * p.cw + c1x], a2 = p.coarse[(size_t)ryl * p.cw + rxr];
+                const px16 b1 = p.coarse[(size_t)c1y * p.cw + c1x], b2 = p.coarse[(size_t)c1y * p.cw + rxr];
+                const px16 c1 = p.coarse[(size_t)ryr * p.cw + c1x], c2 = p.coarse[(size_t)ryr * p.cw + rxr];
+                if (X & 1) {
+                    hl[0] = 4 * (a1.b + a2.b); hl[1] = 4 * (a1.g + a2.g); hl[2] = 4 * (a1.r + a2.r);
+                    hc[0] = 4 * (b1.b + b2.b); hc[1] = 4 * (b1.g + b2.g); hc[2] = 4 * (b1.r + b2.r);
+                    hr[0] = 4 * (c1.b + c2.b); hr[1] = 4 * (c1.g + c2.g); hr[2] = 4 * (c1.r + c2.r);
+                } else {
+                    const px16 a0 = p.coarse[(size_t)ryl * p.cw + rxl], b0 = p.coarse[(size_t)c1y * p.cw + rxl];
+                    const px16 c0 = p.coarse[(size_t)ryr * p.cw + rxl];
+                    hl[0] = a0.b + 6 * a1.b + a2.b; hl[1] = a0.g + 6 * a1.g + a2.g; hl[2] = a0.r + 6 * a1.r + a2.r;
+                    hc[0] = b0.b + 6 * b1.b + b2.b; hc[1] = b0.g + 6 * b1.g + b2.g; hc[2] = b0.r + 6 * b1.r + b2.r;
+                    hr[0] = c0.b + 6 * c1.b + c2.b; hr[1] = c0.g + 6 * c1.g + c2.g; hr[2] = c0.r + 6 * c1.r + c2.r;
+                }
+                px16 f = p.fine[(size_t)Y * p.fw + X];
+                int o[3];
+                const int fv[3] = {f.b, f.g, f.r};
+                for (int ch = 0; ch < 3; ch++) {
+                    const int vv = (Y & 1) ? 4 * (hc[ch] + hr[ch]) : (hl[ch] + 6 * hc[ch] + hr[ch]);
+                    o[ch] = sat16i((int)(short)((vv + 32) >> 6) + fv[ch]);
+                }
+                if (!p.final) {
+                    f.b = (short)o[0]; f.g = (short)o[1]; f.r = (short)o[2];
+                    p.fine[(size_t)Y * p.fw + X] = f;
+                } else if (X < p.o.w && Y < p.o.h) {
+                    const int m = f.a != 0;
+                    const int ob = m ? sat8i(o[0]) : 0, og = m ? sat8i(o[1]) : 0, orr = m ? sat8i(o[2]) : 0;
+                    if (p.o.fmt == 1) {
+                        *(uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 4) =
+                            (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | (m ? 0xff000000u : 0u);
+                    } else {
+                        uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 3;
+                        q[0] = (uint8_t)ob; q[1] = (uint8_t)og; q[2] = (uint8_t)orr;
+                        p.o.mask[(size_t)Y * p.o.mask_pitch + X] = m ? 255 : 0;
+                    }
+                }
+            }
+        }
+    }
+};
+
+// MULTIBAND with zero bands (L == 0): level 0 is the top level; the normalised level IS the result.
+struct FinalizeL0Params {
+    const px16* lvl0; int fw, fh; int y0, y1;
+    OutParams o;
+};
+struct FinalizeL0Body {
+    static constexpr int PER_BLOCK = 1024;
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const FinalizeL0Params& p, int block, int tid, unsigned char*) {
+        const long long n = (long long)p.fw * (p.y1 - p.y0);
+        for (int it = tid; it < PER_BLOCK; it += NT) {
+            const long long idx = (long long)block * PER_BLOCK + it;
+            if (idx >= n) break;
+            const int Y = p.y0 + (int)(idx / p.fw), X = (int)(idx % p.fw);
+            if (X >= p.o.w || Y >= p.o.h) continue;
+            const px16 f = p.lvl0[(size_t)Y * p.fw + X];
+            const int m = f.a != 0;
+            const int ob = m ? sat8i(f.b) : 0, og = m ? sat8i(f.g) : 0, orr = m ? sat8i(f.r) : 0;
+            if (p.o.fmt == 1) {
+                *(uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 4) =
+                    (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | (m ? 0xff000000u : 0u);
+            } else {
+                uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 3;
+                q[0] = (uint8_t)ob; q[1] = (uint8_t)og; q[2] = (uint8_t)orr;
+                p.o.mask[(size_t)Y * p.o.mask_pitch + X] = m ? 255 : 0;
+            }
+        }
+    }
+};

@@ -1,0 +1,903 @@
+// ds_runtime.cu — host runtime + C ABI of libdronestitch_cuda (include/dronestitch.h).
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a. There is no CPU fallback: without a
+// usable CUDA device every computing entry point returns DS_ERR_NO_DEVICE.
+// The same file compiles with -DDS_EMU under g++ into the tests-only emulator (tests/emu), where
+// "device" memory is host memory and a launch is a loop over blocks.
+#include "../../include/dronestitch.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ds_geometry.h"
+#include "ds_kernels.h"
+
+#ifndef DS_VERSION_STRING
+#define DS_VERSION_STRING "0.1.0"
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+// ------------------------------------------------------------------ backend
+#if DS_CUDA
+typedef cudaStream_t stream_t;
+#define DS_CK(call)                                                                          \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(e_ == cudaErrorMemoryAllocation ? DS_ERR_OOM : DS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int dev_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) return DS_OK;
+    DS_CK(cudaMalloc(p, bytes));
+    return DS_OK;
+}
+void dev_free(void* p) { if (p) cudaFree(p); }
+int h2d(void* d, const void* h, size_t n, stream_t s) { DS_CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); return DS_OK; }
+int h2d_2d(void* d, size_t dp, const void* h, size_t hp, size_t wbytes, size_t rows, stream_t s) {
+    DS_CK(cudaMemcpy2DAsync(d, dp, h, hp, wbytes, rows, cudaMemcpyHostToDevice, s));
+    return DS_OK;
+}
+int d2h_2d(void* h, size_t hp, const void* d, size_t dp, size_t wbytes, size_t rows, stream_t s) {
+    DS_CK(cudaMemcpy2DAsync(h, hp, d, dp, wbytes, rows, cudaMemcpyDeviceToHost, s));
+    return DS_OK;
+}
+int d2h(void* h, const void* d, size_t n, stream_t s) { DS_CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); return DS_OK; }
+int stream_sync(stream_t s) { DS_CK(cudaStreamSynchronize(s)); return DS_OK; }
+
+template <class Body, int NT, class P>
+int launch(const P& p, long long blocks, stream_t s, int smem_bytes) {
+    if (blocks <= 0) return DS_OK;
+    if (blocks > 2147483647LL) return fail(DS_ERR_BAD_ARG, "grid too large (%lld blocks)", blocks);
+    static int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem_bytes > 48 * 1024 && configured_dev != dev) {
+        DS_CK(cudaFuncSetAttribute(ds_kernel<Body, NT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured_dev = dev;
+    }
+    ds_kernel<Body, NT, P><<<(unsigned)blocks, NT, smem_bytes, s>>>(p);
+    DS_CK(cudaGetLastError());
+    return DS_OK;
+}
+#else
+typedef int stream_t;
+int dev_alloc(void** p, size_t bytes) {
+    *p = bytes ? malloc(bytes) : nullptr;
+    if (bytes && !*p) return fail(DS_ERR_OOM, "malloc(%zu) failed", bytes);
+    return DS_OK;
+}
+void dev_free(void* p) { free(p); }
+int h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); return DS_OK; }
+int h2d_2d(void* d, size_t dp, const void* h, size_t hp, size_t wbytes, size_t rows, stream_t) {
+    for (size_t r = 0; r < rows; r++) memcpy((char*)d + r * dp, (const char*)h + r * hp, wbytes);
+    return DS_OK;
+}
+int d2h_2d(void* h, size_t hp, const void* d, size_t dp, size_t wbytes, size_t rows, stream_t) {
+    for (size_t r = 0; r < rows; r++) memcpy((char*)h + r * hp, (const char*)d + r * dp, wbytes);
+    return DS_OK;
+}
+int d2h(void* h, const void* d, size_t n, stream_t) { memcpy(h, d, n); return DS_OK; }
+int stream_sync(stream_t) { return DS_OK; }
+
+template <class Body, int NT, class P>
+int launch(const P& p, long long blocks, stream_t, int smem_bytes) {
+    // emulation: one "thread" per block (NT = 1), blocks spread over host threads
+#pragma omp parallel
+    {
+        std::vector<unsigned char> sm((size_t)smem_bytes + 64);
+#pragma omp for schedule(dynamic, 4)
+        for (long long b = 0; b < blocks; b++) Body::template run<1>(p, (int)b, 0, sm.data());
+    }
+    return DS_OK;
+}
+#endif
+
+template <class T>
+int dev_alloc_t(T** p, size_t count) { return dev_alloc((void**)p, count * sizeof(T)); }
+
+struct Range { int lo, hi; };  // [lo, hi)
+
+struct Frame {
+    bool used = false;
+    int w = 0, h = 0;
+    ds_transform xf;
+    uint32_t* d_src = nullptr; int pitch = 0; size_t src_cap = 0;
+    int corner_x = 0, corner_y = 0, bw = 0, bh = 0;  // absolute placement (cv corners[i], sizes[i])
+    int rx = 0, ry = 0, rw = 0, rh = 0;              // feed ROI rel. to padded canvas origin
+    void* d_pyr = nullptr; size_t pyr_cap = 0;       // G/W levels 1..L
+    uint32_t* d_mbits = nullptr; size_t mbits_cap = 0;
+    uint8_t* d_seam = nullptr; size_t seam_cap = 0;
+    FrameDev dev;
+};
+
+struct LevelPlan {
+    int T = 0, tiles_x = 0, tiles_y = 0;
+    Range own{0, 0};   // rows of this level whose tiles run (production + accumulation)
+    Range acc{0, 0};   // rows whose dst is written / consumed by the collapse
+    int* d_off = nullptr; int* d_fr = nullptr; int* d_ids = nullptr;
+    size_t off_cap = 0, fr_cap = 0, ids_cap = 0;
+    int n_ids = 0;
+};
+
+}  // namespace
+
+struct ds_canvas {
+    ds_canvas_desc desc;
+    int L = 0;
+    int pw = 0, ph = 0;      // padded canvas
+    Range band{0, 0};        // level-0 rows this handle owns
+    stream_t stream = 0;
+    bool own_stream = false;
+    int lw[DS_MAXL], lh[DS_MAXL];
+    px16* d_lvl[DS_MAXL];    // allocated rows [lvl_rows[l].lo, lvl_rows[l].hi); pointer is the virtual row-0 base
+    px16* d_lvl_alloc[DS_MAXL];
+    Range lvl_rows[DS_MAXL];
+    uint8_t* d_out = nullptr; size_t out_pitch = 0;    // rows [band.lo, out_hi)
+    uint8_t* d_mask = nullptr; size_t mask_pitch = 0;
+    int out_hi = 0;
+    std::vector<Frame> frames;
+    FrameDev* d_frames = nullptr; size_t frames_cap = 0;
+    LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
+    bool dirty = true;
+    uint8_t* d_stage = nullptr; size_t stage_cap = 0;
+    int feather_R = 0;
+    int64_t device_bytes = 0;
+    int64_t launches = 0;
+    float last_ms = 0.f;
+    bool composited = false;
+    bool profiling = false;
+    struct Prof { const char* name; int level; int64_t ab; float ms; };
+    std::vector<Prof> prof;
+#if DS_CUDA
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    std::vector<cudaEvent_t> prof_ev;   // 2 per launch
+#endif
+};
+
+namespace {
+
+int grow(ds_canvas* c, void** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return DS_OK;
+    if (*p) { dev_free(*p); c->device_bytes -= (int64_t)*cap; *p = nullptr; *cap = 0; }
+    int rc = dev_alloc(p, need);
+    if (rc) return rc;
+    *cap = need;
+    c->device_bytes += (int64_t)need;
+    return DS_OK;
+}
+
+int set_device(const ds_canvas* c) {
+#if DS_CUDA
+    DS_CK(cudaSetDevice(c->desc.device));
+#else
+    (void)c;
+#endif
+    return DS_OK;
+}
+
+Range clip(Range r, int n) { return Range{std::max(r.lo, 0), std::min(r.hi, n)}; }
+
+// Row plan of a band (see DESIGN.md "Row bands"): which rows of every level this handle must
+// accumulate (acc = what the collapse reads) and which tile rows must run (own) so that the
+// per-frame pyramids it reads are locally produced — no inter-band exchange needed.
+void plan_rows(int L, const int* lh, Range band, Range* acc, Range* own) {
+    acc[0] = band;
+    for (int l = 1; l <= L; l++) {
+        Range r{(acc[l - 1].lo >> 1) - 1, ((acc[l - 1].hi - 1) >> 1) + 2};
+        acc[l] = clip(r, lh[l]);
+    }
+    own[L] = acc[L];
+    for (int l = L - 1; l >= 0; l--) {
+        // level l+1 phase 1 reads G_{l+1} rows [own.lo - 4, own.hi + 3); they are produced by level-l rows 2x
+        Range need{2 * (own[l + 1].lo - 4), 2 * (own[l + 1].hi + 3)};
+        Range r{std::min(acc[l].lo, need.lo), std::max(acc[l].hi, need.hi)};
+        r.lo &= ~1; r.hi = (r.hi + 1) & ~1;
+        own[l] = clip(r, lh[l]);
+    }
+}
+
+int level_tile(int l) { return l == 0 ? 64 : 32; }
+
+int fill_frame_dev(ds_canvas* c, Frame& f) {
+    FrameDev& d = f.dev;
+    memset(&d, 0, sizeof(d));
+    d.src = f.d_src; d.src_w = f.w; d.src_h = f.h; d.src_pitch = f.pitch;
+    d.kind = f.xf.kind; d.border = f.xf.border;
+    if (f.xf.kind == DS_XF_PLANE_F32) {
+        const dsgeo::Projector P = dsgeo::make_projector(f.xf.K, f.xf.R, f.xf.affine_warper != 0);
+        memcpy(d.k, P.k_rinv, sizeof(d.k));
+        const float one = 1 - P.t[2];
+        d.t0 = P.t[0]; d.t1 = P.t[1]; d.scale = f.xf.scale;
+        d.k2one = P.k_rinv[2] * one; d.k5one = P.k_rinv[5] * one; d.k8one = P.k_rinv[8] * one;
+        d.tlx = f.corner_x; d.tly = f.corner_y;
+    } else if (f.xf.kind == DS_XF_AFFINE_F64) {
+        dsgeo::invert_affine_f64(f.xf.M, d.inv);
+    } else {
+        if (!dsgeo::invert_3x3_f64(f.xf.M, d.inv)) return fail(DS_ERR_BAD_ARG, "singular homography");
+    }
+    d.cx = f.corner_x - c->desc.x; d.cy = f.corner_y - c->desc.y;
+    d.w = f.bw; d.h = f.bh;
+    d.rx = f.rx; d.ry = f.ry; d.rw = f.rw; d.rh = f.rh;
+    if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L > 0) {
+        char* base = (char*)f.d_pyr;
+        size_t off = 0;
+        for (int l = 1; l <= c->L; l++) {
+            const size_t n = (size_t)(f.rw >> l) * (f.rh >> l);
+            d.G[l] = (px16*)(base + off); off += n * sizeof(px16);
+            d.W[l] = (float*)(base + off); off += ((n * sizeof(float) + 15) & ~(size_t)15);
+        }
+    }
+    d.mbits = f.d_mbits; d.mbits_pitch = (f.bw + 31) / 32;
+    d.seam = f.d_seam; d.seam_pitch = f.bw;
+    if (f.xf.kind >= 0 && f.d_seam == nullptr) d.seam = nullptr;
+    return DS_OK;
+}
+
+size_t pyr_bytes(const ds_canvas* c, const Frame& f) {
+    size_t off = 0;
+    for (int l = 1; l <= c->L; l++) {
+        const size_t n = (size_t)(f.rw >> l) * (f.rh >> l);
+        off += n * sizeof(px16);
+        off += ((n * sizeof(float) + 15) & ~(size_t)15);
+    }
+    return off;
+}
+
+int placement(const ds_transform* xf, int w, int h, int* out) {
+    if (xf->kind == DS_XF_PLANE_F32) {
+        const dsgeo::Projector P = dsgeo::make_projector(xf->K, xf->R, xf->affine_warper != 0);
+        int tlx, tly, brx, bry;
+        dsgeo::plane_result_roi(P, xf->scale, w, h, tlx, tly, brx, bry);
+        out[0] = tlx; out[1] = tly; out[2] = brx - tlx + 1; out[3] = bry - tly + 1;
+    } else if (xf->kind == DS_XF_AFFINE_F64 || xf->kind == DS_XF_HOMOGRAPHY_F64) {
+        out[0] = xf->corner_x; out[1] = xf->corner_y; out[2] = xf->width; out[3] = xf->height;
+    } else {
+        return fail(DS_ERR_BAD_ARG, "unknown transform kind %d", xf->kind);
+    }
+    if (out[2] <= 0 || out[3] <= 0) return fail(DS_ERR_BAD_ARG, "empty warped bbox %dx%d", out[2], out[3]);
+    return DS_OK;
+}
+
+// Build per-level tile -> frame lists (feed order) on the host and upload them.
+int build_lists(ds_canvas* c) {
+    const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
+    const int nl = mb ? c->L + 1 : 1;
+    std::vector<int> counts, off, fr, ids;
+    for (int l = 0; l < nl; l++) {
+        LevelPlan& pl = c->plan[l];
+        const int TW = mb ? pl.T : FeatherBody::TW, TH = mb ? pl.T : FeatherBody::TH;
+        const int ntiles = pl.tiles_x * pl.tiles_y;
+        counts.assign((size_t)ntiles + 1, 0);
+        const int ty_lo = pl.own.lo / TH, ty_hi = (pl.own.hi + TH - 1) / TH;  // tile rows that run
+        auto frame_rect = [&](const Frame& f, int& x0, int& y0, int& x1, int& y1) {
+            if (mb) { x0 = f.rx >> l; y0 = f.ry >> l; x1 = x0 + (f.rw >> l); y1 = y0 + (f.rh >> l); }
+            else { x0 = f.dev.cx; y0 = f.dev.cy; x1 = x0 + f.bw; y1 = y0 + f.bh; }
+        };
+        for (int pass = 0; pass < 2; pass++) {
+            for (size_t fi = 0; fi < c->frames.size(); fi++) {
+                const Frame& f = c->frames[fi];
+                if (!f.used) continue;
+                int x0, y0, x1, y1;
+                frame_rect(f, x0, y0, x1, y1);
+                x0 = std::max(x0, 0); y0 = std::max(y0, 0);
+                x1 = std::min(x1, pl.tiles_x * TW); y1 = std::min(y1, pl.tiles_y * TH);
+                if (x0 >= x1 || y0 >= y1) continue;
+                const int tx0 = x0 / TW, tx1 = (x1 - 1) / TW;
+                const int ty0 = std::max(y0 / TH, ty_lo), ty1 = std::min((y1 - 1) / TH, ty_hi - 1);
+                for (int ty = ty0; ty <= ty1; ty++)
+                    for (int tx = tx0; tx <= tx1; tx++) {
+                        const int t = ty * pl.tiles_x + tx;
+                        if (pass == 0) counts[(size_t)t + 1]++;
+                        else fr[(size_t)off[t]++] = (int)fi;
+                    }
+            }
+            if (pass == 0) {
+                off.assign((size_t)ntiles + 1, 0);
+                for (int t = 0; t < ntiles; t++) off[(size_t)t + 1] = off[t] + counts[(size_t)t + 1];
+                fr.assign((size_t)std::max(off[ntiles], 1), 0);
+                counts = off;  // keep the prefix sums; `off` is consumed as a cursor in pass 1
+            }
+        }
+        // tiles to run: every tile in the own tile rows (empty ones still write zeros)
+        ids.clear();
+        for (int ty = ty_lo; ty < ty_hi; ty++)
+            for (int tx = 0; tx < pl.tiles_x; tx++) ids.push_back(ty * pl.tiles_x + tx);
+        pl.n_ids = (int)ids.size();
+        int rc;
+        if ((rc = grow(c, (void**)&pl.d_off, &pl.off_cap, counts.size() * sizeof(int)))) return rc;
+        if ((rc = grow(c, (void**)&pl.d_fr, &pl.fr_cap, fr.size() * sizeof(int)))) return rc;
+        if ((rc = grow(c, (void**)&pl.d_ids, &pl.ids_cap, std::max<size_t>(ids.size(), 1) * sizeof(int)))) return rc;
+        if ((rc = h2d(pl.d_off, counts.data(), counts.size() * sizeof(int), c->stream))) return rc;
+        if ((rc = h2d(pl.d_fr, fr.data(), fr.size() * sizeof(int), c->stream))) return rc;
+        if (!ids.empty() && (rc = h2d(pl.d_ids, ids.data(), ids.size() * sizeof(int), c->stream))) return rc;
+        // pageable h2d is synchronous w.r.t. the host buffers; vectors may be reused safely
+        if ((rc = stream_sync(c->stream))) return rc;
+    }
+    // frame descriptors
+    std::vector<FrameDev> fd(c->frames.size());
+    for (size_t i = 0; i < c->frames.size(); i++) {
+        if (c->frames[i].used) fd[i] = c->frames[i].dev; else memset(&fd[i], 0, sizeof(FrameDev));
+    }
+    int rc;
+    if ((rc = grow(c, (void**)&c->d_frames, &c->frames_cap, std::max<size_t>(fd.size(), 1) * sizeof(FrameDev)))) return rc;
+    if (!fd.empty() && (rc = h2d(c->d_frames, fd.data(), fd.size() * sizeof(FrameDev), c->stream))) return rc;
+    if ((rc = stream_sync(c->stream))) return rc;
+    c->dirty = false;
+    return DS_OK;
+}
+
+OutParams out_params(const ds_canvas* c) {
+    OutParams o;
+    const int bpp = c->desc.out_format == DS_OUT_BGRA8 ? 4 : 3;
+    (void)bpp;
+    // virtual row-0 bases: rows [band.lo, out_hi) are allocated
+    o.out = c->d_out - (size_t)c->band.lo * c->out_pitch;
+    o.out_pitch = c->out_pitch;
+    o.mask = c->d_mask ? c->d_mask - (size_t)c->band.lo * c->mask_pitch : nullptr;
+    o.mask_pitch = c->mask_pitch;
+    o.fmt = c->desc.out_format == DS_OUT_BGRA8 ? 1 : 0;
+    o.w = c->desc.width; o.h = c->out_hi;
+    return o;
+}
+
+// Marks the start / end of one launch for the per-kernel profile (no-ops unless profiling is on).
+int prof_mark(ds_canvas* c, bool begin, const char* name, int level, int64_t ab) {
+    if (!c->profiling) return DS_OK;
+    if (begin) c->prof.push_back(ds_canvas::Prof{name, level, ab, 0.f});
+#if DS_CUDA
+    const size_t need = c->prof.size() * 2;
+    while (c->prof_ev.size() < need) {
+        cudaEvent_t e;
+        DS_CK(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+    }
+    DS_CK(cudaEventRecord(c->prof_ev[(c->prof.size() - 1) * 2 + (begin ? 0 : 1)], c->stream));
+#endif
+    return DS_OK;
+}
+
+// Algorithmic bytes of the SURVEY.md 8(d) model attributed per launch (see DESIGN.md "Roofline"):
+//   feed level 0   : 3*S (source) + A*(20 RMW dst0 + 10/4 write G1,W1)
+//   feed level l>=1: A/4^l * (20 read G,W twice + 20 RMW dst_l) + A/4^(l+1) * 10 (write next level)
+//   top level      : A/4^L * (20 + 20)
+//   collapse       : C * 17.5 / 4^(l-1) per step into level l-1, minus 2*C for the final uchar4 store
+struct ABModel { double S, A, C; };
+ABModel ab_inputs(const ds_canvas* c) {
+    ABModel m{0, 0, (double)c->desc.width * c->desc.height};
+    for (const Frame& f : c->frames) if (f.used) { m.S += (double)f.w * f.h; m.A += (double)f.bw * f.bh; }
+    return m;
+}
+
+int run_composite(ds_canvas* c) {
+    int rc;
+    if (c->dirty && (rc = build_lists(c))) return rc;
+    c->launches = 0;
+    c->prof.clear();
+    const ABModel abm = ab_inputs(c);
+#if DS_CUDA
+    DS_CK(cudaEventRecord(c->ev0, c->stream));
+#endif
+    if (c->desc.blend_mode == DS_BLEND_FEATHER) {
+        for (size_t i = 0; i < c->frames.size(); i++) {
+            Frame& f = c->frames[i];
+            if (!f.used) continue;
+            MaskBitsParams mp{c->d_frames, (int)i, f.d_mbits};
+            const long long nwords = (long long)f.dev.mbits_pitch * f.bh;
+            if ((rc = prof_mark(c, true, "feather_mask", -1, 0))) return rc;
+            if ((rc = launch<MaskBitsBody, 256>(mp, (nwords + MaskBitsBody::WORDS_PER_BLOCK - 1) / MaskBitsBody::WORDS_PER_BLOCK,
+                                                c->stream, 0))) return rc;
+            if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
+            c->launches++;
+        }
+        LevelPlan& pl = c->plan[0];
+        FeatherParams fp;
+        fp.frames = c->d_frames; fp.tile_off = pl.d_off; fp.tile_frames = pl.d_fr; fp.tile_ids = pl.d_ids;
+        fp.tiles_x = pl.tiles_x; fp.sharpness = c->desc.sharpness; fp.R = c->feather_R;
+        fp.row0 = c->band.lo; fp.row1 = c->out_hi;
+        fp.o = out_params(c);
+        if ((rc = prof_mark(c, true, "feather_blend", 0, (int64_t)(3.0 * abm.S + 4.0 * abm.C)))) return rc;
+        if ((rc = launch<FeatherBody, 256>(fp, pl.n_ids, c->stream, FeatherBody::smem_bytes()))) return rc;
+        if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
+        c->launches++;
+    } else {
+        for (int l = 0; l <= c->L; l++) {
+            LevelPlan& pl = c->plan[l];
+            MBParams mp;
+            mp.frames = c->d_frames; mp.tile_off = pl.d_off; mp.tile_frames = pl.d_fr; mp.tile_ids = pl.d_ids;
+            mp.tiles_x = pl.tiles_x; mp.level = l; mp.L = c->L;
+            mp.dst = c->d_lvl[l]; mp.dst_w = c->lw[l]; mp.dst_h = c->lh[l];
+            mp.acc_y0 = pl.acc.lo; mp.acc_y1 = pl.acc.hi;
+            mp.own_y0 = pl.own.lo; mp.own_y1 = pl.own.hi;
+            const double q = 1.0 / (double)(1ull << (2 * l));
+            double ab;
+            if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
+            else if (l < c->L) ab = abm.A * q * (40.0 + 2.5);
+            else ab = abm.A * q * 40.0;
+            if ((rc = prof_mark(c, true, "mb_feed", l, (int64_t)ab))) return rc;
+            if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBBody<64, true>::smem_bytes());
+            else rc = launch<MBBody<32, false>, 256>(mp, pl.n_ids, c->stream, MBBody<32, false>::smem_bytes());
+            if (rc) return rc;
+            if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
+            c->launches++;
+        }
+        for (int l = c->L; l >= 1; l--) {
+            CollapseParams cp;
+            cp.coarse = c->d_lvl[l]; cp.cw = c->lw[l]; cp.ch = c->lh[l];
+            cp.fine = c->d_lvl[l - 1]; cp.fw = c->lw[l - 1]; cp.fh = c->lh[l - 1];
+            cp.y0 = c->plan[l - 1].acc.lo; cp.y1 = c->plan[l - 1].acc.hi;
+            cp.final = (l == 1);
+            cp.o = out_params(c);
+            const long long items = CollapseBody::items(cp);
+            const double q = 1.0 / (double)(1ull << (2 * (l - 1)));
+            const double ab = abm.C * 17.5 * q - (l == 1 ? 2.0 * abm.C : 0.0);
+            if ((rc = prof_mark(c, true, "mb_collapse", l - 1, (int64_t)ab))) return rc;
+            if ((rc = launch<CollapseBody, 256>(cp, (items + CollapseBody::PER_BLOCK - 1) / CollapseBody::PER_BLOCK, c->stream, 0))) return rc;
+            if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
+            c->launches++;
+        }
+        if (c->L == 0) {
+            FinalizeL0Params fp{c->d_lvl[0], c->lw[0], c->lh[0], c->band.lo, c->out_hi, out_params(c)};
+            const long long n = (long long)fp.fw * (fp.y1 - fp.y0);
+            if ((rc = launch<FinalizeL0Body, 256>(fp, (n + FinalizeL0Body::PER_BLOCK - 1) / FinalizeL0Body::PER_BLOCK, c->stream, 0))) return rc;
+            c->launches++;
+        }
+    }
+#if DS_CUDA
+    DS_CK(cudaEventRecord(c->ev1, c->stream));
+#endif
+    c->composited = true;
+    return DS_OK;
+}
+
+int check_device() {
+#if DS_CUDA
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(DS_ERR_NO_DEVICE, "no usable CUDA device (%s); libdronestitch_cuda has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+#endif
+    return DS_OK;
+}
+
+int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int h, size_t stride,
+              const ds_transform* xf, const ds_frame_opts* opts) {
+    if (!c || !bgr || !xf) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (idx < 0 || idx > (1 << 20)) return fail(DS_ERR_BAD_ARG, "frame_idx %d out of range", idx);
+    if (w <= 0 || h <= 0 || w > 32767 || h > 32767) return fail(DS_ERR_BAD_ARG, "frame size %dx%d (cv::remap needs < 32768)", w, h);
+    if (stride < (size_t)w * 3) return fail(DS_ERR_BAD_ARG, "stride %zu < 3*w", stride);
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    int pl[4];
+    if ((rc = placement(xf, w, h, pl))) return rc;
+    if ((size_t)idx >= c->frames.size()) c->frames.resize((size_t)idx + 1);
+    Frame& f = c->frames[(size_t)idx];
+    f.used = true; f.w = w; f.h = h; f.xf = *xf;
+    f.corner_x = pl[0]; f.corner_y = pl[1]; f.bw = pl[2]; f.bh = pl[3];
+    // the frame must lie inside the canvas ROI (prepare(resultRoi(corners, sizes)) guarantees it in the reference)
+    if (f.corner_x < c->desc.x || f.corner_y < c->desc.y || f.corner_x + f.bw > c->desc.x + c->desc.width ||
+        f.corner_y + f.bh > c->desc.y + c->desc.height) {
+        f.used = false;
+        return fail(DS_ERR_BAD_ARG, "frame %d bbox (%d,%d %dx%d) leaves the canvas ROI (%d,%d %dx%d)", idx, f.corner_x, f.corner_y,
+                    f.bw, f.bh, c->desc.x, c->desc.y, c->desc.width, c->desc.height);
+    }
+    // source: staging copy (dense BGR) -> BGRX expansion
+    f.pitch = (w + 31) & ~31;
+    if ((rc = grow(c, (void**)&f.d_src, &f.src_cap, (size_t)f.pitch * h * sizeof(uint32_t)))) return rc;
+    ExpandParams ep;
+    if (on_device) {
+        ep.src = (const uint8_t*)bgr; ep.src_stride = stride;
+    } else {
+        const size_t dense = (size_t)w * 3;
+        if ((rc = grow(c, (void**)&c->d_stage, &c->stage_cap, dense * h))) return rc;
+        if ((rc = h2d_2d(c->d_stage, dense, bgr, stride, dense, (size_t)h, c->stream))) return rc;
+#if DS_CUDA
+        DS_CK(cudaEventRecord(c->ev_copy, c->stream));
+#endif
+        ep.src = c->d_stage; ep.src_stride = dense;
+    }
+    ep.dst = f.d_src; ep.dst_pitch = f.pitch; ep.w = w; ep.h = h;
+    if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->stream, 0))) return rc;
+    if (!on_device) {
+        // the caller's buffer is only borrowed for the call; the staging buffer is reused by the next
+        // upload, so wait for the expansion too (it is ~20 us for a 20 MP frame)
+        if ((rc = stream_sync(c->stream))) return rc;
+    }
+    // blend-mode specific geometry and buffers
+    if (c->desc.blend_mode == DS_BLEND_MULTIBAND) {
+        dsgeo::feed_roi(c->desc.x, c->desc.y, c->pw, c->ph, c->L, f.corner_x, f.corner_y, f.bw, f.bh, f.rx, f.ry, f.rw, f.rh);
+        if ((rc = grow(c, &f.d_pyr, &f.pyr_cap, pyr_bytes(c, f)))) return rc;
+    } else {
+        if ((rc = grow(c, (void**)&f.d_mbits, &f.mbits_cap, (size_t)((f.bw + 31) / 32) * f.bh * sizeof(uint32_t)))) return rc;
+    }
+    if (opts && opts->seam_mask) {
+        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, (size_t)f.bw * f.bh))) return rc;
+        if ((rc = h2d_2d(f.d_seam, (size_t)f.bw, opts->seam_mask, opts->seam_mask_stride ? opts->seam_mask_stride : (size_t)f.bw,
+                         (size_t)f.bw, (size_t)f.bh, c->stream))) return rc;
+        if ((rc = stream_sync(c->stream))) return rc;
+    } else if (f.d_seam) {
+        dev_free(f.d_seam); c->device_bytes -= (int64_t)f.seam_cap; f.d_seam = nullptr; f.seam_cap = 0;
+    }
+    if ((rc = fill_frame_dev(c, f))) return rc;
+    if (opts && opts->channel_gain) {
+        f.dev.has_gain = 1;
+        for (int k = 0; k < 3; k++) f.dev.gain[k] = opts->channel_gain[k];
+    }
+    c->dirty = true;
+    c->composited = false;
+    return DS_OK;
+}
+
+int smallest_feather_radius(float sharpness) {
+    for (int r = 1; r <= 4096; r++)
+        if ((float)r * sharpness >= 1.f) return r;
+    return 4097;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+
+extern "C" {
+
+DS_API const char* ds_last_error(void) { return g_err.c_str(); }
+DS_API const char* ds_version(void) {
+#if DS_CUDA
+    return "libdronestitch_cuda " DS_VERSION_STRING " (sm_100a)";
+#else
+    return "libdronestitch_emu " DS_VERSION_STRING " (TEST-ONLY CPU emulation of the kernels)";
+#endif
+}
+
+DS_API int ds_warp_roi(const ds_transform* xf, int src_w, int src_h, int32_t out_xywh[4]) {
+    if (!xf || !out_xywh || src_w <= 0 || src_h <= 0) return fail(DS_ERR_BAD_ARG, "null / empty argument");
+    int o[4];
+    int rc = placement(xf, src_w, src_h, o);
+    if (rc) return rc;
+    for (int i = 0; i < 4; i++) out_xywh[i] = o[i];
+    return DS_OK;
+}
+
+static int band_plan_from_desc(const ds_canvas_desc* d, int* L_out, int* pw_out, int* ph_out, Range* band_out, int* lw, int* lh,
+                               Range* acc, Range* own) {
+    if (d->width <= 0 || d->height <= 0) return fail(DS_ERR_BAD_ARG, "empty canvas %dx%d", d->width, d->height);
+    int L = 0, pw = d->width, ph = d->height;
+    if (d->blend_mode == DS_BLEND_MULTIBAND) {
+        if (d->num_bands < 0 || d->num_bands >= DS_MAXL) return fail(DS_ERR_BAD_ARG, "num_bands %d not in [0, %d]", d->num_bands, DS_MAXL - 1);
+        L = dsgeo::effective_bands(d->num_bands, d->width, d->height);
+        pw = dsgeo::pad_to(d->width, 1 << L); ph = dsgeo::pad_to(d->height, 1 << L);
+    } else if (d->blend_mode != DS_BLEND_FEATHER) {
+        return fail(DS_ERR_BAD_ARG, "unknown blend mode %d", d->blend_mode);
+    }
+    Range band{0, ph};
+    if (d->band_y1 > 0) {
+        band.lo = d->band_y0; band.hi = std::min(d->band_y1, ph);
+        if (band.lo < 0 || band.lo >= band.hi) return fail(DS_ERR_BAD_ARG, "bad band [%d, %d)", d->band_y0, d->band_y1);
+        const int m = 1 << L;
+        if (band.lo % m || (band.hi % m && band.hi != ph)) return fail(DS_ERR_BAD_ARG, "band edges must be multiples of %d", m);
+    }
+    lw[0] = pw; lh[0] = ph;
+    for (int l = 1; l <= L; l++) { lw[l] = (lw[l - 1] + 1) / 2; lh[l] = (lh[l - 1] + 1) / 2; }
+    plan_rows(L, lh, band, acc, own);
+    *L_out = L; *pw_out = pw; *ph_out = ph; *band_out = band;
+    return DS_OK;
+}
+
+DS_API int ds_frame_touches_band(const ds_canvas_desc* desc, const int32_t fr[4]) {
+    if (!desc || !fr) return 0;
+    int L, pw, ph, lw[DS_MAXL], lh[DS_MAXL];
+    Range band, acc[DS_MAXL], own[DS_MAXL];
+    if (band_plan_from_desc(desc, &L, &pw, &ph, &band, lw, lh, acc, own)) return 0;
+    int y0, y1;
+    if (desc->blend_mode == DS_BLEND_MULTIBAND) {
+        int rx, ry, rw, rh;
+        dsgeo::feed_roi(desc->x, desc->y, pw, ph, L, fr[0], fr[1], fr[2], fr[3], rx, ry, rw, rh);
+        y0 = ry; y1 = ry + rh;
+        return (y0 < own[0].hi && y1 > own[0].lo) ? 1 : 0;
+    }
+    y0 = fr[1] - desc->y; y1 = y0 + fr[3];
+    return (y0 < band.hi && y1 > band.lo) ? 1 : 0;
+}
+
+DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
+    if (!desc || !out) return fail(DS_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    int rc;
+    if ((rc = check_device())) return rc;
+    if (desc->out_format != DS_OUT_BGR8 && desc->out_format != DS_OUT_BGRA8) return fail(DS_ERR_BAD_ARG, "unknown out_format %d", desc->out_format);
+    ds_canvas* c = new (std::nothrow) ds_canvas();
+    if (!c) return fail(DS_ERR_OOM, "host allocation failed");
+    c->desc = *desc;
+    for (int l = 0; l < DS_MAXL; l++) { c->d_lvl[l] = nullptr; c->d_lvl_alloc[l] = nullptr; c->lw[l] = c->lh[l] = 0; c->lvl_rows[l] = Range{0, 0}; }
+    Range acc[DS_MAXL], own[DS_MAXL];
+    if ((rc = band_plan_from_desc(desc, &c->L, &c->pw, &c->ph, &c->band, c->lw, c->lh, acc, own))) { delete c; return rc; }
+    if (desc->blend_mode == DS_BLEND_FEATHER) {
+        if (!(desc->sharpness > 0.f)) { delete c; return fail(DS_ERR_BAD_ARG, "sharpness must be > 0"); }
+        c->feather_R = smallest_feather_radius(desc->sharpness);
+        if (c->feather_R > FeatherBody::RMAX) {
+            const int need = c->feather_R;
+            delete c;
+            return fail(DS_ERR_UNSUPPORTED, "feather sharpness %g needs a %d px window (max %d)", desc->sharpness, need, FeatherBody::RMAX);
+        }
+    }
+#if DS_CUDA
+    if (cudaSetDevice(desc->device) != cudaSuccess) { delete c; cudaGetLastError(); return fail(DS_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", desc->device); }
+    if (desc->stream) { c->stream = (cudaStream_t)desc->stream; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(DS_ERR_CUDA, "cudaStreamCreate failed"); }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+#endif
+    // output rows [band.lo, out_hi)
+    c->out_hi = std::min(c->band.hi, desc->height);
+    const int out_rows = std::max(c->out_hi - c->band.lo, 0);
+    const int bpp = desc->out_format == DS_OUT_BGRA8 ? 4 : 3;
+    c->out_pitch = ((size_t)desc->width * bpp + 255) & ~(size_t)255;
+    size_t cap = 0;
+    rc = grow(c, (void**)&c->d_out, &cap, c->out_pitch * (size_t)std::max(out_rows, 1));
+    if (!rc && desc->out_format == DS_OUT_BGR8) {
+        c->mask_pitch = ((size_t)desc->width + 255) & ~(size_t)255;
+        cap = 0;
+        rc = grow(c, (void**)&c->d_mask, &cap, c->mask_pitch * (size_t)std::max(out_rows, 1));
+    }
+    if (!rc && desc->blend_mode == DS_BLEND_MULTIBAND) {
+        for (int l = 0; l <= c->L && !rc; l++) {
+            LevelPlan& pl = c->plan[l];
+            pl.T = level_tile(l);
+            pl.tiles_x = (c->lw[l] + pl.T - 1) / pl.T; pl.tiles_y = (c->lh[l] + pl.T - 1) / pl.T;
+            pl.own = own[l]; pl.acc = acc[l];
+            // rows stored: what the collapse touches (acc) — the feed writes only those
+            c->lvl_rows[l] = acc[l];
+            cap = 0;
+            const size_t rows = (size_t)std::max(acc[l].hi - acc[l].lo, 1);
+            rc = grow(c, (void**)&c->d_lvl_alloc[l], &cap, rows * c->lw[l] * sizeof(px16));
+            if (!rc) c->d_lvl[l] = c->d_lvl_alloc[l] - (size_t)acc[l].lo * c->lw[l];
+        }
+    } else if (!rc) {
+        LevelPlan& pl = c->plan[0];
+        pl.T = 0;
+        pl.tiles_x = (desc->width + FeatherBody::TW - 1) / FeatherBody::TW;
+        pl.tiles_y = (desc->height + FeatherBody::TH - 1) / FeatherBody::TH;
+        pl.own = Range{c->band.lo, c->out_hi}; pl.acc = pl.own;
+    }
+    if (rc) { ds_destroy_canvas(c); return rc; }
+    *out = c;
+    return DS_OK;
+}
+
+DS_API void ds_destroy_canvas(ds_canvas* c) {
+    if (!c) return;
+    set_device(c);
+#if DS_CUDA
+    cudaStreamSynchronize(c->stream);
+#endif
+    for (Frame& f : c->frames) { dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); }
+    for (int l = 0; l < DS_MAXL; l++) {
+        dev_free(c->d_lvl_alloc[l]);
+        dev_free(c->plan[l].d_off); dev_free(c->plan[l].d_fr); dev_free(c->plan[l].d_ids);
+    }
+    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_frames); dev_free(c->d_stage);
+#if DS_CUDA
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+#endif
+    delete c;
+}
+
+DS_API int ds_upload_frame(ds_canvas* c, int frame_idx, const uint8_t* bgr, int w, int h, size_t stride,
+                           const ds_transform* xf, const ds_frame_opts* opts) {
+    return do_upload(c, frame_idx, bgr, false, w, h, stride, xf, opts);
+}
+
+DS_API int ds_upload_frame_device(ds_canvas* c, int frame_idx, const void* dev_bgr, int w, int h, size_t stride,
+                                  const ds_transform* xf, const ds_frame_opts* opts) {
+    return do_upload(c, frame_idx, dev_bgr, true, w, h, stride, xf, opts);
+}
+
+DS_API int ds_composite_async(ds_canvas* c) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    return run_composite(c);
+}
+
+DS_API int ds_synchronize(ds_canvas* c) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->stream))) return rc;
+#if DS_CUDA
+    if (c->composited) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; else cudaGetLastError();
+    }
+#endif
+    return DS_OK;
+}
+
+DS_API int ds_composite(ds_canvas* c) {
+    int rc = ds_composite_async(c);
+    if (rc) return rc;
+    return ds_synchronize(c);
+}
+
+DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* out, size_t stride, uint8_t* mask_out, size_t mask_stride) {
+    if (!c || !out) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (!c->composited) return fail(DS_ERR_STATE, "ds_download_tile before ds_composite");
+    if (w <= 0 || h <= 0 || x < 0 || x + w > c->desc.width || y < c->band.lo || y + h > c->out_hi)
+        return fail(DS_ERR_BAD_ARG, "tile (%d,%d %dx%d) outside this handle's rows [%d,%d) x [0,%d)", x, y, w, h, c->band.lo, c->out_hi, c->desc.width);
+    const int bpp = c->desc.out_format == DS_OUT_BGRA8 ? 4 : 3;
+    if (stride < (size_t)w * bpp) return fail(DS_ERR_BAD_ARG, "stride too small");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    const uint8_t* src = c->d_out + (size_t)(y - c->band.lo) * c->out_pitch + (size_t)x * bpp;
+    if ((rc = d2h_2d(out, stride, src, c->out_pitch, (size_t)w * bpp, (size_t)h, c->stream))) return rc;
+    if (mask_out) {
+        if (c->desc.out_format == DS_OUT_BGRA8) return fail(DS_ERR_UNSUPPORTED, "BGRA8 canvases carry the mask in alpha");
+        if (mask_stride < (size_t)w) return fail(DS_ERR_BAD_ARG, "mask stride too small");
+        const uint8_t* ms = c->d_mask + (size_t)(y - c->band.lo) * c->mask_pitch + x;
+        if ((rc = d2h_2d(mask_out, mask_stride, ms, c->mask_pitch, (size_t)w, (size_t)h, c->stream))) return rc;
+    }
+    return ds_synchronize(c);
+}
+
+DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
+    if (!c || !info) return fail(DS_ERR_BAD_ARG, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->padded_width = c->pw; info->padded_height = c->ph; info->num_bands = c->L;
+    int n = 0;
+    double src_px = 0, bbox_px = 0;
+    for (const Frame& f : c->frames) if (f.used) { n++; src_px += (double)f.w * f.h; bbox_px += (double)f.bw * f.bh; }
+    info->num_frames = n;
+    info->band_y0 = c->band.lo; info->band_y1 = c->band.hi;
+    info->device_bytes = c->device_bytes;
+    info->launches_last_composite = c->launches;
+    info->ms_last_composite = c->last_ms;
+    // SURVEY.md §8(d) algorithmic-bytes model
+    const double C = (double)c->desc.width * c->desc.height;
+    if (c->desc.blend_mode == DS_BLEND_FEATHER) info->algorithmic_bytes = (int64_t)(3.0 * src_px + 4.0 * C);
+    else {
+        double g = 0, q = 1;
+        for (int l = 0; l <= c->L; l++) { g += q; q *= 0.25; }
+        info->algorithmic_bytes = (int64_t)(3.0 * src_px + bbox_px * (20.0 * g + 30.0 * (g - 1.0)) + C * (17.5 * g - 2.0));
+    }
+    return DS_OK;
+}
+
+DS_API int ds_set_profiling(ds_canvas* c, int on) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    c->profiling = on != 0;
+    return DS_OK;
+}
+
+DS_API int ds_get_kernel_times(ds_canvas* c, ds_kernel_time* out, int cap, int* n) {
+    if (!c || !n) return fail(DS_ERR_BAD_ARG, "null argument");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->stream))) return rc;
+    *n = (int)c->prof.size();
+    for (size_t i = 0; i < c->prof.size(); i++) {
+#if DS_CUDA
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+        c->prof[i].ms = ms;
+#endif
+        if (out && (int)i < cap) {
+            memset(&out[i], 0, sizeof(out[i]));
+            snprintf(out[i].name, sizeof(out[i].name), "%s", c->prof[i].name);
+            out[i].level = c->prof[i].level; out[i].ms = c->prof[i].ms; out[i].algorithmic_bytes = c->prof[i].ab;
+        }
+    }
+    return DS_OK;
+}
+
+// ---------------------------------------------------------------- debug taps
+
+static int tap_common(ds_canvas* c, int frame_idx, Frame** f) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    if (frame_idx < 0 || (size_t)frame_idx >= c->frames.size() || !c->frames[(size_t)frame_idx].used)
+        return fail(DS_ERR_BAD_ARG, "frame %d not uploaded", frame_idx);
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if (c->dirty && (rc = build_lists(c))) return rc;
+    *f = &c->frames[(size_t)frame_idx];
+    return DS_OK;
+}
+
+DS_API int ds_debug_get_placement(ds_canvas* c, int frame_idx, int32_t out_xywh[4]) {
+    if (!c || !out_xywh) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (frame_idx < 0 || (size_t)frame_idx >= c->frames.size() || !c->frames[(size_t)frame_idx].used)
+        return fail(DS_ERR_BAD_ARG, "frame %d not uploaded", frame_idx);
+    const Frame& f = c->frames[(size_t)frame_idx];
+    out_xywh[0] = f.corner_x; out_xywh[1] = f.corner_y; out_xywh[2] = f.bw; out_xywh[3] = f.bh;
+    return DS_OK;
+}
+
+DS_API int ds_debug_get_maps(ds_canvas* c, int frame_idx, int16_t* xy, uint16_t* a) {
+    Frame* f;
+    int rc = tap_common(c, frame_idx, &f);
+    if (rc) return rc;
+    if (!xy || !a) return fail(DS_ERR_BAD_ARG, "null output");
+    const size_t n = (size_t)f->bw * f->bh;
+    int16_t* d_xy = nullptr; uint16_t* d_a = nullptr;
+    if ((rc = dev_alloc_t(&d_xy, n * 2))) return rc;
+    if ((rc = dev_alloc_t(&d_a, n))) { dev_free(d_xy); return rc; }
+    TapParams tp{c->d_frames, frame_idx, d_xy, d_a, nullptr, nullptr};
+    rc = launch<TapBody, 256>(tp, (long long)((n + TapBody::PER_BLOCK - 1) / TapBody::PER_BLOCK), c->stream, 0);
+    if (!rc) rc = d2h(xy, d_xy, n * 2 * sizeof(int16_t), c->stream);
+    if (!rc) rc = d2h(a, d_a, n * sizeof(uint16_t), c->stream);
+    if (!rc) rc = stream_sync(c->stream);
+    dev_free(d_xy); dev_free(d_a);
+    return rc;
+}
+
+DS_API int ds_debug_get_warped(ds_canvas* c, int frame_idx, uint8_t* bgr, uint8_t* mask) {
+    Frame* f;
+    int rc = tap_common(c, frame_idx, &f);
+    if (rc) return rc;
+    if (!bgr || !mask) return fail(DS_ERR_BAD_ARG, "null output");
+    const size_t n = (size_t)f->bw * f->bh;
+    uint8_t* d_b = nullptr; uint8_t* d_m = nullptr;
+    if ((rc = dev_alloc_t(&d_b, n * 3))) return rc;
+    if ((rc = dev_alloc_t(&d_m, n))) { dev_free(d_b); return rc; }
+    TapParams tp{c->d_frames, frame_idx, nullptr, nullptr, d_b, d_m};
+    rc = launch<TapBody, 256>(tp, (long long)((n + TapBody::PER_BLOCK - 1) / TapBody::PER_BLOCK), c->stream, 0);
+    if (!rc) rc = d2h(bgr, d_b, n * 3, c->stream);
+    if (!rc) rc = d2h(mask, d_m, n, c->stream);
+    if (!rc) rc = stream_sync(c->stream);
+    dev_free(d_b); dev_free(d_m);
+    return rc;
+}
+
+DS_API int ds_debug_get_frame_level(ds_canvas* c, int frame_idx, int level, int16_t* g, float* w, int32_t dims_out[4]) {
+    Frame* f;
+    int rc = tap_common(c, frame_idx, &f);
+    if (rc) return rc;
+    if (c->desc.blend_mode != DS_BLEND_MULTIBAND) return fail(DS_ERR_STATE, "not a multiband canvas");
+    if (level < 1 || level > c->L) return fail(DS_ERR_BAD_ARG, "level %d not in [1, %d]", level, c->L);
+    const int lw = f->rw >> level, lh = f->rh >> level;
+    if (dims_out) { dims_out[0] = f->rx >> level; dims_out[1] = f->ry >> level; dims_out[2] = lw; dims_out[3] = lh; }
+    if (!g && !w) return DS_OK;
+    if (!c->composited) return fail(DS_ERR_STATE, "frame pyramids exist only after ds_composite");
+    const size_t n = (size_t)lw * lh;
+    if (g) {
+        std::vector<px16> tmp(n);
+        if ((rc = d2h(tmp.data(), f->dev.G[level], n * sizeof(px16), c->stream))) return rc;
+        if ((rc = stream_sync(c->stream))) return rc;
+        for (size_t i = 0; i < n; i++) { g[3 * i] = tmp[i].b; g[3 * i + 1] = tmp[i].g; g[3 * i + 2] = tmp[i].r; }
+    }
+    if (w) {
+        if ((rc = d2h(w, f->dev.W[level], n * sizeof(float), c->stream))) return rc;
+        if ((rc = stream_sync(c->stream))) return rc;
+    }
+    return DS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+/*
+ * dronestitch.h — C ABI of libdronestitch_cuda (B200 / sm_100a compositing path).
+ *
+ * Replaces, as a drop-in for that path only, the warp + blend loop of
+ * Akika404/drone_image_stitch_cpp (all file:line below are in /root/reference):
+ *   - src/stitch_robust.cpp:256        stitcher->composePanorama(output)      (HOT PATH #1)
+ *       per frame: AffineWarper::warp (LINEAR/REFLECT), mask warp (NEAREST/CONSTANT),
+ *       ->16S, MultiBandBlender::feed; then blend, ->8U   (components chosen at :203-213)
+ *   - src/stitch_global.cpp:470-486    cv::warpAffine loop                    (HOT PATH #2, coords)
+ *   - src/stitch_global.cpp:632-666    MultiBandBlender prepare / feed / blend / ->8U
+ * The reference has no plugin / FFI layer of its own (direct C++ calls into OpenCV); the four entry
+ * points create_canvas / upload_frame / composite / download_tile are the boundary its north-star
+ * names, with argument conventions taken from the reference's data (8UC3 BGR cv::Mat + step,
+ * cameras[i].K / R float32 3x3, cv::Rect ROI, cv::Stitcher::Status-like int codes).
+ *
+ * Plain C: pointers, sizes and POD structs only. No exceptions cross this boundary.
+ * A ds_canvas is not thread-safe; distinct canvases may be used from distinct threads.
+ * There is no CPU fallback: every entry point that computes fails with DS_ERR_NO_DEVICE
+ * when no CUDA device is usable.
+ */
+#ifndef DRONESTITCH_H_
+#define DRONESTITCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DS_API __declspec(dllexport)
+#else
+#define DS_API __attribute__((visibility("default")))
+#endif
+
+#define DS_MAX_LEVELS 13 /* pyramid levels 0..12 (reference caps bands at 12, stitch_global.cpp:632-635) */
+
+typedef struct ds_canvas ds_canvas; /* opaque; owns all device memory */
+
+/* Status codes (reference: cv::Stitcher::Status ints, src/stitch_common.cpp:29-42). 0 = OK. */
+typedef enum ds_status {
+    DS_OK = 0,
+    DS_ERR_BAD_ARG = 1,
+    DS_ERR_OOM = 2,
+    DS_ERR_CUDA = 3,
+    DS_ERR_P2P_UNAVAILABLE = 4,
+    DS_ERR_STATE = 5,
+    DS_ERR_NO_DEVICE = 6,
+    DS_ERR_UNSUPPORTED = 7
+} ds_status;
+
+typedef enum ds_blend_mode {
+    DS_BLEND_FEATHER = 0,   /* cv::detail::FeatherBlender(sharpness)            (BASELINE cfg 1) */
+    DS_BLEND_MULTIBAND = 1  /* cv::detail::MultiBandBlender(false, bands, 32F)  (stitch_robust.cpp:213) */
+} ds_blend_mode;
+
+typedef enum ds_out_format {
+    DS_OUT_BGR8 = 0, /* 3 B/px, matches result.convertTo(CV_8U); mask is a separate plane */
+    DS_OUT_BGRA8 = 1 /* 4 B/px, alpha = result mask (255 / 0) */
+} ds_out_format;
+
+typedef enum ds_xf_kind {
+    DS_XF_PLANE_F32 = 0,     /* cv::detail::PlaneWarper / cv::AffineWarper (K, R float32, scale) */
+    DS_XF_AFFINE_F64 = 1,    /* cv::warpAffine semantics, forward 2x3 double (stitch_global.cpp:474-480) */
+    DS_XF_HOMOGRAPHY_F64 = 2 /* cv::warpPerspective semantics, forward 3x3 double */
+} ds_xf_kind;
+
+typedef enum ds_border { DS_BORDER_CONSTANT = 0, DS_BORDER_REFLECT = 1 } ds_border;
+
+/* Per-frame transform. Row-major matrices.
+ * PLANE_F32: exactly what cv::Stitcher holds per camera after estimateTransform (:251) and the
+ *   compose-scale update: K (float32 3x3), R (float32 3x3; with affine_warper != 0 it is the 3x3
+ *   affine "H" of cv::AffineWarper), scale = warped_image_scale * compose_work_aspect.
+ *   Placement (corner, size) is computed by the library like warper.warpRoi().
+ * AFFINE_F64 / HOMOGRAPHY_F64: M maps source pixels to pixels of the frame's own warped bbox whose
+ *   top-left is `corner` in canvas coordinates and whose size is `size` (the reference subtracts the
+ *   corner from the translation, stitch_global.cpp:474-476). */
+typedef struct ds_transform {
+    int32_t kind;          /* ds_xf_kind */
+    int32_t affine_warper; /* PLANE_F32 only: 1 = cv::AffineWarper, 0 = cv::PlaneWarper (T = 0) */
+    float K[9];
+    float R[9];
+    float scale;
+    int32_t border;        /* ds_border for the image taps; PLANE default REFLECT, others CONSTANT */
+    double M[9];           /* AFFINE_F64: M[0..5]; HOMOGRAPHY_F64: M[0..8] */
+    int32_t corner_x, corner_y; /* AFFINE / HOMOGRAPHY only */
+    int32_t width, height;      /* AFFINE / HOMOGRAPHY only */
+} ds_transform;
+
+/* Optional per-frame inputs. Pass NULL for none. */
+typedef struct ds_frame_opts {
+    const uint8_t* seam_mask; /* 8UC1, size of the frame's warped bbox, ANDed into the warped mask */
+    size_t seam_mask_stride;
+    const float* channel_gain; /* 3 floats (B, G, R) applied as sat_u8(float(p) * g), stitch_global.cpp:291-305 */
+} ds_frame_opts;
+
+typedef struct ds_canvas_desc {
+    int32_t x, y, width, height; /* canvas ROI = cv::detail::resultRoi(corners, sizes) */
+    int32_t blend_mode;          /* ds_blend_mode */
+    int32_t num_bands;           /* MULTIBAND: requested bands (cropped like MultiBandBlender::prepare) */
+    float sharpness;             /* FEATHER: 0.02f is OpenCV's default */
+    int32_t out_format;          /* ds_out_format */
+    int32_t device;              /* CUDA device ordinal */
+    /* Row band of the 2^bands-padded canvas this handle computes: rows [band_y0, band_y1) relative
+     * to the canvas ROI origin. band_y1 <= 0 means the whole canvas. Band edges must be multiples of
+     * 2^bands (or the canvas end). Frames that do not touch the band (+ its pyramid halo) may be
+     * skipped by the caller; ds_frame_touches_band() tells. */
+    int32_t band_y0, band_y1;
+    void* stream;                /* cudaStream_t to run on, or NULL for a library-owned stream */
+    int32_t reserved[8];
+} ds_canvas_desc;
+
+typedef struct ds_canvas_info {
+    int32_t padded_width, padded_height; /* canvas padded to a multiple of 2^bands */
+    int32_t num_bands;                   /* effective bands */
+    int32_t num_frames;
+    int32_t band_y0, band_y1;
+    int64_t device_bytes;                /* library-owned device memory */
+    int64_t launches_last_composite;     /* kernels launched by the last ds_composite */
+    float ms_last_composite;             /* device time of the last ds_composite (CUDA events) */
+    int64_t algorithmic_bytes;           /* SURVEY.md §8(d) AB model for the uploaded frames */
+    int32_t reserved[8];
+} ds_canvas_info;
+
+/* ---- geometry helpers (host only, no device needed) ---- */
+
+/* warper.warpRoi(src_size, K, R): out_xywh = {corner.x, corner.y, width, height}. PLANE_F32 only;
+ * for the other kinds it echoes corner/size from the transform. */
+DS_API int ds_warp_roi(const ds_transform* xf, int src_w, int src_h, int32_t out_xywh[4]);
+
+/* 1 if a frame placed at out_xywh (from ds_warp_roi) contributes to the band [band_y0, band_y1) of a
+ * canvas described by `desc` (footprint + multi-band gap + pyramid halo), else 0. */
+DS_API int ds_frame_touches_band(const ds_canvas_desc* desc, const int32_t frame_xywh[4]);
+
+/* ---- the four entry points ---- */
+
+/* Replaces blender->prepare(corners, sizes) (stitch_global.cpp:636-638; inside composePanorama). */
+DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out);
+
+/* Replaces, per frame, warper->warp(img) + warper->warp(mask) + convertTo(16S) + blender->feed()'s
+ * input hand-off. bgr: 8UC3 interleaved, `stride` = cv::Mat::step. The host buffer is only borrowed
+ * for the duration of the call. Feed order = frame_idx order. Re-uploading an index replaces it. */
+DS_API int ds_upload_frame(ds_canvas* c, int frame_idx, const uint8_t* bgr, int w, int h, size_t stride,
+                           const ds_transform* xf, const ds_frame_opts* opts);
+
+/* Same, but `dev_bgr` is a device pointer (frames already resident in HBM). */
+DS_API int ds_upload_frame_device(ds_canvas* c, int frame_idx, const void* dev_bgr, int w, int h, size_t stride,
+                                  const ds_transform* xf, const ds_frame_opts* opts);
+
+/* Warp + mask/weights + blend (+ collapse) over all uploaded frames. Synchronous on return. */
+DS_API int ds_composite(ds_canvas* c);
+/* Enqueue only (no host sync); results are valid after the canvas stream is synchronised. */
+DS_API int ds_composite_async(ds_canvas* c);
+DS_API int ds_synchronize(ds_canvas* c);
+
+/* Copy a tile of the composited canvas to host memory. (x, y) relative to the canvas ROI origin.
+ * out: BGR8 (3 B/px) or BGRA8 (4 B/px) per the canvas out_format. mask_out may be NULL. */
+DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* out, size_t stride,
+                            uint8_t* mask_out, size_t mask_stride);
+
+DS_API void ds_destroy_canvas(ds_canvas* c);
+DS_API const char* ds_last_error(void);
+DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info);
+DS_API const char* ds_version(void);
+
+/* ---- per-kernel timing (measurement only) ---- */
+
+typedef struct ds_kernel_time {
+    char name[32];             /* "mb_feed", "mb_collapse", "feather_mask", "feather_blend", ... */
+    int32_t level;             /* pyramid level the launch works on (-1 if not applicable) */
+    float ms;                  /* device time of the launch (CUDA events on the canvas stream) */
+    int64_t algorithmic_bytes; /* share of the SURVEY.md §8(d) model attributed to this launch */
+} ds_kernel_time;
+
+/* With profiling on, ds_composite records a CUDA event pair around every kernel it launches. */
+DS_API int ds_set_profiling(ds_canvas* c, int on);
+/* After a profiled ds_composite: fills up to `cap` entries, *n = number of launches. */
+DS_API int ds_get_kernel_times(ds_canvas* c, ds_kernel_time* out, int cap, int* n);
+
+/* ---- debug taps for the parity tests ---- */
+
+/* Placement of an uploaded frame: {corner.x, corner.y, width, height} (absolute canvas coords). */
+DS_API int ds_debug_get_placement(ds_canvas* c, int frame_idx, int32_t out_xywh[4]);
+/* The INTER_BITS fixed-point remap tables of a frame's warped bbox: xy = int16 pairs (w*h*2),
+ * a = uint16 (w*h) — the same layout as cv::convertMaps(..., CV_16SC2). */
+DS_API int ds_debug_get_maps(ds_canvas* c, int frame_idx, int16_t* xy, uint16_t* a);
+/* The warped 8UC3 image and warped 8UC1 mask of a frame's bbox (dense, w*h*3 and w*h). */
+DS_API int ds_debug_get_warped(ds_canvas* c, int frame_idx, uint8_t* bgr, uint8_t* mask);
+/* MULTIBAND, after ds_composite: a frame's Gaussian level l >= 1 (16SC3 dense) and weight level
+ * (f32 dense) over its aligned feed ROI; dims_out = {roi_x, roi_y, width, height} at level l
+ * relative to the padded canvas origin. Either pointer may be NULL (query dims only). */
+DS_API int ds_debug_get_frame_level(ds_canvas* c, int frame_idx, int level, int16_t* g, float* w,
+                                    int32_t dims_out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONESTITCH_H_ */

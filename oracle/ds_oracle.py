@@ -102,6 +102,20 @@ def persp_tables(H, dw, dh):
     return xy, a
 
 
+def affine_nearest_mask(M, dw, dh, sw, sh):
+    M = np.ascontiguousarray(M, np.float64).reshape(6)
+    m = np.empty((dh, dw), np.uint8)
+    lib().orc_affine_nearest_mask(_p(M), C.c_int(dw), C.c_int(dh), C.c_int(sw), C.c_int(sh), _p(m))
+    return m
+
+
+def persp_nearest_mask(H, dw, dh, sw, sh):
+    H = np.ascontiguousarray(H, np.float64).reshape(9)
+    m = np.empty((dh, dw), np.uint8)
+    lib().orc_persp_nearest_mask(_p(H), C.c_int(dw), C.c_int(dh), C.c_int(sw), C.c_int(sh), _p(m))
+    return m
+
+
 def remap_bilinear(src, xy, a, border="reflect"):
     assert src.dtype == np.uint8 and src.ndim == 3 and src.shape[2] == 3 and src.strides[2] == 1 and src.strides[1] == 3
     dh, dw = a.shape

@@ -1,0 +1,240 @@
+"""Parity cases shared by the CPU-emulation tests (logic check, no GPU) and the GPU tests (the
+parity tests proper). Every case runs the library under test through the C ABI and compares with the
+oracle on the same seeded inputs. Integer / index work must be bit-exact; the blended uint8 output is
+held to the north-star bar (<= 1 LSB on >= 99.99 %) and additionally expected bit-exact."""
+import numpy as np
+
+from drone_image_stitch_cpp_b200 import _lib as L
+from drone_image_stitch_cpp_b200 import compositor as CP
+from drone_image_stitch_cpp_b200 import synth
+from oracle import ds_oracle as O
+
+from helpers import assert_blend_parity
+
+
+def oracle_warp(spec):
+    """spec: dict(img, kind, ...) -> corner, warped, mask, xy, a (oracle side)."""
+    img = spec["img"]
+    h, w = img.shape[:2]
+    if spec["kind"] == "plane":
+        r = O.warp_frame(img, spec["K"], spec["R"], spec["scale"], spec.get("affine", True))
+        corner, warped, mask, xy, a = r["corner"], r["warped"], r["mask"], r["xy"], r["a"]
+    elif spec["kind"] == "affine":
+        dw, dh = spec["size"]
+        xy, a = O.affine_tables(spec["M"], dw, dh)
+        warped = O.remap_bilinear(img, xy, a, "constant")
+        mask = O.affine_nearest_mask(spec["M"], dw, dh, w, h)
+        corner = spec["corner"]
+    else:
+        dw, dh = spec["size"]
+        xy, a = O.persp_tables(spec["M"], dw, dh)
+        warped = O.remap_bilinear(img, xy, a, "constant")
+        mask = O.persp_nearest_mask(spec["M"], dw, dh, w, h)
+        corner = spec["corner"]
+    if spec.get("gain") is not None:
+        g = np.asarray(spec["gain"], np.float32)
+        warped = np.clip(np.rint(warped.astype(np.float32) * g[None, None, :]), 0, 255).astype(np.uint8)
+    if spec.get("seam") is not None:
+        mask = mask & spec["seam"]
+    return corner, warped, mask, xy, a
+
+
+def lib_transform(spec):
+    if spec["kind"] == "plane":
+        return CP.plane_transform(spec["K"], spec["R"], spec["scale"], spec.get("affine", True))
+    if spec["kind"] == "affine":
+        return CP.affine_transform(spec["M"], spec["corner"], spec["size"])
+    return CP.homography_transform(spec["M"], spec["corner"], spec["size"])
+
+
+def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_split=None, exact=True):
+    ow = [oracle_warp(s) for s in specs]
+    corners = [o[0] for o in ow]
+    sizes = [(o[1].shape[1], o[1].shape[0]) for o in ow]
+    roi = O.result_roi(corners, sizes)
+    bl = O.MultiBand(roi, bands) if blend == "multiband" else O.Feather(roi, 0.02)
+    taps = []
+    for o in ow:
+        if blend == "multiband":
+            taps.append(bl.feed(o[1].astype(np.int16), o[2], o[0], taps=check_taps))
+        else:
+            bl.feed(o[1].astype(np.int16), o[2], o[0])
+    ref16, refmask = bl.blend()
+    ref = O.s16_to_u8(ref16)
+
+    xfs = [lib_transform(s) for s in specs]
+    rois = [CP.warp_roi(xf, s["img"].shape[1], s["img"].shape[0], lib) for xf, s in zip(xfs, specs)]
+    for r, c, sz in zip(rois, corners, sizes):
+        assert (r[0], r[1]) == tuple(c) and (r[2], r[3]) == tuple(sz), (r, c, sz)
+    assert CP.result_roi(rois) == roi
+
+    def make(band=None):
+        cv = CP.Canvas(roi, blend, bands, 0.02, out_format, 0, band=band, lib=lib)
+        for i, (s, xf) in enumerate(zip(specs, xfs)):
+            if band is not None and not cv.touches(rois[i]):
+                continue
+            cv.upload(i, s["img"], xf, seam_mask=s.get("seam"), channel_gain=s.get("gain"))
+        cv.composite()
+        return cv
+
+    cv = make()
+    info = cv.info()
+    if blend == "multiband":
+        assert info.num_bands == bl.bands
+        assert (info.padded_width, info.padded_height) == (bl.roi[2], bl.roi[3])
+    pano, mask = cv.download()
+    if out_format == "bgra":
+        mask = pano[:, :, 3].copy()
+        pano = np.ascontiguousarray(pano[:, :, :3])
+    if check_taps:
+        for i, o in enumerate(ow):
+            xy, a = cv.maps(i)
+            assert np.array_equal(xy, o[3]) and np.array_equal(a, o[4]), f"frame {i}: INTER_BITS tables differ"
+            img, mk = cv.warped(i)
+            assert np.array_equal(img, o[1]), f"frame {i}: warped image differs"
+            assert np.array_equal(mk, o[2]), f"frame {i}: warped mask differs"
+            if blend == "multiband":
+                g, gs, ws = taps[i]
+                for l in range(1, bl.bands + 1):
+                    G, W, dims = cv.frame_level(i, l)
+                    assert np.array_equal(G, gs[l]), f"frame {i} level {l}: Gaussian level differs"
+                    assert np.array_equal(W, ws[l]), f"frame {i} level {l}: weight level differs"
+    assert np.array_equal(mask, refmask), "result mask differs"
+    st = assert_blend_parity(pano, ref, exact=exact)
+    if band_split:
+        # virtual bands: K handles over row bands must reproduce the single-handle result exactly
+        m = 1 << info.num_bands
+        H = info.padded_height
+        edges = sorted(set([0] + [min(H, ((H * k // band_split) // m) * m) for k in range(1, band_split)] + [H]))
+        rows = []
+        for y0, y1 in zip(edges[:-1], edges[1:]):
+            if y0 >= roi[3]:
+                continue
+            cb = make(band=(y0, y1))
+            pb, mb_ = cb.download()
+            if out_format == "bgra":
+                pb = np.ascontiguousarray(pb[:, :, :3])
+            rows.append(pb)
+            cb.close()
+        stacked = np.concatenate(rows, axis=0)
+        assert np.array_equal(stacked, pano), "banded result differs from the single-band result"
+    cv.close()
+    return st
+
+
+def plane_specs(sv):
+    return [dict(kind="plane", img=f, K=K, R=R, scale=sv.scale) for f, K, R in zip(sv.frames, sv.Ks, sv.Rs)]
+
+
+def affine_specs(seed=11, n=3, fw=360, fh=260, homography=False):
+    """Frames placed like stitchInterStripsCustom does (stitch_global.cpp:439-480): forward double
+    transform, bbox by floor/ceil of the transformed corners, translation made bbox-relative."""
+    rng = np.random.default_rng(seed)
+    ortho = synth.orthophoto(fh * 2 + 200, fw * 2 + 300, seed).numpy()
+    specs = []
+    for i in range(n):
+        th, s = rng.uniform(-0.15, 0.15), rng.uniform(0.9, 1.1)
+        tx, ty = 40 + i * fw * 0.45 + rng.uniform(-10, 10), 30 + (i % 2) * fh * 0.4 + rng.uniform(-10, 10)
+        Hm = np.array([[s * np.cos(th), -s * np.sin(th), tx], [s * np.sin(th), s * np.cos(th), ty], [0, 0, 1.0]])
+        if homography:
+            Hm[2, 0], Hm[2, 1] = rng.uniform(-5e-5, 5e-5), rng.uniform(-5e-5, 5e-5)
+        pts = np.array([[0, 0, 1], [fw, 0, 1], [fw, fh, 1], [0, fh, 1]], np.float64).T
+        q = Hm @ pts
+        q = q[:2] / q[2:]
+        x0, y0 = int(np.floor(q[0].min())), int(np.floor(q[1].min()))
+        bw, bh = max(1, int(np.ceil(q[0].max())) - x0), max(1, int(np.ceil(q[1].max())) - y0)
+        Tm = np.array([[1, 0, -x0], [0, 1, -y0], [0, 0, 1.0]])
+        M = Tm @ Hm
+        img = np.ascontiguousarray(ortho[10 * i:10 * i + fh, 20 * i:20 * i + fw])
+        specs.append(dict(kind="homography" if homography else "affine", img=img, M=(M if homography else M[:2]),
+                          corner=(x0, y0), size=(bw, bh)))
+    return specs
+
+
+# ---- the case list: name -> callable(lib)
+
+def case_small_feather(lib):
+    return run_case(lib, plane_specs(synth.grid_survey(3, 2, 400, 300, overlap=0.6, seed=1, work_scale=0.37)), "feather", 0, band_split=3)
+
+
+def case_small_mb5(lib):
+    return run_case(lib, plane_specs(synth.grid_survey(3, 2, 400, 300, overlap=0.6, seed=1, work_scale=0.37)), "multiband", 5, band_split=2)
+
+
+def case_small_mb3_bgra(lib):
+    return run_case(lib, plane_specs(synth.grid_survey(2, 2, 333, 251, overlap=0.5, seed=4)), "multiband", 3, out_format="bgra", band_split=3)
+
+
+def case_mb1_and_mb0(lib):
+    sv = synth.grid_survey(2, 1, 200, 150, overlap=0.5, seed=5)
+    run_case(lib, plane_specs(sv), "multiband", 1)
+    return run_case(lib, plane_specs(sv), "multiband", 0)
+
+
+def case_mb8_crops_bands(lib):
+    # 8 requested bands on a small canvas: exercises the gap clamp / shift-back of the feed ROI
+    return run_case(lib, plane_specs(synth.grid_survey(2, 2, 300, 220, overlap=0.7, seed=6, work_scale=0.5)), "multiband", 8)
+
+
+def case_single_frame(lib):
+    sv = synth.grid_survey(1, 1, 257, 131, seed=7)
+    run_case(lib, plane_specs(sv), "feather", 0)
+    return run_case(lib, plane_specs(sv), "multiband", 5)
+
+
+def case_big_rotation(lib):
+    sv = synth.grid_survey(3, 1, 300, 200, overlap=0.5, seed=8, rot_deg=25.0, scale_jit=0.1)
+    run_case(lib, plane_specs(sv), "feather", 0)
+    return run_case(lib, plane_specs(sv), "multiband", 4)
+
+
+def case_plane_warper_general_K(lib):
+    rng = np.random.default_rng(9)
+    sv = synth.grid_survey(2, 1, 240, 180, overlap=0.5, seed=9)
+    specs = plane_specs(sv)
+    for s in specs:
+        s["affine"] = False
+        s["K"] = np.array([[1.0, 0, 3.5], [0, 1.02, -2.25], [0, 0, 1]], np.float32)
+        th = rng.uniform(-0.02, 0.02)
+        s["R"] = np.array([[np.cos(th), -np.sin(th), 0.01], [np.sin(th), np.cos(th), -0.02], [1e-5, -2e-5, 1.0]], np.float32)
+        s["scale"] = 1.0
+    return run_case(lib, specs, "multiband", 3)
+
+
+def case_affine_f64(lib):
+    run_case(lib, affine_specs(11), "multiband", 5)
+    return run_case(lib, affine_specs(12), "feather", 0)
+
+
+def case_homography_f64(lib):
+    return run_case(lib, affine_specs(13, homography=True), "multiband", 4)
+
+
+def case_seam_and_gain(lib):
+    sv = synth.grid_survey(2, 2, 260, 200, overlap=0.6, seed=14)
+    specs = plane_specs(sv)
+    rng = np.random.default_rng(14)
+    for i, s in enumerate(specs):
+        o = O.warp_frame(s["img"], s["K"], s["R"], s["scale"])
+        bw, bh = o["size"]
+        seam = np.full((bh, bw), 255, np.uint8)
+        seam[:, : bw // 3] = rng.integers(0, 256, (bh, bw // 3)).astype(np.uint8) if i % 2 else 0
+        s["seam"] = seam
+        s["gain"] = (1.0 + 0.1 * i, 0.95, 1.2 - 0.1 * i)
+    run_case(lib, specs, "multiband", 4)
+    return run_case(lib, specs, "feather", 0)
+
+
+CASES = {
+    "small_feather": case_small_feather,
+    "small_mb5": case_small_mb5,
+    "small_mb3_bgra": case_small_mb3_bgra,
+    "mb1_and_mb0": case_mb1_and_mb0,
+    "mb8_crops_bands": case_mb8_crops_bands,
+    "single_frame": case_single_frame,
+    "big_rotation": case_big_rotation,
+    "plane_warper_general_K": case_plane_warper_general_K,
+    "affine_f64": case_affine_f64,
+    "homography_f64": case_homography_f64,
+    "seam_and_gain": case_seam_and_gain,
+}

@@ -1,0 +1,107 @@
+"""Pins the C restatement (oracle/ds_oracle.c) against the real OpenCV (cv2 wheel) — the library the
+reference's hot path runs in (/root/reference/CMakeLists.txt:18). CPU only."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from oracle import cv_reference as CR  # noqa: E402
+from oracle import ds_oracle as O  # noqa: E402
+
+SIZES = [(2, 2), (4, 6), (32, 32), (64, 96), (33, 47), (128, 160), (5, 9), (96, 224), (20, 36), (8, 12), (40, 4), (4, 40),
+         (16, 16), (6, 6), (10, 10), (12, 12), (14, 14), (18, 22), (1, 8), (8, 1), (3, 3)]
+
+
+@pytest.mark.parametrize("hw", SIZES)
+def test_pyramids(hw):
+    h, w = hw
+    rng = np.random.default_rng(h * 1000 + w)
+    a = rng.integers(-300, 300, (h, w, 3)).astype(np.int16)
+    assert np.array_equal(O.pyrdown_16s(a), cv2.pyrDown(a))
+    assert np.array_equal(O.pyrup_16s(a), cv2.pyrUp(a))
+    f = rng.random((h, w)).astype(np.float32)
+    assert np.array_equal(O.pyrdown_f32(f), cv2.pyrDown(f))
+
+
+def test_pyrdown_f32_chain_of_binary_mask():
+    # weights of a binary mask pushed down 8 levels stay bit-exact (op order matters from level 4 on)
+    m = np.zeros((768, 1024), np.float32)
+    m[100:600, 200:900] = np.float32(255) * np.float32(1.0 / 255.0)
+    a, b = m, m
+    for _ in range(8):
+        a, b = O.pyrdown_f32(a), cv2.pyrDown(b)
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ws,seed", [(1.0, 1), (0.37, 2), (0.45, 3)])
+def test_maps_warp_mask(ws, seed):
+    from drone_image_stitch_cpp_b200 import synth
+    sv = synth.grid_survey(2, 2, 320, 240, overlap=0.6, seed=seed, work_scale=ws)
+    for f, K, R in zip(sv.frames, sv.Ks, sv.Rs):
+        roi, xm, ym, xy, a = CR.maps_cv2((f.shape[1], f.shape[0]), K, R, sv.scale)
+        w = O.warp_frame(f, K, R, sv.scale)
+        assert (roi[0], roi[1]) == w["corner"]
+        assert np.array_equal(xy, w["xy"]) and np.array_equal(a, w["a"])   # INTER_BITS tables, bit-exact
+        c, wi, mk = CR.warp_frame_cv2(f, K, R, sv.scale)
+        assert tuple(c) == w["corner"]
+        assert np.array_equal(wi, w["warped"])
+        assert np.array_equal(mk, w["mask"])
+
+
+def test_general_K_projector():
+    # K with principal point and non-unit aspect: pins the float32 matmul order of the projector setup
+    rng = np.random.default_rng(7)
+    for _ in range(25):
+        a = np.float32(rng.uniform(1.5, 4))
+        K = np.array([[a, 0, rng.uniform(-50, 50)], [0, a * rng.uniform(0.9, 1.1), rng.uniform(-50, 50)], [0, 0, 1]], np.float32)
+        th, s = rng.uniform(-0.1, 0.1), rng.uniform(0.9, 1.1)
+        H = np.array([[s * np.cos(th), -s * np.sin(th), rng.uniform(-300, 300)],
+                      [s * np.sin(th), s * np.cos(th), rng.uniform(-300, 300)], [0, 0, 1]], np.float32)
+        for affine in (True, False):
+            roi, xm, ym, xy, aa = CR.maps_cv2((200, 150), K, H, float(a), affine)
+            k_rinv, r_kinv, t = O.projector_setup(K, H, affine)
+            tl = O.plane_roi(r_kinv, t, float(a), 200, 150)
+            assert (tl[0], tl[1], tl[2] - tl[0], tl[3] - tl[1]) == tuple(roi)
+            x2, y2 = O.plane_maps(k_rinv, t, float(a), tl[0], tl[1], tl[2] - tl[0] + 1, tl[3] - tl[1] + 1)
+            assert np.array_equal(x2, xm) and np.array_equal(y2, ym)
+
+
+@pytest.mark.parametrize("blend,bands", [("multiband", 5), ("multiband", 3), ("multiband", 8), ("multiband", 1), ("feather", 0)])
+def test_compose_matches_opencv(small_survey, blend, bands):
+    sv = small_survey
+    p1, m1, r1 = O.compose_port(sv.frames, sv.Ks, sv.Rs, sv.scale, blend, bands)
+    p2, m2, r2 = CR.compose_cv2(sv.frames, sv.Ks, sv.Rs, sv.scale, blend, bands)
+    assert r1 == r2
+    assert np.array_equal(p1, p2)
+    assert np.array_equal(m1, m2)
+
+
+def test_warp_affine_and_perspective_tables():
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (300, 400, 3)).astype(np.uint8)
+    for _ in range(6):
+        th, s = rng.uniform(-0.3, 0.3), rng.uniform(0.8, 1.2)
+        M = np.array([[s * np.cos(th), -s * np.sin(th), rng.uniform(-50, 50)], [s * np.sin(th), s * np.cos(th), rng.uniform(-50, 50)]])
+        dw, dh = 450, 380
+        xy, a = O.affine_tables(M, dw, dh)
+        assert np.array_equal(O.remap_bilinear(src, xy, a, "constant"),
+                              cv2.warpAffine(src, M, (dw, dh), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT))
+        H = np.vstack([M, [rng.uniform(-1e-4, 1e-4), rng.uniform(-1e-4, 1e-4), 1]])
+        xy, a = O.persp_tables(H, dw, dh)
+        assert np.array_equal(O.remap_bilinear(src, xy, a, "constant"),
+                              cv2.warpPerspective(src, H, (dw, dh), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT))
+
+
+def test_feather_weight_map():
+    rng = np.random.default_rng(5)
+    m = np.full((200, 300), 255, np.uint8)
+    m[:30, :] = 0
+    m[:, 250:] = 0
+    m[100:120, 100:130] = 0
+    ref = cv2.detail.createWeightMap(m, 0.02, None) if hasattr(cv2.detail, "createWeightMap") else None
+    if ref is None:
+        d = cv2.distanceTransform(m, cv2.DIST_L1, 3)
+        ref = np.minimum(d * np.float32(0.02), np.float32(1.0)).astype(np.float32)
+    assert np.array_equal(O.feather_weight_map(m, 0.02), np.asarray(ref))
+    full = np.full((40, 50), 255, np.uint8)
+    assert np.all(O.feather_weight_map(full, 0.02) == 1.0)
