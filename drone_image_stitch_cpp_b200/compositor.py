@@ -149,7 +149,7 @@ class Canvas:
         self.lib.check(self.lib.dll.ds_get_info(self._h, C.byref(i)))
         return i
 
-    def download(self, x=0, y=None, w=None, h=None, want_mask=True, out=None):
+    def download(self, x=0, y=None, w=None, h=None, want_mask=True, out=None, mask_out=None):
         i = self.info()
         y0 = i.band_y0 if y is None else y
         y1 = min(i.band_y1, self.roi[3])
@@ -157,8 +157,8 @@ class Canvas:
         h = y1 - y0 if h is None else h
         if out is None:
             out = np.empty((h, w, self.bpp), np.uint8)
-        mask = None
-        if want_mask and self.bpp == 3:
+        mask = mask_out
+        if mask is None and want_mask and self.bpp == 3:
             mask = np.empty((h, w), np.uint8)
         self.lib.check(self.lib.dll.ds_download_tile(self._h, int(x), int(y0), int(w), int(h), out.ctypes.data,
                                                      out.strides[0], mask.ctypes.data if mask is not None else None,
@@ -171,10 +171,10 @@ class Canvas:
     def kernel_times(self):
         """-> list of dict(name, level, ms, algorithmic_bytes) for the last profiled composite."""
         n = C.c_int()
-        arr = (L.ds_kernel_time * 256)()
-        self.lib.check(self.lib.dll.ds_get_kernel_times(self._h, arr, 256, C.byref(n)))
+        arr = (L.ds_kernel_time * 8192)()
+        self.lib.check(self.lib.dll.ds_get_kernel_times(self._h, arr, 8192, C.byref(n)))
         return [dict(name=arr[i].name.decode(), level=arr[i].level, ms=arr[i].ms, algorithmic_bytes=arr[i].algorithmic_bytes)
-                for i in range(min(n.value, 256))]
+                for i in range(min(n.value, 8192))]
 
     # ---- debug taps
     def placement(self, idx):

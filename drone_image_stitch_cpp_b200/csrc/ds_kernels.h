@@ -160,11 +160,14 @@ DS_D bool pd_v_is_simd(int j, int dw) { return j < (dw & ~3); }
 // generic launch plumbing
 
 #if DS_CUDA
-template <class Body, int NT, class P>
-__global__ void __launch_bounds__(NT) ds_kernel(const P p) {
-    extern __shared__ __align__(16) unsigned char ds_smem[];
-    Body::template run<NT>(p, (int)blockIdx.x, (int)threadIdx.x, ds_smem);
-}
+// One named __global__ per body (so profiles show ds_mb_feed_l0 etc. instead of one template name).
+template <class Body, int NT> struct KernelOf;
+#define DS_DEFINE_KERNEL(kname, Body, NT, P, MINB)                                         \
+    __global__ void __launch_bounds__(NT, MINB) kname(const P p) {                         \
+        extern __shared__ __align__(16) unsigned char ds_smem[];                           \
+        Body::template run<NT>(p, (int)blockIdx.x, (int)threadIdx.x, ds_smem);             \
+    }                                                                                      \
+    template <> struct KernelOf<Body, NT> { static constexpr void (*fn)(const P) = kname; };
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -463,10 +466,11 @@ struct MBParams {
 template <int T, bool LEVEL0>
 struct MBBody {
     static constexpr int PW = T + 7, GW = T / 2 + 2, JW = T / 2;
-    static constexpr int G_BYTES = PW * PW * (LEVEL0 ? 4 : 8);
-    static constexpr int W_BYTES = LEVEL0 ? 0 : PW * PW * 4;
-    static constexpr int G1_BYTES = GW * GW * 8;
-    static constexpr int H_BYTES = PW * JW * 4;
+    static constexpr int al16(int v) { return (v + 15) & ~15; }   // every smem section starts 16-B aligned
+    static constexpr int G_BYTES = al16(PW * PW * (LEVEL0 ? 4 : 8));
+    static constexpr int W_BYTES = LEVEL0 ? 0 : al16(PW * PW * 4);
+    static constexpr int G1_BYTES = al16(GW * GW * 8);
+    static constexpr int H_BYTES = al16(PW * JW * 4);
     static constexpr int ACC_BYTES = T * T * 8, WS_BYTES = T * T * 4;
     static int smem_bytes() { return G_BYTES + W_BYTES + G1_BYTES + H_BYTES + ACC_BYTES + WS_BYTES; }
 
@@ -763,3 +767,16 @@ struct FinalizeL0Body {
         }
     }
 };
+
+#if DS_CUDA
+typedef MBBody<64, true> MBBodyL0;
+typedef MBBody<32, false> MBBodyLN;
+DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
+DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
+DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
+DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 1)
+DS_DEFINE_KERNEL(ds_mb_feed_l0, MBBodyL0, 512, MBParams, 2)
+DS_DEFINE_KERNEL(ds_mb_feed, MBBodyLN, 256, MBParams, 1)
+DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 1)
+DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)
+#endif

@@ -73,10 +73,10 @@ int launch(const P& p, long long blocks, stream_t s, int smem_bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem_bytes > 48 * 1024 && configured_dev != dev) {
-        DS_CK(cudaFuncSetAttribute(ds_kernel<Body, NT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        DS_CK(cudaFuncSetAttribute(KernelOf<Body, NT>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured_dev = dev;
     }
-    ds_kernel<Body, NT, P><<<(unsigned)blocks, NT, smem_bytes, s>>>(p);
+    KernelOf<Body, NT>::fn<<<(unsigned)blocks, NT, smem_bytes, s>>>(p);
     DS_CK(cudaGetLastError());
     return DS_OK;
 }
@@ -393,7 +393,6 @@ int run_composite(ds_canvas* c) {
     int rc;
     if (c->dirty && (rc = build_lists(c))) return rc;
     c->launches = 0;
-    c->prof.clear();
     const ABModel abm = ab_inputs(c);
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev0, c->stream));
@@ -794,6 +793,7 @@ DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
 DS_API int ds_set_profiling(ds_canvas* c, int on) {
     if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
     c->profiling = on != 0;
+    c->prof.clear();   // a profile accumulates over every composite until profiling is switched again
     return DS_OK;
 }
 

@@ -65,8 +65,22 @@ def cut_frame(ortho_chw, A, fw, fh):
     return out[0].permute(1, 2, 0).round_().clamp_(0, 255).to(torch.uint8).contiguous()
 
 
-def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scale_jit=0.02, trans_jit=20.0,
-                work_scale=1.0, device="cpu", serpentine=True, side_overlap=None):
+@dataclass
+class SurveyPlan:
+    """Transforms of a grid survey without the pixels (cheap); `cut` makes the frames."""
+    fw: int
+    fh: int
+    ortho_w: int
+    ortho_h: int
+    seed: int
+    Ks: List[np.ndarray]
+    Rs: List[np.ndarray]
+    A: List[np.ndarray]
+    scale: float
+
+
+def plan_grid(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scale_jit=0.02, trans_jit=20.0,
+              work_scale=1.0, serpentine=True, side_overlap=None):
     """nx x ny frames of fw x fh, step = (1-overlap) of the frame size, with jitter.
     work_scale != 1 exercises the K = diag(1/ws), scale = 1/ws camera convention."""
     rng = np.random.default_rng(seed)
@@ -75,10 +89,8 @@ def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scal
     margin = int(0.15 * max(fw, fh)) + 64
     W = int(stepx * (nx - 1) + fw) + 2 * margin
     H = int(stepy * (ny - 1) + fh) + 2 * margin
-    ortho = orthophoto(H, W, seed, device)
-    ortho_f = ortho.permute(2, 0, 1)[None].float()
     a = np.float32(1.0 / work_scale)
-    frames, Ks, Rs, As = [], [], [], []
+    Ks, Rs, As = [], [], []
     for j in range(ny):
         cols = range(nx) if (not serpentine or j % 2 == 0) else range(nx - 1, -1, -1)
         for i in cols:
@@ -91,8 +103,6 @@ def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scal
             r00, r01, r10, r11 = s * math.cos(th), -s * math.sin(th), s * math.sin(th), s * math.cos(th)
             A = np.array([[r00, r01, tx + cx - (r00 * cx + r01 * cy)],
                           [r10, r11, ty + cy - (r10 * cx + r11 * cy)]], np.float64)
-            fr = cut_frame(ortho_f, torch.tensor(A, dtype=torch.float32), fw, fh)
-            frames.append(fr.cpu().numpy())
             As.append(A)
             Ks.append(np.array([[a, 0, 0], [0, a, 0], [0, 0, 1]], np.float32))
             # AffineWarper's backward map is x_src = a * L * (u/a + L^T T0) with R = [L | T0] (OpenCV
@@ -102,4 +112,24 @@ def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scal
             Bt = -Bl @ A[:, 2]
             T0 = np.linalg.solve(Bl @ Bl.T, Bt) / float(a)
             Rs.append(np.array([[Bl[0, 0], Bl[0, 1], T0[0]], [Bl[1, 0], Bl[1, 1], T0[1]], [0, 0, 1]], np.float32))
-    return Survey(frames, Ks, Rs, float(a), As)
+    return SurveyPlan(fw, fh, W, H, seed, Ks, Rs, As, float(a))
+
+
+def cut(plan, indices=None, device="cpu", as_torch=False, ortho=None):
+    """Cut the frames `indices` (default all) of a plan out of its orthophoto. Returns a list aligned
+    with `indices` of HxWx3 uint8 arrays (numpy, or torch tensors on `device` when as_torch)."""
+    if ortho is None:
+        ortho = orthophoto(plan.ortho_h, plan.ortho_w, plan.seed, device)
+    ortho_f = ortho.permute(2, 0, 1)[None].float()
+    idx = range(len(plan.A)) if indices is None else indices
+    out = []
+    for i in idx:
+        fr = cut_frame(ortho_f, torch.tensor(plan.A[i], dtype=torch.float32), plan.fw, plan.fh)
+        out.append(fr if as_torch else fr.cpu().numpy())
+    return out
+
+
+def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scale_jit=0.02, trans_jit=20.0,
+                work_scale=1.0, device="cpu", serpentine=True, side_overlap=None):
+    plan = plan_grid(nx, ny, fw, fh, overlap, seed, rot_deg, scale_jit, trans_jit, work_scale, serpentine, side_overlap)
+    return Survey(cut(plan, None, device), plan.Ks, plan.Rs, plan.scale, plan.A)

@@ -173,7 +173,8 @@ typedef struct ds_kernel_time {
     int64_t algorithmic_bytes; /* share of the SURVEY.md §8(d) model attributed to this launch */
 } ds_kernel_time;
 
-/* With profiling on, ds_composite records a CUDA event pair around every kernel it launches. */
+/* With profiling on, ds_composite records a CUDA event pair around every kernel it launches; entries
+ * accumulate over successive composites until ds_set_profiling is called again. */
 DS_API int ds_set_profiling(ds_canvas* c, int on);
 /* After a profiled ds_composite: fills up to `cap` entries, *n = number of launches. */
 DS_API int ds_get_kernel_times(ds_canvas* c, ds_kernel_time* out, int cap, int* n);

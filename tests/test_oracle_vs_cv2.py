@@ -105,3 +105,15 @@ def test_feather_weight_map():
     assert np.array_equal(O.feather_weight_map(m, 0.02), np.asarray(ref))
     full = np.full((40, 50), 255, np.uint8)
     assert np.all(O.feather_weight_map(full, 0.02) == 1.0)
+
+
+def test_degenerate_perspective_maps():
+    # z crosses zero inside the frame: x/z overflows; cvRound's x86 "integer indefinite" must be reproduced
+    K = np.array([[1.0, 0, 3.5], [0, 1.02, -2.25], [0, 0, 1]], np.float32)
+    R = np.array([[0.9998, -0.019, 0.01], [0.019, 0.9998, -0.02], [1e-5, -2e-5, 1.0]], np.float32)
+    img = np.random.default_rng(0).integers(0, 256, (180, 240, 3)).astype(np.uint8)
+    roi, xm, ym, xy, a = CR.maps_cv2((240, 180), K, R, 1.0, affine=False)
+    w = O.warp_frame(img, K, R, 1.0, affine=False)
+    assert np.array_equal(xy, w["xy"]) and np.array_equal(a, w["a"])
+    c, wi, mk = CR.warp_frame_cv2(img, K, R, 1.0, affine=False)
+    assert np.array_equal(wi, w["warped"]) and np.array_equal(mk, w["mask"])
