@@ -156,6 +156,8 @@ DS_D bool pd_h_is_simd(int j, int w, int dw) {
 }
 DS_D bool pd_v_is_simd(int j, int dw) { return j < (dw & ~3); }
 
+constexpr int ds_al16(int v) { return (v + 15) & ~15; }  // every smem section starts 16-B aligned
+
 // ---------------------------------------------------------------------------------------------
 // generic launch plumbing
 
@@ -466,18 +468,16 @@ struct MBParams {
 template <int T, bool LEVEL0>
 struct MBBody {
     static constexpr int PW = T + 7, GW = T / 2 + 2, JW = T / 2;
-    static constexpr int al16(int v) { return (v + 15) & ~15; }   // every smem section starts 16-B aligned
-    static constexpr int G_BYTES = al16(PW * PW * (LEVEL0 ? 4 : 8));
-    static constexpr int W_BYTES = LEVEL0 ? 0 : al16(PW * PW * 4);
-    static constexpr int G1_BYTES = al16(GW * GW * 8);
-    static constexpr int H_BYTES = al16(PW * JW * 4);
+    static constexpr int G_BYTES = ds_al16(PW * PW * 4);
+    static constexpr int W_BYTES = LEVEL0 ? 0 : ds_al16(PW * PW * 4);
+    static constexpr int G1_BYTES = ds_al16(GW * GW * 8);
+    static constexpr int H_BYTES = ds_al16(PW * JW * 4);
     static constexpr int ACC_BYTES = T * T * 8, WS_BYTES = T * T * 4;
     static int smem_bytes() { return G_BYTES + W_BYTES + G1_BYTES + H_BYTES + ACC_BYTES + WS_BYTES; }
 
     template <int NT>
     DS_DM void run(const MBParams& p, int block, int tid, unsigned char* smem) {
         px8* s_g8 = (px8*)smem;
-        px16* s_g16 = (px16*)smem;
         float* s_w = (float*)(smem + G_BYTES);
         px16* s_g1 = (px16*)(smem + G_BYTES + W_BYTES);
         float* s_h = (float*)(smem + G_BYTES + W_BYTES + G1_BYTES);
@@ -526,7 +526,7 @@ struct MBBody {
                     s_g8[i] = s;
                 } else {
                     const size_t gi = (size_t)py * rw + px;
-                    s_g16[i] = F.G[l][gi];
+                    s_g8[i] = F.G[l][gi];
                     s_w[i] = F.W[l][gi];
                 }
             }
@@ -548,8 +548,7 @@ struct MBBody {
                             const int kwx = (kx == 0 || kx == 4) ? 1 : ((kx == 2) ? 6 : 4);
                             const int si = sy * pw + cxi[kx];
                             int vb, vg, vr;
-                            if (LEVEL0) { const px8 q = s_g8[si]; vb = q.b; vg = q.g; vr = q.r; }
-                            else { const px16 q = s_g16[si]; vb = q.b; vg = q.g; vr = q.r; }
+                            { const px8 q = s_g8[si]; vb = q.b; vg = q.g; vr = q.r; }
                             rb += kwx * vb; rg += kwx * vg; rr += kwx * vr;
                         }
                         sb += kwy * rb; sg += kwy * rg; sr += kwy * rr;
@@ -557,7 +556,11 @@ struct MBBody {
                     px16 o;
                     o.b = (short)((sb + 128) >> 8); o.g = (short)((sg + 128) >> 8); o.r = (short)((sr + 128) >> 8); o.a = 0;
                     s_g1[i] = o;
-                    if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1) F.G[l + 1][(size_t)gy * n1x + gx] = o;
+                    if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1) {
+                        px8 o8;
+                        o8.b = (unsigned char)o.b; o8.g = (unsigned char)o.g; o8.r = (unsigned char)o.r; o8.a = 0;
+                        F.G[l + 1][(size_t)gy * n1x + gx] = o8;
+                    }
                 }
                 // ---- phase 2b: horizontal pass of the weight pyrDown, rows hr0..hr1, own columns
                 const int jw = jx1 - jx0;
@@ -616,8 +619,7 @@ struct MBBody {
                     }
                     const int si = (oy - py0) * pw + (ox - px0);
                     int gb, gg, gr; float wv;
-                    if (LEVEL0) { const px8 q = s_g8[si]; gb = q.b; gg = q.g; gr = q.r; wv = f_mul((float)q.a, 1.f / 255.f); }
-                    else { const px16 q = s_g16[si]; gb = q.b; gg = q.g; gr = q.r; wv = s_w[si]; }
+                    { const px8 q = s_g8[si]; gb = q.b; gg = q.g; gr = q.r; wv = LEVEL0 ? f_mul((float)q.a, 1.f / 255.f) : s_w[si]; }
                     const int ti = (ay0 + yy - Y0) * T + (ax0 + xx - X0);
                     px16 a = s_acc[ti];
                     a.b = (short)(a.b + (short)f2i_rz(f_mul((float)sat16i(gb - up[0]), wv)));
@@ -632,8 +634,7 @@ struct MBBody {
                     const int yy = i / ow, xx = i - yy * ow;
                     const int si = yy * pw + xx;
                     int gb, gg, gr; float wv;
-                    if (LEVEL0) { const px8 q = s_g8[si]; gb = q.b; gg = q.g; gr = q.r; wv = f_mul((float)q.a, 1.f / 255.f); }
-                    else { const px16 q = s_g16[si]; gb = q.b; gg = q.g; gr = q.r; wv = s_w[si]; }
+                    { const px8 q = s_g8[si]; gb = q.b; gg = q.g; gr = q.r; wv = LEVEL0 ? f_mul((float)q.a, 1.f / 255.f) : s_w[si]; }
                     const int ti = (ay0 + yy - Y0) * T + (ax0 + xx - X0);
                     px16 a = s_acc[ti];
                     a.b = (short)(a.b + (short)f2i_rz(f_mul((float)gb, wv)));
@@ -658,6 +659,342 @@ struct MBBody {
             o.b = (short)f2i_rz(f_div((float)a.b, den));
             o.g = (short)f2i_rz(f_div((float)a.g, den));
             o.r = (short)f2i_rz(f_div((float)a.r, den));
+            o.a = (short)(wsum > 1e-5f ? 1 : 0);
+            p.dst[(size_t)Y * p.dst_w + X] = o;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MULTIBAND feed, level 0, PLANE_F32 frames: the hot kernel. Same arithmetic and gather structure as
+// MBBody<64, true>, restructured for instruction count:
+//   * per tile-frame column / row tables hold the reflected bbox index and the per-column / per-row
+//     products of the plane map (k0*u', k3*u', k6*u' / k1*v', k4*v', k7*v'), so a pixel costs two adds
+//     per coordinate (each product and sum is still rounded separately, as OpenCV does);
+//   * bilinear taps as packed byte dot products (dp4a) on the BGRX words;
+//   * G_0 / G_1 kept as packed 16-bit lanes (B|R<<16, G) so the separable 5-tap pyrDown and the 2x2
+//     pyrUp quads run two channels per integer op (all partial sums fit 16 bits: <= 255*256);
+//   * block-uniform shortcuts: a tile-frame whose mask is all 255 has W_1 == 1 exactly and
+//     trunc(lap * 1) == lap; all 0 contributes nothing but still produces G_1;
+//   * tile-frames that touch a ROI border use index-reflecting variants of the same phases.
+// acc lanes: B + 65536 * R in one int (exact while |sum| < 2^15, guaranteed by the host for tiles with
+// <= 64 frames; longer lists go to the generic kernel).
+
+struct L0Col { float a0, a3, a6; int u; };  // u = raw bbox column if inside else -1
+struct L0Row { float b1, b4, b7; int v; };
+
+struct MBL0Body {
+    static constexpr int T = 64, PWS = 72, PHM = 71, GWS = 34, JW = 32, NQ = 1024;
+    static constexpr int G0_BYTES = ds_al16(PHM * PWS * 4);
+    static constexpr int G1_BYTES = ds_al16(GWS * GWS * 8);
+    static constexpr int H_BYTES = ds_al16(PHM * GWS * 8);      // also the float H pass of the weights (PHM * JW * 4)
+    static constexpr int ACC_BYTES = T * T * 4;
+    static constexpr int COL_BYTES = ds_al16(PWS * 16), ROW_BYTES = ds_al16(PHM * 16);
+    static int smem_bytes() { return G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES; }
+
+    struct U2 { uint32_t br, g; };
+
+    // 5-tap [1 4 6 4 1] on packed lanes
+    DS_DM uint32_t tap5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a + e + 6u * c + 4u * (b + d); }
+
+    template <int NT>
+    DS_DM void run(const MBParams& p, int block, int tid, unsigned char* smem) {
+        uint32_t* s_g0 = (uint32_t*)smem;
+        U2* s_g1 = (U2*)(smem + G0_BYTES);
+        U2* s_h = (U2*)(smem + G0_BYTES + G1_BYTES);
+        float* s_hw = (float*)(smem + G0_BYTES + G1_BYTES);
+        int* s_abr = (int*)(smem + G0_BYTES + G1_BYTES + H_BYTES);
+        int* s_ag = s_abr + T * T;
+        float* s_ws = (float*)(s_ag + T * T);
+        L0Col* s_col = (L0Col*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES);
+        L0Row* s_row = (L0Row*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES);
+
+        const int tile = p.tile_ids ? p.tile_ids[block] : block;
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int X0 = tx * T, Y0 = ty * T;
+        const float c255 = f_mul(255.f, 1.f / 255.f);
+
+        for (int i = tid; i < T * T; i += NT) { s_abr[i] = 0; s_ag[i] = 0; s_ws[i] = 0.f; }
+        DS_SYNC();
+
+        for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
+            const FrameDev& F = p.frames[p.tile_frames[fi]];
+            const int rx = F.rx, ry = F.ry, rw = F.rw, rh = F.rh;
+            const int ax0 = imax(X0, rx), ax1 = imin(X0 + T, rx + rw);
+            const int ay0 = imax(imax(Y0, ry), p.own_y0), ay1 = imin(imin(Y0 + T, ry + rh), p.own_y1);
+            if (ax0 >= ax1 || ay0 >= ay1) continue;  // block-uniform
+            const int ox0 = ax0 - rx, ox1 = ax1 - rx, oy0 = ay0 - ry, oy1 = ay1 - ry;
+            const int n1x = rw >> 1, n1y = rh >> 1;
+            const int jx0 = ox0 >> 1, jx1 = (ox1 + 1) >> 1, jy0 = oy0 >> 1, jy1 = (oy1 + 1) >> 1;
+            const int gx0 = imax(jx0 - 1, 0), gx1 = imin(jx1, n1x - 1);
+            const int gy0 = imax(jy0 - 1, 0), gy1 = imin(jy1, n1y - 1);
+            const int px0 = imax(2 * gx0 - 2, 0), px1 = imin(2 * gx1 + 2, rw - 1);
+            const int py0 = imax(2 * gy0 - 2, 0), py1 = imin(2 * gy1 + 2, rh - 1);
+            const int pw = px1 - px0 + 1, ph = py1 - py0 + 1;
+            const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
+            const int jw = jx1 - jx0, jh = jy1 - jy0;
+            // no index reflection anywhere in this tile-frame?
+            const bool border = !(2 * gx0 - 2 >= 0 && 2 * gx1 + 2 <= rw - 1 && 2 * gy0 - 2 >= 0 && 2 * gy1 + 2 <= rh - 1 &&
+                                  jx0 >= 1 && jx1 <= n1x - 1 && jy0 >= 1 && jy1 <= n1y - 1);
+            const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
+
+            // ---- tables: reflected bbox index + per-column / per-row map terms
+            for (int i = tid; i < pw + ph; i += NT) {
+                if (i < pw) {
+                    const int u = rx + px0 + i - F.cx;
+                    const int ur = refl(u, F.w, BORDER_REFL);
+                    float U = (float)(F.tlx + ur);
+                    if (F.scale != 1.f) U = f_div(U, F.scale);
+                    const float up = f_sub(U, F.t0);
+                    L0Col c;
+                    c.a0 = f_mul(F.k[0], up); c.a3 = f_mul(F.k[3], up); c.a6 = f_mul(F.k[6], up);
+                    c.u = (unsigned)u < (unsigned)F.w ? u : -1;
+                    s_col[i] = c;
+                } else {
+                    const int yy = i - pw;
+                    const int v = ry + py0 + yy - F.cy;
+                    const int vr = refl(v, F.h, BORDER_REFL);
+                    float V = (float)(F.tly + vr);
+                    if (F.scale != 1.f) V = f_div(V, F.scale);
+                    const float vp = f_sub(V, F.t1);
+                    L0Row r;
+                    r.b1 = f_mul(F.k[1], vp); r.b4 = f_mul(F.k[4], vp); r.b7 = f_mul(F.k[7], vp);
+                    r.v = (unsigned)v < (unsigned)F.h ? v : -1;
+                    s_row[yy] = r;
+                }
+            }
+            DS_SYNC();
+
+            // ---- phase 1: inverse warp of the needed region into s_g0 (b | g<<8 | r<<16 | mask<<24)
+            int all255 = 1, all0 = 1;
+            for (int i = tid; i < PWS * ph; i += NT) {
+                const int yy = i / PWS, xx = i - yy * PWS;
+                if (xx >= pw) continue;
+                const L0Col c = s_col[xx];
+                const L0Row r = s_row[yy];
+                float x = f_add(f_add(c.a0, r.b1), F.k2one);
+                float y = f_add(f_add(c.a3, r.b4), F.k5one);
+                if (proj) {
+                    const float z = f_add(f_add(c.a6, r.b7), F.k8one);
+                    if (z != 1.f) { x = f_div(x, z); y = f_div(y, z); }
+                }
+                int ix, iy, nx, ny;
+                if (fabsf(x) < 67108864.f && fabsf(y) < 67108864.f) {   // |32 x| < 2^31: plain conversions are exact
+#if DS_CUDA
+                    ix = __float2int_rn(f_mul(x, 32.f)); iy = __float2int_rn(f_mul(y, 32.f));
+                    nx = __float2int_rn(x); ny = __float2int_rn(y);
+#else
+                    ix = (int)lrintf(f_mul(x, 32.f)); iy = (int)lrintf(f_mul(y, 32.f));
+                    nx = (int)lrintf(x); ny = (int)lrintf(y);
+#endif
+                } else {
+                    ix = f2i_rn(f_mul(x, 32.f)); iy = f2i_rn(f_mul(y, 32.f));
+                    nx = f2i_rn(x); ny = f2i_rn(y);
+                }
+                const int sx = sat16i(ix >> 5), sy = sat16i(iy >> 5);
+                const int ax = ix & 31, ay = iy & 31;
+                nx = sat16i(nx); ny = sat16i(ny);
+                int m = 0;
+                if ((c.u | r.v) >= 0) {
+                    m = ((unsigned)nx < (unsigned)F.src_w && (unsigned)ny < (unsigned)F.src_h) ? 255 : 0;
+                    if (F.seam) m &= (int)ld_ro(F.seam + (size_t)r.v * F.seam_pitch + c.u);
+                }
+                uint32_t p00, p01, p10, p11;
+                if ((unsigned)sx < (unsigned)(F.src_w - 1) && (unsigned)sy < (unsigned)(F.src_h - 1)) {
+                    const uint32_t* r0 = F.src + (size_t)sy * F.src_pitch + sx;
+                    p00 = ld_ro(r0); p01 = ld_ro(r0 + 1);
+                    p10 = ld_ro(r0 + F.src_pitch); p11 = ld_ro(r0 + F.src_pitch + 1);
+                } else if (F.border == BORDER_CONST) {
+                    const int x0 = (unsigned)sx < (unsigned)F.src_w ? sx : -1;
+                    const int x1 = (unsigned)(sx + 1) < (unsigned)F.src_w ? sx + 1 : -1;
+                    const int y0 = (unsigned)sy < (unsigned)F.src_h ? sy : -1;
+                    const int y1 = (unsigned)(sy + 1) < (unsigned)F.src_h ? sy + 1 : -1;
+                    p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
+                    p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
+                } else {
+                    const int x0 = refl(sx, F.src_w, BORDER_REFL), x1 = refl(sx + 1, F.src_w, BORDER_REFL);
+                    const int y0 = refl(sy, F.src_h, BORDER_REFL), y1 = refl(sy + 1, F.src_h, BORDER_REFL);
+                    p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
+                    p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
+                }
+                // horizontal: bytes (B0,B1,G0,G1) . (wx0,wx1,0,0) etc.; vertical in 32 bit; (v + 512) >> 10
+                const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
+                const uint32_t t0 = byte_perm(p00, p01, 0x5140), t0r = byte_perm(p00, p01, 0x6262);
+                const uint32_t t1 = byte_perm(p10, p11, 0x5140), t1r = byte_perm(p10, p11, 0x6262);
+                const int wy1 = ay, wy0 = 32 - ay;
+                int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
+                int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
+                int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
+                if (F.has_gain) {
+                    ob = sat8i(f2i_rn(f_mul((float)ob, F.gain[0])));
+                    og = sat8i(f2i_rn(f_mul((float)og, F.gain[1])));
+                    orr = sat8i(f2i_rn(f_mul((float)orr, F.gain[2])));
+                }
+                s_g0[i] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | ((uint32_t)m << 24);
+                all255 &= (m == 255);
+                all0 &= (m == 0);
+            }
+            const int uni255 = block_and(all255) && (c255 == 1.f);
+            const int uni0 = block_and(all0);
+
+            // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op
+            for (int i = tid; i < ph * GWS; i += NT) {
+                const int yy = i / GWS, gxx = i - yy * GWS;
+                if (gxx >= gw) continue;
+                const int c0 = 2 * (gx0 + gxx) - 2;
+                uint32_t q[5];
+                if (!border) {
+                    const uint32_t* s = s_g0 + yy * PWS + (c0 - px0);
+                    DS_UNROLL
+                    for (int t = 0; t < 5; t++) q[t] = s[t];
+                } else {
+                    DS_UNROLL
+                    for (int t = 0; t < 5; t++) q[t] = s_g0[yy * PWS + (refl101(c0 + t, rw) - px0)];
+                }
+                U2 h;
+                h.br = tap5(byte_perm(q[0], 0, 0x4240), byte_perm(q[1], 0, 0x4240), byte_perm(q[2], 0, 0x4240),
+                            byte_perm(q[3], 0, 0x4240), byte_perm(q[4], 0, 0x4240));
+                h.g = tap5(byte_perm(q[0], 0, 0x4341), byte_perm(q[1], 0, 0x4341), byte_perm(q[2], 0, 0x4341),
+                           byte_perm(q[3], 0, 0x4341), byte_perm(q[4], 0, 0x4341));
+                s_h[i] = h;
+            }
+            DS_SYNC();
+            for (int i = tid; i < gh * GWS; i += NT) {
+                const int gyy = i / GWS, gxx = i - gyy * GWS;
+                if (gxx >= gw) continue;
+                const int r0 = 2 * (gy0 + gyy) - 2;
+                U2 q[5];
+                if (!border) {
+                    DS_UNROLL
+                    for (int t = 0; t < 5; t++) q[t] = s_h[(r0 - py0 + t) * GWS + gxx];
+                } else {
+                    DS_UNROLL
+                    for (int t = 0; t < 5; t++) q[t] = s_h[(refl101(r0 + t, rh) - py0) * GWS + gxx];
+                }
+                U2 o;
+                o.br = ((tap5(q[0].br, q[1].br, q[2].br, q[3].br, q[4].br) + 0x00800080u) >> 8) & 0x00FF00FFu;
+                o.g = ((tap5(q[0].g, q[1].g, q[2].g, q[3].g, q[4].g) + 0x00000080u) >> 8) & 0x000000FFu;
+                s_g1[gyy * GWS + gxx] = o;
+                const int gx = gx0 + gxx, gy = gy0 + gyy;
+                if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1)
+                    ((uint32_t*)F.G[1])[(size_t)gy * n1x + gx] = byte_perm(o.br, o.g, 0x5240);
+            }
+            DS_SYNC();
+
+            // ---- W_1 = pyrDownF32(W_0) over the own range
+            if (uni255 || uni0) {
+                const float wv = uni255 ? 1.f : 0.f;
+                for (int i = tid; i < jh * JW; i += NT) {
+                    const int jyy = i / JW, jj = i - jyy * JW;
+                    if (jj < jw) F.W[1][(size_t)(jy0 + jyy) * n1x + (jx0 + jj)] = wv;
+                }
+            } else {
+                const int hr0 = imax(2 * jy0 - 2, 0), hr1 = imin(2 * jy1, rh - 1);
+                const int hn = hr1 - hr0 + 1;
+                for (int i = tid; i < hn * JW; i += NT) {
+                    const int rr_ = i / JW, jj = i - rr_ * JW;
+                    if (jj >= jw) continue;
+                    const int row = hr0 + rr_, j = jx0 + jj;
+                    float t[5];
+                    for (int q = 0; q < 5; q++) {
+                        const int si = (row - py0) * PWS + (refl101(2 * j + q - 2, rw) - px0);
+                        t[q] = f_mul((float)(s_g0[si] >> 24), 1.f / 255.f);
+                    }
+                    s_hw[i] = pd_h_is_simd(j, rw, n1x) ? pd_h_simd(t[0], t[1], t[2], t[3], t[4])
+                                                        : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
+                }
+                DS_SYNC();
+                for (int i = tid; i < jh * JW; i += NT) {
+                    const int jyy = i / JW, jj = i - jyy * JW;
+                    if (jj >= jw) continue;
+                    const int jy = jy0 + jyy, j = jx0 + jj;
+                    float t[5];
+                    for (int q = 0; q < 5; q++) t[q] = s_hw[(refl101(2 * jy + q - 2, rh) - hr0) * JW + jj];
+                    const float v = pd_v_is_simd(j, n1x) ? pd_v_simd(t[0], t[1], t[2], t[3], t[4])
+                                                         : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
+                    F.W[1][(size_t)jy * n1x + j] = f_mul(v, 1.f / 256.f);
+                }
+            }
+
+            // ---- phase 3: lap = G_0 - pyrUp(G_1), weighted accumulate, one 2x2 quad per item
+            if (!uni0) {
+                for (int q = tid; q < NQ; q += NT) {
+                    const int qy = q >> 5, qx = q & 31;
+                    const int X = X0 + 2 * qx, Y = Y0 + 2 * qy;
+                    if (X < ax0 || X >= ax1 || Y < ay0 || Y >= ay1) continue;
+                    const int ox = X - rx, oy = Y - ry;
+                    const int c1x = ox >> 1, c1y = oy >> 1;
+                    int ixl, ixr, iyl, iyr;
+                    if (!border) { ixl = c1x - 1; ixr = c1x + 1; iyl = c1y - 1; iyr = c1y + 1; }
+                    else { ixl = up_l(c1x, n1x); ixr = up_r(c1x, n1x); iyl = up_l(c1y, n1y); iyr = up_r(c1y, n1y); }
+                    const int ixc = c1x - gx0, iyc = c1y - gy0;
+                    ixl -= gx0; ixr -= gx0; iyl -= gy0; iyr -= gy0;
+                    const U2 a0 = s_g1[iyl * GWS + ixl], a1 = s_g1[iyl * GWS + ixc], a2 = s_g1[iyl * GWS + ixr];
+                    const U2 b0 = s_g1[iyc * GWS + ixl], b1 = s_g1[iyc * GWS + ixc], b2 = s_g1[iyc * GWS + ixr];
+                    const U2 d0 = s_g1[iyr * GWS + ixl], d1 = s_g1[iyr * GWS + ixc], d2 = s_g1[iyr * GWS + ixr];
+                    // horizontal: even = l + 6c + r, odd = 4(c + r), on rows l / c / r (packed lanes)
+                    const uint32_t El_br = a0.br + 6u * a1.br + a2.br, Ol_br = 4u * (a1.br + a2.br);
+                    const uint32_t Ec_br = b0.br + 6u * b1.br + b2.br, Oc_br = 4u * (b1.br + b2.br);
+                    const uint32_t Er_br = d0.br + 6u * d1.br + d2.br, Or_br = 4u * (d1.br + d2.br);
+                    const uint32_t El_g = a0.g + 6u * a1.g + a2.g, Ol_g = 4u * (a1.g + a2.g);
+                    const uint32_t Ec_g = b0.g + 6u * b1.g + b2.g, Oc_g = 4u * (b1.g + b2.g);
+                    const uint32_t Er_g = d0.g + 6u * d1.g + d2.g, Or_g = 4u * (d1.g + d2.g);
+                    // vertical + (v + 32) >> 6; index [dy][dx]
+                    uint32_t up_br[2][2], up_g[2][2];
+                    up_br[0][0] = ((El_br + 6u * Ec_br + Er_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_br[0][1] = ((Ol_br + 6u * Oc_br + Or_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_br[1][0] = ((4u * (Ec_br + Er_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_br[1][1] = ((4u * (Oc_br + Or_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_g[0][0] = ((El_g + 6u * Ec_g + Er_g + 0x20u) >> 6) & 0x3FFu;
+                    up_g[0][1] = ((Ol_g + 6u * Oc_g + Or_g + 0x20u) >> 6) & 0x3FFu;
+                    up_g[1][0] = ((4u * (Ec_g + Er_g) + 0x20u) >> 6) & 0x3FFu;
+                    up_g[1][1] = ((4u * (Oc_g + Or_g) + 0x20u) >> 6) & 0x3FFu;
+                    DS_UNROLL
+                    for (int dy = 0; dy < 2; dy++) {
+                        DS_UNROLL
+                        for (int dx = 0; dx < 2; dx++) {
+                            const uint32_t g0 = s_g0[(oy + dy - py0) * PWS + (ox + dx - px0)];
+                            const int ti = (2 * qy + dy) * T + 2 * qx + dx;
+                            const uint32_t gbr = byte_perm(g0, 0, 0x4240), gg = (g0 >> 8) & 255u;
+                            if (uni255) {
+                                // lap_b + 65536 * lap_r == gbr - up_br as plain integers
+                                s_abr[ti] += (int)(gbr - up_br[dy][dx]);
+                                s_ag[ti] += (int)gg - (int)up_g[dy][dx];
+                                s_ws[ti] = f_add(s_ws[ti], 1.f);
+                            } else {
+                                const float wv = f_mul((float)(g0 >> 24), 1.f / 255.f);
+                                const int lb = (int)(gbr & 0xFFFFu) - (int)(up_br[dy][dx] & 0xFFFFu);
+                                const int lr = (int)(gbr >> 16) - (int)(up_br[dy][dx] >> 16);
+                                const int lg = (int)gg - (int)up_g[dy][dx];
+                                const int tb = (int)(short)f2i_rz(f_mul((float)lb, wv));
+                                const int tr = (int)(short)f2i_rz(f_mul((float)lr, wv));
+                                const int tg = (int)(short)f2i_rz(f_mul((float)lg, wv));
+                                s_abr[ti] += tb + tr * 65536;
+                                s_ag[ti] += tg;
+                                s_ws[ti] = f_add(s_ws[ti], wv);
+                            }
+                        }
+                    }
+                }
+            }
+            DS_SYNC();
+        }
+
+        // ---- normalise and store level 0 of the canvas pyramid
+        for (int i = tid; i < T * T; i += NT) {
+            const int yy = i / T, xx = i - yy * T;
+            const int X = X0 + xx, Y = Y0 + yy;
+            if (X >= p.dst_w || Y >= p.dst_h || Y < p.acc_y0 || Y >= p.acc_y1) continue;
+            const int abr = s_abr[i];
+            const int sb = (int)(short)(abr & 0xFFFF);
+            const int sr = (abr - sb) >> 16;
+            const int sg = s_ag[i];
+            const float wsum = s_ws[i];
+            const float den = f_add(wsum, 1e-5f);
+            px16 o;
+            o.b = (short)f2i_rz(f_div((float)(short)sb, den));
+            o.g = (short)f2i_rz(f_div((float)(short)sg, den));
+            o.r = (short)f2i_rz(f_div((float)(short)sr, den));
             o.a = (short)(wsum > 1e-5f ? 1 : 0);
             p.dst[(size_t)Y * p.dst_w + X] = o;
         }
@@ -775,7 +1112,8 @@ DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
 DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
 DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 1)
-DS_DEFINE_KERNEL(ds_mb_feed_l0, MBBodyL0, 512, MBParams, 2)
+DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)
+DS_DEFINE_KERNEL(ds_mb_feed_l0, MBL0Body, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed, MBBodyLN, 256, MBParams, 1)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 1)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)

@@ -160,6 +160,7 @@ struct ds_canvas {
     FrameDev* d_frames = nullptr; size_t frames_cap = 0;
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
+    bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
     uint8_t* d_stage = nullptr; size_t stage_cap = 0;
     int feather_R = 0;
     int64_t device_bytes = 0;
@@ -244,7 +245,7 @@ int fill_frame_dev(ds_canvas* c, Frame& f) {
         size_t off = 0;
         for (int l = 1; l <= c->L; l++) {
             const size_t n = (size_t)(f.rw >> l) * (f.rh >> l);
-            d.G[l] = (px16*)(base + off); off += n * sizeof(px16);
+            d.G[l] = (px8*)(base + off); off += ((n * sizeof(px8) + 15) & ~(size_t)15);
             d.W[l] = (float*)(base + off); off += ((n * sizeof(float) + 15) & ~(size_t)15);
         }
     }
@@ -258,7 +259,7 @@ size_t pyr_bytes(const ds_canvas* c, const Frame& f) {
     size_t off = 0;
     for (int l = 1; l <= c->L; l++) {
         const size_t n = (size_t)(f.rw >> l) * (f.rh >> l);
-        off += n * sizeof(px16);
+        off += ((n * sizeof(px8) + 15) & ~(size_t)15);
         off += ((n * sizeof(float) + 15) & ~(size_t)15);
     }
     return off;
@@ -318,6 +319,13 @@ int build_lists(ds_canvas* c) {
                 fr.assign((size_t)std::max(off[ntiles], 1), 0);
                 counts = off;  // keep the prefix sums; `off` is consumed as a cursor in pass 1
             }
+        }
+        if (l == 0) {
+            int longest = 0;
+            for (int t = 0; t < ntiles; t++) longest = std::max(longest, counts[(size_t)t + 1] - counts[t]);
+            bool all_plane = true;
+            for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32) all_plane = false;
+            c->l0_fast_ok = mb && all_plane && longest <= 64;
         }
         // tiles to run: every tile in the own tile rows (empty ones still write zeros)
         ids.clear();
@@ -434,7 +442,8 @@ int run_composite(ds_canvas* c) {
             else if (l < c->L) ab = abm.A * q * (40.0 + 2.5);
             else ab = abm.A * q * 40.0;
             if ((rc = prof_mark(c, true, "mb_feed", l, (int64_t)ab))) return rc;
-            if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBBody<64, true>::smem_bytes());
+            if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBL0Body, 512>(mp, pl.n_ids, c->stream, MBL0Body::smem_bytes());
+            else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBBody<64, true>::smem_bytes());
             else rc = launch<MBBody<32, false>, 256>(mp, pl.n_ids, c->stream, MBBody<32, false>::smem_bytes());
             if (rc) return rc;
             if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
@@ -888,8 +897,8 @@ DS_API int ds_debug_get_frame_level(ds_canvas* c, int frame_idx, int level, int1
     if (!c->composited) return fail(DS_ERR_STATE, "frame pyramids exist only after ds_composite");
     const size_t n = (size_t)lw * lh;
     if (g) {
-        std::vector<px16> tmp(n);
-        if ((rc = d2h(tmp.data(), f->dev.G[level], n * sizeof(px16), c->stream))) return rc;
+        std::vector<px8> tmp(n);
+        if ((rc = d2h(tmp.data(), f->dev.G[level], n * sizeof(px8), c->stream))) return rc;
         if ((rc = stream_sync(c->stream))) return rc;
         for (size_t i = 0; i < n; i++) { g[3 * i] = tmp[i].b; g[3 * i + 1] = tmp[i].g; g[3 * i + 2] = tmp[i].r; }
     }

@@ -21,7 +21,7 @@ struct FrameDev {
     int cx, cy;          // bbox top-left relative to the padded canvas origin
     int w, h;            // warped bbox size (cv sizes[i])
     int rx, ry, rw, rh;  // MultiBandBlender::feed aligned ROI at level 0, relative to padded canvas origin
-    px16* G[DS_MAXL];    // per-frame Gaussian levels 1..L over the feed ROI (index 0 unused)
+    px8* G[DS_MAXL];     // per-frame Gaussian levels 1..L over the feed ROI (values 0..255; index 0 unused)
     float* W[DS_MAXL];   // per-frame weight levels 1..L
     const uint32_t* mbits;  // FEATHER: warped-mask bit plane over the bbox (1 bit/px, tail bits set)
     int mbits_pitch;        // words per row

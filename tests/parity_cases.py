@@ -225,7 +225,13 @@ def case_seam_and_gain(lib):
     return run_case(lib, specs, "feather", 0)
 
 
+def case_medium_mb3_interior(lib):
+    # frames large against the tile size: exercises the border-free / uniform-mask fast paths of the level-0 kernel
+    return run_case(lib, plane_specs(synth.grid_survey(2, 2, 900, 700, overlap=0.6, seed=21, work_scale=0.45)), "multiband", 3, band_split=2)
+
+
 CASES = {
+    "medium_mb3_interior": case_medium_mb3_interior,
     "small_feather": case_small_feather,
     "small_mb5": case_small_mb5,
     "small_mb3_bgra": case_small_mb3_bgra,
