@@ -683,14 +683,18 @@ struct MBBody {
 struct L0Col { float a0, a3, a6; int u; };  // u = raw bbox column if inside else -1
 struct L0Row { float b1, b4, b7; int v; };
 
-struct MBL0Body {
-    static constexpr int T = 64, PWS = 72, PHM = 71, GWS = 34, JW = 32, NQ = 1024;
+template <int T_, bool LEVEL0>
+struct MBFastBody {
+    static constexpr int T = T_, PWS = T_ + 8, PHM = T_ + 7, GWS = T_ / 2 + 2, JW = T_ / 2, NQ = T_ * T_ / 4;
+    static constexpr int W0_BYTES = LEVEL0 ? 0 : ds_al16(PHM * PWS * 4);   // W_l of the needed region (levels >= 1)
     static constexpr int G0_BYTES = ds_al16(PHM * PWS * 4);
     static constexpr int G1_BYTES = ds_al16(GWS * GWS * 8);
-    static constexpr int H_BYTES = ds_al16(PHM * GWS * 8);      // also the float H pass of the weights (PHM * JW * 4)
+    static constexpr int BW = 88, BH = 82;                    // staged source footprint box (BGRX px)
+    static constexpr bool kStage = false;                     // measured on B200: L1 already serves the taps (86 % hit); staging costs more than it saves
+    static constexpr int H_BYTES = kStage ? ds_al16(BW * BH * 4) : ds_al16(PHM * GWS * 8);  // [source box in phase 1;] pyrDown H pass / weight H pass
     static constexpr int ACC_BYTES = T * T * 4;
     static constexpr int COL_BYTES = ds_al16(PWS * 16), ROW_BYTES = ds_al16(PHM * 16);
-    static int smem_bytes() { return G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES; }
+    static int smem_bytes() { return G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES; }
 
     struct U2 { uint32_t br, g; };
 
@@ -702,12 +706,15 @@ struct MBL0Body {
         uint32_t* s_g0 = (uint32_t*)smem;
         U2* s_g1 = (U2*)(smem + G0_BYTES);
         U2* s_h = (U2*)(smem + G0_BYTES + G1_BYTES);
+        uint32_t* s_box = (uint32_t*)(smem + G0_BYTES + G1_BYTES);
         float* s_hw = (float*)(smem + G0_BYTES + G1_BYTES);
         int* s_abr = (int*)(smem + G0_BYTES + G1_BYTES + H_BYTES);
         int* s_ag = s_abr + T * T;
         float* s_ws = (float*)(s_ag + T * T);
         L0Col* s_col = (L0Col*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES);
         L0Row* s_row = (L0Row*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES);
+        float* s_w = (float*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES);
+        const int l = LEVEL0 ? 0 : p.level;
 
         const int tile = p.tile_ids ? p.tile_ids[block] : block;
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -719,7 +726,7 @@ struct MBL0Body {
 
         for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
             const FrameDev& F = p.frames[p.tile_frames[fi]];
-            const int rx = F.rx, ry = F.ry, rw = F.rw, rh = F.rh;
+            const int rx = F.rx >> l, ry = F.ry >> l, rw = F.rw >> l, rh = F.rh >> l;
             const int ax0 = imax(X0, rx), ax1 = imin(X0 + T, rx + rw);
             const int ay0 = imax(imax(Y0, ry), p.own_y0), ay1 = imin(imin(Y0 + T, ry + rh), p.own_y1);
             if (ax0 >= ax1 || ay0 >= ay1) continue;  // block-uniform
@@ -737,7 +744,11 @@ struct MBL0Body {
             const bool border = !(2 * gx0 - 2 >= 0 && 2 * gx1 + 2 <= rw - 1 && 2 * gy0 - 2 >= 0 && 2 * gy1 + 2 <= rh - 1 &&
                                   jx0 >= 1 && jx1 <= n1x - 1 && jy0 >= 1 && jy1 <= n1y - 1);
             const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
+            uint32_t* const G1out = (uint32_t*)F.G[l + 1];
+            float* const W1out = F.W[l + 1];
 
+            int m_and = 255, m_or = 0;   // level 0: AND / OR of the mask bytes; levels >= 1: 255 / 0 flags of (w == 1) / (w != 0)
+            if constexpr (LEVEL0) {
             // ---- tables: reflected bbox index + per-column / per-row map terms
             for (int i = tid; i < pw + ph; i += NT) {
                 if (i < pw) {
@@ -763,78 +774,155 @@ struct MBL0Body {
                     s_row[yy] = r;
                 }
             }
+            // ---- source footprint box: the (reflected) bbox rectangle this tile-frame samples maps to a
+            // parallelogram in the source; stage its bounding box (+ bilinear / rounding margin) in shared
+            // memory with the border mode already resolved. Exactness never depends on the estimate:
+            // a tap outside the box falls back to the global path below.
+            bool staged = false;
+            int bx0 = 0, by0 = 0;
+            if (kStage && !proj) {
+                const int u_lo = rx + px0 - F.cx, u_hi = u_lo + pw - 1, v_lo = ry + py0 - F.cy, v_hi = v_lo + ph - 1;
+                int ulo = imin(refl(u_lo, F.w, BORDER_REFL), refl(u_hi, F.w, BORDER_REFL));
+                int uhi = imax(refl(u_lo, F.w, BORDER_REFL), refl(u_hi, F.w, BORDER_REFL));
+                int vlo = imin(refl(v_lo, F.h, BORDER_REFL), refl(v_hi, F.h, BORDER_REFL));
+                int vhi = imax(refl(v_lo, F.h, BORDER_REFL), refl(v_hi, F.h, BORDER_REFL));
+                if (u_lo < 0 || pw >= F.w) ulo = 0;
+                if (u_hi >= F.w || pw >= F.w) uhi = F.w - 1;
+                if (v_lo < 0 || ph >= F.h) vlo = 0;
+                if (v_hi >= F.h || ph >= F.h) vhi = F.h - 1;
+                float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+                for (int cidx = 0; cidx < 4; cidx++) {
+                    float U = (float)(F.tlx + ((cidx & 1) ? uhi : ulo)), V = (float)(F.tly + ((cidx & 2) ? vhi : vlo));
+                    if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+                    const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+                    const float x = f_add(f_add(f_mul(F.k[0], up), f_mul(F.k[1], vp)), F.k2one);
+                    const float y = f_add(f_add(f_mul(F.k[3], up), f_mul(F.k[4], vp)), F.k5one);
+                    xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+                }
+                if (xmin > -1.0e6f && xmax < 1.0e6f && ymin > -1.0e6f && ymax < 1.0e6f) {
+                    bx0 = (int)floorf(xmin) - 1; by0 = (int)floorf(ymin) - 1;
+                    const int bx1 = (int)floorf(xmax) + 2, by1 = (int)floorf(ymax) + 2;
+                    staged = (bx1 - bx0 + 1 <= BW) && (by1 - by0 + 1 <= BH);
+                }
+            }
+            if (staged) {
+                const uint32_t* const src = F.src;
+                const int pitch = F.src_pitch, sw = F.src_w, sh = F.src_h;
+                const bool inside = bx0 >= 0 && by0 >= 0 && bx0 + BW <= sw && by0 + BH <= sh;
+                const bool bconst = F.border == BORDER_CONST;
+                for (int e = tid; e < BW * BH; e += NT) {
+                    const int yy = e / BW, xx = e - yy * BW;
+                    int gx = bx0 + xx, gy = by0 + yy;
+                    uint32_t v = 0u;
+                    if (inside) {
+                        v = ld_ro(src + (gy * pitch + gx));
+                    } else if (bconst) {
+                        if ((unsigned)gx < (unsigned)sw && (unsigned)gy < (unsigned)sh) v = ld_ro(src + (gy * pitch + gx));
+                    } else {
+                        gx = refl(gx, sw, BORDER_REFL); gy = refl(gy, sh, BORDER_REFL);
+                        v = ld_ro(src + (gy * pitch + gx));
+                    }
+                    s_box[e] = v;
+                }
+            }
             DS_SYNC();
 
             // ---- phase 1: inverse warp of the needed region into s_g0 (b | g<<8 | r<<16 | mask<<24)
-            int all255 = 1, all0 = 1;
-            for (int i = tid; i < PWS * ph; i += NT) {
-                const int yy = i / PWS, xx = i - yy * PWS;
-                if (xx >= pw) continue;
-                const L0Col c = s_col[xx];
-                const L0Row r = s_row[yy];
-                float x = f_add(f_add(c.a0, r.b1), F.k2one);
-                float y = f_add(f_add(c.a3, r.b4), F.k5one);
-                if (proj) {
-                    const float z = f_add(f_add(c.a6, r.b7), F.k8one);
-                    if (z != 1.f) { x = f_div(x, z); y = f_div(y, z); }
-                }
-                int ix, iy, nx, ny;
-                if (fabsf(x) < 67108864.f && fabsf(y) < 67108864.f) {   // |32 x| < 2^31: plain conversions are exact
+            // Frame fields are copied to registers first: F lives in global memory and would otherwise be
+            // re-read around every shared-memory store.
+            {
+                const uint32_t* const src = F.src;
+                const int pitch = F.src_pitch, sw = F.src_w, sh = F.src_h;
+                const float k2 = F.k2one, k5 = F.k5one, k8 = F.k8one;
+                const uint8_t* const seam = F.seam;
+                const int seam_pitch = F.seam_pitch;
+                const bool has_gain = F.has_gain != 0;
+                const bool bconst = F.border == BORDER_CONST;
+                const float g0 = F.gain[0], g1 = F.gain[1], g2 = F.gain[2];
+                for (int i = tid; i < PWS * ph; i += NT) {
+                    const int yy = i / PWS, xx = i - yy * PWS;
+                    if (xx >= pw) continue;
+                    const L0Col c = s_col[xx];
+                    const L0Row r = s_row[yy];
+                    float x = f_add(f_add(c.a0, r.b1), k2);
+                    float y = f_add(f_add(c.a3, r.b4), k5);
+                    if (proj) {
+                        const float z = f_add(f_add(c.a6, r.b7), k8);
+                        if (z != 1.f) { x = f_div(x, z); y = f_div(y, z); }
+                    }
+                    // cvRound: |32 x| >= 2^31 or NaN gives INT_MIN on the oracle's x86 (f2i_rn); below that the
+                    // plain conversion is identical. For the nearest mask the patch is not needed: a
+                    // saturated coordinate is out of the source either way, NaN is excluded through `ok`.
+                    const bool okx = x < 67108864.f, oky = y < 67108864.f;
 #if DS_CUDA
-                    ix = __float2int_rn(f_mul(x, 32.f)); iy = __float2int_rn(f_mul(y, 32.f));
-                    nx = __float2int_rn(x); ny = __float2int_rn(y);
+                    int ix = __float2int_rn(f_mul(x, 32.f)), iy = __float2int_rn(f_mul(y, 32.f));
+                    const int nx = __float2int_rn(x), ny = __float2int_rn(y);
 #else
-                    ix = (int)lrintf(f_mul(x, 32.f)); iy = (int)lrintf(f_mul(y, 32.f));
-                    nx = (int)lrintf(x); ny = (int)lrintf(y);
+                    int ix = f2i_rn(f_mul(x, 32.f)), iy = f2i_rn(f_mul(y, 32.f));
+                    const int nx = okx ? f2i_rn(x) : 0, ny = oky ? f2i_rn(y) : 0;
 #endif
-                } else {
-                    ix = f2i_rn(f_mul(x, 32.f)); iy = f2i_rn(f_mul(y, 32.f));
-                    nx = f2i_rn(x); ny = f2i_rn(y);
+                    ix = okx ? ix : (int)0x80000000;
+                    iy = oky ? iy : (int)0x80000000;
+                    const int sx = sat16i(ix >> 5), sy = sat16i(iy >> 5);
+                    const int ax = ix & 31, ay = iy & 31;
+                    int m = ((c.u | r.v) >= 0 && okx && oky && (unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255 : 0;
+                    if (seam && (c.u | r.v) >= 0) m &= (int)ld_ro(seam + (size_t)r.v * seam_pitch + c.u);
+                    uint32_t p00, p01, p10, p11;
+                    const int bxi = sx - bx0, byi = sy - by0;
+                    if (kStage && staged && (unsigned)bxi < (unsigned)(BW - 1) && (unsigned)byi < (unsigned)(BH - 1)) {
+                        const uint32_t* r0 = s_box + (byi * BW + bxi);
+                        p00 = r0[0]; p01 = r0[1]; p10 = r0[BW]; p11 = r0[BW + 1];
+                    } else if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+                        const uint32_t* r0 = src + (sy * pitch + sx);
+                        p00 = ld_ro(r0); p01 = ld_ro(r0 + 1);
+                        p10 = ld_ro(r0 + pitch); p11 = ld_ro(r0 + pitch + 1);
+                    } else if (bconst) {
+                        const int x0 = (unsigned)sx < (unsigned)sw ? sx : -1;
+                        const int x1 = (unsigned)(sx + 1) < (unsigned)sw ? sx + 1 : -1;
+                        const int y0 = (unsigned)sy < (unsigned)sh ? sy : -1;
+                        const int y1 = (unsigned)(sy + 1) < (unsigned)sh ? sy + 1 : -1;
+                        p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
+                        p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
+                    } else {
+                        const int x0 = refl(sx, sw, BORDER_REFL), x1 = refl(sx + 1, sw, BORDER_REFL);
+                        const int y0 = refl(sy, sh, BORDER_REFL), y1 = refl(sy + 1, sh, BORDER_REFL);
+                        p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
+                        p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
+                    }
+                    // horizontal: bytes (B0,B1,G0,G1) . (wx0,wx1,0,0) etc.; vertical in 32 bit; (v + 512) >> 10
+                    const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
+                    const uint32_t t0 = byte_perm(p00, p01, 0x5140), t0r = byte_perm(p00, p01, 0x6262);
+                    const uint32_t t1 = byte_perm(p10, p11, 0x5140), t1r = byte_perm(p10, p11, 0x6262);
+                    const int wy1 = ay, wy0 = 32 - ay;
+                    int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
+                    int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
+                    int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
+                    if (has_gain) {
+                        ob = sat8i(f2i_rn(f_mul((float)ob, g0)));
+                        og = sat8i(f2i_rn(f_mul((float)og, g1)));
+                        orr = sat8i(f2i_rn(f_mul((float)orr, g2)));
+                    }
+                    s_g0[i] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | ((uint32_t)m << 24);
+                    m_and &= m;
+                    m_or |= m;
                 }
-                const int sx = sat16i(ix >> 5), sy = sat16i(iy >> 5);
-                const int ax = ix & 31, ay = iy & 31;
-                nx = sat16i(nx); ny = sat16i(ny);
-                int m = 0;
-                if ((c.u | r.v) >= 0) {
-                    m = ((unsigned)nx < (unsigned)F.src_w && (unsigned)ny < (unsigned)F.src_h) ? 255 : 0;
-                    if (F.seam) m &= (int)ld_ro(F.seam + (size_t)r.v * F.seam_pitch + c.u);
-                }
-                uint32_t p00, p01, p10, p11;
-                if ((unsigned)sx < (unsigned)(F.src_w - 1) && (unsigned)sy < (unsigned)(F.src_h - 1)) {
-                    const uint32_t* r0 = F.src + (size_t)sy * F.src_pitch + sx;
-                    p00 = ld_ro(r0); p01 = ld_ro(r0 + 1);
-                    p10 = ld_ro(r0 + F.src_pitch); p11 = ld_ro(r0 + F.src_pitch + 1);
-                } else if (F.border == BORDER_CONST) {
-                    const int x0 = (unsigned)sx < (unsigned)F.src_w ? sx : -1;
-                    const int x1 = (unsigned)(sx + 1) < (unsigned)F.src_w ? sx + 1 : -1;
-                    const int y0 = (unsigned)sy < (unsigned)F.src_h ? sy : -1;
-                    const int y1 = (unsigned)(sy + 1) < (unsigned)F.src_h ? sy + 1 : -1;
-                    p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
-                    p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
-                } else {
-                    const int x0 = refl(sx, F.src_w, BORDER_REFL), x1 = refl(sx + 1, F.src_w, BORDER_REFL);
-                    const int y0 = refl(sy, F.src_h, BORDER_REFL), y1 = refl(sy + 1, F.src_h, BORDER_REFL);
-                    p00 = src_tap(F, x0, y0); p01 = src_tap(F, x1, y0);
-                    p10 = src_tap(F, x0, y1); p11 = src_tap(F, x1, y1);
-                }
-                // horizontal: bytes (B0,B1,G0,G1) . (wx0,wx1,0,0) etc.; vertical in 32 bit; (v + 512) >> 10
-                const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
-                const uint32_t t0 = byte_perm(p00, p01, 0x5140), t0r = byte_perm(p00, p01, 0x6262);
-                const uint32_t t1 = byte_perm(p10, p11, 0x5140), t1r = byte_perm(p10, p11, 0x6262);
-                const int wy1 = ay, wy0 = 32 - ay;
-                int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
-                int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
-                int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
-                if (F.has_gain) {
-                    ob = sat8i(f2i_rn(f_mul((float)ob, F.gain[0])));
-                    og = sat8i(f2i_rn(f_mul((float)og, F.gain[1])));
-                    orr = sat8i(f2i_rn(f_mul((float)orr, F.gain[2])));
-                }
-                s_g0[i] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | ((uint32_t)m << 24);
-                all255 &= (m == 255);
-                all0 &= (m == 0);
             }
-            const int uni255 = block_and(all255) && (c255 == 1.f);
+            } else {
+                const uint32_t* const Gin = (const uint32_t*)F.G[l];
+                const float* const Win = F.W[l];
+                for (int i = tid; i < PWS * ph; i += NT) {
+                    const int yy = i / PWS, xx = i - yy * PWS;
+                    if (xx >= pw) continue;
+                    const size_t gi = (size_t)(py0 + yy) * rw + (px0 + xx);
+                    const float w = Win[gi];
+                    s_g0[i] = Gin[gi];
+                    s_w[i] = w;
+                    m_and &= (w == 1.f) ? 255 : 0;
+                    m_or |= (w != 0.f) ? 255 : 0;
+                }
+            }
+            const int all255 = (m_and == 255), all0 = (m_or == 0);
+            const int uni255 = block_and(all255) && (!LEVEL0 || c255 == 1.f);   // every weight of the needed region is exactly 1
             const int uni0 = block_and(all0);
 
             // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op
@@ -877,7 +965,7 @@ struct MBL0Body {
                 s_g1[gyy * GWS + gxx] = o;
                 const int gx = gx0 + gxx, gy = gy0 + gyy;
                 if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1)
-                    ((uint32_t*)F.G[1])[(size_t)gy * n1x + gx] = byte_perm(o.br, o.g, 0x5240);
+                    G1out[(size_t)gy * n1x + gx] = byte_perm(o.br, o.g, 0x5240);
             }
             DS_SYNC();
 
@@ -886,7 +974,7 @@ struct MBL0Body {
                 const float wv = uni255 ? 1.f : 0.f;
                 for (int i = tid; i < jh * JW; i += NT) {
                     const int jyy = i / JW, jj = i - jyy * JW;
-                    if (jj < jw) F.W[1][(size_t)(jy0 + jyy) * n1x + (jx0 + jj)] = wv;
+                    if (jj < jw) W1out[(size_t)(jy0 + jyy) * n1x + (jx0 + jj)] = wv;
                 }
             } else {
                 const int hr0 = imax(2 * jy0 - 2, 0), hr1 = imin(2 * jy1, rh - 1);
@@ -898,7 +986,7 @@ struct MBL0Body {
                     float t[5];
                     for (int q = 0; q < 5; q++) {
                         const int si = (row - py0) * PWS + (refl101(2 * j + q - 2, rw) - px0);
-                        t[q] = f_mul((float)(s_g0[si] >> 24), 1.f / 255.f);
+                        t[q] = LEVEL0 ? f_mul((float)(s_g0[si] >> 24), 1.f / 255.f) : s_w[si];
                     }
                     s_hw[i] = pd_h_is_simd(j, rw, n1x) ? pd_h_simd(t[0], t[1], t[2], t[3], t[4])
                                                         : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
@@ -912,14 +1000,14 @@ struct MBL0Body {
                     for (int q = 0; q < 5; q++) t[q] = s_hw[(refl101(2 * jy + q - 2, rh) - hr0) * JW + jj];
                     const float v = pd_v_is_simd(j, n1x) ? pd_v_simd(t[0], t[1], t[2], t[3], t[4])
                                                          : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
-                    F.W[1][(size_t)jy * n1x + j] = f_mul(v, 1.f / 256.f);
+                    W1out[(size_t)jy * n1x + j] = f_mul(v, 1.f / 256.f);
                 }
             }
 
             // ---- phase 3: lap = G_0 - pyrUp(G_1), weighted accumulate, one 2x2 quad per item
             if (!uni0) {
                 for (int q = tid; q < NQ; q += NT) {
-                    const int qy = q >> 5, qx = q & 31;
+                    const int qy = q / (T / 2), qx = q - qy * (T / 2);
                     const int X = X0 + 2 * qx, Y = Y0 + 2 * qy;
                     if (X < ax0 || X >= ax1 || Y < ay0 || Y >= ay1) continue;
                     const int ox = X - rx, oy = Y - ry;
@@ -953,7 +1041,8 @@ struct MBL0Body {
                     for (int dy = 0; dy < 2; dy++) {
                         DS_UNROLL
                         for (int dx = 0; dx < 2; dx++) {
-                            const uint32_t g0 = s_g0[(oy + dy - py0) * PWS + (ox + dx - px0)];
+                            const int gsi = (oy + dy - py0) * PWS + (ox + dx - px0);
+                            const uint32_t g0 = s_g0[gsi];
                             const int ti = (2 * qy + dy) * T + 2 * qx + dx;
                             const uint32_t gbr = byte_perm(g0, 0, 0x4240), gg = (g0 >> 8) & 255u;
                             if (uni255) {
@@ -962,7 +1051,7 @@ struct MBL0Body {
                                 s_ag[ti] += (int)gg - (int)up_g[dy][dx];
                                 s_ws[ti] = f_add(s_ws[ti], 1.f);
                             } else {
-                                const float wv = f_mul((float)(g0 >> 24), 1.f / 255.f);
+                                const float wv = LEVEL0 ? f_mul((float)(g0 >> 24), 1.f / 255.f) : s_w[gsi];
                                 const int lb = (int)(gbr & 0xFFFFu) - (int)(up_br[dy][dx] & 0xFFFFu);
                                 const int lr = (int)(gbr >> 16) - (int)(up_br[dy][dx] >> 16);
                                 const int lg = (int)gg - (int)up_g[dy][dx];
@@ -1113,8 +1202,11 @@ DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
 DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 1)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)
-DS_DEFINE_KERNEL(ds_mb_feed_l0, MBL0Body, 512, MBParams, 2)
-DS_DEFINE_KERNEL(ds_mb_feed, MBBodyLN, 256, MBParams, 1)
+typedef MBFastBody<64, true> MBFastL0;
+typedef MBFastBody<32, false> MBFastLN;
+DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
+DS_DEFINE_KERNEL(ds_mb_feed_ln, MBFastLN, 256, MBParams, 4)
+DS_DEFINE_KERNEL(ds_mb_feed_generic, MBBodyLN, 256, MBParams, 1)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 1)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)
 #endif

@@ -160,6 +160,7 @@ struct ds_canvas {
     FrameDev* d_frames = nullptr; size_t frames_cap = 0;
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
+    bool ln_fast_ok = false;   // fast kernel for levels 1..L-1 (<= 64 frames per tile at every level)
     bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
     uint8_t* d_stage = nullptr; size_t stage_cap = 0;
     int feather_R = 0;
@@ -320,12 +321,18 @@ int build_lists(ds_canvas* c) {
                 counts = off;  // keep the prefix sums; `off` is consumed as a cursor in pass 1
             }
         }
-        if (l == 0) {
+        if (mb) {
+            // the fast kernels pack two 16-bit accumulator lanes per int: exact while a tile sees <= 64 frames
             int longest = 0;
             for (int t = 0; t < ntiles; t++) longest = std::max(longest, counts[(size_t)t + 1] - counts[t]);
-            bool all_plane = true;
-            for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32) all_plane = false;
-            c->l0_fast_ok = mb && all_plane && longest <= 64;
+            if (l == 0) {
+                bool all_plane = true;
+                for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32) all_plane = false;
+                c->l0_fast_ok = all_plane && longest <= 64;
+                c->ln_fast_ok = true;
+            } else if (longest > 64) {
+                c->ln_fast_ok = false;
+            }
         }
         // tiles to run: every tile in the own tile rows (empty ones still write zeros)
         ids.clear();
@@ -442,7 +449,8 @@ int run_composite(ds_canvas* c) {
             else if (l < c->L) ab = abm.A * q * (40.0 + 2.5);
             else ab = abm.A * q * 40.0;
             if ((rc = prof_mark(c, true, "mb_feed", l, (int64_t)ab))) return rc;
-            if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBL0Body, 512>(mp, pl.n_ids, c->stream, MBL0Body::smem_bytes());
+            if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBFastBody<64, true>::smem_bytes());
+            else if (l > 0 && l < c->L && c->ln_fast_ok) rc = launch<MBFastBody<32, false>, 256>(mp, pl.n_ids, c->stream, MBFastBody<32, false>::smem_bytes());
             else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBBody<64, true>::smem_bytes());
             else rc = launch<MBBody<32, false>, 256>(mp, pl.n_ids, c->stream, MBBody<32, false>::smem_bytes());
             if (rc) return rc;
