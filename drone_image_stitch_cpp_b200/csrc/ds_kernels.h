@@ -839,6 +839,72 @@ struct MBFastBody {
                 const bool has_gain = F.has_gain != 0;
                 const bool bconst = F.border == BORDER_CONST;
                 const float g0 = F.gain[0], g1 = F.gain[1], g2 = F.gain[2];
+                // Interior tile-frames: the needed region lies inside the bbox and its four corners map at
+                // least a pixel inside the source. x(u, v) is monotone in u and in v even in float arithmetic
+                // (a chain of monotone roundings), so the corner values bound every pixel: all taps are
+                // in-bounds inliers, the nearest mask is 255 everywhere and no cvRound patch can trigger.
+                bool interior = false;
+                if (!proj && !seam) {
+                    const int u_lo = rx + px0 - F.cx, v_lo = ry + py0 - F.cy;
+                    if (u_lo >= 0 && u_lo + pw <= F.w && v_lo >= 0 && v_lo + ph <= F.h) {
+                        const L0Col c0 = s_col[0], c1 = s_col[pw - 1];
+                        const L0Row r0 = s_row[0], r1 = s_row[ph - 1];
+                        const float xa = f_add(f_add(c0.a0, r0.b1), k2), xb = f_add(f_add(c1.a0, r0.b1), k2);
+                        const float xc = f_add(f_add(c0.a0, r1.b1), k2), xd = f_add(f_add(c1.a0, r1.b1), k2);
+                        const float ya = f_add(f_add(c0.a3, r0.b4), k5), yb = f_add(f_add(c1.a3, r0.b4), k5);
+                        const float yc = f_add(f_add(c0.a3, r1.b4), k5), yd = f_add(f_add(c1.a3, r1.b4), k5);
+                        const float xmn = fminf(fminf(xa, xb), fminf(xc, xd)), xmx = fmaxf(fmaxf(xa, xb), fmaxf(xc, xd));
+                        const float ymn = fminf(fminf(ya, yb), fminf(yc, yd)), ymx = fmaxf(fmaxf(ya, yb), fmaxf(yc, yd));
+                        interior = xmn >= 1.f && xmx <= (float)(sw - 3) && ymn >= 1.f && ymx <= (float)(sh - 3);
+                    }
+                }
+                if (interior) {
+                    // UB pixels per thread and iteration: all taps are requested before any is used, so each
+                    // warp keeps 4 * UB loads in flight (the loop is otherwise bound by L1/L2 latency)
+                    constexpr int UB = 4;
+                    const int npx = PWS * ph;
+                    for (int i0 = tid; i0 < npx; i0 += UB * NT) {
+                        int ix[UB], iy[UB];
+                        uint32_t p00[UB], p01[UB], p10[UB], p11[UB];
+                        bool ok[UB];
+                        DS_UNROLL
+                        for (int b = 0; b < UB; b++) {
+                            const int i = i0 + b * NT;
+                            const int ii = i < npx ? i : i0;
+                            const int yy = ii / PWS, xx = ii - yy * PWS;
+                            ok[b] = i < npx && xx < pw;
+                            const L0Col c = s_col[xx < pw ? xx : 0];
+                            const L0Row r = s_row[yy];
+                            const float x = f_add(f_add(c.a0, r.b1), k2);
+                            const float y = f_add(f_add(c.a3, r.b4), k5);
+#if DS_CUDA
+                            ix[b] = __float2int_rn(f_mul(x, 32.f)); iy[b] = __float2int_rn(f_mul(y, 32.f));
+#else
+                            ix[b] = f2i_rn(f_mul(x, 32.f)); iy[b] = f2i_rn(f_mul(y, 32.f));
+#endif
+                            const uint32_t* r0 = src + ((iy[b] >> 5) * pitch + (ix[b] >> 5));
+                            p00[b] = ld_ro(r0); p01[b] = ld_ro(r0 + 1); p10[b] = ld_ro(r0 + pitch); p11[b] = ld_ro(r0 + pitch + 1);
+                        }
+                        DS_UNROLL
+                        for (int b = 0; b < UB; b++) {
+                            const int ax = ix[b] & 31, ay = iy[b] & 31;
+                            const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
+                            const uint32_t t0 = byte_perm(p00[b], p01[b], 0x5140), t0r = byte_perm(p00[b], p01[b], 0x6262);
+                            const uint32_t t1 = byte_perm(p10[b], p11[b], 0x5140), t1r = byte_perm(p10[b], p11[b], 0x6262);
+                            const int wy1 = ay, wy0 = 32 - ay;
+                            int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
+                            int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
+                            int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
+                            if (has_gain) {
+                                ob = sat8i(f2i_rn(f_mul((float)ob, g0)));
+                                og = sat8i(f2i_rn(f_mul((float)og, g1)));
+                                orr = sat8i(f2i_rn(f_mul((float)orr, g2)));
+                            }
+                            if (ok[b]) s_g0[i0 + b * NT] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | 0xff000000u;
+                        }
+                    }
+                    m_or = 255;   // m_and stays 255: the mask is uniform 255
+                } else
                 for (int i = tid; i < PWS * ph; i += NT) {
                     const int yy = i / PWS, xx = i - yy * PWS;
                     if (xx >= pw) continue;
@@ -1103,59 +1169,98 @@ struct CollapseParams {
     OutParams o;
 };
 struct CollapseBody {
-    static constexpr int PER_BLOCK = 512;  // items (quads) per block
+    static constexpr int PER_BLOCK = 512;  // items (4-px row segments) per block
     static int smem_bytes() { return 0; }
     static long long items(const CollapseParams& p) { return (long long)((p.fw + 3) / 4) * (p.y1 - p.y0); }
+
+    // one pyrUp output from the horizontally filtered rows (A10), plus the fine value, saturated
+    DS_DM int up1(int hl, int hc, int hr, bool odd_y, int fine) {
+        const int vv = odd_y ? 4 * (hc + hr) : (hl + 6 * hc + hr);
+        return sat16i((int)(short)((vv + 32) >> 6) + fine);
+    }
+
     template <int NT>
     DS_DM void run(const CollapseParams& p, int block, int tid, unsigned char*) {
         const int qw = (p.fw + 3) / 4;
         const long long n = (long long)qw * (p.y1 - p.y0);
+        const px16* const coarse = p.coarse;
+        const int cw = p.cw, chh = p.ch, fw = p.fw;
         for (int it = tid; it < PER_BLOCK; it += NT) {
             const long long idx = (long long)block * PER_BLOCK + it;
             if (idx >= n) break;
             const int Y = p.y0 + (int)(idx / qw), Xq = (int)(idx % qw) * 4;
             const int c1y = Y >> 1;
-            const int ryl = up_l(c1y, p.ch), ryr = up_r(c1y, p.ch);
-            for (int k = 0; k < 4; k++) {
-                const int X = Xq + k;
-                if (X >= p.fw) break;
-                const int c1x = X >> 1;
-                const int rxl = up_l(c1x, p.cw), rxr = up_r(c1x, p.cw);
-                int hl[3], hc[3], hr[3];
-                const px16 a1 = p.coarse[(size_t)ryl * p.cw + c1x], a2 = p.coarse[(size_t)ryl * p.cw + rxr];
-                const px16 b1 = p.coarse[(size_t)c1y * p.cw + c1x], b2 = p.coarse[(size_t)c1y * p.cw + rxr];
-                const px16 c1 = p.coarse[(size_t)ryr * p.cw + c1x], c2 = p.coarse[(size_t)ryr * p.cw + rxr];
-                if (X & 1) {
-                    hl[0] = 4 * (a1.b + a2.b); hl[1] = 4 * (a1.g + a2.g); hl[2] = 4 * (a1.r + a2.r);
-                    hc[0] = 4 * (b1.b + b2.b); hc[1] = 4 * (b1.g + b2.g); hc[2] = 4 * (b1.r + b2.r);
-                    hr[0] = 4 * (c1.b + c2.b); hr[1] = 4 * (c1.g + c2.g); hr[2] = 4 * (c1.r + c2.r);
-                } else {
-                    const px16 a0 = p.coarse[(size_t)ryl * p.cw + rxl], b0 = p.coarse[(size_t)c1y * p.cw + rxl];
-                    const px16 c0 = p.coarse[(size_t)ryr * p.cw + rxl];
-                    hl[0] = a0.b + 6 * a1.b + a2.b; hl[1] = a0.g + 6 * a1.g + a2.g; hl[2] = a0.r + 6 * a1.r + a2.r;
-                    hc[0] = b0.b + 6 * b1.b + b2.b; hc[1] = b0.g + 6 * b1.g + b2.g; hc[2] = b0.r + 6 * b1.r + b2.r;
-                    hr[0] = c0.b + 6 * c1.b + c2.b; hr[1] = c0.g + 6 * c1.g + c2.g; hr[2] = c0.r + 6 * c1.r + c2.r;
-                }
-                px16 f = p.fine[(size_t)Y * p.fw + X];
-                int o[3];
-                const int fv[3] = {f.b, f.g, f.r};
-                for (int ch = 0; ch < 3; ch++) {
-                    const int vv = (Y & 1) ? 4 * (hc[ch] + hr[ch]) : (hl[ch] + 6 * hc[ch] + hr[ch]);
-                    o[ch] = sat16i((int)(short)((vv + 32) >> 6) + fv[ch]);
-                }
-                if (!p.final) {
-                    f.b = (short)o[0]; f.g = (short)o[1]; f.r = (short)o[2];
-                    p.fine[(size_t)Y * p.fw + X] = f;
-                } else if (X < p.o.w && Y < p.o.h) {
-                    const int m = f.a != 0;
-                    const int ob = m ? sat8i(o[0]) : 0, og = m ? sat8i(o[1]) : 0, orr = m ? sat8i(o[2]) : 0;
-                    if (p.o.fmt == 1) {
-                        *(uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 4) =
-                            (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | (m ? 0xff000000u : 0u);
+            const bool oddy = (Y & 1) != 0;
+            const int ry[3] = {up_l(c1y, chh), c1y, up_r(c1y, chh)};
+            const int c0 = Xq >> 1;
+            // coarse columns c0-1, c0, c0+1, c0+2 with the pyrUp border rules
+            const int cx[4] = {up_l(c0, cw), c0, up_r(c0, cw), up_r(imin(c0 + 1, cw - 1), cw)};
+            int cb[3][4], cg[3][4], cr[3][4];
+            DS_UNROLL
+            for (int r = 0; r < 3; r++) {
+                if (r == 0 && oddy) { DS_UNROLL for (int c = 0; c < 4; c++) { cb[0][c] = cg[0][c] = cr[0][c] = 0; } continue; }
+                const px16* row = coarse + (size_t)ry[r] * cw;
+                DS_UNROLL
+                for (int c = 0; c < 4; c++) { const px16 q = row[cx[c]]; cb[r][c] = q.b; cg[r][c] = q.g; cr[r][c] = q.r; }
+            }
+            const int nvalid = imin(4, fw - Xq);
+            alignas(16) px16 f[4];
+            px16* frow = p.fine + (size_t)Y * fw + Xq;
+            if (nvalid == 4) {
+                const uint4 v0 = *(const uint4*)frow, v1 = *(const uint4*)(frow + 2);
+                *(uint4*)&f[0] = v0; *(uint4*)&f[2] = v1;
+            } else {
+                for (int kx = 0; kx < 4; kx++) { if (kx < nvalid) f[kx] = frow[kx]; else { f[kx].b = f[kx].g = f[kx].r = f[kx].a = 0; } }
+            }
+            int ob[4], og[4], orr[4];
+            DS_UNROLL
+            for (int kx = 0; kx < 4; kx++) {
+                // X = Xq + kx: even -> (l, c, r) = columns (kx/2, kx/2+1, kx/2+2); odd -> (c, r) = (kx/2+1, kx/2+2)
+                const int j = kx >> 1;
+                int hb[3], hg[3], hr[3];
+                DS_UNROLL
+                for (int r = 0; r < 3; r++) {
+                    if (kx & 1) {
+                        hb[r] = 4 * (cb[r][j + 1] + cb[r][j + 2]); hg[r] = 4 * (cg[r][j + 1] + cg[r][j + 2]); hr[r] = 4 * (cr[r][j + 1] + cr[r][j + 2]);
                     } else {
-                        uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 3;
-                        q[0] = (uint8_t)ob; q[1] = (uint8_t)og; q[2] = (uint8_t)orr;
-                        p.o.mask[(size_t)Y * p.o.mask_pitch + X] = m ? 255 : 0;
+                        hb[r] = cb[r][j] + 6 * cb[r][j + 1] + cb[r][j + 2]; hg[r] = cg[r][j] + 6 * cg[r][j + 1] + cg[r][j + 2];
+                        hr[r] = cr[r][j] + 6 * cr[r][j + 1] + cr[r][j + 2];
+                    }
+                }
+                ob[kx] = up1(hb[0], hb[1], hb[2], oddy, f[kx].b);
+                og[kx] = up1(hg[0], hg[1], hg[2], oddy, f[kx].g);
+                orr[kx] = up1(hr[0], hr[1], hr[2], oddy, f[kx].r);
+            }
+            if (!p.final) {
+                DS_UNROLL
+                for (int kx = 0; kx < 4; kx++) { f[kx].b = (short)ob[kx]; f[kx].g = (short)og[kx]; f[kx].r = (short)orr[kx]; }
+                if (nvalid == 4) { *(uint4*)frow = *(const uint4*)&f[0]; *(uint4*)(frow + 2) = *(const uint4*)&f[2]; }
+                else { for (int kx = 0; kx < nvalid; kx++) frow[kx] = f[kx]; }
+            } else if (Y < p.o.h) {
+                uint32_t px[4];
+                DS_UNROLL
+                for (int kx = 0; kx < 4; kx++) {
+                    const bool m = f[kx].a != 0;
+                    px[kx] = m ? ((uint32_t)sat8i(ob[kx]) | ((uint32_t)sat8i(og[kx]) << 8) | ((uint32_t)sat8i(orr[kx]) << 16) | 0xff000000u) : 0u;
+                }
+                const int nout = imin(nvalid, p.o.w - Xq);
+                if (p.o.fmt == 1) {
+                    uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch) + Xq;
+                    if (nout == 4) *(uint4*)q = make_u4(px[0], px[1], px[2], px[3]);
+                    else for (int kx = 0; kx < nout; kx++) q[kx] = px[kx];
+                } else if (nout == 4) {
+                    // 12 BGR bytes = 3 aligned words; 4 mask bytes = 1 word (Xq is a multiple of 4, pitches of 256)
+                    uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)Xq * 3);
+                    q[0] = (px[0] & 0xffffffu) | (px[1] << 24);
+                    q[1] = ((px[1] >> 8) & 0xffffu) | (px[2] << 16);
+                    q[2] = ((px[2] >> 16) & 0xffu) | (px[3] << 8);
+                    *(uint32_t*)(p.o.mask + (size_t)Y * p.o.mask_pitch + Xq) =
+                        (px[0] >> 24) | ((px[1] >> 24) << 8) | ((px[2] >> 24) << 16) | ((px[3] >> 24) << 24);
+                } else {
+                    for (int kx = 0; kx < nout; kx++) {
+                        uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)(Xq + kx) * 3;
+                        q[0] = (uint8_t)px[kx]; q[1] = (uint8_t)(px[kx] >> 8); q[2] = (uint8_t)(px[kx] >> 16);
+                        p.o.mask[(size_t)Y * p.o.mask_pitch + Xq + kx] = (uint8_t)(px[kx] >> 24);
                     }
                 }
             }
