@@ -32,14 +32,15 @@ UNIT = "MP/s"
 def workload_plan(name, n_gpus):
     from drone_image_stitch_cpp_b200 import synth
     if name == "cfg2":
-        return synth.plan_grid(3, 3 * n_gpus, 5472, 3648, overlap=0.7, seed=synth.MASTER_SEED), "multiband", 5, \
-            f"cfg2: 3x{3 * n_gpus} grid of 5472x3648 frames, 70% overlap, multi-band 5"
+        return synth.plan_grid(3, 3, 5472, 3648, overlap=0.7, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
+            (f"cfg2: {n_gpus} flight block(s) of 3x3 frames 5472x3648, 70% overlap, multi-band 5"
+             + ("" if n_gpus == 1 else ", blocks stacked in y with 5% overlap, one block per GPU row band"))
     if name == "cfg1":
-        return synth.plan_grid(2, 1 * n_gpus, 4000, 3000, overlap=0.7, seed=synth.MASTER_SEED, rot_deg=1.5), "feather", 0, \
-            f"cfg1: 2x{n_gpus} frames of 4000x3000, feather 0.02"
+        return synth.plan_grid(2, 1, 4000, 3000, overlap=0.7, seed=synth.MASTER_SEED, rot_deg=1.5, blocks=n_gpus), "feather", 0, \
+            f"cfg1: {n_gpus} block(s) of 2 frames 4000x3000, feather 0.02"
     if name == "small":
-        return synth.plan_grid(3, 3 * n_gpus, 912, 608, overlap=0.7, seed=synth.MASTER_SEED), "multiband", 5, \
-            f"small: 3x{3 * n_gpus} grid of 912x608 frames, 70% overlap, multi-band 5"
+        return synth.plan_grid(3, 3, 912, 608, overlap=0.7, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
+            f"small: {n_gpus} block(s) of 3x3 frames 912x608, 70% overlap, multi-band 5"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -130,9 +131,9 @@ class CpuReference:
         import torch
         plan = self.plan
         fw, fh = max(64, plan.fw // div), max(64, plan.fh // div)
-        n = len(plan.A)
-        nx = 3 if n % 3 == 0 else 2
-        self.p = synth.plan_grid(nx, n // nx, fw, fh, overlap=0.7, seed=plan.seed,
+        nx, ny = (3, 3) if self.blend == "multiband" else (2, 1)
+        blocks = max(1, len(plan.A) // (nx * ny))
+        self.p = synth.plan_grid(nx, ny, fw, fh, overlap=0.7, seed=plan.seed, blocks=blocks,
                                  rot_deg=3.0 if self.blend == "multiband" else 1.5, trans_jit=20.0 / div)
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         self.frames = synth.cut(self.p, None, dev)

@@ -80,24 +80,29 @@ class SurveyPlan:
 
 
 def plan_grid(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scale_jit=0.02, trans_jit=20.0,
-              work_scale=1.0, serpentine=True, side_overlap=None):
+              work_scale=1.0, serpentine=True, side_overlap=None, blocks=1, block_overlap=0.05):
     """nx x ny frames of fw x fh, step = (1-overlap) of the frame size, with jitter.
     work_scale != 1 exercises the K = diag(1/ws), scale = 1/ws camera convention."""
     rng = np.random.default_rng(seed)
     so = overlap if side_overlap is None else side_overlap
     stepx, stepy = fw * (1.0 - overlap), fh * (1.0 - so)
     margin = int(0.15 * max(fw, fh)) + 64
+    # `blocks` flight blocks of nx x ny frames stacked in y, adjacent blocks overlapping by
+    # block_overlap * fh (weak-scaling workload of bench.py: one block per GPU row band)
+    block_h = stepy * (ny - 1) + fh
+    block_step = block_h - block_overlap * fh
     W = int(stepx * (nx - 1) + fw) + 2 * margin
-    H = int(stepy * (ny - 1) + fh) + 2 * margin
+    H = int(block_step * (blocks - 1) + block_h) + 2 * margin
     a = np.float32(1.0 / work_scale)
     Ks, Rs, As = [], [], []
-    for j in range(ny):
-        cols = range(nx) if (not serpentine or j % 2 == 0) else range(nx - 1, -1, -1)
+    for jj in range(ny * blocks):
+        blk, j = divmod(jj, ny)
+        cols = range(nx) if (not serpentine or jj % 2 == 0) else range(nx - 1, -1, -1)
         for i in cols:
             th = math.radians(rng.uniform(-rot_deg, rot_deg))
             s = rng.uniform(1 - scale_jit, 1 + scale_jit)
             tx = margin + i * stepx + rng.uniform(-trans_jit, trans_jit)
-            ty = margin + j * stepy + rng.uniform(-trans_jit, trans_jit)
+            ty = margin + blk * block_step + j * stepy + rng.uniform(-trans_jit, trans_jit)
             cx, cy = fw / 2.0, fh / 2.0
             # rotate/scale about the frame centre, then translate
             r00, r01, r10, r11 = s * math.cos(th), -s * math.sin(th), s * math.sin(th), s * math.cos(th)
