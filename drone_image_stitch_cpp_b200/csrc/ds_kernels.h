@@ -708,9 +708,9 @@ struct MBFastBody {
         U2* s_h = (U2*)(smem + G0_BYTES + G1_BYTES);
         uint32_t* s_box = (uint32_t*)(smem + G0_BYTES + G1_BYTES);
         float* s_hw = (float*)(smem + G0_BYTES + G1_BYTES);
-        int* s_abr = (int*)(smem + G0_BYTES + G1_BYTES + H_BYTES);
-        int* s_ag = s_abr + T * T;
-        float* s_ws = (float*)(s_ag + T * T);
+        // accumulators: {B + 65536 R, G} interleaved (one 128-bit access per pixel pair), weight sums apart
+        int2* s_acc = (int2*)(smem + G0_BYTES + G1_BYTES + H_BYTES);
+        float* s_ws = (float*)(s_acc + T * T);
         L0Col* s_col = (L0Col*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES);
         L0Row* s_row = (L0Row*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES);
         float* s_w = (float*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES);
@@ -721,7 +721,7 @@ struct MBFastBody {
         const int X0 = tx * T, Y0 = ty * T;
         const float c255 = f_mul(255.f, 1.f / 255.f);
 
-        for (int i = tid; i < T * T; i += NT) { s_abr[i] = 0; s_ag[i] = 0; s_ws[i] = 0.f; }
+        for (int i = tid; i < T * T; i += NT) { s_acc[i] = make_i2(0, 0); s_ws[i] = 0.f; }
         DS_SYNC();
 
         for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
@@ -870,9 +870,11 @@ struct MBFastBody {
                         DS_UNROLL
                         for (int b = 0; b < UB; b++) {
                             const int i = i0 + b * NT;
-                            const int ii = i < npx ? i : i0;
-                            const int yy = ii / PWS, xx = ii - yy * PWS;
-                            ok[b] = i < npx && xx < pw;
+                            ok[b] = false;
+                            ix[b] = iy[b] = 0; p00[b] = p01[b] = p10[b] = p11[b] = 0u;
+                            if (i >= npx) continue;   // warp-uniform except in one warp of the last iteration
+                            const int yy = i / PWS, xx = i - yy * PWS;
+                            ok[b] = xx < pw;
                             const L0Col c = s_col[xx < pw ? xx : 0];
                             const L0Row r = s_row[yy];
                             const float x = f_add(f_add(c.a0, r.b1), k2);
@@ -1105,30 +1107,41 @@ struct MBFastBody {
                     up_g[1][1] = ((4u * (Oc_g + Or_g) + 0x20u) >> 6) & 0x3FFu;
                     DS_UNROLL
                     for (int dy = 0; dy < 2; dy++) {
+                        // the two pixels of a quad row are adjacent in s_g0 / s_acc / s_ws: one wide access each
+                        const int gsi = (oy + dy - py0) * PWS + (ox - px0);       // even
+                        const int ti = (2 * qy + dy) * T + 2 * qx;                // even
+                        const uint2 g2 = *(const uint2*)(s_g0 + gsi);
+                        int4 av = *(const int4*)(s_acc + ti);
+                        float2 wv2 = *(const float2*)(s_ws + ti);
+                        const uint32_t g0v[2] = {g2.x, g2.y};
+                        int accbr[2] = {av.x, av.z}, accg[2] = {av.y, av.w};
+                        float wsv[2] = {wv2.x, wv2.y};
                         DS_UNROLL
                         for (int dx = 0; dx < 2; dx++) {
-                            const int gsi = (oy + dy - py0) * PWS + (ox + dx - px0);
-                            const uint32_t g0 = s_g0[gsi];
-                            const int ti = (2 * qy + dy) * T + 2 * qx + dx;
+                            const uint32_t g0 = g0v[dx];
                             const uint32_t gbr = byte_perm(g0, 0, 0x4240), gg = (g0 >> 8) & 255u;
                             if (uni255) {
                                 // lap_b + 65536 * lap_r == gbr - up_br as plain integers
-                                s_abr[ti] += (int)(gbr - up_br[dy][dx]);
-                                s_ag[ti] += (int)gg - (int)up_g[dy][dx];
-                                s_ws[ti] = f_add(s_ws[ti], 1.f);
+                                accbr[dx] += (int)(gbr - up_br[dy][dx]);
+                                accg[dx] += (int)gg - (int)up_g[dy][dx];
+                                wsv[dx] = f_add(wsv[dx], 1.f);
                             } else {
-                                const float wv = LEVEL0 ? f_mul((float)(g0 >> 24), 1.f / 255.f) : s_w[gsi];
+                                const float wv = LEVEL0 ? f_mul((float)(g0 >> 24), 1.f / 255.f) : s_w[gsi + dx];
                                 const int lb = (int)(gbr & 0xFFFFu) - (int)(up_br[dy][dx] & 0xFFFFu);
                                 const int lr = (int)(gbr >> 16) - (int)(up_br[dy][dx] >> 16);
                                 const int lg = (int)gg - (int)up_g[dy][dx];
                                 const int tb = (int)(short)f2i_rz(f_mul((float)lb, wv));
                                 const int tr = (int)(short)f2i_rz(f_mul((float)lr, wv));
                                 const int tg = (int)(short)f2i_rz(f_mul((float)lg, wv));
-                                s_abr[ti] += tb + tr * 65536;
-                                s_ag[ti] += tg;
-                                s_ws[ti] = f_add(s_ws[ti], wv);
+                                accbr[dx] += tb + tr * 65536;
+                                accg[dx] += tg;
+                                wsv[dx] = f_add(wsv[dx], wv);
                             }
                         }
+                        av.x = accbr[0]; av.y = accg[0]; av.z = accbr[1]; av.w = accg[1];
+                        *(int4*)(s_acc + ti) = av;
+                        wv2.x = wsv[0]; wv2.y = wsv[1];
+                        *(float2*)(s_ws + ti) = wv2;
                     }
                 }
             }
@@ -1140,16 +1153,20 @@ struct MBFastBody {
             const int yy = i / T, xx = i - yy * T;
             const int X = X0 + xx, Y = Y0 + yy;
             if (X >= p.dst_w || Y >= p.dst_h || Y < p.acc_y0 || Y >= p.acc_y1) continue;
-            const int abr = s_abr[i];
+            const int2 av = s_acc[i];
+            const int abr = av.x;
             const int sb = (int)(short)(abr & 0xFFFF);
             const int sr = (abr - sb) >> 16;
-            const int sg = s_ag[i];
+            const int sg = av.y;
             const float wsum = s_ws[i];
             const float den = f_add(wsum, 1e-5f);
             px16 o;
-            o.b = (short)f2i_rz(f_div((float)(short)sb, den));
-            o.g = (short)f2i_rz(f_div((float)(short)sg, den));
-            o.r = (short)f2i_rz(f_div((float)(short)sr, den));
+            // 0 / den == 0 exactly; skipping it keeps the IEEE division off its special-operand slow path
+            // (zero Laplacian sums are the common case in smooth regions)
+            const short nb = (short)sb, ng = (short)sg, nr = (short)sr;
+            o.b = nb ? (short)f2i_rz(f_div((float)nb, den)) : (short)0;
+            o.g = ng ? (short)f2i_rz(f_div((float)ng, den)) : (short)0;
+            o.r = nr ? (short)f2i_rz(f_div((float)nr, den)) : (short)0;
             o.a = (short)(wsum > 1e-5f ? 1 : 0);
             p.dst[(size_t)Y * p.dst_w + X] = o;
         }
