@@ -157,6 +157,7 @@ DS_D bool pd_h_is_simd(int j, int w, int dw) {
 DS_D bool pd_v_is_simd(int j, int dw) { return j < (dw & ~3); }
 
 constexpr int ds_al16(int v) { return (v + 15) & ~15; }  // every smem section starts 16-B aligned
+constexpr int ds_al128(int v) { return (v + 127) & ~127; }  // TMA destinations need 128 B
 
 // ---------------------------------------------------------------------------------------------
 // generic launch plumbing
@@ -166,7 +167,7 @@ constexpr int ds_al16(int v) { return (v + 15) & ~15; }  // every smem section s
 template <class Body, int NT> struct KernelOf;
 #define DS_DEFINE_KERNEL(kname, Body, NT, P, MINB)                                         \
     __global__ void __launch_bounds__(NT, MINB) kname(const P p) {                         \
-        extern __shared__ __align__(16) unsigned char ds_smem[];                           \
+        extern __shared__ __align__(128) unsigned char ds_smem[];                           \
         Body::template run<NT>(p, (int)blockIdx.x, (int)threadIdx.x, ds_smem);             \
     }                                                                                      \
     template <> struct KernelOf<Body, NT> { static constexpr void (*fn)(const P) = kname; };
@@ -463,6 +464,7 @@ struct MBParams {
     px16* dst; int dst_w, dst_h;  // normalised Laplacian level of the padded canvas
     int acc_y0, acc_y1;           // rows of this level whose dst the band's collapse reads (dst written only there)
     int own_y0, own_y1;           // even-aligned rows of this level the handle processes at all
+    const void* tmaps;            // CUtensorMap[frame][DS_MAXL][2] (G, W) for the TMA tile loads of levels >= 1, or NULL
 };
 
 template <int T, bool LEVEL0>
@@ -525,7 +527,7 @@ struct MBBody {
                     s.a = (unsigned char)(inside ? mask_value(F, c, u, v) : 0);
                     s_g8[i] = s;
                 } else {
-                    const size_t gi = (size_t)py * rw + px;
+                    const size_t gi = (size_t)py * F.gp[l] + px;
                     s_g8[i] = F.G[l][gi];
                     s_w[i] = F.W[l][gi];
                 }
@@ -559,7 +561,7 @@ struct MBBody {
                     if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1) {
                         px8 o8;
                         o8.b = (unsigned char)o.b; o8.g = (unsigned char)o.g; o8.r = (unsigned char)o.r; o8.a = 0;
-                        F.G[l + 1][(size_t)gy * n1x + gx] = o8;
+                        F.G[l + 1][(size_t)gy * F.gp[l + 1] + gx] = o8;
                     }
                 }
                 // ---- phase 2b: horizontal pass of the weight pyrDown, rows hr0..hr1, own columns
@@ -586,7 +588,7 @@ struct MBBody {
                     for (int k = 0; k < 5; k++) t[k] = s_h[(refl101(2 * jy + k - 2, rh) - hr0) * jw + jj];
                     const float v = pd_v_is_simd(j, n1x) ? pd_v_simd(t[0], t[1], t[2], t[3], t[4])
                                                          : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
-                    F.W[l + 1][(size_t)jy * n1x + j] = f_mul(v, 1.f / 256.f);
+                    F.W[l + 1][(size_t)jy * F.gp[l + 1] + j] = f_mul(v, 1.f / 256.f);
                 }
                 // ---- phase 3: Laplacian + weighted accumulate over the own pixels
                 const int ow = ox1 - ox0, oh = oy1 - oy0;
@@ -665,6 +667,37 @@ struct MBBody {
     }
 };
 
+#if DS_CUDA
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: box-shaped tile loads of the per-frame pyramid levels
+DS_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DS_D void mbar_init(void* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DS_D void mbar_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DS_D void tma_load_2d(void* dst, const void* tmap, int c0, int c1, void* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+DS_D void mbar_wait(void* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        uint32_t done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();   // a lost TMA transaction must fail loudly, never hang the device
+}
+DS_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// descriptors live in global memory (one per frame and level): acquire them for the tensormap proxy before use
+DS_D void fence_tensormap_acquire(const void* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // MULTIBAND feed, level 0, PLANE_F32 frames: the hot kernel. Same arithmetic and gather structure as
 // MBBody<64, true>, restructured for instruction count:
@@ -685,16 +718,20 @@ struct L0Row { float b1, b4, b7; int v; };
 
 template <int T_, bool LEVEL0>
 struct MBFastBody {
-    static constexpr int T = T_, PWS = T_ + 8, PHM = T_ + 7, GWS = T_ / 2 + 2, JW = T_ / 2, NQ = T_ * T_ / 4;
-    static constexpr int W0_BYTES = LEVEL0 ? 0 : ds_al16(PHM * PWS * 4);   // W_l of the needed region (levels >= 1)
-    static constexpr int G0_BYTES = ds_al16(PHM * PWS * 4);
-    static constexpr int G1_BYTES = ds_al16(GWS * GWS * 8);
+    // PWS: row pitch of the needed region in smem. Levels >= 1 load it with TMA, whose innermost start
+    // coordinate must be 16-byte aligned: the region starts at px0 rounded down to 4 px (up to 3 extra columns).
+    static constexpr int T = T_, PWS = LEVEL0 ? T_ + 8 : T_ + 12, PHM = T_ + 7, GWS = T_ / 2 + 2, JW = T_ / 2, NQ = T_ * T_ / 4;
+    static constexpr int W0_BYTES = LEVEL0 ? 0 : ds_al128(PHM * PWS * 4);   // W_l of the needed region (levels >= 1)
+    static constexpr int G0_BYTES = ds_al128(PHM * PWS * 4);
+    static constexpr int G1_BYTES = ds_al128(GWS * GWS * 8);
     static constexpr int BW = 88, BH = 82;                    // staged source footprint box (BGRX px)
     static constexpr bool kStage = false;                     // measured on B200: L1 already serves the taps (86 % hit); staging costs more than it saves
-    static constexpr int H_BYTES = kStage ? ds_al16(BW * BH * 4) : ds_al16(PHM * GWS * 8);  // [source box in phase 1;] pyrDown H pass / weight H pass
+    static constexpr int H_BYTES = kStage ? ds_al128(BW * BH * 4) : ds_al128(PHM * GWS * 8);  // [source box in phase 1;] pyrDown H pass / weight H pass
     static constexpr int ACC_BYTES = T * T * 4;
-    static constexpr int COL_BYTES = ds_al16(PWS * 16), ROW_BYTES = ds_al16(PHM * 16);
-    static int smem_bytes() { return G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES; }
+    static constexpr int COL_BYTES = ds_al128(PWS * 16), ROW_BYTES = ds_al128(PHM * 16);
+    static constexpr int MBAR_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
+    static constexpr uint32_t TMA_BYTES = (uint32_t)(PWS * PHM * 4);   // one box (G or W) of the needed region
+    static int smem_bytes() { return MBAR_OFF + 16; }
 
     struct U2 { uint32_t br, g; };
 
@@ -722,6 +759,12 @@ struct MBFastBody {
         const float c255 = f_mul(255.f, 1.f / 255.f);
 
         for (int i = tid; i < T * T; i += NT) { s_acc[i] = make_i2(0, 0); s_ws[i] = 0.f; }
+#if DS_CUDA
+        unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);
+        uint32_t tma_phase = 0;
+        const bool use_tma = !LEVEL0 && p.tmaps != nullptr;
+        if (use_tma && tid == 0) mbar_init(s_bar, 1);
+#endif
         DS_SYNC();
 
         for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
@@ -735,7 +778,7 @@ struct MBFastBody {
             const int jx0 = ox0 >> 1, jx1 = (ox1 + 1) >> 1, jy0 = oy0 >> 1, jy1 = (oy1 + 1) >> 1;
             const int gx0 = imax(jx0 - 1, 0), gx1 = imin(jx1, n1x - 1);
             const int gy0 = imax(jy0 - 1, 0), gy1 = imin(jy1, n1y - 1);
-            const int px0 = imax(2 * gx0 - 2, 0), px1 = imin(2 * gx1 + 2, rw - 1);
+            const int px0 = LEVEL0 ? imax(2 * gx0 - 2, 0) : (imax(2 * gx0 - 2, 0) & ~3), px1 = imin(2 * gx1 + 2, rw - 1);
             const int py0 = imax(2 * gy0 - 2, 0), py1 = imin(2 * gy1 + 2, rh - 1);
             const int pw = px1 - px0 + 1, ph = py1 - py0 + 1;
             const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
@@ -746,6 +789,7 @@ struct MBFastBody {
             const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
             uint32_t* const G1out = (uint32_t*)F.G[l + 1];
             float* const W1out = F.W[l + 1];
+            const int op1 = F.gp[l + 1];   // row pitch of the level-(l+1) arrays
 
             int m_and = 255, m_or = 0;   // level 0: AND / OR of the mask bytes; levels >= 1: 255 / 0 flags of (w == 1) / (w != 0)
             if constexpr (LEVEL0) {
@@ -976,17 +1020,44 @@ struct MBFastBody {
                 }
             }
             } else {
+#if DS_CUDA
+                if (use_tma) {
+                    // box-shaped footprint: one TMA tile load each for G_l and W_l of the needed region
+                    // (PWS x PHM elements from (px0, py0); rows beyond the level are zero-filled and never read)
+                    if (tid == 0) {
+                        const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fi] * DS_MAXL + l) * 2 * 128;
+                        fence_tensormap_acquire(tm);
+                        fence_tensormap_acquire(tm + 128);
+                        fence_proxy_async();   // earlier generic-proxy reads of s_g0 / s_w are done (barrier at loop end)
+                        mbar_expect_tx(s_bar, 2 * TMA_BYTES);
+                        tma_load_2d(s_g0, tm, px0, py0, s_bar);
+                        tma_load_2d(s_w, tm + 128, px0, py0, s_bar);
+                    }
+                    mbar_wait(s_bar, tma_phase);
+                    tma_phase ^= 1u;
+                    for (int i = tid; i < PWS * ph; i += NT) {
+                        const int yy = i / PWS, xx = i - yy * PWS;
+                        if (xx >= pw) continue;
+                        const float w = s_w[i];
+                        m_and &= (w == 1.f) ? 255 : 0;
+                        m_or |= (w != 0.f) ? 255 : 0;
+                    }
+                } else
+#endif
+                {
                 const uint32_t* const Gin = (const uint32_t*)F.G[l];
                 const float* const Win = F.W[l];
+                const int ip = F.gp[l];
                 for (int i = tid; i < PWS * ph; i += NT) {
                     const int yy = i / PWS, xx = i - yy * PWS;
                     if (xx >= pw) continue;
-                    const size_t gi = (size_t)(py0 + yy) * rw + (px0 + xx);
+                    const size_t gi = (size_t)(py0 + yy) * ip + (px0 + xx);
                     const float w = Win[gi];
                     s_g0[i] = Gin[gi];
                     s_w[i] = w;
                     m_and &= (w == 1.f) ? 255 : 0;
                     m_or |= (w != 0.f) ? 255 : 0;
+                }
                 }
             }
             const int all255 = (m_and == 255), all0 = (m_or == 0);
@@ -1033,7 +1104,7 @@ struct MBFastBody {
                 s_g1[gyy * GWS + gxx] = o;
                 const int gx = gx0 + gxx, gy = gy0 + gyy;
                 if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1)
-                    G1out[(size_t)gy * n1x + gx] = byte_perm(o.br, o.g, 0x5240);
+                    G1out[(size_t)gy * op1 + gx] = byte_perm(o.br, o.g, 0x5240);
             }
             DS_SYNC();
 
@@ -1042,7 +1113,7 @@ struct MBFastBody {
                 const float wv = uni255 ? 1.f : 0.f;
                 for (int i = tid; i < jh * JW; i += NT) {
                     const int jyy = i / JW, jj = i - jyy * JW;
-                    if (jj < jw) W1out[(size_t)(jy0 + jyy) * n1x + (jx0 + jj)] = wv;
+                    if (jj < jw) W1out[(size_t)(jy0 + jyy) * op1 + (jx0 + jj)] = wv;
                 }
             } else {
                 const int hr0 = imax(2 * jy0 - 2, 0), hr1 = imin(2 * jy1, rh - 1);
@@ -1068,7 +1139,7 @@ struct MBFastBody {
                     for (int q = 0; q < 5; q++) t[q] = s_hw[(refl101(2 * jy + q - 2, rh) - hr0) * JW + jj];
                     const float v = pd_v_is_simd(j, n1x) ? pd_v_simd(t[0], t[1], t[2], t[3], t[4])
                                                          : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
-                    W1out[(size_t)jy * n1x + j] = f_mul(v, 1.f / 256.f);
+                    W1out[(size_t)jy * op1 + j] = f_mul(v, 1.f / 256.f);
                 }
             }
 

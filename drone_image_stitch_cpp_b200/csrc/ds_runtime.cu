@@ -17,6 +17,9 @@
 
 #include "ds_geometry.h"
 #include "ds_kernels.h"
+#if DS_CUDA
+#include <cuda.h>   // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved at run time, no libcuda link)
+#endif
 
 #ifndef DS_VERSION_STRING
 #define DS_VERSION_STRING "0.1.0"
@@ -113,6 +116,38 @@ int launch(const P& p, long long blocks, stream_t, int smem_bytes) {
 }
 #endif
 
+#if DS_CUDA
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// 2-D tile map over a pitched 4-byte-element array: dims (w, h), row pitch in elements, box (bw, bh).
+bool encode_tile_map(CUtensorMap* m, bool is_float, void* base, int w, int h, int pitch_elems, int bw, int bh) {
+    EncodeTiledFn fn = tma_encoder();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
+
 template <class T>
 int dev_alloc_t(T** p, size_t count) { return dev_alloc((void**)p, count * sizeof(T)); }
 
@@ -158,6 +193,8 @@ struct ds_canvas {
     int out_hi = 0;
     std::vector<Frame> frames;
     FrameDev* d_frames = nullptr; size_t frames_cap = 0;
+    void* d_tmaps = nullptr; size_t tmaps_cap = 0;   // CUtensorMap[frame][DS_MAXL][2], levels 1..L-1
+    bool tmaps_ok = false;
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
     bool ln_fast_ok = false;   // fast kernel for levels 1..L-1 (<= 64 frames per tile at every level)
@@ -245,9 +282,10 @@ int fill_frame_dev(ds_canvas* c, Frame& f) {
         char* base = (char*)f.d_pyr;
         size_t off = 0;
         for (int l = 1; l <= c->L; l++) {
-            const size_t n = (size_t)(f.rw >> l) * (f.rh >> l);
-            d.G[l] = (px8*)(base + off); off += ((n * sizeof(px8) + 15) & ~(size_t)15);
-            d.W[l] = (float*)(base + off); off += ((n * sizeof(float) + 15) & ~(size_t)15);
+            d.gp[l] = ((f.rw >> l) + 3) & ~3;
+            const size_t n = (size_t)d.gp[l] * (f.rh >> l);
+            d.G[l] = (px8*)(base + off); off += ((n * sizeof(px8) + 127) & ~(size_t)127);
+            d.W[l] = (float*)(base + off); off += ((n * sizeof(float) + 127) & ~(size_t)127);
         }
     }
     d.mbits = f.d_mbits; d.mbits_pitch = (f.bw + 31) / 32;
@@ -259,9 +297,9 @@ int fill_frame_dev(ds_canvas* c, Frame& f) {
 size_t pyr_bytes(const ds_canvas* c, const Frame& f) {
     size_t off = 0;
     for (int l = 1; l <= c->L; l++) {
-        const size_t n = (size_t)(f.rw >> l) * (f.rh >> l);
-        off += ((n * sizeof(px8) + 15) & ~(size_t)15);
-        off += ((n * sizeof(float) + 15) & ~(size_t)15);
+        const size_t n = (size_t)(((f.rw >> l) + 3) & ~3) * (f.rh >> l);
+        off += ((n * sizeof(px8) + 127) & ~(size_t)127);
+        off += ((n * sizeof(float) + 127) & ~(size_t)127);
     }
     return off;
 }
@@ -358,6 +396,30 @@ int build_lists(ds_canvas* c) {
     if ((rc = grow(c, (void**)&c->d_frames, &c->frames_cap, std::max<size_t>(fd.size(), 1) * sizeof(FrameDev)))) return rc;
     if (!fd.empty() && (rc = h2d(c->d_frames, fd.data(), fd.size() * sizeof(FrameDev), c->stream))) return rc;
     if ((rc = stream_sync(c->stream))) return rc;
+    c->tmaps_ok = false;
+#if DS_CUDA
+    if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L >= 2 && !c->frames.empty()) {
+        // TMA descriptors for the box-shaped tile loads of the fast level-l kernel (MBFastBody<32,false>)
+        std::vector<CUtensorMap> tm(c->frames.size() * DS_MAXL * 2);
+        memset(tm.data(), 0, tm.size() * sizeof(CUtensorMap));
+        bool ok = true;
+        for (size_t i = 0; i < c->frames.size() && ok; i++) {
+            const Frame& f = c->frames[i];
+            if (!f.used) continue;
+            for (int l = 1; l < c->L && ok; l++) {
+                const int w = f.rw >> l, h = f.rh >> l;
+                ok = encode_tile_map(&tm[(i * DS_MAXL + l) * 2], false, f.dev.G[l], w, h, f.dev.gp[l], MBFastBody<32, false>::PWS, MBFastBody<32, false>::PHM) &&
+                     encode_tile_map(&tm[(i * DS_MAXL + l) * 2 + 1], true, f.dev.W[l], w, h, f.dev.gp[l], MBFastBody<32, false>::PWS, MBFastBody<32, false>::PHM);
+            }
+        }
+        if (ok) {
+            if ((rc = grow(c, &c->d_tmaps, &c->tmaps_cap, tm.size() * sizeof(CUtensorMap)))) return rc;
+            if ((rc = h2d(c->d_tmaps, tm.data(), tm.size() * sizeof(CUtensorMap), c->stream))) return rc;
+            if ((rc = stream_sync(c->stream))) return rc;
+            c->tmaps_ok = true;
+        }
+    }
+#endif
     c->dirty = false;
     return DS_OK;
 }
@@ -443,6 +505,7 @@ int run_composite(ds_canvas* c) {
             mp.dst = c->d_lvl[l]; mp.dst_w = c->lw[l]; mp.dst_h = c->lh[l];
             mp.acc_y0 = pl.acc.lo; mp.acc_y1 = pl.acc.hi;
             mp.own_y0 = pl.own.lo; mp.own_y1 = pl.own.hi;
+            mp.tmaps = c->tmaps_ok ? c->d_tmaps : nullptr;
             const double q = 1.0 / (double)(1ull << (2 * l));
             double ab;
             if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
@@ -716,7 +779,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
         dev_free(c->d_lvl_alloc[l]);
         dev_free(c->plan[l].d_off); dev_free(c->plan[l].d_fr); dev_free(c->plan[l].d_ids);
     }
-    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_frames); dev_free(c->d_stage);
+    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_frames); dev_free(c->d_stage); dev_free(c->d_tmaps);
 #if DS_CUDA
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -903,15 +966,15 @@ DS_API int ds_debug_get_frame_level(ds_canvas* c, int frame_idx, int level, int1
     if (dims_out) { dims_out[0] = f->rx >> level; dims_out[1] = f->ry >> level; dims_out[2] = lw; dims_out[3] = lh; }
     if (!g && !w) return DS_OK;
     if (!c->composited) return fail(DS_ERR_STATE, "frame pyramids exist only after ds_composite");
-    const size_t n = (size_t)lw * lh;
+    const size_t pitch = (size_t)f->dev.gp[level];
     if (g) {
-        std::vector<px8> tmp(n);
-        if ((rc = d2h(tmp.data(), f->dev.G[level], n * sizeof(px8), c->stream))) return rc;
+        std::vector<px8> tmp((size_t)lw * lh);
+        if ((rc = d2h_2d(tmp.data(), (size_t)lw * sizeof(px8), f->dev.G[level], pitch * sizeof(px8), (size_t)lw * sizeof(px8), (size_t)lh, c->stream))) return rc;
         if ((rc = stream_sync(c->stream))) return rc;
-        for (size_t i = 0; i < n; i++) { g[3 * i] = tmp[i].b; g[3 * i + 1] = tmp[i].g; g[3 * i + 2] = tmp[i].r; }
+        for (size_t i = 0; i < (size_t)lw * lh; i++) { g[3 * i] = tmp[i].b; g[3 * i + 1] = tmp[i].g; g[3 * i + 2] = tmp[i].r; }
     }
     if (w) {
-        if ((rc = d2h(w, f->dev.W[level], n * sizeof(float), c->stream))) return rc;
+        if ((rc = d2h_2d(w, (size_t)lw * sizeof(float), f->dev.W[level], pitch * sizeof(float), (size_t)lw * sizeof(float), (size_t)lh, c->stream))) return rc;
         if ((rc = stream_sync(c->stream))) return rc;
     }
     return DS_OK;

@@ -23,6 +23,7 @@ struct FrameDev {
     int rx, ry, rw, rh;  // MultiBandBlender::feed aligned ROI at level 0, relative to padded canvas origin
     px8* G[DS_MAXL];     // per-frame Gaussian levels 1..L over the feed ROI (values 0..255; index 0 unused)
     float* W[DS_MAXL];   // per-frame weight levels 1..L
+    int gp[DS_MAXL];     // row pitch (elements) of G[l] / W[l]: (rw >> l) rounded up to 4 (16-B rows, TMA-able)
     const uint32_t* mbits;  // FEATHER: warped-mask bit plane over the bbox (1 bit/px, tail bits set)
     int mbits_pitch;        // words per row
     const uint8_t* seam;    // optional seam mask over the bbox
