@@ -729,11 +729,22 @@ struct MBFastBody {
     static constexpr int H_BYTES = kStage ? ds_al128(BW * BH * 4) : ds_al128(PHM * GWS * 8);  // [source box in phase 1;] pyrDown H pass / weight H pass
     static constexpr int ACC_BYTES = T * T * 4;
     static constexpr int COL_BYTES = ds_al128(PWS * 16), ROW_BYTES = ds_al128(PHM * 16);
-    static constexpr int MBAR_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
+    static constexpr int MAXF = 64;                            // frames per tile the packed accumulators allow (host-checked)
+    static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
+    static constexpr int MBAR_OFF = GEO_OFF + MAXF * 96;
     static constexpr uint32_t TMA_BYTES = (uint32_t)(PWS * PHM * 4);   // one box (G or W) of the needed region
     static int smem_bytes() { return MBAR_OFF + 16; }
 
     struct U2 { uint32_t br, g; };
+    // tile x frame geometry, computed once per tile by as many threads as the tile has frames
+    struct alignas(16) TFGeo {
+        int skip, rx, ry, rw;
+        int rh, ax0, ax1, ay0;
+        int ay1, gx0, gx1, gy0;
+        int gy1, px0, py0, pw;
+        int ph, jx0, jx1, jy0;
+        int jy1, border, pad0, pad1;
+    };
 
     // 5-tap [1 4 6 4 1] on packed lanes
     DS_DM uint32_t tap5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a + e + 6u * c + 4u * (b + d); }
@@ -767,31 +778,53 @@ struct MBFastBody {
 #endif
         DS_SYNC();
 
-        for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
+        TFGeo* s_geo = (TFGeo*)(smem + GEO_OFF);
+        const int f_begin = p.tile_off[tile], f_end = p.tile_off[tile + 1];
+        for (int j = tid; j < f_end - f_begin && j < MAXF; j += NT) {
+            const FrameDev& F = p.frames[p.tile_frames[f_begin + j]];
+            TFGeo g;
+            g.rx = F.rx >> l; g.ry = F.ry >> l; g.rw = F.rw >> l; g.rh = F.rh >> l;
+            g.ax0 = imax(X0, g.rx); g.ax1 = imin(X0 + T, g.rx + g.rw);
+            g.ay0 = imax(imax(Y0, g.ry), p.own_y0); g.ay1 = imin(imin(Y0 + T, g.ry + g.rh), p.own_y1);
+            g.skip = (g.ax0 >= g.ax1 || g.ay0 >= g.ay1) ? 1 : 0;
+            const int ox0 = g.ax0 - g.rx, ox1 = g.ax1 - g.rx, oy0 = g.ay0 - g.ry, oy1 = g.ay1 - g.ry;
+            const int n1x = g.rw >> 1, n1y = g.rh >> 1;
+            g.jx0 = ox0 >> 1; g.jx1 = (ox1 + 1) >> 1; g.jy0 = oy0 >> 1; g.jy1 = (oy1 + 1) >> 1;
+            g.gx0 = imax(g.jx0 - 1, 0); g.gx1 = imin(g.jx1, n1x - 1);
+            g.gy0 = imax(g.jy0 - 1, 0); g.gy1 = imin(g.jy1, n1y - 1);
+            g.px0 = LEVEL0 ? imax(2 * g.gx0 - 2, 0) : (imax(2 * g.gx0 - 2, 0) & ~3);
+            const int px1 = imin(2 * g.gx1 + 2, g.rw - 1);
+            g.py0 = imax(2 * g.gy0 - 2, 0);
+            const int py1 = imin(2 * g.gy1 + 2, g.rh - 1);
+            g.pw = px1 - g.px0 + 1; g.ph = py1 - g.py0 + 1;
+            // no index reflection anywhere in this tile-frame?
+            g.border = !(2 * g.gx0 - 2 >= 0 && 2 * g.gx1 + 2 <= g.rw - 1 && 2 * g.gy0 - 2 >= 0 && 2 * g.gy1 + 2 <= g.rh - 1 &&
+                         g.jx0 >= 1 && g.jx1 <= n1x - 1 && g.jy0 >= 1 && g.jy1 <= n1y - 1) ? 1 : 0;
+            g.pad0 = g.pad1 = 0;
+            s_geo[j] = g;
+        }
+        DS_SYNC();
+
+        for (int fi = f_begin; fi < f_end; fi++) {
+            const TFGeo g = s_geo[fi - f_begin];
+            if (g.skip) continue;  // block-uniform
             const FrameDev& F = p.frames[p.tile_frames[fi]];
-            const int rx = F.rx >> l, ry = F.ry >> l, rw = F.rw >> l, rh = F.rh >> l;
-            const int ax0 = imax(X0, rx), ax1 = imin(X0 + T, rx + rw);
-            const int ay0 = imax(imax(Y0, ry), p.own_y0), ay1 = imin(imin(Y0 + T, ry + rh), p.own_y1);
-            if (ax0 >= ax1 || ay0 >= ay1) continue;  // block-uniform
-            const int ox0 = ax0 - rx, ox1 = ax1 - rx, oy0 = ay0 - ry, oy1 = ay1 - ry;
+            const int rx = g.rx, ry = g.ry, rw = g.rw, rh = g.rh;
+            const int ax0 = g.ax0, ax1 = g.ax1, ay0 = g.ay0, ay1 = g.ay1;
             const int n1x = rw >> 1, n1y = rh >> 1;
-            const int jx0 = ox0 >> 1, jx1 = (ox1 + 1) >> 1, jy0 = oy0 >> 1, jy1 = (oy1 + 1) >> 1;
-            const int gx0 = imax(jx0 - 1, 0), gx1 = imin(jx1, n1x - 1);
-            const int gy0 = imax(jy0 - 1, 0), gy1 = imin(jy1, n1y - 1);
-            const int px0 = LEVEL0 ? imax(2 * gx0 - 2, 0) : (imax(2 * gx0 - 2, 0) & ~3), px1 = imin(2 * gx1 + 2, rw - 1);
-            const int py0 = imax(2 * gy0 - 2, 0), py1 = imin(2 * gy1 + 2, rh - 1);
-            const int pw = px1 - px0 + 1, ph = py1 - py0 + 1;
+            const int jx0 = g.jx0, jx1 = g.jx1, jy0 = g.jy0, jy1 = g.jy1;
+            const int gx0 = g.gx0, gx1 = g.gx1, gy0 = g.gy0, gy1 = g.gy1;
+            const int px0 = g.px0, py0 = g.py0, pw = g.pw, ph = g.ph;
             const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
             const int jw = jx1 - jx0, jh = jy1 - jy0;
-            // no index reflection anywhere in this tile-frame?
-            const bool border = !(2 * gx0 - 2 >= 0 && 2 * gx1 + 2 <= rw - 1 && 2 * gy0 - 2 >= 0 && 2 * gy1 + 2 <= rh - 1 &&
-                                  jx0 >= 1 && jx1 <= n1x - 1 && jy0 >= 1 && jy1 <= n1y - 1);
+            const bool border = g.border != 0;
             const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
             uint32_t* const G1out = (uint32_t*)F.G[l + 1];
             float* const W1out = F.W[l + 1];
             const int op1 = F.gp[l + 1];   // row pitch of the level-(l+1) arrays
 
             int m_and = 255, m_or = 0;   // level 0: AND / OR of the mask bytes; levels >= 1: 255 / 0 flags of (w == 1) / (w != 0)
+            bool known_uniform = false;  // the mask is known to be 255 everywhere without a block-wide vote
             if constexpr (LEVEL0) {
             // ---- tables: reflected bbox index + per-column / per-row map terms
             for (int i = tid; i < pw + ph; i += NT) {
@@ -950,6 +983,7 @@ struct MBFastBody {
                         }
                     }
                     m_or = 255;   // m_and stays 255: the mask is uniform 255
+                    known_uniform = true;
                 } else
                 for (int i = tid; i < PWS * ph; i += NT) {
                     const int yy = i / PWS, xx = i - yy * PWS;
@@ -1061,8 +1095,14 @@ struct MBFastBody {
                 }
             }
             const int all255 = (m_and == 255), all0 = (m_or == 0);
-            const int uni255 = block_and(all255) && (!LEVEL0 || c255 == 1.f);   // every weight of the needed region is exactly 1
-            const int uni0 = block_and(all0);
+            int uni255, uni0;
+            if (known_uniform) {
+                DS_SYNC();
+                uni255 = (c255 == 1.f); uni0 = 0;
+            } else {
+                uni255 = block_and(all255) && (!LEVEL0 || c255 == 1.f);   // every weight of the needed region is exactly 1
+                uni0 = block_and(all0);
+            }
 
             // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op
             for (int i = tid; i < ph * GWS; i += NT) {
