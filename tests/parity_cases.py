@@ -230,8 +230,29 @@ def case_medium_mb3_interior(lib):
     return run_case(lib, plane_specs(synth.grid_survey(2, 2, 900, 700, overlap=0.6, seed=21, work_scale=0.45)), "multiband", 3, band_split=2)
 
 
+def case_many_frames_one_spot(lib):
+    # 70 frames over the same spot: more than the 64 frames per tile the packed-lane kernels accept, so the
+    # library must route every level through the generic kernels (int16 wrap-around semantics preserved)
+    rng = np.random.default_rng(70)
+    base = synth.orthophoto(160, 200, 70).numpy()
+    specs = []
+    for i in range(70):
+        th = rng.uniform(-0.05, 0.05)
+        R = np.array([[np.cos(th), -np.sin(th), rng.uniform(-6, 6)], [np.sin(th), np.cos(th), rng.uniform(-6, 6)], [0, 0, 1]], np.float32)
+        img = np.ascontiguousarray(base[rng.integers(0, 20):, rng.integers(0, 20):][:120, :150])
+        specs.append(dict(kind="plane", img=img, K=np.eye(3, dtype=np.float32), R=R, scale=1.0))
+    return run_case(lib, specs, "multiband", 2, check_taps=False)
+
+
+def case_serpentine_strip_scaled(lib):
+    # BASELINE config 3 layout at 1/6 linear scale: 3 flight lines x 12 frames, 70 % forward / 32 % side overlap
+    sv = synth.grid_survey(12, 3, 912, 608, overlap=0.7, side_overlap=0.32, seed=303)
+    return run_case(lib, plane_specs(sv), "multiband", 5, check_taps=False, band_split=4)
+
+
 CASES = {
     "medium_mb3_interior": case_medium_mb3_interior,
+    "many_frames_one_spot": case_many_frames_one_spot,
     "small_feather": case_small_feather,
     "small_mb5": case_small_mb5,
     "small_mb3_bgra": case_small_mb3_bgra,

@@ -12,6 +12,13 @@ def test_gpu_case(cuda_lib, name):
     CASES[name](cuda_lib)
 
 
+def test_cfg3_layout_scaled(cuda_lib):
+    """BASELINE config 3 layout (3 serpentine lines, 70 % forward / 32 % side overlap) at 1/6 scale, 36 frames,
+    against the oracle, plus the 4-band decomposition."""
+    from parity_cases import case_serpentine_strip_scaled
+    case_serpentine_strip_scaled(cuda_lib)
+
+
 def test_cfg1_full_size_feather(cuda_lib):
     """BASELINE config 1: 2 x 4000x3000, feather. Oracle finishes in seconds at full size."""
     from drone_image_stitch_cpp_b200 import synth
