@@ -36,7 +36,10 @@ class ds_transform(C.Structure):
 
 
 class ds_frame_opts(C.Structure):
-    _fields_ = [("seam_mask", C.c_void_p), ("seam_mask_stride", C.c_size_t), ("channel_gain", C.POINTER(C.c_float))]
+    _fields_ = [("seam_mask", C.c_void_p), ("seam_mask_stride", C.c_size_t), ("channel_gain", C.POINTER(C.c_float)),
+                ("seam_lowres", C.c_void_p), ("seam_lowres_w", C.c_int32), ("seam_lowres_h", C.c_int32),
+                ("seam_lowres_stride", C.c_size_t),
+                ("compensator_gain", C.POINTER(C.c_double)), ("gain_map", C.c_void_p), ("gain_map_stride", C.c_size_t)]
 
 
 class ds_canvas_desc(C.Structure):

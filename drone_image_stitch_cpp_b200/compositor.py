@@ -108,12 +108,27 @@ class Canvas:
         arr = (C.c_int32 * 4)(*[int(v) for v in frame_roi])
         return bool(self.lib.dll.ds_frame_touches_band(C.byref(self.desc), arr))
 
-    def upload(self, idx, img, xf, seam_mask=None, channel_gain=None):
+    def upload(self, idx, img, xf, seam_mask=None, channel_gain=None, seam_lowres=None, compensator_gain=None, gain_map=None):
         """img: HxWx3 uint8 (numpy; any row stride) or a (ptr, w, h, stride) tuple."""
         opts = None
         keep = []
-        if seam_mask is not None or channel_gain is not None:
+        if any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map)):
             opts = L.ds_frame_opts()
+            if compensator_gain is not None:
+                cg = (C.c_double * 3)(*[float(v) for v in compensator_gain])
+                keep.append(cg)
+                opts.compensator_gain = C.cast(cg, C.POINTER(C.c_double))
+            if gain_map is not None:
+                gm = np.ascontiguousarray(gain_map, np.float32)
+                keep.append(gm)
+                opts.gain_map = gm.ctypes.data
+                opts.gain_map_stride = gm.strides[0]
+            if seam_lowres is not None:
+                sl = np.ascontiguousarray(seam_lowres, np.uint8)
+                keep.append(sl)
+                opts.seam_lowres = sl.ctypes.data
+                opts.seam_lowres_w, opts.seam_lowres_h = sl.shape[1], sl.shape[0]
+                opts.seam_lowres_stride = sl.strides[0]
             if seam_mask is not None:
                 sm = np.ascontiguousarray(seam_mask, np.uint8)
                 keep.append(sm)

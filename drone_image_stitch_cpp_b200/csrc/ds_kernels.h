@@ -88,8 +88,23 @@ DS_D uint32_t src_tap(const FrameDev& F, int x, int y) {
     return ld_ro(F.src + (size_t)y * F.src_pitch + x);
 }
 
-// A4: cv::remap INTER_LINEAR 8UC3 on the fixed-point coordinate, then the optional channel gain.
-DS_D px8 sample_bilinear(const FrameDev& F, const Coord& c) {
+// Radiometric gains applied to a warped pixel, in the reference's order: per-strip channel gain (float32),
+// exposure-compensator scalar gains (float64), block gain map (float32 per pixel at bbox position ur, vr).
+DS_D void apply_gains(const FrameDev& F, int& b, int& g, int& r, int ur, int vr) {
+    if (F.has_gain) {
+        b = sat8i(f2i_rn(f_mul((float)b, F.gain[0]))); g = sat8i(f2i_rn(f_mul((float)g, F.gain[1]))); r = sat8i(f2i_rn(f_mul((float)r, F.gain[2])));
+    }
+    if (F.has_cgain) {
+        b = sat8i(d2i_rn(d_mul((double)b, F.cgain[0]))); g = sat8i(d2i_rn(d_mul((double)g, F.cgain[1]))); r = sat8i(d2i_rn(d_mul((double)r, F.cgain[2])));
+    }
+    if (F.gainmap) {
+        const float gm = ld_ro(F.gainmap + (size_t)vr * F.gainmap_pitch + ur);
+        b = sat8i(f2i_rn(f_mul((float)b, gm))); g = sat8i(f2i_rn(f_mul((float)g, gm))); r = sat8i(f2i_rn(f_mul((float)r, gm)));
+    }
+}
+
+// A4: cv::remap INTER_LINEAR 8UC3 on the fixed-point coordinate of bbox pixel (ur, vr), then the gains.
+DS_D px8 sample_bilinear(const FrameDev& F, const Coord& c, int ur, int vr) {
     uint32_t p00, p01, p10, p11;
     if ((unsigned)c.sx < (unsigned)(F.src_w - 1) && (unsigned)c.sy < (unsigned)(F.src_h - 1)) {
         const uint32_t* r0 = F.src + (size_t)c.sy * F.src_pitch + c.sx;
@@ -119,9 +134,7 @@ DS_D px8 sample_bilinear(const FrameDev& F, const Coord& c) {
         const int hv = (a * wx0 + b * wx1) * wy0 + (d * wx0 + e * wx1) * wy1;
         out[ch] = (hv + 512) >> 10;
     }
-    if (F.has_gain) {
-        for (int ch = 0; ch < 3; ch++) out[ch] = sat8i(f2i_rn(f_mul((float)out[ch], F.gain[ch])));
-    }
+    if (F.any_gain) apply_gains(F, out[0], out[1], out[2], ur, vr);
     px8 r;
     r.b = (unsigned char)out[0]; r.g = (unsigned char)out[1]; r.r = (unsigned char)out[2]; r.a = 0;
     return r;
@@ -199,6 +212,45 @@ struct ExpandBody {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Seam-mask upsizing of composePanorama (A13): dilate 3x3 of the low-res seam mask, then
+// resize(INTER_LINEAR_EXACT) to the warped bbox. The 8.8 fixed-point coefficients are tabulated on the
+// host in double (as OpenCV does, softdouble); the kernel does the dilation on the fly.
+
+struct SeamUpParams {
+    const uint8_t* src; int sw, sh, sstride;   // low-res mask (device copy)
+    const int* ix; const int* cx;              // per output column: left sample, c1 (0..256)
+    const int* iy; const int* cy;              // per output row
+    uint8_t* dst; int dw, dh;                  // full-res seam mask (bbox size)
+};
+struct SeamUpBody {
+    static constexpr int PER_BLOCK = 1024;
+    static int smem_bytes() { return 0; }
+    DS_DM int dil(const SeamUpParams& p, int x, int y) {
+        int m = 0;
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const int yy = y + dy, xx = x + dx;
+                if ((unsigned)yy < (unsigned)p.sh && (unsigned)xx < (unsigned)p.sw) m = imax(m, (int)ld_ro(p.src + (size_t)yy * p.sstride + xx));
+            }
+        return m;
+    }
+    template <int NT>
+    DS_DM void run(const SeamUpParams& p, int block, int tid, unsigned char*) {
+        const long long n = (long long)p.dw * p.dh;
+        for (int it = tid; it < PER_BLOCK; it += NT) {
+            const long long idx = (long long)block * PER_BLOCK + it;
+            if (idx >= n) break;
+            const int y = (int)(idx / p.dw), x = (int)(idx - (long long)y * p.dw);
+            const int x0 = p.ix[x], x1 = imin(x0 + 1, p.sw - 1), c1 = p.cx[x];
+            const int y0 = p.iy[y], y1 = imin(y0 + 1, p.sh - 1), d1 = p.cy[y];
+            const int h0 = (256 - c1) * dil(p, x0, y0) + c1 * dil(p, x1, y0);
+            const int h1 = (256 - c1) * dil(p, x0, y1) + c1 * dil(p, x1, y1);
+            p.dst[idx] = (uint8_t)(((256 - d1) * h0 + d1 * h1 + 32768) >> 16);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Debug taps: fixed-point tables and the warped bbox of one frame.
 
 struct TapParams {
@@ -223,7 +275,7 @@ struct TapBody {
                 p.a[idx] = (uint16_t)(c.ay * 32 + c.ax);
             }
             if (p.bgr) {
-                const px8 s = sample_bilinear(F, c);
+                const px8 s = sample_bilinear(F, c, u, v);
                 p.bgr[3 * idx] = s.b; p.bgr[3 * idx + 1] = s.g; p.bgr[3 * idx + 2] = s.r;
                 p.mask[idx] = (uint8_t)mask_value(F, c, u, v);
             }
@@ -410,7 +462,7 @@ struct FeatherBody {
                     if (d < R) { wgt = f_mul((float)d, p.sharpness); if (wgt > 1.f) wgt = 1.f; }
                 }
                 const Coord c = eval_coord(F, u, v);
-                const px8 s = sample_bilinear(F, c);
+                const px8 s = sample_bilinear(F, c, u, v);
                 acc[k][0] += (int)(short)f2i_rz(f_mul((float)s.b, wgt));
                 acc[k][1] += (int)(short)f2i_rz(f_mul((float)s.g, wgt));
                 acc[k][2] += (int)(short)f2i_rz(f_mul((float)s.r, wgt));
@@ -523,7 +575,7 @@ struct MBBody {
                     const bool inside = (unsigned)u < (unsigned)F.w && (unsigned)v < (unsigned)F.h;
                     const int ur = refl(u, F.w, BORDER_REFL), vr = refl(v, F.h, BORDER_REFL);
                     const Coord c = eval_coord(F, ur, vr);
-                    px8 s = sample_bilinear(F, c);
+                    px8 s = sample_bilinear(F, c, ur, vr);
                     s.a = (unsigned char)(inside ? mask_value(F, c, u, v) : 0);
                     s_g8[i] = s;
                 } else {
@@ -713,7 +765,7 @@ DS_D void fence_tensormap_acquire(const void* tmap) {
 // acc lanes: B + 65536 * R in one int (exact while |sum| < 2^15, guaranteed by the host for tiles with
 // <= 64 frames; longer lists go to the generic kernel).
 
-struct L0Col { float a0, a3, a6; int u; };  // u = raw bbox column if inside else -1
+struct L0Col { float a0, a3, a6; int u; };  // u = bbox column if inside the bbox, else ~(reflected column)
 struct L0Row { float b1, b4, b7; int v; };
 
 template <int T_, bool LEVEL0>
@@ -836,7 +888,7 @@ struct MBFastBody {
                     const float up = f_sub(U, F.t0);
                     L0Col c;
                     c.a0 = f_mul(F.k[0], up); c.a3 = f_mul(F.k[3], up); c.a6 = f_mul(F.k[6], up);
-                    c.u = (unsigned)u < (unsigned)F.w ? u : -1;
+                    c.u = (unsigned)u < (unsigned)F.w ? u : ~ur;   // >= 0: inside (u == ur); < 0: ~(reflected index)
                     s_col[i] = c;
                 } else {
                     const int yy = i - pw;
@@ -847,7 +899,7 @@ struct MBFastBody {
                     const float vp = f_sub(V, F.t1);
                     L0Row r;
                     r.b1 = f_mul(F.k[1], vp); r.b4 = f_mul(F.k[4], vp); r.b7 = f_mul(F.k[7], vp);
-                    r.v = (unsigned)v < (unsigned)F.h ? v : -1;
+                    r.v = (unsigned)v < (unsigned)F.h ? v : ~vr;
                     s_row[yy] = r;
                 }
             }
@@ -913,15 +965,14 @@ struct MBFastBody {
                 const float k2 = F.k2one, k5 = F.k5one, k8 = F.k8one;
                 const uint8_t* const seam = F.seam;
                 const int seam_pitch = F.seam_pitch;
-                const bool has_gain = F.has_gain != 0;
+                const bool has_gain = F.any_gain != 0;
                 const bool bconst = F.border == BORDER_CONST;
-                const float g0 = F.gain[0], g1 = F.gain[1], g2 = F.gain[2];
                 // Interior tile-frames: the needed region lies inside the bbox and its four corners map at
                 // least a pixel inside the source. x(u, v) is monotone in u and in v even in float arithmetic
                 // (a chain of monotone roundings), so the corner values bound every pixel: all taps are
                 // in-bounds inliers, the nearest mask is 255 everywhere and no cvRound patch can trigger.
                 bool interior = false;
-                if (!proj && !seam) {
+                if (!proj && !seam && !F.gainmap) {
                     const int u_lo = rx + px0 - F.cx, v_lo = ry + py0 - F.cy;
                     if (u_lo >= 0 && u_lo + pw <= F.w && v_lo >= 0 && v_lo + ph <= F.h) {
                         const L0Col c0 = s_col[0], c1 = s_col[pw - 1];
@@ -974,11 +1025,7 @@ struct MBFastBody {
                             int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
                             int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
                             int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
-                            if (has_gain) {
-                                ob = sat8i(f2i_rn(f_mul((float)ob, g0)));
-                                og = sat8i(f2i_rn(f_mul((float)og, g1)));
-                                orr = sat8i(f2i_rn(f_mul((float)orr, g2)));
-                            }
+                            if (has_gain) apply_gains(F, ob, og, orr, 0, 0);   // no gain map on this path
                             if (ok[b]) s_g0[i0 + b * NT] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | 0xff000000u;
                         }
                     }
@@ -1043,11 +1090,7 @@ struct MBFastBody {
                     int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
                     int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
                     int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
-                    if (has_gain) {
-                        ob = sat8i(f2i_rn(f_mul((float)ob, g0)));
-                        og = sat8i(f2i_rn(f_mul((float)og, g1)));
-                        orr = sat8i(f2i_rn(f_mul((float)orr, g2)));
-                    }
+                    if (has_gain) apply_gains(F, ob, og, orr, c.u >= 0 ? c.u : ~c.u, r.v >= 0 ? r.v : ~r.v);
                     s_g0[i] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | ((uint32_t)m << 24);
                     m_and &= m;
                     m_or |= m;
@@ -1432,6 +1475,7 @@ typedef MBBody<64, true> MBBodyL0;
 typedef MBBody<32, false> MBBodyLN;
 DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
 DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
+DS_DEFINE_KERNEL(ds_seam_upsize, SeamUpBody, 256, SeamUpParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
 DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 1)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)

@@ -163,6 +163,7 @@ struct Frame {
     void* d_pyr = nullptr; size_t pyr_cap = 0;       // G/W levels 1..L
     uint32_t* d_mbits = nullptr; size_t mbits_cap = 0;
     uint8_t* d_seam = nullptr; size_t seam_cap = 0;
+    float* d_gainmap = nullptr; size_t gainmap_cap = 0;
     FrameDev dev;
 };
 
@@ -612,7 +613,41 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     } else {
         if ((rc = grow(c, (void**)&f.d_mbits, &f.mbits_cap, (size_t)((f.bw + 31) / 32) * f.bh * sizeof(uint32_t)))) return rc;
     }
-    if (opts && opts->seam_mask) {
+    if (opts && opts->seam_lowres) {
+        // composePanorama: dilate(masks_warped[i]) -> resize(mask_warped.size(), INTER_LINEAR_EXACT) -> AND
+        const int sw = opts->seam_lowres_w, sh = opts->seam_lowres_h;
+        if (sw <= 0 || sh <= 0) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", sw, sh);
+        const size_t sst = opts->seam_lowres_stride ? opts->seam_lowres_stride : (size_t)sw;
+        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, (size_t)f.bw * f.bh))) return rc;
+        // coefficient tables in double on the host (OpenCV computes them in softdouble)
+        std::vector<int> tab(2 * ((size_t)f.bw + f.bh));
+        auto coefs = [](int s_, int d_, int* idx, int* c1) {
+            const double scale = (double)s_ / (double)d_;
+            for (int v = 0; v < d_; v++) {
+                const double fv = scale * ((double)v + 0.5) - 0.5;
+                int i = (int)floor(fv);
+                int k1 = (int)lrint((fv - (double)i) * 256.0);
+                if (i < 0 || s_ <= 1) { i = 0; k1 = 0; }
+                if (i >= s_ - 1) { i = s_ - 1; k1 = 0; }
+                idx[v] = i; c1[v] = k1;
+            }
+        };
+        coefs(sw, f.bw, tab.data(), tab.data() + f.bw);
+        coefs(sh, f.bh, tab.data() + 2 * f.bw, tab.data() + 2 * f.bw + f.bh);
+        uint8_t* d_low = nullptr; int* d_tab = nullptr;
+        if ((rc = dev_alloc_t(&d_low, (size_t)sw * sh))) return rc;
+        if ((rc = dev_alloc_t(&d_tab, tab.size()))) { dev_free(d_low); return rc; }
+        rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->stream);
+        if (!rc) rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->stream);
+        if (!rc) {
+            SeamUpParams sp{d_low, sw, sh, sw, d_tab, d_tab + f.bw, d_tab + 2 * f.bw, d_tab + 2 * f.bw + f.bh, f.d_seam, f.bw, f.bh};
+            const long long n = (long long)f.bw * f.bh;
+            rc = launch<SeamUpBody, 256>(sp, (n + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->stream, 0);
+        }
+        if (!rc) rc = stream_sync(c->stream);
+        dev_free(d_low); dev_free(d_tab);
+        if (rc) return rc;
+    } else if (opts && opts->seam_mask) {
         if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, (size_t)f.bw * f.bh))) return rc;
         if ((rc = h2d_2d(f.d_seam, (size_t)f.bw, opts->seam_mask, opts->seam_mask_stride ? opts->seam_mask_stride : (size_t)f.bw,
                          (size_t)f.bw, (size_t)f.bh, c->stream))) return rc;
@@ -621,10 +656,24 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
         dev_free(f.d_seam); c->device_bytes -= (int64_t)f.seam_cap; f.d_seam = nullptr; f.seam_cap = 0;
     }
     if ((rc = fill_frame_dev(c, f))) return rc;
+    if (opts && opts->gain_map) {
+        const size_t gst = opts->gain_map_stride ? opts->gain_map_stride : (size_t)f.bw * sizeof(float);
+        if ((rc = grow(c, (void**)&f.d_gainmap, &f.gainmap_cap, (size_t)f.bw * f.bh * sizeof(float)))) return rc;
+        if ((rc = h2d_2d(f.d_gainmap, (size_t)f.bw * sizeof(float), opts->gain_map, gst, (size_t)f.bw * sizeof(float), (size_t)f.bh, c->stream))) return rc;
+        if ((rc = stream_sync(c->stream))) return rc;
+        f.dev.gainmap = f.d_gainmap; f.dev.gainmap_pitch = f.bw;
+    } else if (f.d_gainmap) {
+        dev_free(f.d_gainmap); c->device_bytes -= (int64_t)f.gainmap_cap; f.d_gainmap = nullptr; f.gainmap_cap = 0;
+    }
     if (opts && opts->channel_gain) {
         f.dev.has_gain = 1;
         for (int k = 0; k < 3; k++) f.dev.gain[k] = opts->channel_gain[k];
     }
+    if (opts && opts->compensator_gain) {
+        f.dev.has_cgain = 1;
+        for (int k = 0; k < 3; k++) f.dev.cgain[k] = opts->compensator_gain[k];
+    }
+    f.dev.any_gain = (f.dev.has_gain || f.dev.has_cgain || f.dev.gainmap) ? 1 : 0;
     c->dirty = true;
     c->composited = false;
     return DS_OK;
@@ -774,7 +823,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
 #if DS_CUDA
     cudaStreamSynchronize(c->stream);
 #endif
-    for (Frame& f : c->frames) { dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); }
+    for (Frame& f : c->frames) { dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_gainmap); }
     for (int l = 0; l < DS_MAXL; l++) {
         dev_free(c->d_lvl_alloc[l]);
         dev_free(c->plan[l].d_off); dev_free(c->plan[l].d_fr); dev_free(c->plan[l].d_ids);

@@ -28,8 +28,13 @@ struct FrameDev {
     int mbits_pitch;        // words per row
     const uint8_t* seam;    // optional seam mask over the bbox
     int seam_pitch;
-    float gain[3];
+    float gain[3];          // applyChannelGainInPlace: float32 multiply (stitch_global.cpp:291-305)
     int has_gain;
+    double cgain[3];        // ExposureCompensator::apply with scalar gains: float64 multiply (stitch_global.cpp:644)
+    int has_cgain;
+    const float* gainmap;   // BlocksGainCompensator::apply: per-pixel float32 gain over the bbox (stitch_robust.cpp:209-211)
+    int gainmap_pitch;
+    int any_gain;           // has_gain | has_cgain | (gainmap != 0)
 };
 
 struct Coord {

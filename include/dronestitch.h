@@ -93,6 +93,19 @@ typedef struct ds_frame_opts {
     const uint8_t* seam_mask; /* 8UC1, size of the frame's warped bbox, ANDed into the warped mask */
     size_t seam_mask_stride;
     const float* channel_gain; /* 3 floats (B, G, R) applied as sat_u8(float(p) * g), stitch_global.cpp:291-305 */
+    /* Low-resolution seam mask as cv::Stitcher holds it after seam finding (masks_warped[i], 8UC1).
+     * The library does what composePanorama does with it per frame: dilate 3x3, resize to the warped bbox
+     * with INTER_LINEAR_EXACT, AND into the warped mask. Overrides seam_mask when non-NULL. */
+    const uint8_t* seam_lowres;
+    int32_t seam_lowres_w, seam_lowres_h;
+    size_t seam_lowres_stride;
+    /* ExposureCompensator::apply with scalar gains (GainCompensator / ChannelsCompensator,
+     * stitch_global.cpp:644): 3 doubles (B, G, R), sat_u8(rint(double(p) * g)); applied after channel_gain. */
+    const double* compensator_gain;
+    /* BlocksGainCompensator::apply (stitch_robust.cpp:209-211): float32 gain per pixel of the warped bbox
+     * (the caller's resize of its block gain map), sat_u8(rint(float(p) * g)); applied last. */
+    const float* gain_map;
+    size_t gain_map_stride; /* bytes */
 } ds_frame_opts;
 
 typedef struct ds_canvas_desc {

@@ -172,6 +172,15 @@ def feather_weight_map(mask, sharpness=0.02):
     return out
 
 
+def seam_mask_upsize(mask, dw, dh):
+    """dilate(3x3) + resize(INTER_LINEAR_EXACT) of a low-res seam mask to (dw, dh)."""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    sh, sw = mask.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_seam_mask_upsize(_p(mask), C.c_int(sw), C.c_int(sh), C.c_size_t(mask.strides[0]), C.c_int(dw), C.c_int(dh), _p(out))
+    return out
+
+
 def mbb_feed_geometry(roi, bands, tl, size):
     out = np.empty(8, np.int32)
     lib().orc_mbb_feed_geometry(C.c_int(roi[0]), C.c_int(roi[1]), C.c_int(roi[2]), C.c_int(roi[3]), C.c_int(bands),

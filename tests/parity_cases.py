@@ -31,10 +31,17 @@ def oracle_warp(spec):
         warped = O.remap_bilinear(img, xy, a, "constant")
         mask = O.persp_nearest_mask(spec["M"], dw, dh, w, h)
         corner = spec["corner"]
-    if spec.get("gain") is not None:
+    if spec.get("gain") is not None:          # applyChannelGainInPlace: float32
         g = np.asarray(spec["gain"], np.float32)
         warped = np.clip(np.rint(warped.astype(np.float32) * g[None, None, :]), 0, 255).astype(np.uint8)
-    if spec.get("seam") is not None:
+    if spec.get("cgain") is not None:         # ExposureCompensator::apply, scalar gains: float64 (pinned vs cv2.multiply)
+        g = np.asarray(spec["cgain"], np.float64)
+        warped = np.clip(np.rint(warped.astype(np.float64) * g[None, None, :]), 0, 255).astype(np.uint8)
+    if spec.get("gain_map") is not None:      # BlocksGainCompensator::apply: float32 per pixel
+        warped = np.clip(np.rint(warped.astype(np.float32) * spec["gain_map"][:, :, None]), 0, 255).astype(np.uint8)
+    if spec.get("seam_lowres") is not None:
+        mask = mask & O.seam_mask_upsize(spec["seam_lowres"], mask.shape[1], mask.shape[0])
+    elif spec.get("seam") is not None:
         mask = mask & spec["seam"]
     return corner, warped, mask, xy, a
 
@@ -73,7 +80,8 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
         for i, (s, xf) in enumerate(zip(specs, xfs)):
             if band is not None and not cv.touches(rois[i]):
                 continue
-            cv.upload(i, s["img"], xf, seam_mask=s.get("seam"), channel_gain=s.get("gain"))
+            cv.upload(i, s["img"], xf, seam_mask=s.get("seam"), channel_gain=s.get("gain"), seam_lowres=s.get("seam_lowres"),
+                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"))
         cv.composite()
         return cv
 
@@ -250,7 +258,44 @@ def case_serpentine_strip_scaled(lib):
     return run_case(lib, plane_specs(sv), "multiband", 5, check_taps=False, band_split=4)
 
 
+def case_seam_lowres_upsizing(lib):
+    # the per-frame seam-mask hand-off of composePanorama: low-res seam mask (seam_estimation_resol) ->
+    # dilate -> LINEAR_EXACT resize -> AND with the warped mask
+    sv = synth.grid_survey(2, 2, 300, 220, overlap=0.6, seed=88)
+    specs = plane_specs(sv)
+    rng = np.random.default_rng(88)
+    for i, s in enumerate(specs):
+        lw, lh = 37 + 3 * i, 29 + 2 * i
+        m = np.zeros((lh, lw), np.uint8)
+        m[rng.integers(0, 5):lh - rng.integers(0, 5), rng.integers(0, 6):lw - rng.integers(0, 6)] = 255
+        m[lh // 2:lh // 2 + 3, : lw // 3] = 0
+        s["seam_lowres"] = m
+    run_case(lib, specs, "multiband", 4)
+    return run_case(lib, specs, "feather", 0)
+
+
+def case_exposure_gains(lib):
+    # the three gain applications of the reference between warp and blend: per-strip channel gain (float32),
+    # compensator scalar gains (float64) and the BlocksGain per-pixel map (float32)
+    sv = synth.grid_survey(2, 2, 280, 210, overlap=0.6, seed=91, work_scale=0.5)
+    specs = plane_specs(sv)
+    rng = np.random.default_rng(91)
+    for i, s in enumerate(specs):
+        o = O.warp_frame(s["img"], s["K"], s["R"], s["scale"])
+        bw, bh = o["size"]
+        if i != 1:
+            s["gain_map"] = (rng.random((bh, bw)) * 0.5 + 0.75).astype(np.float32)
+        if i != 2:
+            s["cgain"] = (1.003 + 0.01 * i, 0.997, 1.1)
+        if i == 0:
+            s["gain"] = (1.07, 0.93, 1.21)
+    run_case(lib, specs, "multiband", 3)
+    return run_case(lib, specs, "feather", 0)
+
+
 CASES = {
+    "exposure_gains": case_exposure_gains,
+    "seam_lowres_upsizing": case_seam_lowres_upsizing,
     "medium_mb3_interior": case_medium_mb3_interior,
     "many_frames_one_spot": case_many_frames_one_spot,
     "small_feather": case_small_feather,

@@ -117,3 +117,33 @@ def test_degenerate_perspective_maps():
     assert np.array_equal(xy, w["xy"]) and np.array_equal(a, w["a"])
     c, wi, mk = CR.warp_frame_cv2(img, K, R, 1.0, affine=False)
     assert np.array_equal(wi, w["warped"]) and np.array_equal(mk, w["mask"])
+
+
+@pytest.mark.parametrize("shape", [(30, 40, 300, 410), (17, 23, 200, 333), (50, 60, 211, 257), (8, 9, 100, 90), (40, 30, 41, 31),
+                                   (25, 31, 512, 640), (1, 7, 20, 70), (12, 12, 12, 12)])
+def test_seam_mask_upsize(shape):
+    # composePanorama: dilate(masks_warped[i]) -> resize(INTER_LINEAR_EXACT) -> AND   
+    sh, sw, dh, dw = shape
+    rng = np.random.default_rng(sh * 7 + sw)
+    for src in ((rng.random((sh, sw)) > 0.5).astype(np.uint8) * 255, rng.integers(0, 256, (sh, sw)).astype(np.uint8)):
+        ref = cv2.resize(cv2.dilate(src, None), (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)
+        assert np.array_equal(O.seam_mask_upsize(src, dw, dh), ref)
+
+
+def test_gain_apply_semantics():
+    """The three gain multiplies between warp and blend: float32 channel gain (stitch_global.cpp:291-305),
+    float64 scalar gains of ExposureCompensator::apply (cv::multiply by a Scalar), float32 per-pixel map of
+    BlocksGainCompensator::apply (cv::multiply 8UC3 x 32FC3 -> 8U). parity_cases.oracle_warp uses these forms."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (120, 160, 3)).astype(np.uint8)
+    for g in [(1.07, 0.93, 1.21), (1.003, 0.997, 1.1)]:
+        ref = cv2.multiply(img, np.array(g + (0,), np.float64))
+        assert np.array_equal(ref, np.clip(np.rint(img.astype(np.float64) * np.array(g)), 0, 255).astype(np.uint8))
+        f32 = img.astype(np.float32)
+        chans = cv2.split(f32)
+        chans = [c * np.float32(gg) for c, gg in zip(chans, g)]
+        ref32 = cv2.convertScaleAbs(cv2.merge(chans))   # == convertTo(CV_8U) for non-negative data: cvRound + saturate
+        assert np.array_equal(ref32, np.clip(np.rint(f32 * np.array(g, np.float32)), 0, 255).astype(np.uint8))
+    gm = (rng.random((120, 160)) * 0.4 + 0.8).astype(np.float32)
+    ref = cv2.multiply(img, cv2.merge([gm, gm, gm]), dtype=cv2.CV_8U)
+    assert np.array_equal(ref, np.clip(np.rint(img.astype(np.float32) * gm[:, :, None]), 0, 255).astype(np.uint8))
