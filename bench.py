@@ -34,10 +34,13 @@ def workload_plan(name, n_gpus):
     if name == "cfg2":
         return synth.plan_grid(3, 3, 5472, 3648, overlap=0.7, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
             (f"cfg2: {n_gpus} flight block(s) of 3x3 frames 5472x3648, 70% overlap, multi-band 5"
-             + ("" if n_gpus == 1 else ", blocks stacked in y with 5% overlap, one block per GPU row band"))
+             + ("" if n_gpus == 1 else ", blocks stacked in y with 2% overlap, one block per GPU row band"))
     if name == "cfg1":
         return synth.plan_grid(2, 1, 4000, 3000, overlap=0.7, seed=synth.MASTER_SEED, rot_deg=1.5, blocks=n_gpus), "feather", 0, \
             f"cfg1: {n_gpus} block(s) of 2 frames 4000x3000, feather 0.02"
+    if name == "cfg3":
+        return synth.plan_grid(40, 3, 5472, 3648, overlap=0.7, side_overlap=0.32, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
+            f"cfg3: {n_gpus} block(s) of 3 serpentine lines x 40 frames 5472x3648, 70% forward / 32% side overlap, multi-band 5"
     if name == "small":
         return synth.plan_grid(3, 3, 912, 608, overlap=0.7, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
             f"small: {n_gpus} block(s) of 3x3 frames 912x608, 70% overlap, multi-band 5"
@@ -45,46 +48,62 @@ def workload_plan(name, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread
+    (nvidia-smi -lms is the fallback; its start-up alone is longer than a short timed region)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self.t = None
+        self.src = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.src = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.src = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.src != "nvml":
+            return self._smi_once()
+        self._stop.set()
+        self.t.join(timeout=1.0)
+        reasons = sorted(n for n, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.sm), "source": "nvml polled every 2 ms during the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                           "--format=csv,noheader,nounits"], text=True, timeout=10)
+            f = [x.strip() for x in out.strip().split(",")]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": [], "samples": 1,
+                    "source": "nvidia-smi once after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 def hbm_peak():
@@ -346,7 +365,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1", "small"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1", "cfg3", "small"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -776,9 +776,7 @@ struct MBFastBody {
     static constexpr int W0_BYTES = LEVEL0 ? 0 : ds_al128(PHM * PWS * 4);   // W_l of the needed region (levels >= 1)
     static constexpr int G0_BYTES = ds_al128(PHM * PWS * 4);
     static constexpr int G1_BYTES = ds_al128(GWS * GWS * 8);
-    static constexpr int BW = 88, BH = 82;                    // staged source footprint box (BGRX px)
-    static constexpr bool kStage = false;                     // measured on B200: L1 already serves the taps (86 % hit); staging costs more than it saves
-    static constexpr int H_BYTES = kStage ? ds_al128(BW * BH * 4) : ds_al128(PHM * GWS * 8);  // [source box in phase 1;] pyrDown H pass / weight H pass
+    static constexpr int H_BYTES = ds_al128(PHM * GWS * 8);   // pyrDown H pass; later the float H pass of the weights (PHM * JW * 4)
     static constexpr int ACC_BYTES = T * T * 4;
     static constexpr int COL_BYTES = ds_al128(PWS * 16), ROW_BYTES = ds_al128(PHM * 16);
     static constexpr int MAXF = 64;                            // frames per tile the packed accumulators allow (host-checked)
@@ -806,7 +804,6 @@ struct MBFastBody {
         uint32_t* s_g0 = (uint32_t*)smem;
         U2* s_g1 = (U2*)(smem + G0_BYTES);
         U2* s_h = (U2*)(smem + G0_BYTES + G1_BYTES);
-        uint32_t* s_box = (uint32_t*)(smem + G0_BYTES + G1_BYTES);
         float* s_hw = (float*)(smem + G0_BYTES + G1_BYTES);
         // accumulators: {B + 65536 R, G} interleaved (one 128-bit access per pixel pair), weight sums apart
         int2* s_acc = (int2*)(smem + G0_BYTES + G1_BYTES + H_BYTES);
@@ -901,57 +898,6 @@ struct MBFastBody {
                     r.b1 = f_mul(F.k[1], vp); r.b4 = f_mul(F.k[4], vp); r.b7 = f_mul(F.k[7], vp);
                     r.v = (unsigned)v < (unsigned)F.h ? v : ~vr;
                     s_row[yy] = r;
-                }
-            }
-            // ---- source footprint box: the (reflected) bbox rectangle this tile-frame samples maps to a
-            // parallelogram in the source; stage its bounding box (+ bilinear / rounding margin) in shared
-            // memory with the border mode already resolved. Exactness never depends on the estimate:
-            // a tap outside the box falls back to the global path below.
-            bool staged = false;
-            int bx0 = 0, by0 = 0;
-            if (kStage && !proj) {
-                const int u_lo = rx + px0 - F.cx, u_hi = u_lo + pw - 1, v_lo = ry + py0 - F.cy, v_hi = v_lo + ph - 1;
-                int ulo = imin(refl(u_lo, F.w, BORDER_REFL), refl(u_hi, F.w, BORDER_REFL));
-                int uhi = imax(refl(u_lo, F.w, BORDER_REFL), refl(u_hi, F.w, BORDER_REFL));
-                int vlo = imin(refl(v_lo, F.h, BORDER_REFL), refl(v_hi, F.h, BORDER_REFL));
-                int vhi = imax(refl(v_lo, F.h, BORDER_REFL), refl(v_hi, F.h, BORDER_REFL));
-                if (u_lo < 0 || pw >= F.w) ulo = 0;
-                if (u_hi >= F.w || pw >= F.w) uhi = F.w - 1;
-                if (v_lo < 0 || ph >= F.h) vlo = 0;
-                if (v_hi >= F.h || ph >= F.h) vhi = F.h - 1;
-                float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
-                for (int cidx = 0; cidx < 4; cidx++) {
-                    float U = (float)(F.tlx + ((cidx & 1) ? uhi : ulo)), V = (float)(F.tly + ((cidx & 2) ? vhi : vlo));
-                    if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
-                    const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
-                    const float x = f_add(f_add(f_mul(F.k[0], up), f_mul(F.k[1], vp)), F.k2one);
-                    const float y = f_add(f_add(f_mul(F.k[3], up), f_mul(F.k[4], vp)), F.k5one);
-                    xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
-                }
-                if (xmin > -1.0e6f && xmax < 1.0e6f && ymin > -1.0e6f && ymax < 1.0e6f) {
-                    bx0 = (int)floorf(xmin) - 1; by0 = (int)floorf(ymin) - 1;
-                    const int bx1 = (int)floorf(xmax) + 2, by1 = (int)floorf(ymax) + 2;
-                    staged = (bx1 - bx0 + 1 <= BW) && (by1 - by0 + 1 <= BH);
-                }
-            }
-            if (staged) {
-                const uint32_t* const src = F.src;
-                const int pitch = F.src_pitch, sw = F.src_w, sh = F.src_h;
-                const bool inside = bx0 >= 0 && by0 >= 0 && bx0 + BW <= sw && by0 + BH <= sh;
-                const bool bconst = F.border == BORDER_CONST;
-                for (int e = tid; e < BW * BH; e += NT) {
-                    const int yy = e / BW, xx = e - yy * BW;
-                    int gx = bx0 + xx, gy = by0 + yy;
-                    uint32_t v = 0u;
-                    if (inside) {
-                        v = ld_ro(src + (gy * pitch + gx));
-                    } else if (bconst) {
-                        if ((unsigned)gx < (unsigned)sw && (unsigned)gy < (unsigned)sh) v = ld_ro(src + (gy * pitch + gx));
-                    } else {
-                        gx = refl(gx, sw, BORDER_REFL); gy = refl(gy, sh, BORDER_REFL);
-                        v = ld_ro(src + (gy * pitch + gx));
-                    }
-                    s_box[e] = v;
                 }
             }
             DS_SYNC();
@@ -1061,11 +1007,7 @@ struct MBFastBody {
                     int m = ((c.u | r.v) >= 0 && okx && oky && (unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255 : 0;
                     if (seam && (c.u | r.v) >= 0) m &= (int)ld_ro(seam + (size_t)r.v * seam_pitch + c.u);
                     uint32_t p00, p01, p10, p11;
-                    const int bxi = sx - bx0, byi = sy - by0;
-                    if (kStage && staged && (unsigned)bxi < (unsigned)(BW - 1) && (unsigned)byi < (unsigned)(BH - 1)) {
-                        const uint32_t* r0 = s_box + (byi * BW + bxi);
-                        p00 = r0[0]; p01 = r0[1]; p10 = r0[BW]; p11 = r0[BW + 1];
-                    } else if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+                    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
                         const uint32_t* r0 = src + (sy * pitch + sx);
                         p00 = ld_ro(r0); p01 = ld_ro(r0 + 1);
                         p10 = ld_ro(r0 + pitch); p11 = ld_ro(r0 + pitch + 1);

@@ -601,11 +601,9 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     }
     ep.dst = f.d_src; ep.dst_pitch = f.pitch; ep.w = w; ep.h = h;
     if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->stream, 0))) return rc;
-    if (!on_device) {
-        // the caller's buffer is only borrowed for the call; the staging buffer is reused by the next
-        // upload, so wait for the expansion too (it is ~20 us for a 20 MP frame)
-        if ((rc = stream_sync(c->stream))) return rc;
-    }
+    // the caller's buffer (host or device) is only borrowed for the call, and the staging buffer is reused
+    // by the next upload: wait for the expansion (~20 us for a 20 MP frame)
+    if ((rc = stream_sync(c->stream))) return rc;
     // blend-mode specific geometry and buffers
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND) {
         dsgeo::feed_roi(c->desc.x, c->desc.y, c->pw, c->ph, c->L, f.corner_x, f.corner_y, f.bw, f.bh, f.rx, f.ry, f.rw, f.rh);

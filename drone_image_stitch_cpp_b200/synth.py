@@ -80,7 +80,7 @@ class SurveyPlan:
 
 
 def plan_grid(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scale_jit=0.02, trans_jit=20.0,
-              work_scale=1.0, serpentine=True, side_overlap=None, blocks=1, block_overlap=0.05):
+              work_scale=1.0, serpentine=True, side_overlap=None, blocks=1, block_overlap=0.02):
     """nx x ny frames of fw x fh, step = (1-overlap) of the frame size, with jitter.
     work_scale != 1 exercises the K = diag(1/ws), scale = 1/ws camera convention."""
     rng = np.random.default_rng(seed)

@@ -1,0 +1,84 @@
+"""Handle life-cycle behaviour through the C ABI: re-upload, sparse frame indices, repeated composites,
+tile download, per-kernel profile. Run on the emulator (host logic is shared) and, marked gpu, on the GPU
+(plus the device-pointer upload, which only exists there)."""
+import numpy as np
+import pytest
+
+from drone_image_stitch_cpp_b200 import compositor as CP
+from drone_image_stitch_cpp_b200 import synth
+from oracle import ds_oracle as O
+
+
+def _behaviour(lib):
+    sv = synth.grid_survey(2, 2, 240, 180, overlap=0.6, seed=41, work_scale=0.5)
+    xfs = [CP.plane_transform(K, R, sv.scale) for K, R in zip(sv.Ks, sv.Rs)]
+    rois = [CP.warp_roi(xf, 240, 180, lib) for xf in xfs]
+    roi = CP.result_roi(rois)
+    ref, refmask, _ = O.compose_port(sv.frames, sv.Ks, sv.Rs, sv.scale, "multiband", 4)
+    cv = CP.Canvas(roi, "multiband", 4, lib=lib)
+    # sparse indices (feed order = index order), uploaded out of order
+    idx = [7, 2, 11, 30]
+    order = sorted(range(4), key=lambda i: idx[i])          # frame i gets index idx[i]; feed order follows indices
+    for i in (3, 0, 2, 1):
+        cv.upload(idx[i], sv.frames[i], xfs[i])
+    cv.composite()
+    pano, mask = cv.download()
+    ref2, refmask2, _ = O.compose_port([sv.frames[i] for i in order], [sv.Ks[i] for i in order], [sv.Rs[i] for i in order],
+                                       sv.scale, "multiband", 4)
+    assert np.array_equal(pano, ref2) and np.array_equal(mask, refmask2)
+    # repeated composite is idempotent
+    cv.composite()
+    pano_b, _ = cv.download()
+    assert np.array_equal(pano_b, pano)
+    # re-upload an index with different pixels: result changes accordingly
+    other = np.ascontiguousarray(sv.frames[1][::-1, ::-1])
+    cv.upload(idx[1], other, xfs[1])
+    cv.composite()
+    pano_c, _ = cv.download()
+    fr = list(sv.frames)
+    fr[1] = other
+    ref3, _, _ = O.compose_port([fr[i] for i in order], [sv.Ks[i] for i in order], [sv.Rs[i] for i in order], sv.scale, "multiband", 4)
+    assert np.array_equal(pano_c, ref3)
+    # tile download equals the crop of the full download
+    t, tm = cv.download(x=33, y=21, w=100, h=77)
+    assert np.array_equal(t, pano_c[21:98, 33:133])
+    # strided host buffers (cv::Mat::step > 3*w) are accepted
+    wide = np.zeros((180, 300, 3), np.uint8)
+    wide[:, :240] = sv.frames[0]
+    cv.upload(idx[0], wide[:, :240], xfs[0])
+    # per-kernel profile covers every launch of a composite
+    cv.set_profiling(True)
+    cv.composite()
+    kt = cv.kernel_times()
+    assert len(kt) == cv.info().launches_last_composite and any(k["name"] == "mb_feed" for k in kt)
+    cv.close()
+    return ref, refmask
+
+
+def test_behaviour_emu(emu_lib):
+    _behaviour(emu_lib)
+
+
+@pytest.mark.gpu
+def test_behaviour_gpu(cuda_lib):
+    _behaviour(cuda_lib)
+
+
+@pytest.mark.gpu
+def test_upload_from_device_pointer(cuda_lib):
+    import torch
+    sv = synth.grid_survey(2, 1, 320, 240, overlap=0.5, seed=42)
+    xfs = [CP.plane_transform(K, R, sv.scale) for K, R in zip(sv.Ks, sv.Rs)]
+    roi = CP.result_roi([CP.warp_roi(xf, 320, 240, cuda_lib) for xf in xfs])
+    ref, refmask, _ = O.compose_port(sv.frames, sv.Ks, sv.Rs, sv.scale, "multiband", 3)
+    cv = CP.Canvas(roi, "multiband", 3, lib=cuda_lib)
+    keep = []
+    for i, f in enumerate(sv.frames):
+        t = torch.from_numpy(f).cuda()
+        keep.append(t)
+        torch.cuda.synchronize()
+        cv.upload_device(i, t.data_ptr(), 320, 240, 320 * 3, xfs[i])
+    cv.composite()
+    pano, mask = cv.download()
+    assert np.array_equal(pano, ref) and np.array_equal(mask, refmask)
+    cv.close()
