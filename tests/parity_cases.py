@@ -293,8 +293,30 @@ def case_exposure_gains(lib):
     return run_case(lib, specs, "feather", 0)
 
 
+def case_bands8_and_row_bands(lib):
+    # 8 bands (BASELINE config 5's blend depth) on a canvas just large enough, split into 3 row bands
+    sv = synth.grid_survey(2, 3, 520, 400, overlap=0.55, seed=95)
+    return run_case(lib, plane_specs(sv), "multiband", 8, check_taps=False, band_split=3)
+
+
+def case_very_wide_canvas(lib):
+    # one flight line whose canvas is wider than 65 535 px (BASELINE configs 3-5 are 69 k - 135 k px wide):
+    # 64-bit row offsets, large TMA coordinates, tile indices beyond 16 bits
+    n, fw, fh = 240, 512, 96
+    plan = synth.plan_grid(n, 1, fw, fh, overlap=0.4, seed=97, rot_deg=1.0, trans_jit=6.0)
+    rng = np.random.default_rng(97)
+    base = synth.orthophoto(fh, fw, 97).numpy()
+    frames = [np.ascontiguousarray(np.roll(base, int(rng.integers(0, fw)), axis=1)) for _ in range(n)]
+    specs = [dict(kind="plane", img=f, K=K, R=R, scale=plan.scale) for f, K, R in zip(frames, plan.Ks, plan.Rs)]
+    rois = [CP.warp_roi(lib_transform(s), fw, fh, lib) for s in specs]
+    assert CP.result_roi(rois)[2] > 65535
+    return run_case(lib, specs, "multiband", 5, check_taps=False)
+
+
 CASES = {
     "exposure_gains": case_exposure_gains,
+    "bands8_and_row_bands": case_bands8_and_row_bands,
+    "very_wide_canvas": case_very_wide_canvas,
     "seam_lowres_upsizing": case_seam_lowres_upsizing,
     "medium_mb3_interior": case_medium_mb3_interior,
     "many_frames_one_spot": case_many_frames_one_spot,
