@@ -1282,9 +1282,12 @@ struct CollapseParams {
     OutParams o;
 };
 struct CollapseBody {
-    static constexpr int PER_BLOCK = 512;  // items (4-px row segments) per block
+    static constexpr int PER_BLOCK = 256;  // items per block; one item = 4 columns x 2 rows (an even / odd row pair)
     static int smem_bytes() { return 0; }
-    static long long items(const CollapseParams& p) { return (long long)((p.fw + 3) / 4) * (p.y1 - p.y0); }
+    static long long items(const CollapseParams& p) {
+        const int m0 = p.y0 >> 1, m1 = (p.y1 + 1) >> 1;   // row pairs (2m, 2m+1) touching [y0, y1)
+        return (long long)((p.fw + 3) / 4) * (m1 - m0);
+    }
 
     // one pyrUp output from the horizontally filtered rows (A10), plus the fine value, saturated
     DS_DM int up1(int hl, int hc, int hr, bool odd_y, int fine) {
@@ -1295,85 +1298,93 @@ struct CollapseBody {
     template <int NT>
     DS_DM void run(const CollapseParams& p, int block, int tid, unsigned char*) {
         const int qw = (p.fw + 3) / 4;
-        const long long n = (long long)qw * (p.y1 - p.y0);
+        const int m0 = p.y0 >> 1, m1 = (p.y1 + 1) >> 1;
+        const long long n = (long long)qw * (m1 - m0);
         const px16* const coarse = p.coarse;
         const int cw = p.cw, chh = p.ch, fw = p.fw;
         for (int it = tid; it < PER_BLOCK; it += NT) {
             const long long idx = (long long)block * PER_BLOCK + it;
             if (idx >= n) break;
-            const int Y = p.y0 + (int)(idx / qw), Xq = (int)(idx % qw) * 4;
-            const int c1y = Y >> 1;
-            const bool oddy = (Y & 1) != 0;
+            const int c1y = m0 + (int)(idx / qw), Xq = (int)(idx % qw) * 4;
+            // both rows of the pair read coarse rows (l, c, r) around c1y; columns c0-1 .. c0+2 with the pyrUp border rules
             const int ry[3] = {up_l(c1y, chh), c1y, up_r(c1y, chh)};
             const int c0 = Xq >> 1;
-            // coarse columns c0-1, c0, c0+1, c0+2 with the pyrUp border rules
             const int cx[4] = {up_l(c0, cw), c0, up_r(c0, cw), up_r(imin(c0 + 1, cw - 1), cw)};
             int cb[3][4], cg[3][4], cr[3][4];
             DS_UNROLL
             for (int r = 0; r < 3; r++) {
-                if (r == 0 && oddy) { DS_UNROLL for (int c = 0; c < 4; c++) { cb[0][c] = cg[0][c] = cr[0][c] = 0; } continue; }
                 const px16* row = coarse + (size_t)ry[r] * cw;
                 DS_UNROLL
                 for (int c = 0; c < 4; c++) { const px16 q = row[cx[c]]; cb[r][c] = q.b; cg[r][c] = q.g; cr[r][c] = q.r; }
             }
-            const int nvalid = imin(4, fw - Xq);
-            alignas(16) px16 f[4];
-            px16* frow = p.fine + (size_t)Y * fw + Xq;
-            if (nvalid == 4) {
-                const uint4 v0 = *(const uint4*)frow, v1 = *(const uint4*)(frow + 2);
-                *(uint4*)&f[0] = v0; *(uint4*)&f[2] = v1;
-            } else {
-                for (int kx = 0; kx < 4; kx++) { if (kx < nvalid) f[kx] = frow[kx]; else { f[kx].b = f[kx].g = f[kx].r = f[kx].a = 0; } }
-            }
-            int ob[4], og[4], orr[4];
+            // horizontal pass once for the 4 columns x 3 coarse rows
+            int hb[3][4], hg[3][4], hr[3][4];
             DS_UNROLL
             for (int kx = 0; kx < 4; kx++) {
-                // X = Xq + kx: even -> (l, c, r) = columns (kx/2, kx/2+1, kx/2+2); odd -> (c, r) = (kx/2+1, kx/2+2)
-                const int j = kx >> 1;
-                int hb[3], hg[3], hr[3];
+                const int j = kx >> 1;   // even X: (l, c, r) = columns (j, j+1, j+2); odd X: (c, r) = (j+1, j+2)
                 DS_UNROLL
                 for (int r = 0; r < 3; r++) {
                     if (kx & 1) {
-                        hb[r] = 4 * (cb[r][j + 1] + cb[r][j + 2]); hg[r] = 4 * (cg[r][j + 1] + cg[r][j + 2]); hr[r] = 4 * (cr[r][j + 1] + cr[r][j + 2]);
+                        hb[r][kx] = 4 * (cb[r][j + 1] + cb[r][j + 2]); hg[r][kx] = 4 * (cg[r][j + 1] + cg[r][j + 2]);
+                        hr[r][kx] = 4 * (cr[r][j + 1] + cr[r][j + 2]);
                     } else {
-                        hb[r] = cb[r][j] + 6 * cb[r][j + 1] + cb[r][j + 2]; hg[r] = cg[r][j] + 6 * cg[r][j + 1] + cg[r][j + 2];
-                        hr[r] = cr[r][j] + 6 * cr[r][j + 1] + cr[r][j + 2];
+                        hb[r][kx] = cb[r][j] + 6 * cb[r][j + 1] + cb[r][j + 2]; hg[r][kx] = cg[r][j] + 6 * cg[r][j + 1] + cg[r][j + 2];
+                        hr[r][kx] = cr[r][j] + 6 * cr[r][j + 1] + cr[r][j + 2];
                     }
                 }
-                ob[kx] = up1(hb[0], hb[1], hb[2], oddy, f[kx].b);
-                og[kx] = up1(hg[0], hg[1], hg[2], oddy, f[kx].g);
-                orr[kx] = up1(hr[0], hr[1], hr[2], oddy, f[kx].r);
             }
-            if (!p.final) {
-                DS_UNROLL
-                for (int kx = 0; kx < 4; kx++) { f[kx].b = (short)ob[kx]; f[kx].g = (short)og[kx]; f[kx].r = (short)orr[kx]; }
-                if (nvalid == 4) { *(uint4*)frow = *(const uint4*)&f[0]; *(uint4*)(frow + 2) = *(const uint4*)&f[2]; }
-                else { for (int kx = 0; kx < nvalid; kx++) frow[kx] = f[kx]; }
-            } else if (Y < p.o.h) {
-                uint32_t px[4];
+            const int nvalid = imin(4, fw - Xq);
+            DS_UNROLL
+            for (int dy = 0; dy < 2; dy++) {
+                const int Y = 2 * c1y + dy;
+                if (Y < p.y0 || Y >= p.y1) continue;
+                const bool oddy = dy != 0;
+                alignas(16) px16 f[4];
+                px16* frow = p.fine + (size_t)Y * fw + Xq;
+                if (nvalid == 4) {
+                    const uint4 v0 = *(const uint4*)frow, v1 = *(const uint4*)(frow + 2);
+                    *(uint4*)&f[0] = v0; *(uint4*)&f[2] = v1;
+                } else {
+                    for (int kx = 0; kx < 4; kx++) { if (kx < nvalid) f[kx] = frow[kx]; else { f[kx].b = f[kx].g = f[kx].r = f[kx].a = 0; } }
+                }
+                int ob[4], og[4], orr[4];
                 DS_UNROLL
                 for (int kx = 0; kx < 4; kx++) {
-                    const bool m = f[kx].a != 0;
-                    px[kx] = m ? ((uint32_t)sat8i(ob[kx]) | ((uint32_t)sat8i(og[kx]) << 8) | ((uint32_t)sat8i(orr[kx]) << 16) | 0xff000000u) : 0u;
+                    ob[kx] = up1(hb[0][kx], hb[1][kx], hb[2][kx], oddy, f[kx].b);
+                    og[kx] = up1(hg[0][kx], hg[1][kx], hg[2][kx], oddy, f[kx].g);
+                    orr[kx] = up1(hr[0][kx], hr[1][kx], hr[2][kx], oddy, f[kx].r);
                 }
-                const int nout = imin(nvalid, p.o.w - Xq);
-                if (p.o.fmt == 1) {
-                    uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch) + Xq;
-                    if (nout == 4) *(uint4*)q = make_u4(px[0], px[1], px[2], px[3]);
-                    else for (int kx = 0; kx < nout; kx++) q[kx] = px[kx];
-                } else if (nout == 4) {
-                    // 12 BGR bytes = 3 aligned words; 4 mask bytes = 1 word (Xq is a multiple of 4, pitches of 256)
-                    uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)Xq * 3);
-                    q[0] = (px[0] & 0xffffffu) | (px[1] << 24);
-                    q[1] = ((px[1] >> 8) & 0xffffu) | (px[2] << 16);
-                    q[2] = ((px[2] >> 16) & 0xffu) | (px[3] << 8);
-                    *(uint32_t*)(p.o.mask + (size_t)Y * p.o.mask_pitch + Xq) =
-                        (px[0] >> 24) | ((px[1] >> 24) << 8) | ((px[2] >> 24) << 16) | ((px[3] >> 24) << 24);
-                } else {
-                    for (int kx = 0; kx < nout; kx++) {
-                        uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)(Xq + kx) * 3;
-                        q[0] = (uint8_t)px[kx]; q[1] = (uint8_t)(px[kx] >> 8); q[2] = (uint8_t)(px[kx] >> 16);
-                        p.o.mask[(size_t)Y * p.o.mask_pitch + Xq + kx] = (uint8_t)(px[kx] >> 24);
+                if (!p.final) {
+                    DS_UNROLL
+                    for (int kx = 0; kx < 4; kx++) { f[kx].b = (short)ob[kx]; f[kx].g = (short)og[kx]; f[kx].r = (short)orr[kx]; }
+                    if (nvalid == 4) { *(uint4*)frow = *(const uint4*)&f[0]; *(uint4*)(frow + 2) = *(const uint4*)&f[2]; }
+                    else { for (int kx = 0; kx < nvalid; kx++) frow[kx] = f[kx]; }
+                } else if (Y < p.o.h) {
+                    uint32_t px[4];
+                    DS_UNROLL
+                    for (int kx = 0; kx < 4; kx++) {
+                        const bool m = f[kx].a != 0;
+                        px[kx] = m ? ((uint32_t)sat8i(ob[kx]) | ((uint32_t)sat8i(og[kx]) << 8) | ((uint32_t)sat8i(orr[kx]) << 16) | 0xff000000u) : 0u;
+                    }
+                    const int nout = imin(nvalid, p.o.w - Xq);
+                    if (p.o.fmt == 1) {
+                        uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch) + Xq;
+                        if (nout == 4) *(uint4*)q = make_u4(px[0], px[1], px[2], px[3]);
+                        else for (int kx = 0; kx < nout; kx++) q[kx] = px[kx];
+                    } else if (nout == 4) {
+                        // 12 BGR bytes = 3 aligned words; 4 mask bytes = 1 word (Xq is a multiple of 4, pitches of 256)
+                        uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)Xq * 3);
+                        q[0] = (px[0] & 0xffffffu) | (px[1] << 24);
+                        q[1] = ((px[1] >> 8) & 0xffffu) | (px[2] << 16);
+                        q[2] = ((px[2] >> 16) & 0xffu) | (px[3] << 8);
+                        *(uint32_t*)(p.o.mask + (size_t)Y * p.o.mask_pitch + Xq) =
+                            (px[0] >> 24) | ((px[1] >> 24) << 8) | ((px[2] >> 24) << 16) | ((px[3] >> 24) << 24);
+                    } else {
+                        for (int kx = 0; kx < nout; kx++) {
+                            uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)(Xq + kx) * 3;
+                            q[0] = (uint8_t)px[kx]; q[1] = (uint8_t)(px[kx] >> 8); q[2] = (uint8_t)(px[kx] >> 16);
+                            p.o.mask[(size_t)Y * p.o.mask_pitch + Xq + kx] = (uint8_t)(px[kx] >> 24);
+                        }
                     }
                 }
             }

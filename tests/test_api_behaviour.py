@@ -82,3 +82,38 @@ def test_upload_from_device_pointer(cuda_lib):
     pano, mask = cv.download()
     assert np.array_equal(pano, ref) and np.array_equal(mask, refmask)
     cv.close()
+
+
+def _edges(lib):
+    # empty input: a canvas composited with no frame is all zero with an all-zero mask (what blend() gives
+    # when nothing was fed)
+    for blend in ("multiband", "feather"):
+        cv = CP.Canvas((5, -3, 70, 45), blend, 3, lib=lib)
+        cv.composite()
+        pano, mask = cv.download()
+        assert pano.shape == (45, 70, 3) and not pano.any() and not mask.any()
+        cv.close()
+    # tiny ragged frames: 9x7 and 1x1 sources, canvas smaller than one tile, bands cropped by the canvas size
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 256, (7, 9, 3)).astype(np.uint8), rng.integers(0, 256, (1, 1, 3)).astype(np.uint8)]
+    Ks = [np.eye(3, dtype=np.float32)] * 2
+    Rs = [np.array([[1, 0, 2.25], [0, 1, -1.5], [0, 0, 1]], np.float32), np.array([[1, 0, 6.0], [0, 1, 3.0], [0, 0, 1]], np.float32)]
+    for blend, bands in (("multiband", 5), ("feather", 0)):
+        ref, refmask, roi = O.compose_port(frames, Ks, Rs, 1.0, blend, bands)
+        pano, mask, roi2 = CP.compose_panorama(frames, Ks, Rs, 1.0, blend, bands, lib=lib)
+        assert roi == roi2 and np.array_equal(mask, refmask) and np.array_equal(pano, ref)
+    # maximum source size: cv::remap asserts < 32768 per side; the library refuses instead of asserting
+    cv = CP.Canvas((0, 0, 64, 64), "multiband", 2, lib=lib)
+    from drone_image_stitch_cpp_b200 import _lib as L
+    with pytest.raises(L.DroneStitchError):
+        cv.upload(0, (0x1000, 40000, 2, 40000 * 3), CP.plane_transform(np.eye(3), np.eye(3), 1.0))
+    cv.close()
+
+
+def test_edges_emu(emu_lib):
+    _edges(emu_lib)
+
+
+@pytest.mark.gpu
+def test_edges_gpu(cuda_lib):
+    _edges(cuda_lib)
