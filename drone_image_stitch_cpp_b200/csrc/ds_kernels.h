@@ -360,13 +360,16 @@ struct FeatherParams {
 
 struct FeatherBody {
     static constexpr int TW = 64, TH = 32, RMAX = 64;
-    static int smem_bytes() { return (TW + 2 * RMAX) * (TH + 2 * RMAX) + 16; }
+    static constexpr int D_BYTES = ((TW + 2 * RMAX) * (TH + 2 * RMAX) + 16 + 15) & ~15;
+    static int smem_bytes() { return D_BYTES + (TW + TH) * 8; }
     template <int NT>
     DS_DM void run(const FeatherParams& p, int block, int tid, unsigned char* smem) {
         constexpr int PPT = TW * TH / NT;
         const int tile = p.tile_ids ? p.tile_ids[block] : block;
         unsigned char* s_d = smem + 16;
         int* s_flag = (int*)smem;
+        float2* s_cx = (float2*)(smem + D_BYTES);   // per tile column: k0*u', k3*u'
+        float2* s_ry = s_cx + TW;                   // per tile row:    k1*v', k4*v'
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int X0 = tx * TW, Y0 = ty * TH;
         const int R = p.R;
@@ -449,6 +452,98 @@ struct FeatherBody {
                 DS_SYNC();
             }
             // 3) sample + accumulate
+            // Interior tile-frames (tile inside the bbox, its four corners at least a pixel inside the source;
+            // the plane map is monotone in u and in v, so the corners bound every pixel): border-free loop
+            // with all taps of the thread's PPT pixels requested before any is used.
+            bool interior = false;
+            if (F.kind == XF_PLANE && !F.seam && !F.gainmap &&
+                F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f) {
+                const int u0 = X0 - F.cx, v0 = Y0 - F.cy;
+                if (u0 >= 0 && u0 + TW <= F.w && v0 >= 0 && v0 + TH <= F.h) {
+                    float xs[4], ys[4];
+                    for (int cidx = 0; cidx < 4; cidx++) {
+                        float U = (float)(F.tlx + u0 + ((cidx & 1) ? TW - 1 : 0)), V = (float)(F.tly + v0 + ((cidx & 2) ? TH - 1 : 0));
+                        if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+                        const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+                        xs[cidx] = f_add(f_add(f_mul(F.k[0], up), f_mul(F.k[1], vp)), F.k2one);
+                        ys[cidx] = f_add(f_add(f_mul(F.k[3], up), f_mul(F.k[4], vp)), F.k5one);
+                    }
+                    const float xmn = fminf(fminf(xs[0], xs[1]), fminf(xs[2], xs[3])), xmx = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3]));
+                    const float ymn = fminf(fminf(ys[0], ys[1]), fminf(ys[2], ys[3])), ymx = fmaxf(fmaxf(ys[0], ys[1]), fmaxf(ys[2], ys[3]));
+                    interior = xmn >= 1.f && xmx <= (float)(F.src_w - 3) && ymn >= 1.f && ymx <= (float)(F.src_h - 3);
+                }
+            }
+            if (interior) {
+                const uint32_t* const src = F.src;
+                const int pitch = F.src_pitch;
+                const float k2 = F.k2one, k5 = F.k5one;
+                for (int i = tid; i < TW + TH; i += NT) {
+                    if (i < TW) {
+                        float U = (float)(F.tlx + X0 + i - F.cx);
+                        if (F.scale != 1.f) U = f_div(U, F.scale);
+                        const float up = f_sub(U, F.t0);
+                        float2 c; c.x = f_mul(F.k[0], up); c.y = f_mul(F.k[3], up);
+                        s_cx[i] = c;
+                    } else {
+                        float V = (float)(F.tly + Y0 + (i - TW) - F.cy);
+                        if (F.scale != 1.f) V = f_div(V, F.scale);
+                        const float vp = f_sub(V, F.t1);
+                        float2 r; r.x = f_mul(F.k[1], vp); r.y = f_mul(F.k[4], vp);
+                        s_ry[i - TW] = r;
+                    }
+                }
+                DS_SYNC();
+                constexpr int UB = PPT < 4 ? PPT : 4;   // pixels in flight per thread
+                DS_UNROLL
+                for (int k0 = 0; k0 < PPT; k0 += UB) {
+                    int ix[UB], iy[UB];
+                    uint32_t p00[UB], p01[UB], p10[UB], p11[UB];
+                    DS_UNROLL
+                    for (int b = 0; b < UB; b++) {
+                        const int pidx = tid + (k0 + b) * NT;
+                        const int yy = pidx / TW, xx = pidx - yy * TW;
+                        const float2 c = s_cx[xx], r = s_ry[yy];
+                        const float x = f_add(f_add(c.x, r.x), k2);
+                        const float y = f_add(f_add(c.y, r.y), k5);
+#if DS_CUDA
+                        ix[b] = __float2int_rn(f_mul(x, 32.f)); iy[b] = __float2int_rn(f_mul(y, 32.f));
+#else
+                        ix[b] = f2i_rn(f_mul(x, 32.f)); iy[b] = f2i_rn(f_mul(y, 32.f));
+#endif
+                        const uint32_t* r0 = src + ((iy[b] >> 5) * pitch + (ix[b] >> 5));
+                        p00[b] = ld_ro(r0); p01[b] = ld_ro(r0 + 1); p10[b] = ld_ro(r0 + pitch); p11[b] = ld_ro(r0 + pitch + 1);
+                    }
+                    DS_UNROLL
+                    for (int b = 0; b < UB; b++) {
+                        const int k = k0 + b;
+                        const int pidx = tid + k * NT;
+                        const int yy = pidx / TW, xx = pidx - yy * TW;
+                        float wgt = 1.f;
+                        if (has_zero) {
+                            const int d = s_d[(yy + R) * ww + (xx + R)];
+                            if (d == 0) continue;
+                            if (d < R) { wgt = f_mul((float)d, p.sharpness); if (wgt > 1.f) wgt = 1.f; }
+                        }
+                        const int ax = ix[b] & 31, ay = iy[b] & 31;
+                        const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
+                        const uint32_t t0 = byte_perm(p00[b], p01[b], 0x5140), t0r = byte_perm(p00[b], p01[b], 0x6262);
+                        const uint32_t t1 = byte_perm(p10[b], p11[b], 0x5140), t1r = byte_perm(p10[b], p11[b], 0x6262);
+                        const int wy1 = ay, wy0 = 32 - ay;
+                        int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
+                        int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
+                        int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
+                        if (F.any_gain) apply_gains(F, ob, og, orr, 0, 0);
+                        if (wgt == 1.f) {   // trunc(p * 1) == p
+                            acc[k][0] += ob; acc[k][1] += og; acc[k][2] += orr;
+                        } else {
+                            acc[k][0] += (int)(short)f2i_rz(f_mul((float)ob, wgt));
+                            acc[k][1] += (int)(short)f2i_rz(f_mul((float)og, wgt));
+                            acc[k][2] += (int)(short)f2i_rz(f_mul((float)orr, wgt));
+                        }
+                        ws[k] = f_add(ws[k], wgt);
+                    }
+                }
+            } else {
             DS_UNROLL
             for (int k = 0; k < PPT; k++) {
                 const int pidx = tid + k * NT;
@@ -467,6 +562,7 @@ struct FeatherBody {
                 acc[k][1] += (int)(short)f2i_rz(f_mul((float)s.g, wgt));
                 acc[k][2] += (int)(short)f2i_rz(f_mul((float)s.r, wgt));
                 ws[k] = f_add(ws[k], wgt);
+            }
             }
             DS_SYNC();
         }
@@ -1430,7 +1526,7 @@ DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
 DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
 DS_DEFINE_KERNEL(ds_seam_upsize, SeamUpBody, 256, SeamUpParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
-DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 1)
+DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 3)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)
 typedef MBFastBody<64, true> MBFastL0;
 typedef MBFastBody<32, false> MBFastLN;
