@@ -877,7 +877,9 @@ struct MBFastBody {
     static constexpr int COL_BYTES = ds_al128(PWS * 16), ROW_BYTES = ds_al128(PHM * 16);
     static constexpr int MAXF = 64;                            // frames per tile the packed accumulators allow (host-checked)
     static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
-    static constexpr int MBAR_OFF = GEO_OFF + MAXF * 96;
+    static constexpr int FDEV_BYTES = (int)((sizeof(FrameDev) + 15) & ~(size_t)15);
+    static constexpr int FDEV_OFF = GEO_OFF + MAXF * 96;      // two FrameDev slots: current frame / prefetch of the next
+    static constexpr int MBAR_OFF = FDEV_OFF + 2 * FDEV_BYTES;
     static constexpr uint32_t TMA_BYTES = (uint32_t)(PWS * PHM * 4);   // one box (G or W) of the needed region
     static int smem_bytes() { return MBAR_OFF + 16; }
 
@@ -950,10 +952,22 @@ struct MBFastBody {
         }
         DS_SYNC();
 
+        // Frame descriptors are staged in shared memory: slot (fi & 1) holds frame fi, and while it is being
+        // processed the first threads prefetch frame fi + 1 into the other slot (visible after the barriers
+        // every iteration ends with). Keeps the dependent global loads off the per-tile-frame critical path.
+        auto stage_frame = [&](int fi_) {
+            const uint4* srcw = (const uint4*)(p.frames + p.tile_frames[fi_]);
+            uint4* dstw = (uint4*)(smem + FDEV_OFF + (fi_ & 1) * FDEV_BYTES);
+            for (int w = tid; w < (int)(sizeof(FrameDev) / 16); w += NT) dstw[w] = srcw[w];
+        };
+        if (f_begin < f_end) stage_frame(f_begin);
+        DS_SYNC();
+
         for (int fi = f_begin; fi < f_end; fi++) {
             const TFGeo g = s_geo[fi - f_begin];
-            if (g.skip) continue;  // block-uniform
-            const FrameDev& F = p.frames[p.tile_frames[fi]];
+            if (fi + 1 < f_end) stage_frame(fi + 1);   // slot ((fi + 1) & 1) was last read in iteration fi - 1
+            if (g.skip) { DS_SYNC(); continue; }       // block-uniform
+            const FrameDev& F = *(const FrameDev*)(smem + FDEV_OFF + (fi & 1) * FDEV_BYTES);
             const int rx = g.rx, ry = g.ry, rw = g.rw, rh = g.rh;
             const int ax0 = g.ax0, ax1 = g.ax1, ay0 = g.ay0, ay1 = g.ay1;
             const int n1x = rw >> 1, n1y = rh >> 1;

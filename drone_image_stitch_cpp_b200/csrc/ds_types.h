@@ -8,7 +8,7 @@ enum { XF_PLANE = 0, XF_AFFINE = 1, XF_HOMOGRAPHY = 2 };
 enum { BORDER_CONST = 0, BORDER_REFL = 1, BORDER_REFL101 = 2 };
 
 // One uploaded frame as the kernels see it (array in device memory).
-struct FrameDev {
+struct alignas(16) FrameDev {
     const uint32_t* src;  // BGRX pixels, row pitch in pixels
     int src_w, src_h, src_pitch;
     int kind, border;
