@@ -879,9 +879,12 @@ struct MBFastBody {
     static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
     static constexpr int FDEV_BYTES = (int)((sizeof(FrameDev) + 15) & ~(size_t)15);
     static constexpr int FDEV_OFF = GEO_OFF + MAXF * 96;      // two FrameDev slots: current frame / prefetch of the next
-    static constexpr int MBAR_OFF = FDEV_OFF + 2 * FDEV_BYTES;
+    // levels >= 1: second copy of the G / W boxes so the TMA load of the next frame overlaps this frame's compute
+    static constexpr int G0B_OFF = ds_al128(FDEV_OFF + 2 * FDEV_BYTES);   // TMA destinations: 128-B aligned
+    static constexpr int W0B_OFF = G0B_OFF + (LEVEL0 ? 0 : G0_BYTES);
+    static constexpr int MBAR_OFF = W0B_OFF + W0_BYTES;
     static constexpr uint32_t TMA_BYTES = (uint32_t)(PWS * PHM * 4);   // one box (G or W) of the needed region
-    static int smem_bytes() { return MBAR_OFF + 16; }
+    static int smem_bytes() { return MBAR_OFF + 32; }
 
     struct U2 { uint32_t br, g; };
     // tile x frame geometry, computed once per tile by as many threads as the tile has frames
@@ -899,7 +902,7 @@ struct MBFastBody {
 
     template <int NT>
     DS_DM void run(const MBParams& p, int block, int tid, unsigned char* smem) {
-        uint32_t* s_g0 = (uint32_t*)smem;
+        uint32_t* s_g0 = (uint32_t*)smem;   // levels >= 1 with TMA: alternates between two box buffers
         U2* s_g1 = (U2*)(smem + G0_BYTES);
         U2* s_h = (U2*)(smem + G0_BYTES + G1_BYTES);
         float* s_hw = (float*)(smem + G0_BYTES + G1_BYTES);
@@ -918,10 +921,14 @@ struct MBFastBody {
 
         for (int i = tid; i < T * T; i += NT) { s_acc[i] = make_i2(0, 0); s_ws[i] = 0.f; }
 #if DS_CUDA
-        unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);
-        uint32_t tma_phase = 0;
+        unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);   // two barriers, one per box buffer
+        uint32_t tma_phase0 = 0u, tma_phase1 = 0u;
+        int tma_cur = 0;
         const bool use_tma = !LEVEL0 && p.tmaps != nullptr;
-        if (use_tma && tid == 0) mbar_init(s_bar, 1);
+        if (use_tma && tid == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
+        constexpr int W0A_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES;
+        auto g0_buf = [&](int b_) { return (uint32_t*)(smem + (b_ ? G0B_OFF : 0)); };
+        auto w_buf = [&](int b_) { return (float*)(smem + (b_ ? W0B_OFF : W0A_OFF)); };
 #endif
         DS_SYNC();
 
@@ -961,6 +968,22 @@ struct MBFastBody {
             for (int w = tid; w < (int)(sizeof(FrameDev) / 16); w += NT) dstw[w] = srcw[w];
         };
         if (f_begin < f_end) stage_frame(f_begin);
+#if DS_CUDA
+        // TMA pipeline over the tile's frame list: the boxes of the next non-skipped frame are requested while
+        // the current one is processed (two buffers, two mbarriers)
+        auto next_live = [&](int from) { int j = from; while (j < f_end && s_geo[j - f_begin].skip) j++; return j; };
+        auto tma_issue = [&](int fi_, int buf) {
+            const TFGeo gg = s_geo[fi_ - f_begin];
+            const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fi_] * DS_MAXL + l) * 2 * 128;
+            fence_tensormap_acquire(tm);
+            fence_tensormap_acquire(tm + 128);
+            fence_proxy_async();   // generic-proxy reads of this buffer ended before the last barrier
+            mbar_expect_tx(s_bar + buf, 2 * TMA_BYTES);
+            tma_load_2d(g0_buf(buf), tm, gg.px0, gg.py0, s_bar + buf);
+            tma_load_2d(w_buf(buf), tm + 128, gg.px0, gg.py0, s_bar + buf);
+        };
+        if (use_tma && tid == 0) { const int j0 = next_live(f_begin); if (j0 < f_end) tma_issue(j0, 0); }
+#endif
         DS_SYNC();
 
         for (int fi = f_begin; fi < f_end; fi++) {
@@ -1152,18 +1175,13 @@ struct MBFastBody {
 #if DS_CUDA
                 if (use_tma) {
                     // box-shaped footprint: one TMA tile load each for G_l and W_l of the needed region
-                    // (PWS x PHM elements from (px0, py0); rows beyond the level are zero-filled and never read)
-                    if (tid == 0) {
-                        const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fi] * DS_MAXL + l) * 2 * 128;
-                        fence_tensormap_acquire(tm);
-                        fence_tensormap_acquire(tm + 128);
-                        fence_proxy_async();   // earlier generic-proxy reads of s_g0 / s_w are done (barrier at loop end)
-                        mbar_expect_tx(s_bar, 2 * TMA_BYTES);
-                        tma_load_2d(s_g0, tm, px0, py0, s_bar);
-                        tma_load_2d(s_w, tm + 128, px0, py0, s_bar);
-                    }
-                    mbar_wait(s_bar, tma_phase);
-                    tma_phase ^= 1u;
+                    // (PWS x PHM elements from (px0, py0); rows beyond the level are zero-filled and never read).
+                    // This frame's boxes were requested one iteration ago; request the next frame's now.
+                    s_g0 = g0_buf(tma_cur); s_w = w_buf(tma_cur);
+                    mbar_wait(s_bar + tma_cur, tma_cur ? tma_phase1 : tma_phase0);
+                    if (tma_cur) tma_phase1 ^= 1u; else tma_phase0 ^= 1u;
+                    if (tid == 0) { const int jn = next_live(fi + 1); if (jn < f_end) tma_issue(jn, tma_cur ^ 1); }
+                    tma_cur ^= 1;
                     for (int i = tid; i < PWS * ph; i += NT) {
                         const int yy = i / PWS, xx = i - yy * PWS;
                         if (xx >= pw) continue;
