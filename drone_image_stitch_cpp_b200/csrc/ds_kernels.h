@@ -839,6 +839,10 @@ DS_D void mbar_wait(void* bar, uint32_t parity) {
     }
     __trap();   // a lost TMA transaction must fail loudly, never hang the device
 }
+// L2 prefetch of a tile (no shared memory, no completion tracking): warms L2 for loads that follow later
+DS_D void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 DS_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // descriptors live in global memory (one per frame and level): acquire them for the tensormap proxy before use
 DS_D void fence_tensormap_acquire(const void* tmap) {
@@ -1034,6 +1038,32 @@ struct MBFastBody {
                 }
             }
             DS_SYNC();
+#if DS_CUDA
+            // L2 prefetch (TMA) of the source footprint of the NEXT frame of this tile: its descriptor was staged
+            // at the top of this iteration and is visible after the barrier above. One thread, fire and forget.
+            if (p.tmaps != nullptr && tid == 0 && fi + 1 < f_end) {
+                const TFGeo ng = s_geo[fi + 1 - f_begin];
+                const FrameDev& N = *(const FrameDev*)(smem + FDEV_OFF + ((fi + 1) & 1) * FDEV_BYTES);
+                if (!ng.skip && N.kind == XF_PLANE) {
+                    const int u_lo = ng.rx + ng.px0 - N.cx, u_hi = u_lo + ng.pw - 1, v_lo = ng.ry + ng.py0 - N.cy, v_hi = v_lo + ng.ph - 1;
+                    const int ulo = imax(imin(u_lo, N.w - 1), 0), uhi = imax(imin(u_hi, N.w - 1), 0);
+                    const int vlo = imax(imin(v_lo, N.h - 1), 0), vhi = imax(imin(v_hi, N.h - 1), 0);
+                    float xmin = 3.0e38f, ymin = 3.0e38f;
+                    for (int cidx = 0; cidx < 4; cidx++) {
+                        float U = (float)(N.tlx + ((cidx & 1) ? uhi : ulo)), V = (float)(N.tly + ((cidx & 2) ? vhi : vlo));
+                        if (N.scale != 1.f) { U = U / N.scale; V = V / N.scale; }
+                        const float up = U - N.t0, vp = V - N.t1;
+                        xmin = fminf(xmin, N.k[0] * up + N.k[1] * vp + N.k2one);
+                        ymin = fminf(ymin, N.k[3] * up + N.k[4] * vp + N.k5one);
+                    }
+                    if (xmin > -1.0e6f && xmin < 1.0e6f && ymin > -1.0e6f && ymin < 1.0e6f) {
+                        const char* tm = (const char*)p.tmaps + (size_t)p.tile_frames[fi + 1] * DS_MAXL * 2 * 128;   // slot [frame][0][0]: source
+                        fence_tensormap_acquire(tm);
+                        tma_prefetch_l2_2d(tm, ((int)floorf(xmin) - 1) & ~3, (int)floorf(ymin) - 1);
+                    }
+                }
+            }
+#endif
 
             // ---- phase 1: inverse warp of the needed region into s_g0 (b | g<<8 | r<<16 | mask<<24)
             // Frame fields are copied to registers first: F lives in global memory and would otherwise be

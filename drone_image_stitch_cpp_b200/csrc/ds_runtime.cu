@@ -399,7 +399,7 @@ int build_lists(ds_canvas* c) {
     if ((rc = stream_sync(c->stream))) return rc;
     c->tmaps_ok = false;
 #if DS_CUDA
-    if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L >= 2 && !c->frames.empty()) {
+    if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L >= 1 && !c->frames.empty()) {
         // TMA descriptors for the box-shaped tile loads of the fast level-l kernel (MBFastBody<32,false>)
         std::vector<CUtensorMap> tm(c->frames.size() * DS_MAXL * 2);
         memset(tm.data(), 0, tm.size() * sizeof(CUtensorMap));
@@ -407,6 +407,9 @@ int build_lists(ds_canvas* c) {
         for (size_t i = 0; i < c->frames.size() && ok; i++) {
             const Frame& f = c->frames[i];
             if (!f.used) continue;
+            // slot [frame][0][0]: the BGRX source, box = footprint of a 71x71 tile region under a few degrees of
+            // rotation (L2 prefetch only: correctness never depends on it)
+            ok = encode_tile_map(&tm[(i * DS_MAXL) * 2], false, f.d_src, f.w, f.h, f.pitch, 96, 88);
             for (int l = 1; l < c->L && ok; l++) {
                 const int w = f.rw >> l, h = f.rh >> l;
                 ok = encode_tile_map(&tm[(i * DS_MAXL + l) * 2], false, f.dev.G[l], w, h, f.dev.gp[l], MBFastBody<32, false>::PWS, MBFastBody<32, false>::PHM) &&
