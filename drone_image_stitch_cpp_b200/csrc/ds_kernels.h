@@ -1332,6 +1332,7 @@ struct MBFastBody {
                     const int qy = q / (T / 2), qx = q - qy * (T / 2);
                     const int X = X0 + 2 * qx, Y = Y0 + 2 * qy;
                     if (X < ax0 || X >= ax1 || Y < ay0 || Y >= ay1) continue;
+                    if (Y + 1 < p.acc_y0 || Y >= p.acc_y1) continue;   // halo rows of a band only produce G_{l+1} / W_{l+1}
                     const int ox = X - rx, oy = Y - ry;
                     const int c1x = ox >> 1, c1y = oy >> 1;
                     int ixl, ixr, iyl, iyr;
