@@ -251,7 +251,6 @@ def run_native(args):
         info = cv.info()
         out_rows = min(info.band_y1, roi[3]) - info.band_y0
         out_pin = torch.empty((out_rows, roi[2], 3), dtype=torch.uint8, pin_memory=True)
-        mask_pin = torch.empty((out_rows, roi[2]), dtype=torch.uint8, pin_memory=True)
 
         def barrier():
             torch.cuda.synchronize()
@@ -286,14 +285,16 @@ def run_native(args):
 
         # ---------------- e2e: upload from pinned host + composite + download, every step
         e2e_steps = max(2, min(args.steps, 5))
+        # the step's result is the panorama (what composePanorama hands back, stitch_robust.cpp:256); the
+        # result mask stays on the device unless asked for
         h2d = sum(int(a.nbytes) for a in host_np)
-        d2h = int(out_pin.numel() + mask_pin.numel())
+        d2h = int(out_pin.numel())
 
         def e2e_step():
             for i, arr in zip(mine, host_np):
                 cv.upload(i, arr, xfs[i])
             cv.composite()
-            cv.download(out=out_pin.numpy(), mask_out=mask_pin.numpy())
+            cv.download(out=out_pin.numpy(), want_mask=False)
 
         e2e_step()
         barrier()
