@@ -335,6 +335,8 @@ def run_native(args):
                     traffic = None
             roof = {"bound": "hbm", "kernel": f"{name}[level {level}]", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                    "note": "achieved = SURVEY 8(d) algorithmic bytes / CUDA-event time; the gather formulation moves fewer real bytes "
+                            "(traffic) than the model, the kernel is issue-bound (profiles/README.md)",
                     "ms_per_launch": ms,
                     "whole_step": {"algorithmic_bytes": ab_total, "achieved": ab_total / (ms_total / args.steps / 1e3) / 1e9,
                                    "frac": ab_total / (ms_total / args.steps / 1e3) / 1e9 / peak},

@@ -291,7 +291,6 @@ int fill_frame_dev(ds_canvas* c, Frame& f) {
     }
     d.mbits = f.d_mbits; d.mbits_pitch = (f.bw + 31) / 32;
     d.seam = f.d_seam; d.seam_pitch = f.bw;
-    if (f.xf.kind >= 0 && f.d_seam == nullptr) d.seam = nullptr;
     return DS_OK;
 }
 
