@@ -291,10 +291,14 @@ def run_native(args):
         d2h = int(out_pin.numel())
 
         def e2e_step():
+            # the caller's frames stay valid for the step, so the uploads are queued (DS_UPLOAD_ASYNC), the composite
+            # works through the canvas in row slices as the frames arrive and the download copies every slice out
+            # as soon as it is final: host->device copies, kernels and device->host copies overlap
             for i, arr in zip(mine, host_np):
-                cv.upload(i, arr, xfs[i])
-            cv.composite()
+                cv.upload(i, arr, xfs[i], async_=True)
+            cv.composite_async()
             cv.download(out=out_pin.numpy(), want_mask=False)
+            cv.synchronize()
 
         e2e_step()
         barrier()

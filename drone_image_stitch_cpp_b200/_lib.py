@@ -35,11 +35,15 @@ class ds_transform(C.Structure):
     ]
 
 
+DS_UPLOAD_ASYNC = 1
+
+
 class ds_frame_opts(C.Structure):
     _fields_ = [("seam_mask", C.c_void_p), ("seam_mask_stride", C.c_size_t), ("channel_gain", C.POINTER(C.c_float)),
                 ("seam_lowres", C.c_void_p), ("seam_lowres_w", C.c_int32), ("seam_lowres_h", C.c_int32),
                 ("seam_lowres_stride", C.c_size_t),
-                ("compensator_gain", C.POINTER(C.c_double)), ("gain_map", C.c_void_p), ("gain_map_stride", C.c_size_t)]
+                ("compensator_gain", C.POINTER(C.c_double)), ("gain_map", C.c_void_p), ("gain_map_stride", C.c_size_t),
+                ("flags", C.c_uint32)]
 
 
 class ds_canvas_desc(C.Structure):
@@ -49,7 +53,8 @@ class ds_canvas_desc(C.Structure):
         ("out_format", C.c_int32), ("device", C.c_int32),
         ("band_y0", C.c_int32), ("band_y1", C.c_int32),
         ("stream", C.c_void_p),
-        ("reserved", C.c_int32 * 8),
+        ("pipeline_rows", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

@@ -75,7 +75,7 @@ class Canvas:
     """One ds_canvas handle (one GPU, one row band)."""
 
     def __init__(self, roi, blend="multiband", bands=5, sharpness=0.02, out_format="bgr", device=0, band=None,
-                 stream=None, lib=None):
+                 stream=None, lib=None, pipeline_rows=0):
         self.lib = lib or L.default_library()
         d = L.ds_canvas_desc()
         d.x, d.y, d.width, d.height = [int(v) for v in roi]
@@ -87,7 +87,9 @@ class Canvas:
         if band is not None:
             d.band_y0, d.band_y1 = int(band[0]), int(band[1])
         d.stream = C.c_void_p(stream) if stream else None
+        d.pipeline_rows = int(pipeline_rows)   # 0 auto, > 0 always row slices of about that height, < 0 never
         self.desc = d
+        self._pending = []   # buffers lent to asynchronous uploads
         self.roi = tuple(int(v) for v in roi)
         self.bpp = 4 if out_format == "bgra" else 3
         self._h = C.c_void_p()
@@ -108,12 +110,16 @@ class Canvas:
         arr = (C.c_int32 * 4)(*[int(v) for v in frame_roi])
         return bool(self.lib.dll.ds_frame_touches_band(C.byref(self.desc), arr))
 
-    def upload(self, idx, img, xf, seam_mask=None, channel_gain=None, seam_lowres=None, compensator_gain=None, gain_map=None):
-        """img: HxWx3 uint8 (numpy; any row stride) or a (ptr, w, h, stride) tuple."""
+    def upload(self, idx, img, xf, seam_mask=None, channel_gain=None, seam_lowres=None, compensator_gain=None, gain_map=None,
+               async_=False):
+        """img: HxWx3 uint8 (numpy; any row stride) or a (ptr, w, h, stride) tuple.
+        async_: DS_UPLOAD_ASYNC - `img` (pinned) must stay valid and unchanged until composite() / synchronize() /
+        a full download() has returned."""
         opts = None
         keep = []
-        if any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map)):
+        if async_ or any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map)):
             opts = L.ds_frame_opts()
+            opts.flags = L.DS_UPLOAD_ASYNC if async_ else 0
             if compensator_gain is not None:
                 cg = (C.c_double * 3)(*[float(v) for v in compensator_gain])
                 keep.append(cg)
@@ -145,6 +151,8 @@ class Canvas:
             ptr, w, h, stride = img.ctypes.data, img.shape[1], img.shape[0], img.strides[0]
         self.lib.check(self.lib.dll.ds_upload_frame(self._h, int(idx), C.c_void_p(ptr), int(w), int(h), int(stride),
                                                     C.byref(xf), C.byref(opts) if opts is not None else None))
+        if async_:
+            self._pending.append((img, keep))
 
     def upload_device(self, idx, dev_ptr, w, h, stride, xf):
         self.lib.check(self.lib.dll.ds_upload_frame_device(self._h, int(idx), C.c_void_p(dev_ptr), int(w), int(h),
@@ -152,12 +160,14 @@ class Canvas:
 
     def composite(self):
         self.lib.check(self.lib.dll.ds_composite(self._h))
+        self._pending.clear()
 
     def composite_async(self):
         self.lib.check(self.lib.dll.ds_composite_async(self._h))
 
     def synchronize(self):
         self.lib.check(self.lib.dll.ds_synchronize(self._h))
+        self._pending.clear()
 
     def info(self):
         i = L.ds_canvas_info()
@@ -229,10 +239,13 @@ def compose_panorama(images, Ks, Rs, scale, blend="multiband", bands=5, sharpnes
     rois = [warp_roi(xf, im.shape[1], im.shape[0], lib) for xf, im in zip(xfs, images)]
     roi = result_roi(rois)
     cv = Canvas(roi, blend, bands, sharpness, out_format, device, lib=lib)
+    # the images outlive this call: queue the uploads, let the composite chase them slice by slice, and copy each
+    # slice out as it completes (DS_UPLOAD_ASYNC, include/dronestitch.h)
     for i, (im, xf) in enumerate(zip(images, xfs)):
-        cv.upload(i, im, xf)
-    cv.composite()
+        cv.upload(i, im, xf, async_=True)
+    cv.composite_async()
     pano, mask = cv.download()
+    cv.synchronize()
     if return_canvas:
         return pano, mask, roi, cv
     cv.close()

@@ -195,18 +195,43 @@ struct ExpandParams {
     int w, h;
 };
 struct ExpandBody {
-    static constexpr int PER_BLOCK = 2048;
+    static constexpr int PER_BLOCK = 1024;   // items per block; one item = 4 consecutive pixels of a row
     static int smem_bytes() { return 0; }
-    static long long blocks(const ExpandParams& p) { return ((long long)p.w * p.h + PER_BLOCK - 1) / PER_BLOCK; }
+    static long long blocks(const ExpandParams& p) { return ((long long)((p.w + 3) / 4) * p.h + PER_BLOCK - 1) / PER_BLOCK; }
     template <int NT>
     DS_DM void run(const ExpandParams& p, int block, int tid, unsigned char*) {
-        const long long n = (long long)p.w * p.h;
+        const int qw = (p.w + 3) / 4;
+        const long long n = (long long)qw * p.h;
         for (int i = tid; i < PER_BLOCK; i += NT) {
             const long long idx = (long long)block * PER_BLOCK + i;
             if (idx >= n) break;
-            const int y = (int)(idx / p.w), x = (int)(idx - (long long)y * p.w);
+            const int y = (int)(idx / qw), x = (int)(idx - (long long)y * qw) * 4;
             const uint8_t* s = p.src + (size_t)y * p.src_stride + (size_t)x * 3;
-            p.dst[(size_t)y * p.dst_pitch + x] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16);
+            uint32_t* d = p.dst + (size_t)y * p.dst_pitch + x;   // dst_pitch is a multiple of 4 pixels: 16-byte aligned
+            if (x + 4 <= p.w && (((size_t)s) & 3) == 0) {
+                // 12 source bytes as three words -> four BGRX words, one 128-bit store
+                const uint32_t w0 = ld_ro((const uint32_t*)s), w1 = ld_ro((const uint32_t*)s + 1), w2 = ld_ro((const uint32_t*)s + 2);
+                *(uint4*)d = make_u4(w0 & 0xffffffu, (w0 >> 24) | ((w1 & 0xffffu) << 8), (w1 >> 16) | ((w2 & 0xffu) << 16), w2 >> 8);
+            } else {
+                for (int k = 0; k < 4 && x + k < p.w; k++)
+                    d[k] = (uint32_t)s[3 * k] | ((uint32_t)s[3 * k + 1] << 8) | ((uint32_t)s[3 * k + 2] << 16);
+            }
+        }
+    }
+};
+
+// Copies the host-built launch metadata (tile lists, frame descriptors, tensor maps) from mapped pinned host
+// memory into its device arena: a kernel instead of a DMA so that it never queues behind frame uploads.
+struct MetaCopyParams { const uint4* src; uint4* dst; long long n16; };
+struct MetaCopyBody {
+    static constexpr int PER_BLOCK = 1024;
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const MetaCopyParams& p, int block, int tid, unsigned char*) {
+        for (int i = tid; i < PER_BLOCK; i += NT) {
+            const long long idx = (long long)block * PER_BLOCK + i;
+            if (idx >= p.n16) break;
+            p.dst[idx] = p.src[idx];
         }
     }
 };
@@ -1586,6 +1611,7 @@ struct FinalizeL0Body {
 typedef MBBody<64, true> MBBodyL0;
 typedef MBBody<32, false> MBBodyLN;
 DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
+DS_DEFINE_KERNEL(ds_meta_copy, MetaCopyBody, 256, MetaCopyParams, 1)
 DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
 DS_DEFINE_KERNEL(ds_seam_upsize, SeamUpBody, 256, SeamUpParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)

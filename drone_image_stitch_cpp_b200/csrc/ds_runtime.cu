@@ -67,6 +67,20 @@ int d2h_2d(void* h, size_t hp, const void* d, size_t dp, size_t wbytes, size_t r
 }
 int d2h(void* h, const void* d, size_t n, stream_t s) { DS_CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); return DS_OK; }
 int stream_sync(stream_t s) { DS_CK(cudaStreamSynchronize(s)); return DS_OK; }
+// events order the upload, compute and download streams against each other
+typedef cudaEvent_t event_t;
+int ev_make(event_t* e) { if (!*e) DS_CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); return DS_OK; }
+void ev_drop(event_t e) { if (e) cudaEventDestroy(e); }
+int ev_record(event_t e, stream_t s) { DS_CK(cudaEventRecord(e, s)); return DS_OK; }
+int ev_wait(stream_t s, event_t e) { DS_CK(cudaStreamWaitEvent(s, e, 0)); return DS_OK; }
+int ev_sync(event_t e) { DS_CK(cudaEventSynchronize(e)); return DS_OK; }
+// pinned host memory the device can read directly (zero-copy source of the launch metadata)
+int pinned_alloc(void** host, void** dev_view, size_t bytes) {
+    DS_CK(cudaHostAlloc(host, bytes, cudaHostAllocMapped));
+    DS_CK(cudaHostGetDevicePointer(dev_view, *host, 0));
+    return DS_OK;
+}
+void pinned_free(void* host) { if (host) cudaFreeHost(host); }
 
 template <class Body, int NT, class P>
 int launch(const P& p, long long blocks, stream_t s, int smem_bytes) {
@@ -102,6 +116,19 @@ int d2h_2d(void* h, size_t hp, const void* d, size_t dp, size_t wbytes, size_t r
 }
 int d2h(void* h, const void* d, size_t n, stream_t) { memcpy(h, d, n); return DS_OK; }
 int stream_sync(stream_t) { return DS_OK; }
+typedef int event_t;
+int ev_make(event_t* e) { *e = 1; return DS_OK; }
+void ev_drop(event_t) {}
+int ev_record(event_t, stream_t) { return DS_OK; }
+int ev_wait(stream_t, event_t) { return DS_OK; }
+int ev_sync(event_t) { return DS_OK; }
+int pinned_alloc(void** host, void** dev_view, size_t bytes) {
+    *host = malloc(bytes ? bytes : 1);
+    if (!*host) return fail(DS_ERR_OOM, "malloc(%zu) failed", bytes);
+    *dev_view = *host;
+    return DS_OK;
+}
+void pinned_free(void* host) { free(host); }
 
 template <class Body, int NT, class P>
 int launch(const P& p, long long blocks, stream_t, int smem_bytes) {
@@ -164,16 +191,29 @@ struct Frame {
     uint32_t* d_mbits = nullptr; size_t mbits_cap = 0;
     uint8_t* d_seam = nullptr; size_t seam_cap = 0;
     float* d_gainmap = nullptr; size_t gainmap_cap = 0;
-    FrameDev dev;
+    FrameDev dev{};
+    event_t ready = 0;      // recorded on the upload stream once the frame's device data is complete
+    uint64_t seq = 0;       // position in upload order
+    bool mask_done = false; // FEATHER: mask bit plane built for the current composite
 };
 
 struct LevelPlan {
     int T = 0, tiles_x = 0, tiles_y = 0;
     Range own{0, 0};   // rows of this level whose tiles run (production + accumulation)
     Range acc{0, 0};   // rows whose dst is written / consumed by the collapse
-    int* d_off = nullptr; int* d_fr = nullptr; int* d_ids = nullptr;
-    size_t off_cap = 0, fr_cap = 0, ids_cap = 0;
+    int* d_off = nullptr; int* d_fr = nullptr; int* d_ids = nullptr;   // inside the canvas meta arena
     int n_ids = 0;
+};
+
+// One internally pipelined slice of the handle's rows (DESIGN.md "Upload / compute / download pipeline").
+struct SubBand {
+    Range rows{0, 0};          // level-0 output rows
+    Range own[DS_MAXL];        // feed rows per level: [previous slice's end, this slice's end) - nothing is recomputed
+    Range coll[DS_MAXL];       // rows of level l the collapse into level l finalises in this slice
+    int ids_first[DS_MAXL], ids_count[DS_MAXL];   // the slice's run of LevelPlan::d_ids per level (heaviest tiles first)
+    event_t fed0 = 0;          // recorded after the slice's level-0 feed
+    event_t fed = 0;           // (unused)
+    event_t done = 0;          // recorded after the slice's last launch
 };
 
 }  // namespace
@@ -183,8 +223,22 @@ struct ds_canvas {
     int L = 0;
     int pw = 0, ph = 0;      // padded canvas
     Range band{0, 0};        // level-0 rows this handle owns
-    stream_t stream = 0;
+    stream_t stream = 0;     // compute
+    stream_t bulk = 0, tail = 0;   // sliced schedule: level-0 feeds (low priority) / the rest of each slice (high)
+    event_t ev_start = 0;
+    stream_t up = 0, dl = 0; // uploads (H2D + expansion), downloads (D2H)
+    int meta_slice_rows = -2;   // slice height the launch metadata was built for
     bool own_stream = false;
+    event_t ev_done = 0;     // end of the last composite (compute stream)
+    bool ev_done_valid = false;
+    event_t ev_meta = 0;     // metadata copy kernel finished reading h_meta
+    bool ev_meta_valid = false;
+    uint64_t up_seq = 0;     // uploads so far
+    uint64_t waited_seq = 0; // the compute stream already waits for uploads up to this one
+    bool async_pending = false;   // an upload with DS_UPLOAD_ASYNC since the last composite
+    std::vector<SubBand> subs;    // slices of the last composite
+    void* h_meta = nullptr; void* h_meta_dev = nullptr; size_t h_meta_cap = 0;
+    void* d_meta = nullptr; size_t d_meta_cap = 0;
     int lw[DS_MAXL], lh[DS_MAXL];
     px16* d_lvl[DS_MAXL];    // allocated rows [lvl_rows[l].lo, lvl_rows[l].hi); pointer is the virtual row-0 base
     px16* d_lvl_alloc[DS_MAXL];
@@ -193,8 +247,8 @@ struct ds_canvas {
     uint8_t* d_mask = nullptr; size_t mask_pitch = 0;
     int out_hi = 0;
     std::vector<Frame> frames;
-    FrameDev* d_frames = nullptr; size_t frames_cap = 0;
-    void* d_tmaps = nullptr; size_t tmaps_cap = 0;   // CUtensorMap[frame][DS_MAXL][2], levels 1..L-1
+    FrameDev* d_frames = nullptr;                    // inside the meta arena
+    void* d_tmaps = nullptr;                         // CUtensorMap[frame][DS_MAXL][2], levels 1..L-1 (meta arena)
     bool tmaps_ok = false;
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
@@ -210,12 +264,51 @@ struct ds_canvas {
     struct Prof { const char* name; int level; int64_t ab; float ms; };
     std::vector<Prof> prof;
 #if DS_CUDA
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    struct Trace { char label[40]; cudaEvent_t ev; };
+    std::vector<Trace> trace;           // DS_TRACE=1: stream timeline of one step, printed by ds_synchronize
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> prof_ev;   // 2 per launch
 #endif
 };
 
 namespace {
+
+// DS_TRACE=1 (measurement aid): timestamps on the upload / compute / download streams.
+#if DS_CUDA
+bool trace_on() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DS_TRACE"); v = (e && atoi(e) > 0) ? 1 : 0; }
+    return v == 1;
+}
+#endif
+void trace_mark(ds_canvas* c, stream_t s, const char* what, int idx) {
+#if DS_CUDA
+    if (!trace_on() || c->trace.size() > 4096) return;
+    ds_canvas::Trace t;
+    snprintf(t.label, sizeof(t.label), "%s %d", what, idx);
+    if (cudaEventCreate(&t.ev) != cudaSuccess) return;
+    cudaEventRecord(t.ev, s);
+    c->trace.push_back(t);
+#else
+    (void)c; (void)s; (void)what; (void)idx;
+#endif
+}
+void trace_dump(ds_canvas* c) {
+#if DS_CUDA
+    if (c->trace.empty()) return;
+    for (const ds_canvas::Trace& t : c->trace) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->trace[0].ev, t.ev);
+        fprintf(stderr, "[ds_trace] %8.3f ms  %s\n", ms, t.label);
+        if (&t != &c->trace[0]) cudaEventDestroy(t.ev);
+    }
+    cudaEventDestroy(c->trace[0].ev);
+    c->trace.clear();
+    cudaGetLastError();
+#else
+    (void)c;
+#endif
+}
 
 int grow(ds_canvas* c, void** p, size_t* cap, size_t need) {
     if (need <= *cap && *p) return DS_OK;
@@ -237,6 +330,7 @@ int set_device(const ds_canvas* c) {
 }
 
 Range clip(Range r, int n) { return Range{std::max(r.lo, 0), std::min(r.hi, n)}; }
+Range meet(Range a, Range b) { return Range{std::max(a.lo, b.lo), std::max(std::max(a.lo, b.lo), std::min(a.hi, b.hi))}; }
 
 // Row plan of a band (see DESIGN.md "Row bands"): which rows of every level this handle must
 // accumulate (acc = what the collapse reads) and which tile rows must run (own) so that the
@@ -320,9 +414,109 @@ int placement(const ds_transform* xf, int w, int h, int* out) {
 }
 
 // Build per-level tile -> frame lists (feed order) on the host and upload them.
+int default_pipeline_rows() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DS_PIPELINE_ROWS");
+        v = e ? atoi(e) : 0;
+        if (v <= 0) v = 768;
+    }
+    return v;
+}
+
+// Cuts the handle's rows into slices that run one after the other on the compute stream. Slice b feeds, at every
+// level, the rows between the end of slice b-1 and its own end (band rows + the pyramid halo below them, as
+// plan_rows gives for a band ending there): the per-frame pyramids and the Laplacian levels a slice leaves behind
+// are final, so the next slice continues from them and no row is computed twice. Its collapse finalises the rows
+// up to its band edge (+ the 1-2 rows the next level down taps), again continuing where the previous one ended.
+void plan_subbands(ds_canvas* c, int rows_per_slice) {
+    const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
+    const int align = mb ? (1 << c->L) : FeatherBody::TH;
+    const Range band{c->band.lo, mb ? c->band.hi : c->out_hi};
+    std::vector<int> edges{band.lo, band.hi};
+    if (rows_per_slice > 0 && band.hi - band.lo >= 2 * rows_per_slice) {
+        const int step = std::max((rows_per_slice + align - 1) / align * align, align);
+        // (1) edges where the set of frames a slice waits for changes: the last row a slice may end at without
+        // reading frame f is f's first row minus the pyramid halo below a band edge
+        int halo = 0;
+        if (mb) {
+            Range acc[DS_MAXL], own[DS_MAXL];
+            const int mid = band.lo + (band.hi - band.lo) / 2 / align * align;
+            plan_rows(c->L, c->lh, Range{band.lo, mid}, acc, own);
+            halo = std::max(own[0].hi - mid, 0);
+        }
+        std::vector<int> dep;
+        for (const Frame& f : c->frames) {
+            if (!f.used) continue;
+            const int top = mb ? f.ry : f.dev.cy;
+            int y = (top - halo) / align * align;
+            if (top - halo < 0) y = band.lo;
+            if (y > band.lo + step / 3 && y < band.hi - step / 3) dep.push_back(y);
+        }
+        std::sort(dep.begin(), dep.end());
+        int prev = band.lo;   // keep an edge only if it is at least a third of a slice below the previous one
+        for (int y : dep)
+            if (y - prev >= step / 3) { edges.insert(edges.end() - 1, y); prev = y; }
+        // (2) cut what is left into pieces of about `step` rows
+        std::vector<int> fine;
+        for (size_t i = 0; i + 1 < edges.size(); i++) {
+            const int lo = edges[i], hi = edges[i + 1];
+            const int n = std::max(1, (hi - lo + step / 2) / step);
+            const int piece = ((hi - lo + n - 1) / n + align - 1) / align * align;
+            for (int k = 0; k < n && lo + k * piece < hi; k++) fine.push_back(lo + k * piece);
+        }
+        fine.push_back(band.hi);
+        edges.swap(fine);
+    }
+    std::vector<event_t> keep_done, keep_fed, keep_fed0;
+    for (SubBand& sb : c->subs) { keep_done.push_back(sb.done); keep_fed.push_back(sb.fed); keep_fed0.push_back(sb.fed0); }
+    c->subs.clear();
+    Range prev_own[DS_MAXL], prev_coll[DS_MAXL];
+    for (int l = 0; l <= c->L; l++) { prev_own[l] = Range{0, c->plan[l].own.lo}; prev_coll[l] = Range{0, c->plan[l].acc.lo}; }
+    for (size_t i = 0; i + 1 < edges.size(); i++) {
+        SubBand sb;
+        sb.rows = Range{edges[i], edges[i + 1]};
+        const bool last = i + 2 == edges.size();
+        for (int l = 0; l < DS_MAXL; l++) { sb.own[l] = sb.coll[l] = Range{0, 0}; sb.ids_first[l] = sb.ids_count[l] = 0; }
+        if (mb) {
+            Range acc[DS_MAXL], own[DS_MAXL];
+            plan_rows(c->L, c->lh, sb.rows, acc, own);
+            for (int l = 0; l <= c->L; l++) {
+                const Range O = c->plan[l].own, A = c->plan[l].acc;
+                const int h = std::max(last ? O.hi : std::min(own[l].hi, O.hi), prev_own[l].hi);
+                sb.own[l] = Range{prev_own[l].hi, h};
+                const int k = std::max(last ? A.hi : std::min(acc[l].hi, A.hi), prev_coll[l].hi);
+                sb.coll[l] = Range{prev_coll[l].hi, k};
+                prev_own[l] = sb.own[l]; prev_coll[l] = sb.coll[l];
+            }
+        }
+        if (c->subs.size() < keep_done.size()) {
+            sb.done = keep_done[c->subs.size()]; sb.fed = keep_fed[c->subs.size()]; sb.fed0 = keep_fed0[c->subs.size()];
+        }
+        c->subs.push_back(sb);
+    }
+    for (size_t i = c->subs.size(); i < keep_done.size(); i++) { ev_drop(keep_done[i]); ev_drop(keep_fed[i]); ev_drop(keep_fed0[i]); }
+}
+
+// Launch metadata of a composite: per level the CSR tile -> frames lists and the ids of the tiles that run,
+// the frame descriptors and the TMA tensor maps. Everything is assembled in one host buffer and moved to one
+// device arena by a copy kernel on the compute stream (ds_meta_copy), so rebuilding it neither blocks the host
+// nor waits behind frame uploads in flight.
+struct MetaBuilder {
+    std::vector<unsigned char> buf;
+    size_t add(const void* src, size_t bytes) {
+        const size_t off = (buf.size() + 255) & ~(size_t)255;
+        buf.resize(off + std::max<size_t>(bytes, 16), 0);
+        if (bytes) memcpy(buf.data() + off, src, bytes);
+        return off;
+    }
+};
+
 int build_lists(ds_canvas* c) {
     const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
     const int nl = mb ? c->L + 1 : 1;
+    MetaBuilder mbd;
+    size_t off_off[DS_MAXL], fr_off[DS_MAXL], ids_off[DS_MAXL];
     std::vector<int> counts, off, fr, ids;
     for (int l = 0; l < nl; l++) {
         LevelPlan& pl = c->plan[l];
@@ -372,30 +566,35 @@ int build_lists(ds_canvas* c) {
                 c->ln_fast_ok = false;
             }
         }
-        // tiles to run: every tile in the own tile rows (empty ones still write zeros)
+        // tiles to run, per slice: every tile in the slice's tile rows (empty ones still write zeros), the ones with
+        // the most frames first - blocks are dispatched in id order, so the launch drains on its cheapest tiles
         ids.clear();
-        for (int ty = ty_lo; ty < ty_hi; ty++)
-            for (int tx = 0; tx < pl.tiles_x; tx++) ids.push_back(ty * pl.tiles_x + tx);
+        for (SubBand& sb : c->subs) {
+            const Range rows = mb ? sb.own[l] : meet(sb.rows, pl.own);
+            sb.ids_first[l] = (int)ids.size();
+            if (rows.lo < rows.hi) {
+                const int ty0 = rows.lo / TH, ty1 = (rows.hi + TH - 1) / TH;
+                for (int ty = ty0; ty < ty1; ty++)
+                    for (int tx = 0; tx < pl.tiles_x; tx++) ids.push_back(ty * pl.tiles_x + tx);
+                static const bool sort_tiles = getenv("DS_SORT_TILES") && atoi(getenv("DS_SORT_TILES")) != 0;   // experiment: row-major order wins (L2 locality)
+                if (sort_tiles) std::stable_sort(ids.begin() + sb.ids_first[l], ids.end(), [&](int a, int b) {
+                    return counts[(size_t)a + 1] - counts[a] > counts[(size_t)b + 1] - counts[b];
+                });
+            }
+            sb.ids_count[l] = (int)ids.size() - sb.ids_first[l];
+        }
         pl.n_ids = (int)ids.size();
-        int rc;
-        if ((rc = grow(c, (void**)&pl.d_off, &pl.off_cap, counts.size() * sizeof(int)))) return rc;
-        if ((rc = grow(c, (void**)&pl.d_fr, &pl.fr_cap, fr.size() * sizeof(int)))) return rc;
-        if ((rc = grow(c, (void**)&pl.d_ids, &pl.ids_cap, std::max<size_t>(ids.size(), 1) * sizeof(int)))) return rc;
-        if ((rc = h2d(pl.d_off, counts.data(), counts.size() * sizeof(int), c->stream))) return rc;
-        if ((rc = h2d(pl.d_fr, fr.data(), fr.size() * sizeof(int), c->stream))) return rc;
-        if (!ids.empty() && (rc = h2d(pl.d_ids, ids.data(), ids.size() * sizeof(int), c->stream))) return rc;
-        // pageable h2d is synchronous w.r.t. the host buffers; vectors may be reused safely
-        if ((rc = stream_sync(c->stream))) return rc;
+        off_off[l] = mbd.add(counts.data(), counts.size() * sizeof(int));
+        fr_off[l] = mbd.add(fr.data(), fr.size() * sizeof(int));
+        ids_off[l] = mbd.add(ids.data(), ids.size() * sizeof(int));
     }
     // frame descriptors
     std::vector<FrameDev> fd(c->frames.size());
     for (size_t i = 0; i < c->frames.size(); i++) {
         if (c->frames[i].used) fd[i] = c->frames[i].dev; else memset(&fd[i], 0, sizeof(FrameDev));
     }
-    int rc;
-    if ((rc = grow(c, (void**)&c->d_frames, &c->frames_cap, std::max<size_t>(fd.size(), 1) * sizeof(FrameDev)))) return rc;
-    if (!fd.empty() && (rc = h2d(c->d_frames, fd.data(), fd.size() * sizeof(FrameDev), c->stream))) return rc;
-    if ((rc = stream_sync(c->stream))) return rc;
+    const size_t frames_off = mbd.add(fd.data(), fd.size() * sizeof(FrameDev));
+    size_t tmaps_off = 0;
     c->tmaps_ok = false;
 #if DS_CUDA
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L >= 1 && !c->frames.empty()) {
@@ -416,13 +615,35 @@ int build_lists(ds_canvas* c) {
             }
         }
         if (ok) {
-            if ((rc = grow(c, &c->d_tmaps, &c->tmaps_cap, tm.size() * sizeof(CUtensorMap)))) return rc;
-            if ((rc = h2d(c->d_tmaps, tm.data(), tm.size() * sizeof(CUtensorMap), c->stream))) return rc;
-            if ((rc = stream_sync(c->stream))) return rc;
+            tmaps_off = mbd.add(tm.data(), tm.size() * sizeof(CUtensorMap));
             c->tmaps_ok = true;
         }
     }
 #endif
+    // arenas (grown geometrically so that steady-state rebuilds allocate nothing)
+    int rc;
+    const size_t need = (mbd.buf.size() + 255) & ~(size_t)255;
+    if (c->ev_meta_valid && (rc = ev_sync(c->ev_meta))) return rc;   // the previous copy kernel has read h_meta
+    if (need > c->h_meta_cap) {
+        pinned_free(c->h_meta); c->h_meta = nullptr; c->h_meta_cap = 0;
+        const size_t cap = need + need / 2;
+        if ((rc = pinned_alloc(&c->h_meta, &c->h_meta_dev, cap))) return rc;
+        c->h_meta_cap = cap;
+    }
+    if (need > c->d_meta_cap && (rc = grow(c, &c->d_meta, &c->d_meta_cap, need + need / 2))) return rc;
+    memcpy(c->h_meta, mbd.buf.data(), mbd.buf.size());
+    MetaCopyParams cp{(const uint4*)c->h_meta_dev, (uint4*)c->d_meta, (long long)(need / 16)};
+    if ((rc = launch<MetaCopyBody, 256>(cp, (cp.n16 + MetaCopyBody::PER_BLOCK - 1) / MetaCopyBody::PER_BLOCK, c->stream, 0))) return rc;
+    if ((rc = ev_make(&c->ev_meta)) || (rc = ev_record(c->ev_meta, c->stream))) return rc;
+    c->ev_meta_valid = true;
+    char* base = (char*)c->d_meta;
+    for (int l = 0; l < nl; l++) {
+        c->plan[l].d_off = (int*)(base + off_off[l]);
+        c->plan[l].d_fr = (int*)(base + fr_off[l]);
+        c->plan[l].d_ids = (int*)(base + ids_off[l]);
+    }
+    c->d_frames = (FrameDev*)(base + frames_off);
+    c->d_tmaps = c->tmaps_ok ? (void*)(base + tmaps_off) : nullptr;
     c->dirty = false;
     return DS_OK;
 }
@@ -442,7 +663,7 @@ OutParams out_params(const ds_canvas* c) {
 }
 
 // Marks the start / end of one launch for the per-kernel profile (no-ops unless profiling is on).
-int prof_mark(ds_canvas* c, bool begin, const char* name, int level, int64_t ab) {
+int prof_mark(ds_canvas* c, stream_t st, bool begin, const char* name, int level, int64_t ab) {
     if (!c->profiling) return DS_OK;
     if (begin) c->prof.push_back(ds_canvas::Prof{name, level, ab, 0.f});
 #if DS_CUDA
@@ -452,7 +673,9 @@ int prof_mark(ds_canvas* c, bool begin, const char* name, int level, int64_t ab)
         DS_CK(cudaEventCreate(&e));
         c->prof_ev.push_back(e);
     }
-    DS_CK(cudaEventRecord(c->prof_ev[(c->prof.size() - 1) * 2 + (begin ? 0 : 1)], c->stream));
+    DS_CK(cudaEventRecord(c->prof_ev[(c->prof.size() - 1) * 2 + (begin ? 0 : 1)], st));
+#else
+    (void)st;
 #endif
     return DS_OK;
 }
@@ -469,85 +692,192 @@ ABModel ab_inputs(const ds_canvas* c) {
     return m;
 }
 
+// ---- launches of one composite, per row slice (SubBand). A handle that is not pipelined has one slice.
+
+int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABModel& abm) {
+    int rc;
+    LevelPlan& pl = c->plan[l];
+    const Range own = sb.own[l];
+    if (own.lo >= own.hi) return DS_OK;
+    const int first = sb.ids_first[l], count = sb.ids_count[l];
+    const Range acc = meet(own, pl.acc);   // every row that runs also writes its dst (if this handle stores it)
+    MBParams mp;
+    mp.frames = c->d_frames; mp.tile_off = pl.d_off; mp.tile_frames = pl.d_fr; mp.tile_ids = pl.d_ids + first;
+    mp.tiles_x = pl.tiles_x; mp.level = l; mp.L = c->L;
+    mp.dst = c->d_lvl[l]; mp.dst_w = c->lw[l]; mp.dst_h = c->lh[l];
+    mp.acc_y0 = acc.lo; mp.acc_y1 = acc.hi;
+    mp.own_y0 = own.lo; mp.own_y1 = own.hi;
+    mp.tmaps = c->tmaps_ok ? c->d_tmaps : nullptr;
+    const double q = 1.0 / (double)(1ull << (2 * l));
+    double ab;
+    if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
+    else if (l < c->L) ab = abm.A * q * (40.0 + 2.5);
+    else ab = abm.A * q * 40.0;
+    ab *= (double)count / (double)std::max(pl.n_ids, 1);
+    if ((rc = prof_mark(c, st, true, "mb_feed", l, (int64_t)ab))) return rc;
+    if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, count, st, MBFastBody<64, true>::smem_bytes());
+    else if (l > 0 && l < c->L && c->ln_fast_ok) rc = launch<MBFastBody<32, false>, 256>(mp, count, st, MBFastBody<32, false>::smem_bytes());
+    else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, count, st, MBBody<64, true>::smem_bytes());
+    else rc = launch<MBBody<32, false>, 256>(mp, count, st, MBBody<32, false>::smem_bytes());
+    if (rc) return rc;
+    if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
+    c->launches++;
+    return DS_OK;
+}
+
+// collapse step l: lvl_{l-1} = sat(pyrUp(lvl_l) + lvl_{l-1}) over the rows of level l-1 this slice finalises
+int launch_collapse(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABModel& abm) {
+    int rc;
+    const Range rows = sb.coll[l - 1];
+    if (rows.lo >= rows.hi) return DS_OK;
+    CollapseParams cp;
+    cp.coarse = c->d_lvl[l]; cp.cw = c->lw[l]; cp.ch = c->lh[l];
+    cp.fine = c->d_lvl[l - 1]; cp.fw = c->lw[l - 1]; cp.fh = c->lh[l - 1];
+    cp.y0 = rows.lo; cp.y1 = rows.hi;
+    cp.final = (l == 1);
+    cp.o = out_params(c);
+    const long long items = CollapseBody::items(cp);
+    const double q = 1.0 / (double)(1ull << (2 * (l - 1)));
+    const Range all = c->plan[l - 1].acc;
+    const double ab = (abm.C * 17.5 * q - (l == 1 ? 2.0 * abm.C : 0.0)) * (double)(rows.hi - rows.lo) / (double)std::max(all.hi - all.lo, 1);
+    if ((rc = prof_mark(c, st, true, "mb_collapse", l - 1, (int64_t)ab))) return rc;
+    if ((rc = launch<CollapseBody, 256>(cp, (items + CollapseBody::PER_BLOCK - 1) / CollapseBody::PER_BLOCK, st, 0))) return rc;
+    if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
+    c->launches++;
+    return DS_OK;
+}
+
+int launch_finalize_l0(ds_canvas* c, stream_t st, const SubBand& sb) {
+    const Range rows = meet(sb.rows, Range{c->band.lo, c->out_hi});
+    if (rows.lo >= rows.hi) return DS_OK;
+    FinalizeL0Params fp{c->d_lvl[0], c->lw[0], c->lh[0], rows.lo, rows.hi, out_params(c)};
+    const long long n = (long long)fp.fw * (fp.y1 - fp.y0);
+    int rc = launch<FinalizeL0Body, 256>(fp, (n + FinalizeL0Body::PER_BLOCK - 1) / FinalizeL0Body::PER_BLOCK, st, 0);
+    if (!rc) c->launches++;
+    return rc;
+}
+
+int launch_feather(ds_canvas* c, stream_t st, const SubBand& sb, const ABModel& abm) {
+    int rc;
+    LevelPlan& pl = c->plan[0];
+    const Range rows = meet(sb.rows, pl.own);
+    if (rows.lo >= rows.hi) return DS_OK;
+    const int TH = FeatherBody::TH;
+    const int ty0 = rows.lo / TH, ty1 = (rows.hi + TH - 1) / TH;
+    // mask bit planes of the frames this slice blends (once per composite)
+    for (size_t i = 0; i < c->frames.size(); i++) {
+        Frame& f = c->frames[i];
+        if (!f.used || f.mask_done) continue;
+        if (f.dev.cy >= ty1 * TH || f.dev.cy + f.bh <= ty0 * TH) continue;
+        MaskBitsParams mp{c->d_frames, (int)i, f.d_mbits};
+        const long long nwords = (long long)f.dev.mbits_pitch * f.bh;
+        if ((rc = prof_mark(c, st, true, "feather_mask", -1, 0))) return rc;
+        if ((rc = launch<MaskBitsBody, 256>(mp, (nwords + MaskBitsBody::WORDS_PER_BLOCK - 1) / MaskBitsBody::WORDS_PER_BLOCK, st, 0))) return rc;
+        if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
+        c->launches++;
+        f.mask_done = true;
+    }
+    const int first = sb.ids_first[0], count = sb.ids_count[0];
+    FeatherParams fp;
+    fp.frames = c->d_frames; fp.tile_off = pl.d_off; fp.tile_frames = pl.d_fr; fp.tile_ids = pl.d_ids + first;
+    fp.tiles_x = pl.tiles_x; fp.sharpness = c->desc.sharpness; fp.R = c->feather_R;
+    fp.row0 = rows.lo; fp.row1 = rows.hi;
+    fp.o = out_params(c);
+    const double ab = (3.0 * abm.S + 4.0 * abm.C) * (double)count / (double)std::max(pl.n_ids, 1);
+    if ((rc = prof_mark(c, st, true, "feather_blend", 0, (int64_t)ab))) return rc;
+    if ((rc = launch<FeatherBody, 256>(fp, count, st, FeatherBody::smem_bytes()))) return rc;
+    if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
+    c->launches++;
+    return DS_OK;
+}
+
+// The compute stream waits for the uploads slice `sb` reads: every frame whose rows meet the slice's feed rows at
+// some level. The upload stream is in order, so waiting for the latest of them is enough.
+int wait_for_frames(ds_canvas* c, stream_t st, uint64_t* waited_seq, const SubBand& sb) {
+    const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
+    const Frame* latest = nullptr;
+    for (const Frame& f : c->frames) {
+        if (!f.used || f.seq <= *waited_seq) continue;
+        bool touches = false;
+        if (mb) {
+            for (int l = 0; l <= c->L && !touches; l++) {
+                const Range o = sb.own[l];
+                touches = o.lo < o.hi && (f.ry >> l) < o.hi && ((f.ry + f.rh) >> l) > o.lo;
+            }
+        } else {
+            const int TH = FeatherBody::TH;
+            const int y0 = sb.rows.lo / TH * TH, y1 = (sb.rows.hi + TH - 1) / TH * TH;
+            touches = f.dev.cy < y1 && f.dev.cy + f.bh > y0;
+        }
+        if (touches && (!latest || f.seq > latest->seq)) latest = &f;
+    }
+    if (!latest) return DS_OK;
+    int rc;
+    if ((rc = ev_wait(st, latest->ready))) return rc;
+    *waited_seq = latest->seq;
+    return DS_OK;
+}
+
 int run_composite(ds_canvas* c) {
     int rc;
-    if (c->dirty && (rc = build_lists(c))) return rc;
+    // pipelined (sliced) when asked for, or when frames are still arriving on the upload stream
+    int slice_rows = 0;
+    if (c->desc.pipeline_rows > 0) slice_rows = c->desc.pipeline_rows;
+    else if (c->desc.pipeline_rows == 0 && c->async_pending) slice_rows = default_pipeline_rows();
+    c->async_pending = false;
+    if (c->dirty || slice_rows != c->meta_slice_rows || c->subs.empty()) {
+        plan_subbands(c, slice_rows);
+        if ((rc = build_lists(c))) return rc;
+        c->meta_slice_rows = slice_rows;
+    }
     c->launches = 0;
     const ABModel abm = ab_inputs(c);
+    for (Frame& f : c->frames) f.mask_done = false;
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev0, c->stream));
 #endif
-    if (c->desc.blend_mode == DS_BLEND_FEATHER) {
-        for (size_t i = 0; i < c->frames.size(); i++) {
-            Frame& f = c->frames[i];
-            if (!f.used) continue;
-            MaskBitsParams mp{c->d_frames, (int)i, f.d_mbits};
-            const long long nwords = (long long)f.dev.mbits_pitch * f.bh;
-            if ((rc = prof_mark(c, true, "feather_mask", -1, 0))) return rc;
-            if ((rc = launch<MaskBitsBody, 256>(mp, (nwords + MaskBitsBody::WORDS_PER_BLOCK - 1) / MaskBitsBody::WORDS_PER_BLOCK,
-                                                c->stream, 0))) return rc;
-            if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
-            c->launches++;
+    // Sliced schedule: the level-0 feeds (the bulk of the work) of all slices run back to back on a low-priority
+    // stream; everything else of a slice - its feeds of level >= 1 and its collapse, small launches that are
+    // latency-bound - follows on a high-priority stream as soon as the slice's level-0 feed is done, and overlaps
+    // the next slice's level-0 feed. Stream order on the second stream gives the cross-slice order for free: a
+    // slice's level >= 1 feeds read the pyramid rows the previous slice left, its collapse continues from the rows
+    // the previous collapse finalised. With one slice, or per-kernel profiling, everything is on the canvas stream.
+    const bool feather = c->desc.blend_mode == DS_BLEND_FEATHER;
+    const bool two = c->subs.size() > 1 && !c->profiling && c->bulk && c->tail;
+    const stream_t P = two ? c->bulk : c->stream, Q = two ? c->tail : c->stream;
+    if (two) {
+        // after the previous composite and the metadata copy (both on the canvas stream)
+        if ((rc = ev_make(&c->ev_start)) || (rc = ev_record(c->ev_start, c->stream))) return rc;
+        if ((rc = ev_wait(P, c->ev_start)) || (rc = ev_wait(Q, c->ev_start))) return rc;
+    }
+    for (size_t b = 0; b < c->subs.size(); b++) {
+        SubBand& sb = c->subs[b];
+        if ((rc = wait_for_frames(c, P, &c->waited_seq, sb))) return rc;
+        trace_mark(c, P, "slice begin, row", sb.rows.lo);
+        if (feather) {
+            if ((rc = launch_feather(c, P, sb, abm))) return rc;
+            if ((rc = ev_make(&sb.done)) || (rc = ev_record(sb.done, P))) return rc;
+            trace_mark(c, P, "slice end, row", sb.rows.hi);
+            continue;
         }
-        LevelPlan& pl = c->plan[0];
-        FeatherParams fp;
-        fp.frames = c->d_frames; fp.tile_off = pl.d_off; fp.tile_frames = pl.d_fr; fp.tile_ids = pl.d_ids;
-        fp.tiles_x = pl.tiles_x; fp.sharpness = c->desc.sharpness; fp.R = c->feather_R;
-        fp.row0 = c->band.lo; fp.row1 = c->out_hi;
-        fp.o = out_params(c);
-        if ((rc = prof_mark(c, true, "feather_blend", 0, (int64_t)(3.0 * abm.S + 4.0 * abm.C)))) return rc;
-        if ((rc = launch<FeatherBody, 256>(fp, pl.n_ids, c->stream, FeatherBody::smem_bytes()))) return rc;
-        if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
-        c->launches++;
-    } else {
-        for (int l = 0; l <= c->L; l++) {
-            LevelPlan& pl = c->plan[l];
-            MBParams mp;
-            mp.frames = c->d_frames; mp.tile_off = pl.d_off; mp.tile_frames = pl.d_fr; mp.tile_ids = pl.d_ids;
-            mp.tiles_x = pl.tiles_x; mp.level = l; mp.L = c->L;
-            mp.dst = c->d_lvl[l]; mp.dst_w = c->lw[l]; mp.dst_h = c->lh[l];
-            mp.acc_y0 = pl.acc.lo; mp.acc_y1 = pl.acc.hi;
-            mp.own_y0 = pl.own.lo; mp.own_y1 = pl.own.hi;
-            mp.tmaps = c->tmaps_ok ? c->d_tmaps : nullptr;
-            const double q = 1.0 / (double)(1ull << (2 * l));
-            double ab;
-            if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
-            else if (l < c->L) ab = abm.A * q * (40.0 + 2.5);
-            else ab = abm.A * q * 40.0;
-            if ((rc = prof_mark(c, true, "mb_feed", l, (int64_t)ab))) return rc;
-            if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBFastBody<64, true>::smem_bytes());
-            else if (l > 0 && l < c->L && c->ln_fast_ok) rc = launch<MBFastBody<32, false>, 256>(mp, pl.n_ids, c->stream, MBFastBody<32, false>::smem_bytes());
-            else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, pl.n_ids, c->stream, MBBody<64, true>::smem_bytes());
-            else rc = launch<MBBody<32, false>, 256>(mp, pl.n_ids, c->stream, MBBody<32, false>::smem_bytes());
-            if (rc) return rc;
-            if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
-            c->launches++;
-        }
-        for (int l = c->L; l >= 1; l--) {
-            CollapseParams cp;
-            cp.coarse = c->d_lvl[l]; cp.cw = c->lw[l]; cp.ch = c->lh[l];
-            cp.fine = c->d_lvl[l - 1]; cp.fw = c->lw[l - 1]; cp.fh = c->lh[l - 1];
-            cp.y0 = c->plan[l - 1].acc.lo; cp.y1 = c->plan[l - 1].acc.hi;
-            cp.final = (l == 1);
-            cp.o = out_params(c);
-            const long long items = CollapseBody::items(cp);
-            const double q = 1.0 / (double)(1ull << (2 * (l - 1)));
-            const double ab = abm.C * 17.5 * q - (l == 1 ? 2.0 * abm.C : 0.0);
-            if ((rc = prof_mark(c, true, "mb_collapse", l - 1, (int64_t)ab))) return rc;
-            if ((rc = launch<CollapseBody, 256>(cp, (items + CollapseBody::PER_BLOCK - 1) / CollapseBody::PER_BLOCK, c->stream, 0))) return rc;
-            if ((rc = prof_mark(c, false, nullptr, 0, 0))) return rc;
-            c->launches++;
-        }
-        if (c->L == 0) {
-            FinalizeL0Params fp{c->d_lvl[0], c->lw[0], c->lh[0], c->band.lo, c->out_hi, out_params(c)};
-            const long long n = (long long)fp.fw * (fp.y1 - fp.y0);
-            if ((rc = launch<FinalizeL0Body, 256>(fp, (n + FinalizeL0Body::PER_BLOCK - 1) / FinalizeL0Body::PER_BLOCK, c->stream, 0))) return rc;
-            c->launches++;
-        }
+        if ((rc = launch_feed(c, P, 0, sb, abm))) return rc;
+        trace_mark(c, P, "  level-0 feed end, row", sb.rows.hi);
+        if (two && ((rc = ev_make(&sb.fed0)) || (rc = ev_record(sb.fed0, P)) || (rc = ev_wait(Q, sb.fed0)))) return rc;
+        for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, Q, l, sb, abm))) return rc;
+        for (int l = c->L; l >= 1; l--) if ((rc = launch_collapse(c, Q, l, sb, abm))) return rc;
+        if (c->L == 0 && (rc = launch_finalize_l0(c, Q, sb))) return rc;
+        if ((rc = ev_make(&sb.done)) || (rc = ev_record(sb.done, Q))) return rc;
+        trace_mark(c, Q, "slice end, row", sb.rows.hi);
+    }
+    if (two) {
+        // join: the canvas stream is the one callers synchronise on
+        if ((rc = ev_wait(c->stream, c->subs.back().done))) return rc;
     }
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev1, c->stream));
 #endif
+    if ((rc = ev_make(&c->ev_done)) || (rc = ev_record(c->ev_done, c->stream))) return rc;
+    c->ev_done_valid = true;
     c->composited = true;
     return DS_OK;
 }
@@ -577,6 +907,11 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     if ((rc = placement(xf, w, h, pl))) return rc;
     if ((size_t)idx >= c->frames.size()) c->frames.resize((size_t)idx + 1);
     Frame& f = c->frames[(size_t)idx];
+    const bool async = opts && (opts->flags & DS_UPLOAD_ASYNC);
+    const bool was_used = f.used;
+    const FrameDev before = f.dev;
+    // the frame's buffers may still be read by the previous composite
+    if (c->ev_done_valid && (rc = ev_wait(c->up, c->ev_done))) return rc;
     f.used = true; f.w = w; f.h = h; f.xf = *xf;
     f.corner_x = pl[0]; f.corner_y = pl[1]; f.bw = pl[2]; f.bh = pl[3];
     // the frame must lie inside the canvas ROI (prepare(resultRoi(corners, sizes)) guarantees it in the reference)
@@ -595,17 +930,16 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     } else {
         const size_t dense = (size_t)w * 3;
         if ((rc = grow(c, (void**)&c->d_stage, &c->stage_cap, dense * h))) return rc;
-        if ((rc = h2d_2d(c->d_stage, dense, bgr, stride, dense, (size_t)h, c->stream))) return rc;
-#if DS_CUDA
-        DS_CK(cudaEventRecord(c->ev_copy, c->stream));
-#endif
+        trace_mark(c, c->up, "h2d begin, frame", idx);
+        if ((rc = h2d_2d(c->d_stage, dense, bgr, stride, dense, (size_t)h, c->up))) return rc;
+        trace_mark(c, c->up, "h2d end, frame", idx);
         ep.src = c->d_stage; ep.src_stride = dense;
     }
     ep.dst = f.d_src; ep.dst_pitch = f.pitch; ep.w = w; ep.h = h;
-    if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->stream, 0))) return rc;
-    // the caller's buffer (host or device) is only borrowed for the call, and the staging buffer is reused
-    // by the next upload: wait for the expansion (~20 us for a 20 MP frame)
-    if ((rc = stream_sync(c->stream))) return rc;
+    if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->up, 0))) return rc;
+    trace_mark(c, c->up, "expand end, frame", idx);
+    // The upload stream is in order, so the staging buffer is free again when the next copy starts. Without
+    // DS_UPLOAD_ASYNC the caller's buffers are only borrowed for the call: the stream is drained before returning.
     // blend-mode specific geometry and buffers
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND) {
         dsgeo::feed_roi(c->desc.x, c->desc.y, c->pw, c->ph, c->L, f.corner_x, f.corner_y, f.bw, f.bh, f.rx, f.ry, f.rw, f.rh);
@@ -637,21 +971,20 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
         uint8_t* d_low = nullptr; int* d_tab = nullptr;
         if ((rc = dev_alloc_t(&d_low, (size_t)sw * sh))) return rc;
         if ((rc = dev_alloc_t(&d_tab, tab.size()))) { dev_free(d_low); return rc; }
-        rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->stream);
-        if (!rc) rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->stream);
+        rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->up);
+        if (!rc) rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->up);
         if (!rc) {
             SeamUpParams sp{d_low, sw, sh, sw, d_tab, d_tab + f.bw, d_tab + 2 * f.bw, d_tab + 2 * f.bw + f.bh, f.d_seam, f.bw, f.bh};
             const long long n = (long long)f.bw * f.bh;
-            rc = launch<SeamUpBody, 256>(sp, (n + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->stream, 0);
+            rc = launch<SeamUpBody, 256>(sp, (n + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->up, 0);
         }
-        if (!rc) rc = stream_sync(c->stream);
+        if (!rc) rc = stream_sync(c->up);   // temporaries below are freed: this (rare) path always drains
         dev_free(d_low); dev_free(d_tab);
         if (rc) return rc;
     } else if (opts && opts->seam_mask) {
         if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, (size_t)f.bw * f.bh))) return rc;
         if ((rc = h2d_2d(f.d_seam, (size_t)f.bw, opts->seam_mask, opts->seam_mask_stride ? opts->seam_mask_stride : (size_t)f.bw,
-                         (size_t)f.bw, (size_t)f.bh, c->stream))) return rc;
-        if ((rc = stream_sync(c->stream))) return rc;
+                         (size_t)f.bw, (size_t)f.bh, c->up))) return rc;
     } else if (f.d_seam) {
         dev_free(f.d_seam); c->device_bytes -= (int64_t)f.seam_cap; f.d_seam = nullptr; f.seam_cap = 0;
     }
@@ -659,8 +992,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     if (opts && opts->gain_map) {
         const size_t gst = opts->gain_map_stride ? opts->gain_map_stride : (size_t)f.bw * sizeof(float);
         if ((rc = grow(c, (void**)&f.d_gainmap, &f.gainmap_cap, (size_t)f.bw * f.bh * sizeof(float)))) return rc;
-        if ((rc = h2d_2d(f.d_gainmap, (size_t)f.bw * sizeof(float), opts->gain_map, gst, (size_t)f.bw * sizeof(float), (size_t)f.bh, c->stream))) return rc;
-        if ((rc = stream_sync(c->stream))) return rc;
+        if ((rc = h2d_2d(f.d_gainmap, (size_t)f.bw * sizeof(float), opts->gain_map, gst, (size_t)f.bw * sizeof(float), (size_t)f.bh, c->up))) return rc;
         f.dev.gainmap = f.d_gainmap; f.dev.gainmap_pitch = f.bw;
     } else if (f.d_gainmap) {
         dev_free(f.d_gainmap); c->device_bytes -= (int64_t)f.gainmap_cap; f.d_gainmap = nullptr; f.gainmap_cap = 0;
@@ -674,7 +1006,12 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
         for (int k = 0; k < 3; k++) f.dev.cgain[k] = opts->compensator_gain[k];
     }
     f.dev.any_gain = (f.dev.has_gain || f.dev.has_cgain || f.dev.gainmap) ? 1 : 0;
-    c->dirty = true;
+    f.seq = ++c->up_seq;
+    if ((rc = ev_make(&f.ready)) || (rc = ev_record(f.ready, c->up))) return rc;
+    if (async) c->async_pending = true;
+    else if ((rc = stream_sync(c->up))) return rc;
+    // same geometry, buffers and gains as before (a new image for the same slot): the launch metadata stands
+    if (!was_used || memcmp(&before, &f.dev, sizeof(FrameDev)) != 0) c->dirty = true;
     c->composited = false;
     return DS_OK;
 }
@@ -778,7 +1115,21 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(DS_ERR_CUDA, "cudaStreamCreate failed"); }
         c->own_stream = true;
     }
-    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+    {
+        // uploads get the higher priority: the expansion kernel of an arriving frame must not queue behind the
+        // blocks of a running slice, or the copy engine idles
+        int lo_prio = 0, hi_prio = 0;   // numerically lower = higher priority
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        const int mid_prio = hi_prio < lo_prio - 1 ? hi_prio + 1 : hi_prio;
+        if (cudaStreamCreateWithPriority(&c->up, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->dl, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, lo_prio) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, mid_prio) != cudaSuccess) {
+            ds_destroy_canvas(c);
+            return fail(DS_ERR_CUDA, "cudaStreamCreate failed");
+        }
+    }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
 #endif
     // output rows [band.lo, out_hi)
     c->out_hi = std::min(c->band.hi, desc->height);
@@ -821,20 +1172,30 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     if (!c) return;
     set_device(c);
 #if DS_CUDA
-    cudaStreamSynchronize(c->stream);
+    if (c->up) cudaStreamSynchronize(c->up);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->bulk) cudaStreamSynchronize(c->bulk);
+    if (c->tail) cudaStreamSynchronize(c->tail);
+    if (c->dl) cudaStreamSynchronize(c->dl);
 #endif
-    for (Frame& f : c->frames) { dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_gainmap); }
-    for (int l = 0; l < DS_MAXL; l++) {
-        dev_free(c->d_lvl_alloc[l]);
-        dev_free(c->plan[l].d_off); dev_free(c->plan[l].d_fr); dev_free(c->plan[l].d_ids);
+    for (Frame& f : c->frames) {
+        dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_gainmap);
+        ev_drop(f.ready);
     }
-    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_frames); dev_free(c->d_stage); dev_free(c->d_tmaps);
+    for (int l = 0; l < DS_MAXL; l++) dev_free(c->d_lvl_alloc[l]);
+    for (SubBand& sb : c->subs) { ev_drop(sb.done); ev_drop(sb.fed); ev_drop(sb.fed0); }
+    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_stage); dev_free(c->d_meta);
+    pinned_free(c->h_meta);
+    ev_drop(c->ev_done); ev_drop(c->ev_meta); ev_drop(c->ev_start);
 #if DS_CUDA
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->up) cudaStreamDestroy(c->up);
+    if (c->dl) cudaStreamDestroy(c->dl);
+    if (c->bulk) cudaStreamDestroy(c->bulk);
+    if (c->tail) cudaStreamDestroy(c->tail);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 #endif
     delete c;
 }
@@ -860,7 +1221,10 @@ DS_API int ds_synchronize(ds_canvas* c) {
     if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
     int rc;
     if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->up))) return rc;
     if ((rc = stream_sync(c->stream))) return rc;
+    if ((rc = stream_sync(c->dl))) return rc;
+    trace_dump(c);
 #if DS_CUDA
     if (c->composited) {
         float ms = 0.f;
@@ -885,15 +1249,35 @@ DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* o
     if (stride < (size_t)w * bpp) return fail(DS_ERR_BAD_ARG, "stride too small");
     int rc;
     if ((rc = set_device(c))) return rc;
-    const uint8_t* src = c->d_out + (size_t)(y - c->band.lo) * c->out_pitch + (size_t)x * bpp;
-    if ((rc = d2h_2d(out, stride, src, c->out_pitch, (size_t)w * bpp, (size_t)h, c->stream))) return rc;
     if (mask_out) {
         if (c->desc.out_format == DS_OUT_BGRA8) return fail(DS_ERR_UNSUPPORTED, "BGRA8 canvases carry the mask in alpha");
         if (mask_stride < (size_t)w) return fail(DS_ERR_BAD_ARG, "mask stride too small");
-        const uint8_t* ms = c->d_mask + (size_t)(y - c->band.lo) * c->mask_pitch + x;
-        if ((rc = d2h_2d(mask_out, mask_stride, ms, c->mask_pitch, (size_t)w, (size_t)h, c->stream))) return rc;
     }
-    return ds_synchronize(c);
+    // slice by slice, each as soon as its rows are final: the copies of the first slices overlap the compute of
+    // the later ones (and the uploads those still wait for)
+    for (const SubBand& sb : c->subs) {
+        const int y0 = std::max(y, sb.rows.lo), y1 = std::min(y + h, sb.rows.hi);
+        if (y0 >= y1) continue;
+        if ((rc = ev_wait(c->dl, sb.done))) return rc;
+        trace_mark(c, c->dl, "d2h begin, row", y0);
+        const uint8_t* src = c->d_out + (size_t)(y0 - c->band.lo) * c->out_pitch + (size_t)x * bpp;
+        if ((rc = d2h_2d(out + (size_t)(y0 - y) * stride, stride, src, c->out_pitch, (size_t)w * bpp, (size_t)(y1 - y0), c->dl))) return rc;
+        if (mask_out) {
+            const uint8_t* ms = c->d_mask + (size_t)(y0 - c->band.lo) * c->mask_pitch + x;
+            if ((rc = d2h_2d(mask_out + (size_t)(y0 - y) * mask_stride, mask_stride, ms, c->mask_pitch, (size_t)w, (size_t)(y1 - y0), c->dl))) return rc;
+        }
+    }
+    trace_mark(c, c->dl, "d2h end, row", y + h);
+    if ((rc = stream_sync(c->dl))) return rc;
+#if DS_CUDA
+    if (cudaEventQuery(c->ev1) == cudaSuccess) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; else cudaGetLastError();
+    } else {
+        cudaGetLastError();
+    }
+#endif
+    return DS_OK;
 }
 
 DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
@@ -955,6 +1339,7 @@ static int tap_common(ds_canvas* c, int frame_idx, Frame** f) {
         return fail(DS_ERR_BAD_ARG, "frame %d not uploaded", frame_idx);
     int rc;
     if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->up))) return rc;
     if (c->dirty && (rc = build_lists(c))) return rc;
     *f = &c->frames[(size_t)frame_idx];
     return DS_OK;

@@ -106,7 +106,16 @@ typedef struct ds_frame_opts {
      * (the caller's resize of its block gain map), sat_u8(rint(float(p) * g)); applied last. */
     const float* gain_map;
     size_t gain_map_stride; /* bytes */
+    /* DS_UPLOAD_ASYNC: return as soon as the copies are queued. The caller keeps `bgr` and every buffer named
+     * here valid and unchanged until ds_composite / ds_synchronize / a ds_download_tile covering the canvas has
+     * returned; host buffers should be pinned (cudaHostAlloc / cudaHostRegister), or the copy is synchronous
+     * anyway. With frames still in flight, ds_composite_async works through the canvas in row slices, each
+     * starting as soon as the frames it reads have arrived, and ds_download_tile copies every slice out as soon
+     * as it is final - upload, compute and download overlap. Results are identical. */
+    uint32_t flags;
 } ds_frame_opts;
+
+enum { DS_UPLOAD_ASYNC = 1u };
 
 typedef struct ds_canvas_desc {
     int32_t x, y, width, height; /* canvas ROI = cv::detail::resultRoi(corners, sizes) */
@@ -121,7 +130,10 @@ typedef struct ds_canvas_desc {
      * skipped by the caller; ds_frame_touches_band() tells. */
     int32_t band_y0, band_y1;
     void* stream;                /* cudaStream_t to run on, or NULL for a library-owned stream */
-    int32_t reserved[8];
+    /* Row slices of ds_composite: 0 = automatic (slices of a default height only while DS_UPLOAD_ASYNC uploads
+     * are in flight), > 0 = always slices of about this many rows, < 0 = never. Output does not depend on it. */
+    int32_t pipeline_rows;
+    int32_t reserved[7];
 } ds_canvas_desc;
 
 typedef struct ds_canvas_info {
@@ -153,7 +165,8 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out);
 
 /* Replaces, per frame, warper->warp(img) + warper->warp(mask) + convertTo(16S) + blender->feed()'s
  * input hand-off. bgr: 8UC3 interleaved, `stride` = cv::Mat::step. The host buffer is only borrowed
- * for the duration of the call. Feed order = frame_idx order. Re-uploading an index replaces it. */
+ * for the duration of the call (unless opts->flags has DS_UPLOAD_ASYNC). Feed order = frame_idx order.
+ * Re-uploading an index replaces it. */
 DS_API int ds_upload_frame(ds_canvas* c, int frame_idx, const uint8_t* bgr, int w, int h, size_t stride,
                            const ds_transform* xf, const ds_frame_opts* opts);
 

@@ -75,14 +75,19 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
         assert (r[0], r[1]) == tuple(c) and (r[2], r[3]) == tuple(sz), (r, c, sz)
     assert CP.result_roi(rois) == roi
 
-    def make(band=None):
-        cv = CP.Canvas(roi, blend, bands, 0.02, out_format, 0, band=band, lib=lib)
+    def make(band=None, slice_rows=0):
+        """slice_rows > 0: the pipelined schedule - asynchronous uploads, composite in row slices of that height,
+        download slice by slice."""
+        cv = CP.Canvas(roi, blend, bands, 0.02, out_format, 0, band=band, lib=lib, pipeline_rows=slice_rows)
         for i, (s, xf) in enumerate(zip(specs, xfs)):
             if band is not None and not cv.touches(rois[i]):
                 continue
             cv.upload(i, s["img"], xf, seam_mask=s.get("seam"), channel_gain=s.get("gain"), seam_lowres=s.get("seam_lowres"),
-                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"))
-        cv.composite()
+                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"), async_=slice_rows > 0)
+        if slice_rows > 0:
+            cv.composite_async()
+        else:
+            cv.composite()
         return cv
 
     cv = make()
@@ -109,6 +114,22 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
                     assert np.array_equal(W, ws[l]), f"frame {i} level {l}: weight level differs"
     assert np.array_equal(mask, refmask), "result mask differs"
     st = assert_blend_parity(pano, ref, exact=exact)
+    # the pipelined schedule (row slices chasing the uploads) must give the same bytes, per-frame pyramids included
+    for slice_rows in sorted({max(1 << info.num_bands, roi[3] // 5), max(1 << info.num_bands, roi[3] // 2)}):
+        cs = make(slice_rows=slice_rows)
+        ps, ms = cs.download()
+        cs.synchronize()
+        if out_format == "bgra":
+            ms = ps[:, :, 3].copy()
+            ps = np.ascontiguousarray(ps[:, :, :3])
+        assert np.array_equal(ps, pano) and np.array_equal(ms, mask), f"sliced composite ({slice_rows} rows) differs"
+        if check_taps and blend == "multiband":
+            for i in range(len(specs)):
+                for l in range(1, bl.bands + 1):
+                    G, W, _ = cs.frame_level(i, l)
+                    G0, W0, _ = cv.frame_level(i, l)
+                    assert np.array_equal(G, G0) and np.array_equal(W, W0), f"sliced: frame {i} level {l} differs"
+        cs.close()
     if band_split:
         # virtual bands: K handles over row bands must reproduce the single-handle result exactly
         m = 1 << info.num_bands
@@ -118,7 +139,8 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
         for y0, y1 in zip(edges[:-1], edges[1:]):
             if y0 >= roi[3]:
                 continue
-            cb = make(band=(y0, y1))
+            cb = make(band=(y0, y1), slice_rows=(1 << info.num_bands) * 2 if len(rows) % 2 else 0)
+            cb.synchronize()
             pb, mb_ = cb.download()
             if out_format == "bgra":
                 pb = np.ascontiguousarray(pb[:, :, :3])

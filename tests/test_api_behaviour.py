@@ -117,3 +117,59 @@ def test_edges_emu(emu_lib):
 @pytest.mark.gpu
 def test_edges_gpu(cuda_lib):
     _edges(cuda_lib)
+
+
+def _pipelined(lib, blend):
+    """DS_UPLOAD_ASYNC + ds_composite_async + ds_download_tile: the sliced schedule, tile downloads that cross slice
+    edges, a second step into the same handle (same geometry: launch metadata is reused), and the switch back to
+    synchronous uploads - always the bytes of the plain schedule."""
+    sv = synth.grid_survey(2, 3, 200, 160, overlap=0.5, seed=43, work_scale=0.5)
+    xfs = [CP.plane_transform(K, R, sv.scale) for K, R in zip(sv.Ks, sv.Rs)]
+    rois = [CP.warp_roi(xf, 200, 160, lib) for xf in xfs]
+    roi = CP.result_roi(rois)
+    ref, refmask, _ = O.compose_port(sv.frames, sv.Ks, sv.Rs, sv.scale, blend, 3)
+    other = [np.ascontiguousarray(f[::-1]) for f in sv.frames]
+    ref_b, refmask_b, _ = O.compose_port(other, sv.Ks, sv.Rs, sv.scale, blend, 3)
+    for rows in (32, 96):
+        cv = CP.Canvas(roi, blend, 3, lib=lib, pipeline_rows=rows)
+        for i, (f, xf) in enumerate(zip(sv.frames, xfs)):
+            cv.upload(i, f, xf, async_=True)
+        cv.composite_async()
+        # a tile that starts and ends inside slices
+        y0, h = roi[3] // 3 + 5, roi[3] // 2
+        x0, w = 7, roi[2] - 20
+        tile, tmask = cv.download(x=x0, y=y0, w=w, h=h)
+        assert np.array_equal(tile, ref[y0:y0 + h, x0:x0 + w]) and np.array_equal(tmask, refmask[y0:y0 + h, x0:x0 + w])
+        pano, mask = cv.download()
+        cv.synchronize()
+        assert np.array_equal(pano, ref) and np.array_equal(mask, refmask)
+        n_sliced = cv.info().launches_last_composite
+        # next step: new pixels, same slots and geometry
+        for i, (f, xf) in enumerate(zip(other, xfs)):
+            cv.upload(i, f, xf, async_=True)
+        cv.composite_async()
+        pano, mask = cv.download()
+        cv.synchronize()
+        assert np.array_equal(pano, ref_b) and np.array_equal(mask, refmask_b)
+        assert cv.info().launches_last_composite == n_sliced
+        cv.close()
+    # automatic mode: slices only while asynchronous uploads are pending; never with pipeline_rows < 0
+    cv = CP.Canvas(roi, blend, 3, lib=lib, pipeline_rows=-1)
+    for i, (f, xf) in enumerate(zip(sv.frames, xfs)):
+        cv.upload(i, f, xf, async_=True)
+    cv.composite()
+    pano, mask = cv.download()
+    assert np.array_equal(pano, ref) and np.array_equal(mask, refmask)
+    assert cv.info().launches_last_composite < n_sliced
+    cv.close()
+
+
+@pytest.mark.parametrize("blend", ["multiband", "feather"])
+def test_pipelined_emu(emu_lib, blend):
+    _pipelined(emu_lib, blend)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blend", ["multiband", "feather"])
+def test_pipelined_gpu(cuda_lib, blend):
+    _pipelined(cuda_lib, blend)
