@@ -192,9 +192,14 @@ struct Frame {
     uint8_t* d_seam = nullptr; size_t seam_cap = 0;
     float* d_gainmap = nullptr; size_t gainmap_cap = 0;
     FrameDev dev{};
-    event_t ready = 0;      // recorded on the upload stream once the frame's device data is complete
-    uint64_t seq = 0;       // position in upload order
     bool mask_done = false; // FEATHER: mask bit plane built for the current composite
+    // Source pixels still to be brought in (DS_UPLOAD_ASYNC): the copy is cut into chunks of source rows that
+    // ds_composite_async issues in the order its row slices need them.
+    struct Pending {
+        const uint8_t* src = nullptr; size_t stride = 0; bool on_device = false;
+        int nchunks = 0, left = 0;
+        std::vector<unsigned char> issued;
+    } pend;
 };
 
 struct LevelPlan {
@@ -226,15 +231,23 @@ struct ds_canvas {
     stream_t stream = 0;     // compute
     stream_t bulk = 0, tail = 0;   // sliced schedule: level-0 feeds (low priority) / the rest of each slice (high)
     event_t ev_start = 0;
-    stream_t up = 0, dl = 0; // uploads (H2D + expansion), downloads (D2H)
+    stream_t up = 0, dl = 0; // host-to-device copies (and the optional per-frame inputs), device-to-host copies
+    stream_t xp = 0;         // BGR -> BGRX expansion of the chunks the copies deliver
+    static const int NSLOT = 4;          // staging ring: one chunk of dense BGR rows per slot
+    uint8_t* d_slot[NSLOT] = {nullptr, nullptr, nullptr, nullptr}; size_t slot_cap = 0;
+    event_t slot_copied[NSLOT] = {0, 0, 0, 0}, slot_free[NSLOT] = {0, 0, 0, 0};
+    bool slot_used[NSLOT] = {false, false, false, false};
+    int slot_next = 0;
+    int chunk_rows = 512;    // source rows per upload chunk (DS_UPLOAD_CHUNK_ROWS)
+    int n_pending = 0;       // frames with chunks still to issue
+    event_t ev_chunks = 0;   // scratch: recorded on xp after the chunks a slice needs
+    event_t ev_opts = 0;     // scratch: recorded on up at the start of a composite
     int meta_slice_rows = -2;   // slice height the launch metadata was built for
     bool own_stream = false;
     event_t ev_done = 0;     // end of the last composite (compute stream)
     bool ev_done_valid = false;
     event_t ev_meta = 0;     // metadata copy kernel finished reading h_meta
     bool ev_meta_valid = false;
-    uint64_t up_seq = 0;     // uploads so far
-    uint64_t waited_seq = 0; // the compute stream already waits for uploads up to this one
     bool async_pending = false;   // an upload with DS_UPLOAD_ASYNC since the last composite
     std::vector<SubBand> subs;    // slices of the last composite
     void* h_meta = nullptr; void* h_meta_dev = nullptr; size_t h_meta_cap = 0;
@@ -254,7 +267,6 @@ struct ds_canvas {
     bool dirty = true;
     bool ln_fast_ok = false;   // fast kernel for levels 1..L-1 (<= 64 frames per tile at every level)
     bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
-    uint8_t* d_stage = nullptr; size_t stage_cap = 0;
     int feather_R = 0;
     int64_t device_bytes = 0;
     int64_t launches = 0;
@@ -414,6 +426,150 @@ int placement(const ds_transform* xf, int w, int h, int* out) {
 }
 
 // Build per-level tile -> frame lists (feed order) on the host and upload them.
+// Source rows a frame's bbox rows [v0, v1] can read: the backward map (in double) at the four corners of the row
+// strip, +- the bilinear tap and a rounding margin, with the rows border reflection folds back in. Returns false
+// when no bound can be given (degenerate projective maps): the caller then takes the whole frame.
+bool source_row_range(const FrameDev& F, int v0, int v1, int* lo_out, int* hi_out) {
+    const int h = F.src_h;
+    double mn = 1e300, mx = -1e300;
+    int zsign = 0;
+    for (int ci = 0; ci < 4; ci++) {
+        const double u = (ci & 1) ? (double)(F.w - 1) : 0.0, v = (ci & 2) ? (double)v1 : (double)v0;
+        double y, z = 1.0;
+        if (F.kind == XF_PLANE) {
+            const double U = ((double)F.tlx + u) / (double)F.scale - (double)F.t0, V = ((double)F.tly + v) / (double)F.scale - (double)F.t1;
+            y = (double)F.k[3] * U + (double)F.k[4] * V + (double)F.k5one;
+            z = (double)F.k[6] * U + (double)F.k[7] * V + (double)F.k8one;
+        } else if (F.kind == XF_AFFINE) {
+            y = F.inv[3] * u + F.inv[4] * v + F.inv[5];
+        } else {
+            y = F.inv[3] * u + F.inv[4] * v + F.inv[5];
+            z = F.inv[6] * u + F.inv[7] * v + F.inv[8];
+        }
+        if (!(fabs(z) > 1e-9)) return false;
+        const int sg = z > 0 ? 1 : -1;
+        if (zsign && sg != zsign) return false;   // the horizon crosses the strip
+        zsign = sg;
+        const double sy = y / z;
+        if (!(fabs(sy) < 1e9)) return false;
+        mn = std::min(mn, sy); mx = std::max(mx, sy);
+    }
+    mn -= 2.0; mx += 3.0;
+    if (mn < -(double)h || mx > 2.0 * (double)h) return false;
+    const int L = (int)floor(mn), H = (int)ceil(mx);
+    int lo = std::max(L, 0), hi = std::min(H, h - 1);
+    if (L < 0) { lo = 0; hi = std::max(hi, std::min(-L, h - 1)); }
+    if (H > h - 1) { hi = h - 1; lo = std::min(lo, std::max(2 * (h - 1) - H - 1, 0)); }
+    if (lo > hi) { lo = 0; hi = h - 1; }
+    *lo_out = lo; *hi_out = hi;
+    return true;
+}
+
+// ---- chunked source upload: host rows -> staging slot (copy stream) -> BGRX rows of the frame (expansion stream)
+
+int issue_chunk(ds_canvas* c, int fi, int k) {
+    Frame& f = c->frames[(size_t)fi];
+    Frame::Pending& pd = f.pend;
+    if (k < 0 || k >= pd.nchunks || pd.issued[(size_t)k]) return DS_OK;
+    int rc;
+    const int r0 = k * c->chunk_rows, nr = std::min(c->chunk_rows, f.h - r0);
+    ExpandParams ep;
+    ep.dst = f.d_src + (size_t)r0 * f.pitch; ep.dst_pitch = f.pitch; ep.w = f.w; ep.h = nr;
+    if (pd.on_device) {
+        ep.src = pd.src + (size_t)r0 * pd.stride; ep.src_stride = pd.stride;
+        if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->xp, 0))) return rc;
+    } else {
+        const size_t dense = (size_t)f.w * 3;
+        const int sl = c->slot_next;
+        c->slot_next = (c->slot_next + 1) % ds_canvas::NSLOT;
+        if (c->slot_used[sl] && (rc = ev_wait(c->up, c->slot_free[sl]))) return rc;   // its previous chunk is expanded
+        trace_mark(c, c->up, "h2d begin, frame", fi);
+        if ((rc = h2d_2d(c->d_slot[sl], dense, pd.src + (size_t)r0 * pd.stride, pd.stride, dense, (size_t)nr, c->up))) return rc;
+        if ((rc = ev_make(&c->slot_copied[sl])) || (rc = ev_record(c->slot_copied[sl], c->up)) || (rc = ev_wait(c->xp, c->slot_copied[sl]))) return rc;
+        ep.src = c->d_slot[sl]; ep.src_stride = dense;
+        if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->xp, 0))) return rc;
+        if ((rc = ev_make(&c->slot_free[sl])) || (rc = ev_record(c->slot_free[sl], c->xp))) return rc;
+        c->slot_used[sl] = true;
+    }
+    pd.issued[(size_t)k] = 1;
+    if (--pd.left == 0) { pd.src = nullptr; c->n_pending--; trace_mark(c, c->xp, "frame complete", fi); }
+    return DS_OK;
+}
+
+// chunks of frame fi holding source rows [lo, hi]
+int issue_rows(ds_canvas* c, int fi, int lo, int hi) {
+    int rc;
+    for (int k = lo / c->chunk_rows; k <= hi / c->chunk_rows; k++)
+        if ((rc = issue_chunk(c, fi, k))) return rc;
+    return DS_OK;
+}
+
+// everything still pending, in frame order (plain uploads, taps, ds_synchronize, the end of a composite)
+int issue_all(ds_canvas* c) {
+    int rc;
+    for (size_t fi = 0; fi < c->frames.size() && c->n_pending > 0; fi++) {
+        Frame& f = c->frames[fi];
+        if (!f.used || f.pend.left == 0) continue;
+        if ((rc = issue_rows(c, (int)fi, 0, f.h - 1))) return rc;
+    }
+    return DS_OK;
+}
+
+// The chunks slice `sb` reads, then an event on the expansion stream the slice's stream waits for.
+int issue_for_slice(ds_canvas* c, const SubBand& sb, stream_t waiter) {
+    if (c->n_pending == 0) return DS_OK;
+    const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
+    int rc;
+    bool any = false;
+    for (size_t fi = 0; fi < c->frames.size(); fi++) {
+        Frame& f = c->frames[fi];
+        if (!f.used || f.pend.left == 0) continue;
+        // bbox rows whose warped pixels the slice's kernels evaluate
+        int v0, v1;
+        if (mb) {
+            if (sb.own[0].lo >= sb.own[0].hi) continue;
+            v0 = sb.own[0].lo - 5 - f.dev.cy; v1 = sb.own[0].hi + 4 - f.dev.cy;
+        } else {
+            const int TH = FeatherBody::TH;
+            v0 = sb.rows.lo / TH * TH - 1 - f.dev.cy; v1 = (sb.rows.hi + TH - 1) / TH * TH + 1 - f.dev.cy;
+        }
+        if (mb) {
+            // MultiBandBlender::feed extends the warped image over the gap of its ROI with BORDER_REFLECT
+            // (copyMakeBorder): ROI rows above / below the bbox read the bbox rows mirrored at its edge
+            const int r0 = f.ry - f.dev.cy, r1 = f.ry + f.rh - 1 - f.dev.cy;   // ROI rows, bbox-relative
+            const int a = std::max(v0, r0), b = std::min(v1, r1);
+            if (a > b) continue;
+            v0 = std::max(a, 0); v1 = std::min(b, f.bh - 1);
+            if (a < 0) { v0 = 0; v1 = std::max(v1, std::min(-a - 1, f.bh - 1)); }
+            if (b > f.bh - 1) { v1 = f.bh - 1; v0 = std::min(v0, std::max(2 * f.bh - b - 1, 0)); }
+        } else {
+            v0 = std::max(v0, 0); v1 = std::min(v1, f.bh - 1);
+        }
+        if (v0 > v1) continue;
+        int lo = 0, hi = f.h - 1;
+        if (!source_row_range(f.dev, v0, v1, &lo, &hi)) { lo = 0; hi = f.h - 1; }
+        const int before = f.pend.left;
+        static const bool debug_plan = getenv("DS_DEBUG_PLAN") != nullptr;
+        if (debug_plan) fprintf(stderr, "slice rows [%d,%d) own0 [%d,%d): frame %zu bbox rows [%d,%d] -> src rows [%d,%d]\n", sb.rows.lo, sb.rows.hi, sb.own[0].lo, sb.own[0].hi, fi, v0, v1, lo, hi);
+        if ((rc = issue_rows(c, (int)fi, lo, hi))) return rc;
+        any = any || f.pend.left != before;
+    }
+    if (!any) return DS_OK;   // everything it reads was ordered before an earlier slice's event (same waiter stream)
+    if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(waiter, c->ev_chunks))) return rc;
+    return DS_OK;
+}
+
+// Uploads declared with DS_UPLOAD_ASYNC that no composite has consumed yet: copy them now and drain the streams.
+int flush_uploads(ds_canvas* c) {
+    int rc;
+    if (c->n_pending > 0) {
+        if (c->ev_done_valid && (rc = ev_wait(c->xp, c->ev_done))) return rc;
+        if ((rc = issue_all(c))) return rc;
+    }
+    if ((rc = stream_sync(c->up))) return rc;
+    return stream_sync(c->xp);
+}
+
 int default_pipeline_rows() {
     static int v = -1;
     if (v < 0) {
@@ -791,33 +947,6 @@ int launch_feather(ds_canvas* c, stream_t st, const SubBand& sb, const ABModel& 
     return DS_OK;
 }
 
-// The compute stream waits for the uploads slice `sb` reads: every frame whose rows meet the slice's feed rows at
-// some level. The upload stream is in order, so waiting for the latest of them is enough.
-int wait_for_frames(ds_canvas* c, stream_t st, uint64_t* waited_seq, const SubBand& sb) {
-    const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
-    const Frame* latest = nullptr;
-    for (const Frame& f : c->frames) {
-        if (!f.used || f.seq <= *waited_seq) continue;
-        bool touches = false;
-        if (mb) {
-            for (int l = 0; l <= c->L && !touches; l++) {
-                const Range o = sb.own[l];
-                touches = o.lo < o.hi && (f.ry >> l) < o.hi && ((f.ry + f.rh) >> l) > o.lo;
-            }
-        } else {
-            const int TH = FeatherBody::TH;
-            const int y0 = sb.rows.lo / TH * TH, y1 = (sb.rows.hi + TH - 1) / TH * TH;
-            touches = f.dev.cy < y1 && f.dev.cy + f.bh > y0;
-        }
-        if (touches && (!latest || f.seq > latest->seq)) latest = &f;
-    }
-    if (!latest) return DS_OK;
-    int rc;
-    if ((rc = ev_wait(st, latest->ready))) return rc;
-    *waited_seq = latest->seq;
-    return DS_OK;
-}
-
 int run_composite(ds_canvas* c) {
     int rc;
     // pipelined (sliced) when asked for, or when frames are still arriving on the upload stream
@@ -825,11 +954,23 @@ int run_composite(ds_canvas* c) {
     if (c->desc.pipeline_rows > 0) slice_rows = c->desc.pipeline_rows;
     else if (c->desc.pipeline_rows == 0 && c->async_pending) slice_rows = default_pipeline_rows();
     c->async_pending = false;
-    if (c->dirty || slice_rows != c->meta_slice_rows || c->subs.empty()) {
-        plan_subbands(c, slice_rows);
+    const bool replan = c->dirty || slice_rows != c->meta_slice_rows || c->subs.empty();
+    if (replan) plan_subbands(c, slice_rows);
+    const bool feather = c->desc.blend_mode == DS_BLEND_FEATHER;
+    const bool two = c->subs.size() > 1 && !c->profiling && c->bulk && c->tail;
+    const stream_t P = two ? c->bulk : c->stream, Q = two ? c->tail : c->stream;
+    if (c->n_pending > 0) {
+        // the expansions overwrite frame sources the previous composite may still read
+        if (c->ev_done_valid && (rc = ev_wait(c->xp, c->ev_done))) return rc;
+        // get the copy engine going before the host builds the launch metadata
+        if ((rc = issue_for_slice(c, c->subs[0], P))) return rc;
+    }
+    if (replan) {
         if ((rc = build_lists(c))) return rc;
         c->meta_slice_rows = slice_rows;
     }
+    // optional per-frame inputs (seam masks, gain maps) were copied on the upload stream when the frame was declared
+    if ((rc = ev_make(&c->ev_opts)) || (rc = ev_record(c->ev_opts, c->up)) || (rc = ev_wait(c->stream, c->ev_opts))) return rc;
     c->launches = 0;
     const ABModel abm = ab_inputs(c);
     for (Frame& f : c->frames) f.mask_done = false;
@@ -842,9 +983,6 @@ int run_composite(ds_canvas* c) {
     // the next slice's level-0 feed. Stream order on the second stream gives the cross-slice order for free: a
     // slice's level >= 1 feeds read the pyramid rows the previous slice left, its collapse continues from the rows
     // the previous collapse finalised. With one slice, or per-kernel profiling, everything is on the canvas stream.
-    const bool feather = c->desc.blend_mode == DS_BLEND_FEATHER;
-    const bool two = c->subs.size() > 1 && !c->profiling && c->bulk && c->tail;
-    const stream_t P = two ? c->bulk : c->stream, Q = two ? c->tail : c->stream;
     if (two) {
         // after the previous composite and the metadata copy (both on the canvas stream)
         if ((rc = ev_make(&c->ev_start)) || (rc = ev_record(c->ev_start, c->stream))) return rc;
@@ -852,7 +990,7 @@ int run_composite(ds_canvas* c) {
     }
     for (size_t b = 0; b < c->subs.size(); b++) {
         SubBand& sb = c->subs[b];
-        if ((rc = wait_for_frames(c, P, &c->waited_seq, sb))) return rc;
+        if (b > 0 && (rc = issue_for_slice(c, sb, P))) return rc;
         trace_mark(c, P, "slice begin, row", sb.rows.lo);
         if (feather) {
             if ((rc = launch_feather(c, P, sb, abm))) return rc;
@@ -872,6 +1010,11 @@ int run_composite(ds_canvas* c) {
     if (two) {
         // join: the canvas stream is the one callers synchronise on
         if ((rc = ev_wait(c->stream, c->subs.back().done))) return rc;
+    }
+    // source rows no slice of this handle reads still belong to the resident frame
+    if (c->n_pending > 0) {
+        if ((rc = issue_all(c))) return rc;
+        if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->stream, c->ev_chunks))) return rc;
     }
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev1, c->stream));
@@ -911,7 +1054,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     const bool was_used = f.used;
     const FrameDev before = f.dev;
     // the frame's buffers may still be read by the previous composite
-    if (c->ev_done_valid && (rc = ev_wait(c->up, c->ev_done))) return rc;
+    if (c->ev_done_valid && ((rc = ev_wait(c->up, c->ev_done)) || (rc = ev_wait(c->xp, c->ev_done)))) return rc;
     f.used = true; f.w = w; f.h = h; f.xf = *xf;
     f.corner_x = pl[0]; f.corner_y = pl[1]; f.bw = pl[2]; f.bh = pl[3];
     // the frame must lie inside the canvas ROI (prepare(resultRoi(corners, sizes)) guarantees it in the reference)
@@ -921,25 +1064,30 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
         return fail(DS_ERR_BAD_ARG, "frame %d bbox (%d,%d %dx%d) leaves the canvas ROI (%d,%d %dx%d)", idx, f.corner_x, f.corner_y,
                     f.bw, f.bh, c->desc.x, c->desc.y, c->desc.width, c->desc.height);
     }
-    // source: staging copy (dense BGR) -> BGRX expansion
+    // source: dense BGR rows -> staging slot -> BGRX expansion, in chunks of source rows
     f.pitch = (w + 31) & ~31;
     if ((rc = grow(c, (void**)&f.d_src, &f.src_cap, (size_t)f.pitch * h * sizeof(uint32_t)))) return rc;
-    ExpandParams ep;
-    if (on_device) {
-        ep.src = (const uint8_t*)bgr; ep.src_stride = stride;
-    } else {
-        const size_t dense = (size_t)w * 3;
-        if ((rc = grow(c, (void**)&c->d_stage, &c->stage_cap, dense * h))) return rc;
-        trace_mark(c, c->up, "h2d begin, frame", idx);
-        if ((rc = h2d_2d(c->d_stage, dense, bgr, stride, dense, (size_t)h, c->up))) return rc;
-        trace_mark(c, c->up, "h2d end, frame", idx);
-        ep.src = c->d_stage; ep.src_stride = dense;
+#if !DS_CUDA
+    memset(f.d_src, 0xA5, (size_t)f.pitch * h * sizeof(uint32_t));   // emulator: a slice reading rows that were not delivered yet shows
+#endif
+    if (!on_device) {
+        const size_t need = (size_t)std::min(c->chunk_rows, h) * w * 3;
+        if (need > c->slot_cap) {
+            for (int k = 0; k < ds_canvas::NSLOT; k++) {
+                size_t cap = c->slot_cap;
+                if ((rc = grow(c, (void**)&c->d_slot[k], &cap, need))) return rc;   // cudaFree waits for chunks in flight
+                c->slot_used[k] = false;
+            }
+            c->slot_cap = need;
+        }
     }
-    ep.dst = f.d_src; ep.dst_pitch = f.pitch; ep.w = w; ep.h = h;
-    if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->up, 0))) return rc;
-    trace_mark(c, c->up, "expand end, frame", idx);
-    // The upload stream is in order, so the staging buffer is free again when the next copy starts. Without
-    // DS_UPLOAD_ASYNC the caller's buffers are only borrowed for the call: the stream is drained before returning.
+    if (f.pend.left > 0) c->n_pending--;   // replaced before it was copied
+    f.pend.src = (const uint8_t*)bgr; f.pend.stride = stride; f.pend.on_device = on_device;
+    f.pend.nchunks = (h + c->chunk_rows - 1) / c->chunk_rows; f.pend.left = f.pend.nchunks;
+    f.pend.issued.assign((size_t)f.pend.nchunks, 0);
+    c->n_pending++;
+    // Without DS_UPLOAD_ASYNC the caller's buffers are only borrowed for the call: copy now, drain before returning.
+    if (!async && (rc = issue_rows(c, idx, 0, h - 1))) return rc;
     // blend-mode specific geometry and buffers
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND) {
         dsgeo::feed_roi(c->desc.x, c->desc.y, c->pw, c->ph, c->L, f.corner_x, f.corner_y, f.bw, f.bh, f.rx, f.ry, f.rw, f.rh);
@@ -1006,10 +1154,8 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
         for (int k = 0; k < 3; k++) f.dev.cgain[k] = opts->compensator_gain[k];
     }
     f.dev.any_gain = (f.dev.has_gain || f.dev.has_cgain || f.dev.gainmap) ? 1 : 0;
-    f.seq = ++c->up_seq;
-    if ((rc = ev_make(&f.ready)) || (rc = ev_record(f.ready, c->up))) return rc;
     if (async) c->async_pending = true;
-    else if ((rc = stream_sync(c->up))) return rc;
+    else if ((rc = stream_sync(c->up)) || (rc = stream_sync(c->xp))) return rc;
     // same geometry, buffers and gains as before (a new image for the same slot): the launch metadata stands
     if (!was_used || memcmp(&before, &f.dev, sizeof(FrameDev)) != 0) c->dirty = true;
     c->composited = false;
@@ -1123,6 +1269,7 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
         const int mid_prio = hi_prio < lo_prio - 1 ? hi_prio + 1 : hi_prio;
         if (cudaStreamCreateWithPriority(&c->up, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->dl, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&c->xp, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
             cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, lo_prio) != cudaSuccess ||
             cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, mid_prio) != cudaSuccess) {
             ds_destroy_canvas(c);
@@ -1131,6 +1278,7 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
 #endif
+    if (const char* e = getenv("DS_UPLOAD_CHUNK_ROWS")) { if (atoi(e) > 0) c->chunk_rows = atoi(e); }
     // output rows [band.lo, out_hi)
     c->out_hi = std::min(c->band.hi, desc->height);
     const int out_rows = std::max(c->out_hi - c->band.lo, 0);
@@ -1173,6 +1321,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     set_device(c);
 #if DS_CUDA
     if (c->up) cudaStreamSynchronize(c->up);
+    if (c->xp) cudaStreamSynchronize(c->xp);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->bulk) cudaStreamSynchronize(c->bulk);
     if (c->tail) cudaStreamSynchronize(c->tail);
@@ -1180,11 +1329,12 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
 #endif
     for (Frame& f : c->frames) {
         dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_gainmap);
-        ev_drop(f.ready);
     }
     for (int l = 0; l < DS_MAXL; l++) dev_free(c->d_lvl_alloc[l]);
     for (SubBand& sb : c->subs) { ev_drop(sb.done); ev_drop(sb.fed); ev_drop(sb.fed0); }
-    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_stage); dev_free(c->d_meta);
+    dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_meta);
+    for (int k = 0; k < ds_canvas::NSLOT; k++) { dev_free(c->d_slot[k]); ev_drop(c->slot_copied[k]); ev_drop(c->slot_free[k]); }
+    ev_drop(c->ev_chunks); ev_drop(c->ev_opts);
     pinned_free(c->h_meta);
     ev_drop(c->ev_done); ev_drop(c->ev_meta); ev_drop(c->ev_start);
 #if DS_CUDA
@@ -1192,6 +1342,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->up) cudaStreamDestroy(c->up);
+    if (c->xp) cudaStreamDestroy(c->xp);
     if (c->dl) cudaStreamDestroy(c->dl);
     if (c->bulk) cudaStreamDestroy(c->bulk);
     if (c->tail) cudaStreamDestroy(c->tail);
@@ -1221,7 +1372,7 @@ DS_API int ds_synchronize(ds_canvas* c) {
     if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
     int rc;
     if ((rc = set_device(c))) return rc;
-    if ((rc = stream_sync(c->up))) return rc;
+    if ((rc = flush_uploads(c))) return rc;
     if ((rc = stream_sync(c->stream))) return rc;
     if ((rc = stream_sync(c->dl))) return rc;
     trace_dump(c);
@@ -1339,8 +1490,11 @@ static int tap_common(ds_canvas* c, int frame_idx, Frame** f) {
         return fail(DS_ERR_BAD_ARG, "frame %d not uploaded", frame_idx);
     int rc;
     if ((rc = set_device(c))) return rc;
-    if ((rc = stream_sync(c->up))) return rc;
-    if (c->dirty && (rc = build_lists(c))) return rc;
+    if ((rc = flush_uploads(c))) return rc;
+    if (c->dirty || c->subs.empty()) {
+        plan_subbands(c, c->meta_slice_rows > 0 ? c->meta_slice_rows : 0);
+        if ((rc = build_lists(c))) return rc;
+    }
     *f = &c->frames[(size_t)frame_idx];
     return DS_OK;
 }

@@ -2,6 +2,7 @@
 parity tests proper). Every case runs the library under test through the C ABI and compares with the
 oracle on the same seeded inputs. Integer / index work must be bit-exact; the blended uint8 output is
 held to the north-star bar (<= 1 LSB on >= 99.99 %) and additionally expected bit-exact."""
+import os
 import numpy as np
 
 from drone_image_stitch_cpp_b200 import _lib as L
@@ -78,7 +79,17 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
     def make(band=None, slice_rows=0):
         """slice_rows > 0: the pipelined schedule - asynchronous uploads, composite in row slices of that height,
         download slice by slice."""
-        cv = CP.Canvas(roi, blend, bands, 0.02, out_format, 0, band=band, lib=lib, pipeline_rows=slice_rows)
+        # small upload chunks for the pipelined schedule, so that every slice waits for its own source rows only
+        old = os.environ.get("DS_UPLOAD_CHUNK_ROWS")
+        if slice_rows > 0:
+            os.environ["DS_UPLOAD_CHUNK_ROWS"] = "24"
+        try:
+            cv = CP.Canvas(roi, blend, bands, 0.02, out_format, 0, band=band, lib=lib, pipeline_rows=slice_rows)
+        finally:
+            if old is None:
+                os.environ.pop("DS_UPLOAD_CHUNK_ROWS", None)
+            else:
+                os.environ["DS_UPLOAD_CHUNK_ROWS"] = old
         for i, (s, xf) in enumerate(zip(specs, xfs)):
             if band is not None and not cv.touches(rois[i]):
                 continue
