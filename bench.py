@@ -287,7 +287,6 @@ def run_native(args):
         e2e_steps = max(2, min(args.steps, 5))
         # the step's result is the panorama (what composePanorama hands back, stitch_robust.cpp:256); the
         # result mask stays on the device unless asked for
-        h2d = sum(int(a.nbytes) for a in host_np)
         d2h = int(out_pin.numel())
 
         def e2e_step():
@@ -302,16 +301,19 @@ def run_native(args):
 
         e2e_step()
         barrier()
+        h2d0 = int(cv.info().h2d_bytes_total)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
         dt = time.perf_counter() - t0
+        # bytes the library actually copied (a row-band handle only pulls the source rows its band reads)
+        h2d = (int(cv.info().h2d_bytes_total) - h2d0) // e2e_steps
         t = torch.tensor([dt], device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_val = canvas_mp * e2e_steps / float(t.item())
-        h2d_t = torch.tensor([float(h2d), float(d2h)], device=f"cuda:{local}")
+        h2d_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(h2d_t)
         ab_total = int(cv.info().algorithmic_bytes)

@@ -64,7 +64,8 @@ class ds_canvas_info(C.Structure):
         ("band_y0", C.c_int32), ("band_y1", C.c_int32),
         ("device_bytes", C.c_int64), ("launches_last_composite", C.c_int64),
         ("ms_last_composite", C.c_float), ("algorithmic_bytes", C.c_int64),
-        ("reserved", C.c_int32 * 8),
+        ("h2d_bytes_total", C.c_int64),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

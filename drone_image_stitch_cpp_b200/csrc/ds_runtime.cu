@@ -193,6 +193,7 @@ struct Frame {
     float* d_gainmap = nullptr; size_t gainmap_cap = 0;
     FrameDev dev{};
     bool mask_done = false; // FEATHER: mask bit plane built for the current composite
+    bool partial = false;   // only the source rows a row-band handle reads are resident
     // Source pixels still to be brought in (DS_UPLOAD_ASYNC): the copy is cut into chunks of source rows that
     // ds_composite_async issues in the order its row slices need them.
     struct Pending {
@@ -269,6 +270,7 @@ struct ds_canvas {
     bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
     int feather_R = 0;
     int64_t device_bytes = 0;
+    int64_t h2d_bytes = 0;   // frame bytes copied host -> device so far
     int64_t launches = 0;
     float last_ms = 0.f;
     bool composited = false;
@@ -485,6 +487,7 @@ int issue_chunk(ds_canvas* c, int fi, int k) {
         if (c->slot_used[sl] && (rc = ev_wait(c->up, c->slot_free[sl]))) return rc;   // its previous chunk is expanded
         trace_mark(c, c->up, "h2d begin, frame", fi);
         if ((rc = h2d_2d(c->d_slot[sl], dense, pd.src + (size_t)r0 * pd.stride, pd.stride, dense, (size_t)nr, c->up))) return rc;
+        c->h2d_bytes += (int64_t)(dense * (size_t)nr);
         if ((rc = ev_make(&c->slot_copied[sl])) || (rc = ev_record(c->slot_copied[sl], c->up)) || (rc = ev_wait(c->xp, c->slot_copied[sl]))) return rc;
         ep.src = c->d_slot[sl]; ep.src_stride = dense;
         if ((rc = launch<ExpandBody, 256>(ep, ExpandBody::blocks(ep), c->xp, 0))) return rc;
@@ -1011,10 +1014,18 @@ int run_composite(ds_canvas* c) {
         // join: the canvas stream is the one callers synchronise on
         if ((rc = ev_wait(c->stream, c->subs.back().done))) return rc;
     }
-    // source rows no slice of this handle reads still belong to the resident frame
     if (c->n_pending > 0) {
-        if ((rc = issue_all(c))) return rc;
-        if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->stream, c->ev_chunks))) return rc;
+        const bool whole = c->band.lo == 0 && c->band.hi >= (feather ? c->desc.height : c->ph);
+        if (whole) {
+            // source rows no slice read (none, normally) still belong to the resident frame
+            if ((rc = issue_all(c))) return rc;
+            if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->stream, c->ev_chunks))) return rc;
+        } else {
+            // a row-band handle never reads the source rows that map outside its band + halo: they are not
+            // transferred at all (the frame stays partially resident; only the whole-frame debug taps mind)
+            for (Frame& f : c->frames)
+                if (f.used && f.pend.left > 0) { f.pend.left = 0; f.pend.src = nullptr; f.partial = true; c->n_pending--; }
+        }
     }
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev1, c->stream));
@@ -1085,6 +1096,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     f.pend.src = (const uint8_t*)bgr; f.pend.stride = stride; f.pend.on_device = on_device;
     f.pend.nchunks = (h + c->chunk_rows - 1) / c->chunk_rows; f.pend.left = f.pend.nchunks;
     f.pend.issued.assign((size_t)f.pend.nchunks, 0);
+    f.partial = false;
     c->n_pending++;
     // Without DS_UPLOAD_ASYNC the caller's buffers are only borrowed for the call: copy now, drain before returning.
     if (!async && (rc = issue_rows(c, idx, 0, h - 1))) return rc;
@@ -1443,6 +1455,7 @@ DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
     info->device_bytes = c->device_bytes;
     info->launches_last_composite = c->launches;
     info->ms_last_composite = c->last_ms;
+    info->h2d_bytes_total = c->h2d_bytes;
     // SURVEY.md §8(d) algorithmic-bytes model
     const double C = (double)c->desc.width * c->desc.height;
     if (c->desc.blend_mode == DS_BLEND_FEATHER) info->algorithmic_bytes = (int64_t)(3.0 * src_px + 4.0 * C);
@@ -1531,6 +1544,7 @@ DS_API int ds_debug_get_warped(ds_canvas* c, int frame_idx, uint8_t* bgr, uint8_
     int rc = tap_common(c, frame_idx, &f);
     if (rc) return rc;
     if (!bgr || !mask) return fail(DS_ERR_BAD_ARG, "null output");
+    if (f->partial) return fail(DS_ERR_STATE, "frame %d is only partially resident (asynchronous upload into a row-band handle)", frame_idx);
     const size_t n = (size_t)f->bw * f->bh;
     uint8_t* d_b = nullptr; uint8_t* d_m = nullptr;
     if ((rc = dev_alloc_t(&d_b, n * 3))) return rc;

@@ -145,7 +145,9 @@ typedef struct ds_canvas_info {
     int64_t launches_last_composite;     /* kernels launched by the last ds_composite */
     float ms_last_composite;             /* device time of the last ds_composite (CUDA events) */
     int64_t algorithmic_bytes;           /* SURVEY.md §8(d) AB model for the uploaded frames */
-    int32_t reserved[8];
+    int64_t h2d_bytes_total;             /* frame bytes copied host -> device by this handle so far (a row-band
+                                          * handle fed with DS_UPLOAD_ASYNC transfers only the source rows it reads) */
+    int32_t reserved[6];
 } ds_canvas_info;
 
 /* ---- geometry helpers (host only, no device needed) ---- */

@@ -173,3 +173,55 @@ def test_pipelined_emu(emu_lib, blend):
 @pytest.mark.parametrize("blend", ["multiband", "feather"])
 def test_pipelined_gpu(cuda_lib, blend):
     _pipelined(cuda_lib, blend)
+
+
+def _band_partial_upload(lib):
+    """A row-band handle fed with DS_UPLOAD_ASYNC copies only the source rows that map into its band (+ halo):
+    fewer bytes than the frames hold, the same output rows, and the whole-frame debug tap refuses."""
+    import os
+    from drone_image_stitch_cpp_b200 import _lib as L
+    sv = synth.grid_survey(1, 4, 160, 240, overlap=0.3, seed=47, work_scale=0.5)
+    xfs = [CP.plane_transform(K, R, sv.scale) for K, R in zip(sv.Ks, sv.Rs)]
+    rois = [CP.warp_roi(xf, 160, 240, lib) for xf in xfs]
+    roi = CP.result_roi(rois)
+    whole = CP.Canvas(roi, "multiband", 2, lib=lib)
+    for i, (f, xf) in enumerate(zip(sv.frames, xfs)):
+        whole.upload(i, f, xf)
+    whole.composite()
+    ref, _ = whole.download()
+    assert whole.info().h2d_bytes_total == sum(f.nbytes for f in sv.frames)
+    H = whole.info().padded_height
+    y0, y1 = (H // 3) // 4 * 4, (2 * H // 3) // 4 * 4
+    os.environ["DS_UPLOAD_CHUNK_ROWS"] = "16"
+    try:
+        band = CP.Canvas(roi, "multiband", 2, band=(y0, y1), lib=lib)
+    finally:
+        os.environ.pop("DS_UPLOAD_CHUNK_ROWS", None)
+    sent = 0
+    for i, (f, xf) in enumerate(zip(sv.frames, xfs)):
+        if band.touches(rois[i]):
+            band.upload(i, f, xf, async_=True)
+            sent += f.nbytes
+    band.composite_async()
+    rows, _ = band.download()
+    band.synchronize()
+    assert np.array_equal(rows, ref[y0:min(y1, roi[3])])
+    copied = band.info().h2d_bytes_total
+    assert 0 < copied < 0.8 * sent, (copied, sent)
+    # a second composite over the resident rows gives the same bytes
+    band.composite()
+    rows2, _ = band.download()
+    assert np.array_equal(rows2, rows)
+    with pytest.raises(L.DroneStitchError):
+        band.warped(0 if band.touches(rois[0]) else 1)
+    band.close()
+    whole.close()
+
+
+def test_band_partial_upload_emu(emu_lib):
+    _band_partial_upload(emu_lib)
+
+
+@pytest.mark.gpu
+def test_band_partial_upload_gpu(cuda_lib):
+    _band_partial_upload(cuda_lib)
