@@ -1038,9 +1038,9 @@ struct MBFastBody {
             bool known_uniform = false;  // the mask is known to be 255 everywhere without a block-wide vote
             if constexpr (LEVEL0) {
             // ---- tables: reflected bbox index + per-column / per-row map terms
-            for (int i = tid; i < pw + ph; i += NT) {
-                if (i < pw) {
-                    const int u = rx + px0 + i - F.cx;
+            for (int i = tid; i < PWS + ph; i += NT) {
+                if (i < PWS) {
+                    const int u = rx + px0 + imin(i, pw - 1) - F.cx;   // padding columns repeat the last one
                     const int ur = refl(u, F.w, BORDER_REFL);
                     float U = (float)(F.tlx + ur);
                     if (F.scale != 1.f) U = f_div(U, F.scale);
@@ -1050,7 +1050,7 @@ struct MBFastBody {
                     c.u = (unsigned)u < (unsigned)F.w ? u : ~ur;   // >= 0: inside (u == ur); < 0: ~(reflected index)
                     s_col[i] = c;
                 } else {
-                    const int yy = i - pw;
+                    const int yy = i - PWS;
                     const int v = ry + py0 + yy - F.cy;
                     const int vr = refl(v, F.h, BORDER_REFL);
                     float V = (float)(F.tly + vr);
@@ -1122,25 +1122,25 @@ struct MBFastBody {
                 }
                 if (interior) {
                     // UB pixels per thread and iteration: all taps are requested before any is used, so each
-                    // warp keeps 4 * UB loads in flight (the loop is otherwise bound by L1/L2 latency)
+                    // warp keeps 4 * UB loads in flight (the loop is otherwise bound by L1/L2 latency).
+                    // Branch-free body: slots past the end of the region repeat its last pixel (and do not
+                    // store); the column table is valid over the whole pitch, so padding columns compute a
+                    // harmless value nobody reads.
                     constexpr int UB = 4;
-                    const int npx = PWS * ph;
+                    const int npx = PWS * ph, last = npx - 1;
+                    const SAddr a_col = s_addr(s_col), a_row = s_addr(s_row), a_g0 = s_addr(s_g0);
                     for (int i0 = tid; i0 < npx; i0 += UB * NT) {
                         int ix[UB], iy[UB];
                         uint32_t p00[UB], p01[UB], p10[UB], p11[UB];
-                        bool ok[UB];
                         DS_UNROLL
                         for (int b = 0; b < UB; b++) {
-                            const int i = i0 + b * NT;
-                            ok[b] = false;
-                            ix[b] = iy[b] = 0; p00[b] = p01[b] = p10[b] = p11[b] = 0u;
-                            if (i >= npx) continue;   // warp-uniform except in one warp of the last iteration
+                            const int i = imin(i0 + b * NT, last);
                             const int yy = i / PWS, xx = i - yy * PWS;
-                            ok[b] = xx < pw;
-                            const L0Col c = s_col[xx < pw ? xx : 0];
-                            const L0Row r = s_row[yy];
-                            const float x = f_add(f_add(c.a0, r.b1), k2);
-                            const float y = f_add(f_add(c.a3, r.b4), k5);
+                            float ca0, ca3, rb1, rb4;
+                            lds_f2(a_col + xx * 16, ca0, ca3);
+                            lds_f2(a_row + yy * 16, rb1, rb4);
+                            const float x = f_add(f_add(ca0, rb1), k2);
+                            const float y = f_add(f_add(ca3, rb4), k5);
 #if DS_CUDA
                             ix[b] = __float2int_rn(f_mul(x, 32.f)); iy[b] = __float2int_rn(f_mul(y, 32.f));
 #else
@@ -1160,7 +1160,8 @@ struct MBFastBody {
                             int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
                             int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
                             if (has_gain) apply_gains(F, ob, og, orr, 0, 0);   // no gain map on this path
-                            if (ok[b]) s_g0[i0 + b * NT] = (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | 0xff000000u;
+                            const int i = i0 + b * NT;
+                            if (i < npx) sts_u1(a_g0 + i * 4, (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | 0xff000000u);
                         }
                     }
                     m_or = 255;   // m_and stays 255: the mask is uniform 255
