@@ -204,6 +204,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(idx):
+    """Pin this process (and so its pinned host buffers, first-touch) to the CPU cores NVML reports as local to
+    GPU `idx`: with several ranks per box the host<->device copies otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cores local to GPU {idx}"
+    except Exception as e:  # measurement nicety only
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -217,6 +237,7 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (libdronestitch_cuda has no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.default_library()
@@ -356,7 +377,7 @@ def run_native(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/int16/f32", "data": "synthetic",
                 "config": {"workload": desc, "canvas": [roi[2], roi[3]], "frames": len(xfs), "bands_per_gpu": 1,
-                           "parallelism": f"row-bands x{world}", "l2": "inputs larger than L2 (720 MB of BGRX frames per band)"},
+                           "parallelism": f"row-bands x{world}", "host_affinity": numa, "l2": "inputs larger than L2 (720 MB of BGRX frames per band)"},
                 "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_t[0].item()),
                         "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": e2e_steps},
