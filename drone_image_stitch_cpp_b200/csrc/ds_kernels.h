@@ -1121,17 +1121,18 @@ struct MBFastBody {
                     }
                 }
                 if (interior) {
-                    // UB pixels per thread and iteration: all taps are requested before any is used, so each
-                    // warp keeps 4 * UB loads in flight (the loop is otherwise bound by L1/L2 latency).
-                    // Branch-free body: slots past the end of the region repeat its last pixel (and do not
-                    // store); the column table is valid over the whole pitch, so padding columns compute a
-                    // harmless value nobody reads.
-                    constexpr int UB = 4;
+                    // Software-pipelined in two register sets of UB pixels per thread: the taps of stage k+1 are
+                    // requested before stage k is interpolated, so the L1 / L2 latency of the gathers hides behind
+                    // the arithmetic of the same warp (occupancy is 2 CTAs / SM; other warps alone do not cover it).
+                    // Branch-free: stages are block-uniform, slots past the end of the region repeat its last
+                    // pixel and do not store; the column table is valid over the whole pitch, so padding
+                    // columns compute a harmless value nobody reads.
+                    constexpr int UB = 2, STEP = UB * NT;
                     const int npx = PWS * ph, last = npx - 1;
+                    const int nst = (npx + STEP - 1) / STEP;
                     const SAddr a_col = s_addr(s_col), a_row = s_addr(s_row), a_g0 = s_addr(s_g0);
-                    for (int i0 = tid; i0 < npx; i0 += UB * NT) {
-                        int ix[UB], iy[UB];
-                        uint32_t p00[UB], p01[UB], p10[UB], p11[UB];
+                    struct Taps { int ix[UB], iy[UB]; uint32_t p00[UB], p01[UB], p10[UB], p11[UB]; };
+                    auto fetch = [&](int i0, Taps& t) {
                         DS_UNROLL
                         for (int b = 0; b < UB; b++) {
                             const int i = imin(i0 + b * NT, last);
@@ -1142,19 +1143,21 @@ struct MBFastBody {
                             const float x = f_add(f_add(ca0, rb1), k2);
                             const float y = f_add(f_add(ca3, rb4), k5);
 #if DS_CUDA
-                            ix[b] = __float2int_rn(f_mul(x, 32.f)); iy[b] = __float2int_rn(f_mul(y, 32.f));
+                            t.ix[b] = __float2int_rn(f_mul(x, 32.f)); t.iy[b] = __float2int_rn(f_mul(y, 32.f));
 #else
-                            ix[b] = f2i_rn(f_mul(x, 32.f)); iy[b] = f2i_rn(f_mul(y, 32.f));
+                            t.ix[b] = f2i_rn(f_mul(x, 32.f)); t.iy[b] = f2i_rn(f_mul(y, 32.f));
 #endif
-                            const uint32_t* r0 = src + ((iy[b] >> 5) * pitch + (ix[b] >> 5));
-                            p00[b] = ld_ro(r0); p01[b] = ld_ro(r0 + 1); p10[b] = ld_ro(r0 + pitch); p11[b] = ld_ro(r0 + pitch + 1);
+                            const uint32_t* r0 = src + ((t.iy[b] >> 5) * pitch + (t.ix[b] >> 5));
+                            t.p00[b] = ld_ro(r0); t.p01[b] = ld_ro(r0 + 1); t.p10[b] = ld_ro(r0 + pitch); t.p11[b] = ld_ro(r0 + pitch + 1);
                         }
+                    };
+                    auto finish = [&](int i0, const Taps& t) {
                         DS_UNROLL
                         for (int b = 0; b < UB; b++) {
-                            const int ax = ix[b] & 31, ay = iy[b] & 31;
+                            const int ax = t.ix[b] & 31, ay = t.iy[b] & 31;
                             const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
-                            const uint32_t t0 = byte_perm(p00[b], p01[b], 0x5140), t0r = byte_perm(p00[b], p01[b], 0x6262);
-                            const uint32_t t1 = byte_perm(p10[b], p11[b], 0x5140), t1r = byte_perm(p10[b], p11[b], 0x6262);
+                            const uint32_t t0 = byte_perm(t.p00[b], t.p01[b], 0x5140), t0r = byte_perm(t.p00[b], t.p01[b], 0x6262);
+                            const uint32_t t1 = byte_perm(t.p10[b], t.p11[b], 0x5140), t1r = byte_perm(t.p10[b], t.p11[b], 0x6262);
                             const int wy1 = ay, wy0 = 32 - ay;
                             int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
                             int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
@@ -1163,7 +1166,17 @@ struct MBFastBody {
                             const int i = i0 + b * NT;
                             if (i < npx) sts_u1(a_g0 + i * 4, (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | 0xff000000u);
                         }
+                    };
+                    Taps A, B;
+                    fetch(tid, A);
+                    int st = 0;
+                    for (; st + 2 <= nst; st += 2) {
+                        fetch(tid + (st + 1) * STEP, B);
+                        finish(tid + st * STEP, A);
+                        fetch(tid + (st + 2) * STEP, A);   // past the end on the last trip: clamped, unused
+                        finish(tid + (st + 1) * STEP, B);
                     }
+                    if (st < nst) finish(tid + st * STEP, A);
                     m_or = 255;   // m_and stays 255: the mask is uniform 255
                     known_uniform = true;
                 } else
