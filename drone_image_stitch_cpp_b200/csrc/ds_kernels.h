@@ -949,6 +949,8 @@ struct MBFastBody {
         const float c255 = f_mul(255.f, 1.f / 255.f);
 
         for (int i = tid; i < T * T; i += NT) { s_acc[i] = make_i2(0, 0); s_ws[i] = 0.f; }
+        int* const s_vote = (int*)(smem + MBAR_OFF + 16);   // block-wide OR of the uniformity bits (block_or_bits)
+        if (tid == 0) *s_vote = 0;
 #if DS_CUDA
         unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);   // two barriers, one per box buffer
         uint32_t tma_phase0 = 0u, tma_phase1 = 0u;
@@ -1251,13 +1253,24 @@ struct MBFastBody {
                     if (tma_cur) tma_phase1 ^= 1u; else tma_phase0 ^= 1u;
                     if (tid == 0) { const int jn = next_live(fi + 1); if (jn < f_end) tma_issue(jn, tma_cur ^ 1); }
                     tma_cur ^= 1;
-                    for (int i = tid; i < PWS * ph; i += NT) {
-                        const int yy = i / PWS, xx = i - yy * PWS;
-                        if (xx >= pw) continue;
-                        const float w = s_w[i];
-                        m_and &= (w == 1.f) ? 255 : 0;
-                        m_or |= (w != 0.f) ? 255 : 0;
+                    // weights lie in [0, 1]: all == 1 <=> min == 1, all == 0 <=> max == 0; four per 128-bit load
+                    float wmn = 1.f, wmx = 0.f;
+                    constexpr int Q = PWS / 4;
+                    static_assert(PWS % 4 == 0, "rows of the weight box are read as float4");
+                    for (int q = tid; q < Q * ph; q += NT) {
+                        const int yy = q / Q, x4 = (q - yy * Q) * 4;
+                        if (x4 >= pw) continue;
+                        const float4 v = *(const float4*)(s_w + yy * PWS + x4);
+                        wmn = fminf(wmn, v.x); wmx = fmaxf(wmx, v.x);
+                        if (x4 + 3 < pw) {
+                            wmn = fminf(fminf(wmn, v.y), fminf(v.z, v.w)); wmx = fmaxf(fmaxf(wmx, v.y), fmaxf(v.z, v.w));
+                        } else {
+                            if (x4 + 1 < pw) { wmn = fminf(wmn, v.y); wmx = fmaxf(wmx, v.y); }
+                            if (x4 + 2 < pw) { wmn = fminf(wmn, v.z); wmx = fmaxf(wmx, v.z); }
+                        }
                     }
+                    m_and = (wmn == 1.f) ? 255 : 0;
+                    m_or = (wmx != 0.f) ? 255 : 0;
                 } else
 #endif
                 {
@@ -1282,8 +1295,10 @@ struct MBFastBody {
                 DS_SYNC();
                 uni255 = (c255 == 1.f); uni0 = 0;
             } else {
-                uni255 = block_and(all255) && (!LEVEL0 || c255 == 1.f);   // every weight of the needed region is exactly 1
-                uni0 = block_and(all0);
+                // one barrier for both votes: bit 0 = some weight is not 1, bit 1 = some weight is not 0
+                const int bits = block_or_bits((all255 ? 0 : 1) | (all0 ? 0 : 2), s_vote);
+                uni255 = !(bits & 1) && (!LEVEL0 || c255 == 1.f);   // every weight of the needed region is exactly 1
+                uni0 = !(bits & 2);
             }
 
             // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op
@@ -1329,6 +1344,7 @@ struct MBFastBody {
                     G1out[(size_t)gy * op1 + gx] = byte_perm(o.br, o.g, 0x5240);
             }
             DS_SYNC();
+            if (tid == 0) *s_vote = 0;   // read by everyone two barriers ago; next written after this frame's last barrier
 
             // ---- W_1 = pyrDownF32(W_0) over the own range
             if (uni255 || uni0) {
