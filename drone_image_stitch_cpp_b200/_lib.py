@@ -20,6 +20,7 @@ DS_BORDER_CONSTANT, DS_BORDER_REFLECT = 0, 1
 EXPORTS = [
     "ds_warp_roi", "ds_frame_touches_band", "ds_create_canvas", "ds_upload_frame", "ds_upload_frame_device",
     "ds_composite", "ds_composite_async", "ds_synchronize", "ds_download_tile", "ds_destroy_canvas",
+    "ds_p2p_export", "ds_p2p_connect", "ds_p2p_disconnect", "ds_composite_stage",
     "ds_last_error", "ds_get_info", "ds_version", "ds_debug_get_placement", "ds_debug_get_maps",
     "ds_debug_get_warped", "ds_debug_get_frame_level", "ds_set_profiling", "ds_get_kernel_times",
 ]
@@ -112,6 +113,10 @@ class Library:
         d.ds_debug_get_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         d.ds_debug_get_warped.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         d.ds_debug_get_frame_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        d.ds_p2p_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        d.ds_p2p_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        d.ds_p2p_disconnect.argtypes = [C.c_void_p]
+        d.ds_composite_stage.argtypes = [C.c_void_p, C.c_int]
 
     def check(self, rc):
         if rc != DS_OK:

@@ -165,6 +165,25 @@ class Canvas:
     def composite_async(self):
         self.lib.check(self.lib.dll.ds_composite_async(self._h))
 
+    # ---- NVLink P2P halo exchange between row-band handles (include/dronestitch.h)
+    def p2p_export(self):
+        """-> bytes describing this handle's band, counters and per-frame level-1 arrays, for the neighbours."""
+        n = C.c_size_t()
+        self.lib.check(self.lib.dll.ds_p2p_export(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self.lib.check(self.lib.dll.ds_p2p_export(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def p2p_connect(self, side, blob):
+        """side 0: the handle of the band above, 1: below."""
+        self.lib.check(self.lib.dll.ds_p2p_connect(self._h, int(side), blob, len(blob)))
+
+    def p2p_disconnect(self):
+        self.lib.check(self.lib.dll.ds_p2p_disconnect(self._h))
+
+    def composite_stage(self, stage):
+        self.lib.check(self.lib.dll.ds_composite_stage(self._h, int(stage)))
+
     def synchronize(self):
         self.lib.check(self.lib.dll.ds_synchronize(self._h))
         self._pending.clear()

@@ -220,6 +220,37 @@ struct ExpandBody {
     }
 };
 
+// NVLink P2P halo pull: every segment is a run of whole rows of a straddling frame's level-1 Gaussian or weight
+// level in the neighbouring handle's memory (peer-mapped), copied to the same rows of the local arrays. Loads
+// bypass the local caches (the data was written by another GPU).
+struct PullSeg { const uint4* src; uint4* dst; long long n16; };
+struct PullParams { const PullSeg* segs; int nsegs; };
+struct PullBody {
+    static constexpr int BLOCKS_PER_SEG = 24;
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const PullParams& p, int block, int tid, unsigned char*) {
+        const int si = block / BLOCKS_PER_SEG, part = block - si * BLOCKS_PER_SEG;
+        if (si >= p.nsegs) return;
+        const PullSeg sg = p.segs[si];
+        for (long long i = (long long)part * NT + tid; i < sg.n16; i += (long long)BLOCKS_PER_SEG * NT) sg.dst[i] = ld_peer(sg.src + i);
+    }
+};
+
+// Hand-over counters between neighbouring handles: one thread publishes `value` into up to two words of the
+// neighbours' memory after making this stream's earlier writes visible system-wide.
+struct SignalParams { int* a; int* b; int value; };
+struct SignalBody {
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const SignalParams& p, int block, int tid, unsigned char*) {
+        if (block != 0 || tid != 0) return;
+        fence_system();
+        if (p.a) st_flag(p.a, p.value);
+        if (p.b) st_flag(p.b, p.value);
+    }
+};
+
 // Copies the host-built launch metadata (tile lists, frame descriptors, tensor maps) from mapped pinned host
 // memory into its device arena: a kernel instead of a DMA so that it never queues behind frame uploads.
 struct MetaCopyParams { const uint4* src; uint4* dst; long long n16; };
@@ -1642,6 +1673,8 @@ typedef MBBody<64, true> MBBodyL0;
 typedef MBBody<32, false> MBBodyLN;
 DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
 DS_DEFINE_KERNEL(ds_meta_copy, MetaCopyBody, 256, MetaCopyParams, 1)
+DS_DEFINE_KERNEL(ds_p2p_pull, PullBody, 256, PullParams, 1)
+DS_DEFINE_KERNEL(ds_p2p_signal, SignalBody, 32, SignalParams, 1)
 DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
 DS_DEFINE_KERNEL(ds_seam_upsize, SeamUpBody, 256, SeamUpParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)

@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <new>
 #include <string>
@@ -74,6 +76,27 @@ void ev_drop(event_t e) { if (e) cudaEventDestroy(e); }
 int ev_record(event_t e, stream_t s) { DS_CK(cudaEventRecord(e, s)); return DS_OK; }
 int ev_wait(stream_t s, event_t e) { DS_CK(cudaStreamWaitEvent(s, e, 0)); return DS_OK; }
 int ev_sync(event_t e) { DS_CK(cudaEventSynchronize(e)); return DS_OK; }
+// The stream waits until the 32-bit word at `addr` (device memory of this GPU) is >= value (cyclic compare): a
+// stream memory operation, no kernel spins. Resolved from the driver at run time like the tensor-map encoder.
+typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+int stream_wait_value(stream_t s, int* addr, int value) {
+    static WaitValue32Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (WaitValue32Fn)f;
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return fail(DS_ERR_P2P_UNAVAILABLE, "cuStreamWaitValue32 is not available");
+    const int r = fn(s, (unsigned long long)(uintptr_t)addr, (unsigned int)value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (r != 0) return fail(DS_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", r);
+    return DS_OK;
+}
+int dev_zero(void* p, size_t n) { DS_CK(cudaMemset(p, 0, n)); return DS_OK; }
 // pinned host memory the device can read directly (zero-copy source of the launch metadata)
 int pinned_alloc(void** host, void** dev_view, size_t bytes) {
     DS_CK(cudaHostAlloc(host, bytes, cudaHostAllocMapped));
@@ -122,6 +145,13 @@ void ev_drop(event_t) {}
 int ev_record(event_t, stream_t) { return DS_OK; }
 int ev_wait(stream_t, event_t) { return DS_OK; }
 int ev_sync(event_t) { return DS_OK; }
+// emulation: everything is synchronous, so the word must already hold the value - anything else is a sequencing
+// error of the caller (stage 0 of every connected handle has to run before any stage 1)
+int stream_wait_value(stream_t, int* addr, int value) {
+    if (*addr - value < 0) return fail(DS_ERR_STATE, "neighbour handle is behind (counter %d, expected %d): run stage 0 on every handle first", *addr, value);
+    return DS_OK;
+}
+int dev_zero(void* p, size_t n) { memset(p, 0, n); return DS_OK; }
 int pinned_alloc(void** host, void** dev_view, size_t bytes) {
     *host = malloc(bytes ? bytes : 1);
     if (!*host) return fail(DS_ERR_OOM, "malloc(%zu) failed", bytes);
@@ -241,6 +271,22 @@ struct ds_canvas {
     int slot_next = 0;
     int chunk_rows = 512;    // source rows per upload chunk (DS_UPLOAD_CHUNK_ROWS)
     int n_pending = 0;       // frames with chunks still to issue
+    // NVLink P2P halo exchange with the handles of the bands above (0) and below (1)
+    struct PeerFrame { int idx, ry, rh, rw, gp1; const char* pyr; size_t g_off, w_off; };
+    struct Peer {
+        bool connected = false;
+        int* flags = nullptr;            // the neighbour's counter words (peer-mapped)
+        Range band{0, 0};
+        std::vector<PeerFrame> frames;
+        std::vector<void*> mapped;       // cudaIpcOpenMemHandle results to close
+    } peer[2];
+    int* d_flags = nullptr;              // [0] / [1]: level-1 rows ready, written by the neighbour above / below; [2] / [3]: pulled
+    int p2p_seq = 0;                     // composites run in exchange mode
+    bool exchange = false;               // the launch metadata (and plan[0].own) are those of the exchange mode
+    bool exchange_now = false;           // the composite being queued runs in exchange mode
+    bool stage_open = false;             // ds_composite_stage(c, 0) ran, stage 1 is outstanding
+    Range own0_recompute{0, 0};          // level-0 feed rows without / with the exchange
+    PullSeg* d_segs = nullptr; int n_segs = 0;   // meta arena
     event_t ev_chunks = 0;   // scratch: recorded on xp after the chunks a slice needs
     event_t ev_opts = 0;     // scratch: recorded on up at the start of a composite
     int meta_slice_rows = -2;   // slice height the launch metadata was built for
@@ -562,6 +608,53 @@ int issue_for_slice(ds_canvas* c, const SubBand& sb, stream_t waiter) {
     return DS_OK;
 }
 
+// ---- NVLink P2P halo exchange (include/dronestitch.h, DESIGN.md "Row bands")
+
+// Level-1 canvas rows this handle's level >= 1 feeds read beyond the band, per side: they come from the neighbour.
+Range pulled_rows(const ds_canvas* c, int side) {
+    const Range own1 = c->plan[1].own;
+    const int b_lo = c->band.lo >> 1, b_hi = std::min(c->band.hi >> 1, c->lh[1]);
+    if (side == 0) return Range{std::max(own1.lo - 4, 0), b_lo};
+    return Range{b_hi, std::min(own1.hi + 3, c->lh[1])};
+}
+
+// Can the next composite exchange halos instead of recomputing them?
+bool exchange_ready(const ds_canvas* c) {
+    if (c->desc.blend_mode != DS_BLEND_MULTIBAND || c->L < 1) return false;
+    const bool need_up = c->band.lo > 0, need_down = c->band.hi < c->ph;
+    if (!need_up && !need_down) return false;
+    return (!need_up || c->peer[0].connected) && (!need_down || c->peer[1].connected);
+}
+
+// Segments of the pull kernel: whole rows of G_1 / W_1 of every frame that reaches into the pulled rows.
+int build_pull_segments(ds_canvas* c, std::vector<PullSeg>& segs) {
+    segs.clear();
+    for (int side = 0; side < 2; side++) {
+        const ds_canvas::Peer& pr = c->peer[side];
+        if (!pr.connected) continue;
+        const Range rows = pulled_rows(c, side);
+        if (rows.lo >= rows.hi) continue;
+        for (size_t fi = 0; fi < c->frames.size(); fi++) {
+            const Frame& f = c->frames[fi];
+            if (!f.used) continue;
+            const int ry1 = f.ry >> 1, rh1 = f.rh >> 1;
+            const int a = std::max(rows.lo, ry1) - ry1, b = std::min(rows.hi, ry1 + rh1) - ry1;   // frame-local rows
+            if (a >= b) continue;
+            const ds_canvas::PeerFrame* pf = nullptr;
+            for (const ds_canvas::PeerFrame& q : pr.frames) if (q.idx == (int)fi) { pf = &q; break; }
+            if (!pf) return fail(DS_ERR_STATE, "the neighbour %s does not hold frame %zu, which reaches into its band", side ? "below" : "above", fi);
+            if (pf->ry != f.ry || pf->rh != f.rh || pf->rw != f.rw || pf->gp1 != f.dev.gp[1])
+                return fail(DS_ERR_STATE, "frame %zu has a different geometry on the neighbouring handle", fi);
+            const size_t pitch = (size_t)f.dev.gp[1] * 4;   // bytes per row of either array
+            const size_t g_local = (size_t)((const char*)f.dev.G[1] - (const char*)f.d_pyr), w_local = (size_t)((const char*)f.dev.W[1] - (const char*)f.d_pyr);
+            PullSeg g{(const uint4*)(pf->pyr + pf->g_off + (size_t)a * pitch), (uint4*)((char*)f.d_pyr + g_local + (size_t)a * pitch), (long long)((size_t)(b - a) * pitch / 16)};
+            PullSeg w{(const uint4*)(pf->pyr + pf->w_off + (size_t)a * pitch), (uint4*)((char*)f.d_pyr + w_local + (size_t)a * pitch), (long long)((size_t)(b - a) * pitch / 16)};
+            segs.push_back(g); segs.push_back(w);
+        }
+    }
+    return DS_OK;
+}
+
 // Uploads declared with DS_UPLOAD_ASYNC that no composite has consumed yet: copy them now and drain the streams.
 int flush_uploads(ds_canvas* c) {
     int rc;
@@ -753,6 +846,9 @@ int build_lists(ds_canvas* c) {
         if (c->frames[i].used) fd[i] = c->frames[i].dev; else memset(&fd[i], 0, sizeof(FrameDev));
     }
     const size_t frames_off = mbd.add(fd.data(), fd.size() * sizeof(FrameDev));
+    std::vector<PullSeg> segs;
+    if (c->exchange) { int rcs = build_pull_segments(c, segs); if (rcs) return rcs; }
+    const size_t segs_off = mbd.add(segs.data(), segs.size() * sizeof(PullSeg));
     size_t tmaps_off = 0;
     c->tmaps_ok = false;
 #if DS_CUDA
@@ -802,6 +898,7 @@ int build_lists(ds_canvas* c) {
         c->plan[l].d_ids = (int*)(base + ids_off[l]);
     }
     c->d_frames = (FrameDev*)(base + frames_off);
+    c->d_segs = (PullSeg*)(base + segs_off); c->n_segs = (int)segs.size();
     c->d_tmaps = c->tmaps_ok ? (void*)(base + tmaps_off) : nullptr;
     c->dirty = false;
     return DS_OK;
@@ -950,15 +1047,102 @@ int launch_feather(ds_canvas* c, stream_t st, const SubBand& sb, const ABModel& 
     return DS_OK;
 }
 
-int run_composite(ds_canvas* c) {
+// Tail of every composite: uploads nobody asked for, timing events, the "done" event later uploads wait for.
+int composite_epilogue(ds_canvas* c) {
     int rc;
+    const bool feather = c->desc.blend_mode == DS_BLEND_FEATHER;
+    if (c->n_pending > 0) {
+        const bool whole = c->band.lo == 0 && c->band.hi >= (feather ? c->desc.height : c->ph);
+        if (whole) {
+            // source rows no slice read (none, normally) still belong to the resident frame
+            if ((rc = issue_all(c))) return rc;
+            if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->stream, c->ev_chunks))) return rc;
+        } else {
+            // a row-band handle never reads the source rows that map outside its band + halo: they are not
+            // transferred at all (the frame stays partially resident; only the whole-frame debug taps mind)
+            for (Frame& f : c->frames)
+                if (f.used && f.pend.left > 0) { f.pend.left = 0; f.pend.src = nullptr; f.partial = true; c->n_pending--; }
+        }
+    }
+#if DS_CUDA
+    DS_CK(cudaEventRecord(c->ev1, c->stream));
+#endif
+    if ((rc = ev_make(&c->ev_done)) || (rc = ev_record(c->ev_done, c->stream))) return rc;
+    c->ev_done_valid = true;
+    c->composited = true;
+    c->stage_open = false;
+    return DS_OK;
+}
+
+int launch_signal(ds_canvas* c, int* a, int* b, int value) {
+    if (!a && !b) return DS_OK;
+    SignalParams sp{a, b, value};
+    int rc = launch<SignalBody, 32>(sp, 1, c->stream, 0);
+    if (!rc) c->launches++;
+    return rc;
+}
+
+// Exchange mode, first half: level-0 feed over exactly the band's rows, then tell the neighbours that this
+// handle's level-1 rows of composite `seq` are in place.
+int composite_exchange_begin(ds_canvas* c, const ABModel& abm) {
+    int rc;
+    const int seq = ++c->p2p_seq;
+    SubBand& sb = c->subs[0];
+    // the neighbours have pulled what they needed of the previous composite's rows (which this feed overwrites)
+    for (int side = 0; side < 2; side++)
+        if (c->peer[side].connected && (rc = stream_wait_value(c->stream, c->d_flags + 2 + side, seq - 1))) return rc;
+    if ((rc = launch_feed(c, c->stream, 0, sb, abm))) return rc;
+    // seen from the neighbour above this handle is the one below: its word [1]; and vice versa
+    return launch_signal(c, c->peer[0].connected ? c->peer[0].flags + 1 : nullptr, c->peer[1].connected ? c->peer[1].flags + 0 : nullptr, seq);
+}
+
+// Second half: wait for the neighbours' level-1 rows, pull the halo rows over NVLink, release the neighbours, and
+// run the levels above and the collapse from local memory.
+int composite_exchange_finish(ds_canvas* c) {
+    int rc;
+    const ABModel abm = ab_inputs(c);
+    const int seq = c->p2p_seq;
+    SubBand& sb = c->subs[0];
+    for (int side = 0; side < 2; side++)
+        if (c->peer[side].connected && (rc = stream_wait_value(c->stream, c->d_flags + side, seq))) return rc;
+    if (c->n_segs > 0) {
+        PullParams pp{c->d_segs, c->n_segs};
+        if ((rc = prof_mark(c, c->stream, true, "p2p_pull", 1, 0))) return rc;
+        if ((rc = launch<PullBody, 256>(pp, (long long)c->n_segs * PullBody::BLOCKS_PER_SEG, c->stream, 0))) return rc;
+        if ((rc = prof_mark(c, c->stream, false, nullptr, 0, 0))) return rc;
+        c->launches++;
+    }
+    if ((rc = launch_signal(c, c->peer[0].connected ? c->peer[0].flags + 3 : nullptr, c->peer[1].connected ? c->peer[1].flags + 2 : nullptr, seq))) return rc;
+    for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, c->stream, l, sb, abm))) return rc;
+    for (int l = c->L; l >= 1; l--) if ((rc = launch_collapse(c, c->stream, l, sb, abm))) return rc;
+    if ((rc = ev_make(&sb.done)) || (rc = ev_record(sb.done, c->stream))) return rc;
+    return composite_epilogue(c);
+}
+
+// stage: -1 = the whole composite; 0 / 1 = its two halves (ds_composite_stage)
+int run_composite(ds_canvas* c, int stage) {
+    int rc;
+    if (stage == 1) {
+        if (!c->stage_open) return fail(DS_ERR_STATE, "ds_composite_stage(c, 1) without stage 0");
+        if (c->exchange_now) return composite_exchange_finish(c);
+        c->stage_open = false;   // nothing was left to do
+        return DS_OK;
+    }
+    if (c->stage_open) return fail(DS_ERR_STATE, "the previous composite is half done: call ds_composite_stage(c, 1)");
     // pipelined (sliced) when asked for, or when frames are still arriving on the upload stream
     int slice_rows = 0;
     if (c->desc.pipeline_rows > 0) slice_rows = c->desc.pipeline_rows;
     else if (c->desc.pipeline_rows == 0 && c->async_pending) slice_rows = default_pipeline_rows();
     c->async_pending = false;
-    const bool replan = c->dirty || slice_rows != c->meta_slice_rows || c->subs.empty();
-    if (replan) plan_subbands(c, slice_rows);
+    // halos from the neighbours instead of recomputing them: only the unsliced schedule can wait for a neighbour
+    const bool xmode = slice_rows == 0 && exchange_ready(c);
+    const bool replan = c->dirty || slice_rows != c->meta_slice_rows || xmode != c->exchange || c->subs.empty();
+    if (replan) {
+        c->exchange = xmode;
+        if (c->desc.blend_mode == DS_BLEND_MULTIBAND) c->plan[0].own = xmode ? c->plan[0].acc : c->own0_recompute;
+        plan_subbands(c, slice_rows);
+    }
+    c->exchange_now = xmode;
     const bool feather = c->desc.blend_mode == DS_BLEND_FEATHER;
     const bool two = c->subs.size() > 1 && !c->profiling && c->bulk && c->tail;
     const stream_t P = two ? c->bulk : c->stream, Q = two ? c->tail : c->stream;
@@ -980,6 +1164,11 @@ int run_composite(ds_canvas* c) {
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev0, c->stream));
 #endif
+    c->stage_open = true;
+    if (xmode) {
+        if ((rc = composite_exchange_begin(c, abm))) return rc;
+        return stage == -1 ? composite_exchange_finish(c) : DS_OK;
+    }
     // Sliced schedule: the level-0 feeds (the bulk of the work) of all slices run back to back on a low-priority
     // stream; everything else of a slice - its feeds of level >= 1 and its collapse, small launches that are
     // latency-bound - follows on a high-priority stream as soon as the slice's level-0 feed is done, and overlaps
@@ -1014,26 +1203,30 @@ int run_composite(ds_canvas* c) {
         // join: the canvas stream is the one callers synchronise on
         if ((rc = ev_wait(c->stream, c->subs.back().done))) return rc;
     }
-    if (c->n_pending > 0) {
-        const bool whole = c->band.lo == 0 && c->band.hi >= (feather ? c->desc.height : c->ph);
-        if (whole) {
-            // source rows no slice read (none, normally) still belong to the resident frame
-            if ((rc = issue_all(c))) return rc;
-            if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->stream, c->ev_chunks))) return rc;
-        } else {
-            // a row-band handle never reads the source rows that map outside its band + halo: they are not
-            // transferred at all (the frame stays partially resident; only the whole-frame debug taps mind)
-            for (Frame& f : c->frames)
-                if (f.used && f.pend.left > 0) { f.pend.left = 0; f.pend.src = nullptr; f.partial = true; c->n_pending--; }
-        }
-    }
+    return composite_epilogue(c);
+}
+
+struct BlobHeader {
+    uint32_t magic, version;
+    int64_t pid;
+    int32_t device, L, pw, ph, band_lo, band_hi, nframes, pad;
+    uint64_t flags_ptr;
+    unsigned char flags_handle[64];
+};
+struct BlobFrame {
+    int32_t idx, ry, rh, rw, gp1, pad;
+    uint64_t g_off, w_off, pyr_ptr;
+    unsigned char pyr_handle[64];
+};
+const uint32_t BLOB_MAGIC = 0x50325044u;   // "DP2P"
+
+void peer_close(ds_canvas* c, int side) {
+    ds_canvas::Peer& pr = c->peer[side];
 #if DS_CUDA
-    DS_CK(cudaEventRecord(c->ev1, c->stream));
+    for (void* m : pr.mapped) cudaIpcCloseMemHandle(m);
+    cudaGetLastError();
 #endif
-    if ((rc = ev_make(&c->ev_done)) || (rc = ev_record(c->ev_done, c->stream))) return rc;
-    c->ev_done_valid = true;
-    c->composited = true;
-    return DS_OK;
+    pr = ds_canvas::Peer();
 }
 
 int check_device() {
@@ -1309,6 +1502,7 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
             pl.T = level_tile(l);
             pl.tiles_x = (c->lw[l] + pl.T - 1) / pl.T; pl.tiles_y = (c->lh[l] + pl.T - 1) / pl.T;
             pl.own = own[l]; pl.acc = acc[l];
+            if (l == 0) c->own0_recompute = own[0];
             // rows stored: what the collapse touches (acc) — the feed writes only those
             c->lvl_rows[l] = acc[l];
             cap = 0;
@@ -1345,6 +1539,8 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     for (int l = 0; l < DS_MAXL; l++) dev_free(c->d_lvl_alloc[l]);
     for (SubBand& sb : c->subs) { ev_drop(sb.done); ev_drop(sb.fed); ev_drop(sb.fed0); }
     dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_meta);
+    peer_close(c, 0); peer_close(c, 1);
+    dev_free(c->d_flags);
     for (int k = 0; k < ds_canvas::NSLOT; k++) { dev_free(c->d_slot[k]); ev_drop(c->slot_copied[k]); ev_drop(c->slot_free[k]); }
     ev_drop(c->ev_chunks); ev_drop(c->ev_opts);
     pinned_free(c->h_meta);
@@ -1377,7 +1573,7 @@ DS_API int ds_composite_async(ds_canvas* c) {
     if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
     int rc;
     if ((rc = set_device(c))) return rc;
-    return run_composite(c);
+    return run_composite(c, -1);
 }
 
 DS_API int ds_synchronize(ds_canvas* c) {
@@ -1493,6 +1689,139 @@ DS_API int ds_get_kernel_times(ds_canvas* c, ds_kernel_time* out, int cap, int* 
         }
     }
     return DS_OK;
+}
+
+// ---------------------------------------------------------------- NVLink P2P halo exchange
+
+DS_API int ds_p2p_export(ds_canvas* c, void* blob, size_t capacity, size_t* size) {
+    if (!c || !size) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (c->desc.blend_mode != DS_BLEND_MULTIBAND || c->L < 1) return fail(DS_ERR_UNSUPPORTED, "the halo exchange exists for multi-band canvases with at least one band");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    std::vector<const Frame*> fr;
+    for (const Frame& f : c->frames) if (f.used && f.d_pyr) fr.push_back(&f);
+    const size_t need = sizeof(BlobHeader) + fr.size() * sizeof(BlobFrame);
+    *size = need;
+    if (!blob) return DS_OK;   // size query
+    if (capacity < need) return fail(DS_ERR_BAD_ARG, "blob needs %zu bytes", need);
+    if (!c->d_flags) {
+        if ((rc = dev_alloc_t(&c->d_flags, 64))) return rc;   // own allocation: it gets its own IPC handle
+        if ((rc = dev_zero(c->d_flags, 64 * sizeof(int)))) return rc;
+    }
+    BlobHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = BLOB_MAGIC; h.version = 1; h.pid = (int64_t)getpid();
+    h.device = c->desc.device; h.L = c->L; h.pw = c->pw; h.ph = c->ph; h.band_lo = c->band.lo; h.band_hi = c->band.hi;
+    h.nframes = (int32_t)fr.size();
+    h.flags_ptr = (uint64_t)(uintptr_t)c->d_flags;
+#if DS_CUDA
+    { cudaIpcMemHandle_t mh; DS_CK(cudaIpcGetMemHandle(&mh, c->d_flags)); static_assert(sizeof(mh) == 64, "ipc handle size"); memcpy(h.flags_handle, &mh, 64); }
+#endif
+    memcpy(blob, &h, sizeof(h));
+    BlobFrame* out = (BlobFrame*)((char*)blob + sizeof(h));
+    for (size_t i = 0; i < fr.size(); i++) {
+        const Frame& f = *fr[i];
+        BlobFrame bf;
+        memset(&bf, 0, sizeof(bf));
+        bf.idx = (int32_t)(&f - c->frames.data()); bf.ry = f.ry; bf.rh = f.rh; bf.rw = f.rw; bf.gp1 = f.dev.gp[1];
+        bf.g_off = (uint64_t)((const char*)f.dev.G[1] - (const char*)f.d_pyr);
+        bf.w_off = (uint64_t)((const char*)f.dev.W[1] - (const char*)f.d_pyr);
+        bf.pyr_ptr = (uint64_t)(uintptr_t)f.d_pyr;
+#if DS_CUDA
+        { cudaIpcMemHandle_t mh; DS_CK(cudaIpcGetMemHandle(&mh, f.d_pyr)); memcpy(bf.pyr_handle, &mh, 64); }
+#endif
+        memcpy(&out[i], &bf, sizeof(bf));
+    }
+    return DS_OK;
+}
+
+DS_API int ds_p2p_connect(ds_canvas* c, int side, const void* blob, size_t size) {
+    if (!c || !blob) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (side != 0 && side != 1) return fail(DS_ERR_BAD_ARG, "side must be 0 (the band above) or 1 (the band below)");
+    if (c->desc.blend_mode != DS_BLEND_MULTIBAND || c->L < 1) return fail(DS_ERR_UNSUPPORTED, "the halo exchange exists for multi-band canvases with at least one band");
+    if (c->stage_open) return fail(DS_ERR_STATE, "a composite is half done");
+    if (size < sizeof(BlobHeader)) return fail(DS_ERR_BAD_ARG, "blob too small");
+    BlobHeader h;
+    memcpy(&h, blob, sizeof(h));
+    if (h.magic != BLOB_MAGIC || h.version != 1 || size < sizeof(BlobHeader) + (size_t)h.nframes * sizeof(BlobFrame))
+        return fail(DS_ERR_BAD_ARG, "not a ds_p2p_export blob");
+    if (h.L != c->L || h.pw != c->pw || h.ph != c->ph) return fail(DS_ERR_BAD_ARG, "the neighbour describes a different canvas");
+    if (side == 0 ? h.band_hi != c->band.lo : h.band_lo != c->band.hi)
+        return fail(DS_ERR_BAD_ARG, "band [%d, %d) is not the neighbour %s of [%d, %d)", h.band_lo, h.band_hi, side ? "below" : "above", c->band.lo, c->band.hi);
+    // the rows pulled from this neighbour must all be its own
+    const Range rows = pulled_rows(c, side);
+    if (rows.lo < (h.band_lo >> 1) || rows.hi > ((h.band_hi + 1) >> 1))
+        return fail(DS_ERR_P2P_UNAVAILABLE, "the neighbour's band [%d, %d) is thinner than the pyramid halo (level-1 rows [%d, %d))", h.band_lo, h.band_hi, rows.lo, rows.hi);
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->stream))) return rc;
+    if (!c->d_flags) {
+        if ((rc = dev_alloc_t(&c->d_flags, 64))) return rc;
+        if ((rc = dev_zero(c->d_flags, 64 * sizeof(int)))) return rc;
+    }
+    peer_close(c, side);
+    ds_canvas::Peer& pr = c->peer[side];
+    const bool same_process = h.pid == (int64_t)getpid();
+    auto map = [&](uint64_t raw, const unsigned char* handle, void** out) -> int {
+        if (same_process) {
+#if DS_CUDA
+            if (h.device != c->desc.device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return fail(DS_ERR_P2P_UNAVAILABLE, "no peer access from device %d to %d", c->desc.device, h.device); }
+                cudaGetLastError();
+            }
+#endif
+            *out = (void*)(uintptr_t)raw;
+            return DS_OK;
+        }
+#if DS_CUDA
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handle, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(out, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(DS_ERR_P2P_UNAVAILABLE, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+        pr.mapped.push_back(*out);
+        return DS_OK;
+#else
+        (void)handle;
+        return fail(DS_ERR_P2P_UNAVAILABLE, "no inter-process mapping in the emulator");
+#endif
+    };
+    void* fl = nullptr;
+    if ((rc = map(h.flags_ptr, h.flags_handle, &fl))) { peer_close(c, side); return rc; }
+    pr.flags = (int*)fl;
+    pr.band = Range{h.band_lo, h.band_hi};
+    const BlobFrame* in = (const BlobFrame*)((const char*)blob + sizeof(h));
+    for (int i = 0; i < h.nframes; i++) {
+        BlobFrame bf;
+        memcpy(&bf, &in[i], sizeof(bf));
+        // only frames that reach into the rows pulled from this neighbour are mapped
+        const int ry1 = bf.ry >> 1, rh1 = bf.rh >> 1;
+        if (std::max(rows.lo, ry1) >= std::min(rows.hi, ry1 + rh1)) continue;
+        void* base = nullptr;
+        if ((rc = map(bf.pyr_ptr, bf.pyr_handle, &base))) { peer_close(c, side); return rc; }
+        pr.frames.push_back(ds_canvas::PeerFrame{bf.idx, bf.ry, bf.rh, bf.rw, bf.gp1, (const char*)base, (size_t)bf.g_off, (size_t)bf.w_off});
+    }
+    pr.connected = true;
+    c->dirty = true;
+    return DS_OK;
+}
+
+DS_API int ds_p2p_disconnect(ds_canvas* c) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->stream))) return rc;
+    peer_close(c, 0); peer_close(c, 1);
+    c->dirty = true;
+    return DS_OK;
+}
+
+DS_API int ds_composite_stage(ds_canvas* c, int stage) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    if (stage != 0 && stage != 1) return fail(DS_ERR_BAD_ARG, "stage must be 0 or 1");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    return run_composite(c, stage);
 }
 
 // ---------------------------------------------------------------- debug taps

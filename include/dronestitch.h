@@ -187,6 +187,27 @@ DS_API int ds_synchronize(ds_canvas* c);
 DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* out, size_t stride,
                             uint8_t* mask_out, size_t mask_stride);
 
+/* ---- NVLink peer-to-peer halo exchange between row-band handles (one handle per GPU, any process layout) ----
+ * Without it a band recomputes the pyramid halo beyond its edges from the frames themselves: no communication,
+ * about 9 % extra work per band at 5 bands. With it the level-0 feed (warp + first pyrDown, the bulk of the work)
+ * runs over exactly the band's own rows, and the ~140 rows of every straddling frame's level-1 Gaussian / weight
+ * level needed beyond each edge are pulled from the neighbouring handle's memory by one kernel of NVLink P2P loads
+ * per composite; the levels above are rebuilt from them locally. No collective, no host round trip: neighbours
+ * order themselves with a counter word in each other's memory (a one-thread kernel writes it, the reader's stream
+ * waits for it with a stream memory operation).
+ * Usage: upload every frame that touches the band (+ halo; ds_frame_touches_band), ds_p2p_export on every handle,
+ * move the blobs between the processes by any means, ds_p2p_connect the neighbour above (side 0) and below
+ * (side 1), then composite in lock step - every connected handle the same number of composites. Export again
+ * and reconnect after frames were added or changed geometry. The exchange is used for composites over resident
+ * frames; the pipelined schedule of DS_UPLOAD_ASYNC keeps the recomputed halo (its slices cannot wait for a
+ * neighbour's last slice). Output is identical in all modes. */
+DS_API int ds_p2p_export(ds_canvas* c, void* blob, size_t capacity, size_t* size);
+DS_API int ds_p2p_connect(ds_canvas* c, int side, const void* blob, size_t size);
+DS_API int ds_p2p_disconnect(ds_canvas* c);
+/* ds_composite_async in two halves, for one thread driving several connected handles: stage 0 queues everything
+ * up to the hand-over of this handle's level-1 rows, stage 1 the rest. Call stage 0 on every handle, then stage 1. */
+DS_API int ds_composite_stage(ds_canvas* c, int stage);
+
 DS_API void ds_destroy_canvas(ds_canvas* c);
 DS_API const char* ds_last_error(void);
 DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info);
