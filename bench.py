@@ -243,6 +243,9 @@ def run_native(args):
     lib = _lib.default_library()
 
     plan, blend, bands, desc = workload_plan(args.workload, world)
+    if args.bands is not None and blend == "multiband":
+        bands = args.bands
+        desc += f" [bands overridden: {bands}]"
     xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
     rois = [CP.warp_roi(xf, plan.fw, plan.fh, lib) for xf in xfs]
     roi = CP.result_roi(rois)
@@ -272,6 +275,32 @@ def run_native(args):
         info = cv.info()
         out_rows = min(info.band_y1, roi[3]) - info.band_y0
         out_pin = torch.empty((out_rows, roi[2], 3), dtype=torch.uint8, pin_memory=True)
+
+        # neighbouring bands hand each other the level-1 halo rows over NVLink (no collective on the data path;
+        # torch.distributed only carries the 64-byte IPC handles once, here)
+        # Measured on cfg2 (5 bands, halo of ~280 rows): recomputing the halo costs 0.05-0.18 ms per composite, the
+        # exchange 0.06 ms of pull per edge plus two cross-GPU hand-overs - a wash. From 6 bands up (halo >= 560
+        # rows, doubling per band) the exchange wins, so "auto" connects only then.
+        halo = "recomputed per band (no exchange)"
+        use_p2p = args.p2p == "on" or (args.p2p == "auto" and info.num_bands >= 6)
+        if world > 1 and blend == "multiband" and use_p2p:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, cv.p2p_export())
+            ok, why = True, ""
+            try:
+                if rank > 0:
+                    cv.p2p_connect(0, blobs[rank - 1])
+                if rank < world - 1:
+                    cv.p2p_connect(1, blobs[rank + 1])
+            except _lib.DroneStitchError as e:
+                ok, why = False, str(e)
+            oks = [None] * world
+            dist.all_gather_object(oks, (ok, why))
+            if all(o[0] for o in oks):
+                halo = "NVLink P2P pull of the level-1 halo rows (ds_p2p_connect), recomputed in the pipelined e2e schedule"
+            else:
+                cv.p2p_disconnect()
+                halo = "recomputed per band (P2P unavailable: " + next(o[1] for o in oks if not o[0])[:120] + ")"
 
         def barrier():
             torch.cuda.synchronize()
@@ -377,7 +406,7 @@ def run_native(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/int16/f32", "data": "synthetic",
                 "config": {"workload": desc, "canvas": [roi[2], roi[3]], "frames": len(xfs), "bands_per_gpu": 1,
-                           "parallelism": f"row-bands x{world}", "host_affinity": numa, "l2": "inputs larger than L2 (720 MB of BGRX frames per band)"},
+                           "parallelism": f"row-bands x{world}", "halo": halo, "host_affinity": numa, "l2": "inputs larger than L2 (720 MB of BGRX frames per band)"},
                 "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_t[0].item()),
                         "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": e2e_steps},
@@ -397,6 +426,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1", "cfg3", "small"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bands", type=int, default=None, help="override the workload's multi-band depth (experiments)")
+    ap.add_argument("--p2p", default="auto", choices=["auto", "on", "off"],
+                    help="row bands exchange their level-1 halo rows over NVLink (on), recompute them (off), or decide by pyramid depth (auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -226,14 +226,21 @@ struct ExpandBody {
 struct PullSeg { const uint4* src; uint4* dst; long long n16; };
 struct PullParams { const PullSeg* segs; int nsegs; };
 struct PullBody {
-    static constexpr int BLOCKS_PER_SEG = 24;
+    static constexpr int BLOCKS_PER_SEG = 48;
     static int smem_bytes() { return 0; }
     template <int NT>
     DS_DM void run(const PullParams& p, int block, int tid, unsigned char*) {
         const int si = block / BLOCKS_PER_SEG, part = block - si * BLOCKS_PER_SEG;
         if (si >= p.nsegs) return;
         const PullSeg sg = p.segs[si];
-        for (long long i = (long long)part * NT + tid; i < sg.n16; i += (long long)BLOCKS_PER_SEG * NT) sg.dst[i] = ld_peer(sg.src + i);
+        // four independent 16-byte peer loads in flight per thread: an NVLink round trip is a few microseconds
+        const long long stride = (long long)BLOCKS_PER_SEG * NT;
+        long long i = (long long)part * NT + tid;
+        for (; i + 3 * stride < sg.n16; i += 4 * stride) {
+            const uint4 v0 = ld_peer(sg.src + i), v1 = ld_peer(sg.src + i + stride), v2 = ld_peer(sg.src + i + 2 * stride), v3 = ld_peer(sg.src + i + 3 * stride);
+            sg.dst[i] = v0; sg.dst[i + stride] = v1; sg.dst[i + 2 * stride] = v2; sg.dst[i + 3 * stride] = v3;
+        }
+        for (; i < sg.n16; i += stride) sg.dst[i] = ld_peer(sg.src + i);
     }
 };
 
