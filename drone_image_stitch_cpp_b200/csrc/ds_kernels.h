@@ -676,6 +676,7 @@ struct MBParams {
     int acc_y0, acc_y1;           // rows of this level whose dst the band's collapse reads (dst written only there)
     int own_y0, own_y1;           // even-aligned rows of this level the handle processes at all
     const void* tmaps;            // CUtensorMap[frame][DS_MAXL][2] (G, W) for the TMA tile loads of levels >= 1, or NULL
+    int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI
 };
 
 template <int T, bool LEVEL0>
@@ -928,6 +929,7 @@ DS_D void fence_tensormap_acquire(const void* tmap) {
 // acc lanes: B + 65536 * R in one int (exact while |sum| < 2^15, guaranteed by the host for tiles with
 // <= 64 frames; longer lists go to the generic kernel).
 
+template <bool V> struct BoolTag { static constexpr bool value = V; };
 struct L0Col { float a0, a3, a6; int u; };  // u = bbox column if inside the bbox, else ~(reflected column)
 struct L0Row { float b1, b4, b7; int v; };
 
@@ -1141,26 +1143,47 @@ struct MBFastBody {
                 const int seam_pitch = F.seam_pitch;
                 const bool has_gain = F.any_gain != 0;
                 const bool bconst = F.border == BORDER_CONST;
-                // Interior tile-frames: the needed region lies inside the bbox and its four corners map at
-                // least a pixel inside the source. x(u, v) is monotone in u and in v even in float arithmetic
-                // (a chain of monotone roundings), so the corner values bound every pixel: all taps are
-                // in-bounds inliers, the nearest mask is 255 everywhere and no cvRound patch can trigger.
-                bool interior = false;
+                // Fast tile-frames: every tap of the needed region is an in-bounds inlier. The region's bbox
+                // indices (mirrored into the bbox where it lies in the gap of the feed ROI, BORDER_REFLECT of
+                // copyMakeBorder) cover one contiguous interval per axis, and x(u, v) is monotone in u and in v
+                // even in float arithmetic (a chain of monotone roundings), so the values at the interval ends
+                // bound every pixel: no border handling, no cvRound patch, nearest mask = "inside the bbox".
+                // `interior`: the region is inside the bbox as well, so the mask is 255 everywhere.
+                bool inbounds = false, interior = false;
                 if (!proj && !seam && !F.gainmap) {
-                    const int u_lo = rx + px0 - F.cx, v_lo = ry + py0 - F.cy;
-                    if (u_lo >= 0 && u_lo + pw <= F.w && v_lo >= 0 && v_lo + ph <= F.h) {
-                        const L0Col c0 = s_col[0], c1 = s_col[pw - 1];
-                        const L0Row r0 = s_row[0], r1 = s_row[ph - 1];
-                        const float xa = f_add(f_add(c0.a0, r0.b1), k2), xb = f_add(f_add(c1.a0, r0.b1), k2);
-                        const float xc = f_add(f_add(c0.a0, r1.b1), k2), xd = f_add(f_add(c1.a0, r1.b1), k2);
-                        const float ya = f_add(f_add(c0.a3, r0.b4), k5), yb = f_add(f_add(c1.a3, r0.b4), k5);
-                        const float yc = f_add(f_add(c0.a3, r1.b4), k5), yd = f_add(f_add(c1.a3, r1.b4), k5);
-                        const float xmn = fminf(fminf(xa, xb), fminf(xc, xd)), xmx = fmaxf(fmaxf(xa, xb), fmaxf(xc, xd));
-                        const float ymn = fminf(fminf(ya, yb), fminf(yc, yd)), ymx = fmaxf(fmaxf(ya, yb), fmaxf(yc, yd));
-                        interior = xmn >= 1.f && xmx <= (float)(sw - 3) && ymn >= 1.f && ymx <= (float)(sh - 3);
+                    const int u_lo = rx + px0 - F.cx, u_hi = u_lo + pw - 1, v_lo = ry + py0 - F.cy, v_hi = v_lo + ph - 1;
+                    // mirrored index interval [mn, mx] of [lo, hi] on an axis of length n (single reflection only)
+                    auto fold = [](int lo, int hi, int n, int& mn, int& mx) {
+                        if (lo < -n || hi >= 2 * n) return false;
+                        mn = lo >= 0 ? imin(lo, n - 1) : (hi >= 0 ? 0 : -hi - 1);
+                        mx = hi < n ? imax(hi, 0) : (lo < n ? n - 1 : 2 * n - 1 - lo);
+                        if (lo < 0) mx = imax(mx, imin(-lo - 1, n - 1));
+                        if (hi >= n) mn = imin(mn, imax(2 * n - 1 - hi, 0));
+                        return true;
+                    };
+                    int umn = 0, umx = 0, vmn = 0, vmx = 0;
+                    if (fold(u_lo, u_hi, F.w, umn, umx) && fold(v_lo, v_hi, F.h, vmn, vmx)) {
+                        float ca0[2], ca3[2], rb1[2], rb4[2];
+                        DS_UNROLL
+                        for (int e = 0; e < 2; e++) {
+                            float U = (float)(F.tlx + (e ? umx : umn)), V = (float)(F.tly + (e ? vmx : vmn));
+                            if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+                            const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+                            ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
+                            rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
+                        }
+                        float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+                        DS_UNROLL
+                        for (int e = 0; e < 4; e++) {
+                            const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), k2), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), k5);
+                            xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
+                        }
+                        inbounds = xmn >= 1.f && xmx <= (float)(sw - 3) && ymn >= 1.f && ymx <= (float)(sh - 3);
+                        interior = inbounds && u_lo >= 0 && u_hi < F.w && v_lo >= 0 && v_hi < F.h;
+                        if (!interior && !(p.flags & 1)) inbounds = false;
                     }
                 }
-                if (interior) {
+                if (inbounds) {
                     // Software-pipelined in two register sets of UB pixels per thread: the taps of stage k+1 are
                     // requested before stage k is interpolated, so the L1 / L2 latency of the gathers hides behind
                     // the arithmetic of the same warp (occupancy is 2 CTAs / SM; other warps alone do not cover it).
@@ -1191,7 +1214,7 @@ struct MBFastBody {
                             t.p00[b] = ld_ro(r0); t.p01[b] = ld_ro(r0 + 1); t.p10[b] = ld_ro(r0 + pitch); t.p11[b] = ld_ro(r0 + pitch + 1);
                         }
                     };
-                    auto finish = [&](int i0, const Taps& t) {
+                    auto finish = [&](int i0, const Taps& t, auto masked) {   // masked: integral_constant<bool>
                         DS_UNROLL
                         for (int b = 0; b < UB; b++) {
                             const int ax = t.ix[b] & 31, ay = t.iy[b] & 31;
@@ -1204,21 +1227,37 @@ struct MBFastBody {
                             int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
                             if (has_gain) apply_gains(F, ob, og, orr, 0, 0);   // no gain map on this path
                             const int i = i0 + b * NT;
-                            if (i < npx) sts_u1(a_g0 + i * 4, (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | 0xff000000u);
+                            uint32_t mbyte = 0xff000000u;
+                            if constexpr (decltype(masked)::value) {
+                                // gap of the feed ROI: the pixel is a mirror image, its mask (CONSTANT 0 border) is 0
+                                const int ic = imin(i, last);
+                                const int yy = ic / PWS, xx = ic - yy * PWS;
+                                const int inside = ((int)(lds_u1(a_col + xx * 16 + 12) | lds_u1(a_row + yy * 16 + 12)) >= 0) ? 255 : 0;
+                                mbyte = (uint32_t)inside << 24;
+                                if (i < npx && xx < pw) { m_and &= inside; m_or |= inside; }
+                            }
+                            if (i < npx) sts_u1(a_g0 + i * 4, (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | mbyte);
                         }
                     };
-                    Taps A, B;
-                    fetch(tid, A);
-                    int st = 0;
-                    for (; st + 2 <= nst; st += 2) {
-                        fetch(tid + (st + 1) * STEP, B);
-                        finish(tid + st * STEP, A);
-                        fetch(tid + (st + 2) * STEP, A);   // past the end on the last trip: clamped, unused
-                        finish(tid + (st + 1) * STEP, B);
+                    auto pipeline = [&](auto masked) {
+                        Taps A, B;
+                        fetch(tid, A);
+                        int st = 0;
+                        for (; st + 2 <= nst; st += 2) {
+                            fetch(tid + (st + 1) * STEP, B);
+                            finish(tid + st * STEP, A, masked);
+                            fetch(tid + (st + 2) * STEP, A);   // past the end on the last trip: clamped, unused
+                            finish(tid + (st + 1) * STEP, B, masked);
+                        }
+                        if (st < nst) finish(tid + st * STEP, A, masked);
+                    };
+                    if (interior) {
+                        pipeline(BoolTag<false>());
+                        m_or = 255;   // m_and stays 255: the mask is uniform 255
+                        known_uniform = true;
+                    } else {
+                        pipeline(BoolTag<true>());
                     }
-                    if (st < nst) finish(tid + st * STEP, A);
-                    m_or = 255;   // m_and stays 255: the mask is uniform 255
-                    known_uniform = true;
                 } else
                 for (int i = tid; i < PWS * ph; i += NT) {
                     const int yy = i / PWS, xx = i - yy * PWS;

@@ -964,6 +964,8 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     mp.acc_y0 = acc.lo; mp.acc_y1 = acc.hi;
     mp.own_y0 = own.lo; mp.own_y1 = own.hi;
     mp.tmaps = c->tmaps_ok ? c->d_tmaps : nullptr;
+    static const bool gap_fast = !(getenv("DS_GAP_FAST") && atoi(getenv("DS_GAP_FAST")) == 0);
+    mp.flags = gap_fast ? 1 : 0;
     const double q = 1.0 / (double)(1ull << (2 * l));
     double ab;
     if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
