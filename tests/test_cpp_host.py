@@ -1,0 +1,79 @@
+"""The C++ host side (include/dronestitch.hpp: ds::composePanorama, ds::Blender) compiled with g++ and run as the
+reference's call site would run it; its panorama must be the oracle's. CPU: linked against the tests-only emulator
+build of the library; marked gpu: against libdronestitch_cuda.so."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from drone_image_stitch_cpp_b200 import _lib as L
+from drone_image_stitch_cpp_b200 import synth
+from oracle import ds_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
+
+
+def build_driver(lib_path, tag):
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, f"host_compose_{tag}")
+    src = os.path.join(ROOT, "tests", "cpp", "host_compose.cpp")
+    deps = [src, os.path.join(ROOT, "include", "dronestitch.hpp"), os.path.join(ROOT, "include", "dronestitch.h"), lib_path]
+    if os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(d) for d in deps):
+        return exe
+    d, name = os.path.dirname(lib_path), os.path.basename(lib_path)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", d, "-l:" + name, "-Wl,-rpath," + d])
+    return exe
+
+
+def run_case(exe, tmp_path, blend, bands, work_scale):
+    sv = synth.grid_survey(2, 2, 260, 200, overlap=0.55, seed=61, work_scale=0.5)
+    # cameras as cv::Stitcher holds them at registration scale: the driver rescales them by 1 / work_scale
+    case = os.path.join(tmp_path, "case.bin")
+    out = os.path.join(tmp_path, "out.bin")
+    with open(case, "wb") as f:
+        f.write(b"DSC1")
+        f.write(struct.pack("<iiii", len(sv.frames), bands, 1 if blend == "feather" else 0, 1))
+        f.write(struct.pack("<f", float(np.float32(sv.scale) * np.float32(work_scale))))
+        f.write(struct.pack("<d", work_scale))
+        for img, K, R in zip(sv.frames, sv.Ks, sv.Rs):
+            K = np.asarray(K, np.float32)
+            focal, ppx, ppy = float(K[0, 0]) * work_scale, float(K[0, 2]) * work_scale, float(K[1, 2]) * work_scale
+            aspect = float(K[1, 1]) / float(K[0, 0])
+            f.write(struct.pack("<ii", img.shape[1], img.shape[0]))
+            f.write(struct.pack("<dddd", focal, aspect, ppx, ppy))
+            f.write(np.ascontiguousarray(R, np.float32).tobytes())
+            f.write(np.ascontiguousarray(img).tobytes())
+    r = subprocess.run([exe, case, out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    x, y, w, h = struct.unpack("<iiii", raw[:16])
+    pano = np.frombuffer(raw, np.uint8, w * h * 3, 16).reshape(h, w, 3)
+    mask = np.frombuffer(raw, np.uint8, w * h, 16 + w * h * 3).reshape(h, w)
+    # what the driver must have derived: K scaled by 1 / work_scale (back to sv.Ks), scale = sv.scale
+    Ks = []
+    for K in sv.Ks:
+        K = np.asarray(K, np.float32)
+        a = 1.0 / work_scale
+        focal, ppx, ppy = float(K[0, 0]) * work_scale * a, float(K[0, 2]) * work_scale * a, float(K[1, 2]) * work_scale * a
+        aspect = float(K[1, 1]) / float(K[0, 0])
+        Ks.append(np.array([[focal, 0, ppx], [0, focal * aspect, ppy], [0, 0, 1]], np.float64).astype(np.float32))
+    scale = np.float32(np.float64(np.float32(sv.scale) * np.float32(work_scale)) * (1.0 / work_scale))
+    ref, refmask, roi = O.compose_port(sv.frames, Ks, sv.Rs, scale, blend, bands)
+    assert (x, y, w, h) == tuple(roi)
+    assert np.array_equal(mask, refmask)
+    assert np.array_equal(pano, ref)
+
+
+@pytest.mark.parametrize("blend,bands,work_scale", [("multiband", 4, 1.0), ("multiband", 5, 0.5), ("feather", 0, 1.0)])
+def test_cpp_host_emu(emu_lib, tmp_path, blend, bands, work_scale):
+    run_case(build_driver(emu_lib.path, "emu"), str(tmp_path), blend, bands, work_scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blend,bands,work_scale", [("multiband", 5, 0.5), ("feather", 0, 1.0)])
+def test_cpp_host_gpu(cuda_lib, tmp_path, blend, bands, work_scale):
+    run_case(build_driver(cuda_lib.path, "cuda"), str(tmp_path), blend, bands, work_scale)
