@@ -205,7 +205,10 @@ struct ExpandBody {
         for (int i = tid; i < PER_BLOCK; i += NT) {
             const long long idx = (long long)block * PER_BLOCK + i;
             if (idx >= n) break;
-            const int y = (int)(idx / qw), x = (int)(idx - (long long)y * qw) * 4;
+            int y, xq;   // 32-bit arithmetic when the frame allows it: a 64-bit division would dominate this copy kernel
+            if (n <= 0x7fffffffLL) { const unsigned u = (unsigned)idx; y = (int)(u / (unsigned)qw); xq = (int)(u - (unsigned)y * (unsigned)qw); }
+            else { y = (int)(idx / qw); xq = (int)(idx - (long long)y * qw); }
+            const int x = xq * 4;
             const uint8_t* s = p.src + (size_t)y * p.src_stride + (size_t)x * 3;
             uint32_t* d = p.dst + (size_t)y * p.dst_pitch + x;   // dst_pitch is a multiple of 4 pixels: 16-byte aligned
             if (x + 4 <= p.w && (((size_t)s) & 3) == 0) {
@@ -1596,7 +1599,11 @@ struct CollapseBody {
         for (int it = tid; it < PER_BLOCK; it += NT) {
             const long long idx = (long long)block * PER_BLOCK + it;
             if (idx >= n) break;
-            const int c1y = m0 + (int)(idx / qw), Xq = (int)(idx % qw) * 4;
+            // 32-bit index arithmetic whenever the launch allows it (a 64-bit division costs ~80 instructions)
+            int rowi, coli;
+            if (n <= 0x7fffffffLL) { const unsigned u = (unsigned)idx; rowi = (int)(u / (unsigned)qw); coli = (int)(u - (unsigned)rowi * (unsigned)qw); }
+            else { rowi = (int)(idx / qw); coli = (int)(idx - (long long)rowi * qw); }
+            const int c1y = m0 + rowi, Xq = coli * 4;
             // both rows of the pair read coarse rows (l, c, r) around c1y; columns c0-1 .. c0+2 with the pyrUp border rules
             const int ry[3] = {up_l(c1y, chh), c1y, up_r(c1y, chh)};
             const int c0 = Xq >> 1;
@@ -1630,31 +1637,47 @@ struct CollapseBody {
                 const int Y = 2 * c1y + dy;
                 if (Y < p.y0 || Y >= p.y1) continue;
                 const bool oddy = dy != 0;
-                alignas(16) px16 f[4];
+                // the four fine pixels as words (b | g << 16, r | flag << 16): kept in registers, never as an
+                // addressable array (that would live in local memory)
+                uint32_t fw0[4], fw1[4];
                 px16* frow = p.fine + (size_t)Y * fw + Xq;
                 if (nvalid == 4) {
                     const uint4 v0 = *(const uint4*)frow, v1 = *(const uint4*)(frow + 2);
-                    *(uint4*)&f[0] = v0; *(uint4*)&f[2] = v1;
+                    fw0[0] = v0.x; fw1[0] = v0.y; fw0[1] = v0.z; fw1[1] = v0.w;
+                    fw0[2] = v1.x; fw1[2] = v1.y; fw0[3] = v1.z; fw1[3] = v1.w;
                 } else {
-                    for (int kx = 0; kx < 4; kx++) { if (kx < nvalid) f[kx] = frow[kx]; else { f[kx].b = f[kx].g = f[kx].r = f[kx].a = 0; } }
+                    DS_UNROLL
+                    for (int kx = 0; kx < 4; kx++) {
+                        fw0[kx] = fw1[kx] = 0u;
+                        if (kx < nvalid) { const uint2 v = *(const uint2*)(frow + kx); fw0[kx] = v.x; fw1[kx] = v.y; }
+                    }
                 }
                 int ob[4], og[4], orr[4];
                 DS_UNROLL
                 for (int kx = 0; kx < 4; kx++) {
-                    ob[kx] = up1(hb[0][kx], hb[1][kx], hb[2][kx], oddy, f[kx].b);
-                    og[kx] = up1(hg[0][kx], hg[1][kx], hg[2][kx], oddy, f[kx].g);
-                    orr[kx] = up1(hr[0][kx], hr[1][kx], hr[2][kx], oddy, f[kx].r);
+                    ob[kx] = up1(hb[0][kx], hb[1][kx], hb[2][kx], oddy, (int)(short)(fw0[kx] & 0xffffu));
+                    og[kx] = up1(hg[0][kx], hg[1][kx], hg[2][kx], oddy, (int)(short)(fw0[kx] >> 16));
+                    orr[kx] = up1(hr[0][kx], hr[1][kx], hr[2][kx], oddy, (int)(short)(fw1[kx] & 0xffffu));
                 }
                 if (!p.final) {
                     DS_UNROLL
-                    for (int kx = 0; kx < 4; kx++) { f[kx].b = (short)ob[kx]; f[kx].g = (short)og[kx]; f[kx].r = (short)orr[kx]; }
-                    if (nvalid == 4) { *(uint4*)frow = *(const uint4*)&f[0]; *(uint4*)(frow + 2) = *(const uint4*)&f[2]; }
-                    else { for (int kx = 0; kx < nvalid; kx++) frow[kx] = f[kx]; }
+                    for (int kx = 0; kx < 4; kx++) {
+                        fw0[kx] = ((uint32_t)ob[kx] & 0xffffu) | ((uint32_t)og[kx] << 16);
+                        fw1[kx] = ((uint32_t)orr[kx] & 0xffffu) | (fw1[kx] & 0xffff0000u);
+                    }
+                    if (nvalid == 4) {
+                        *(uint4*)frow = make_u4(fw0[0], fw1[0], fw0[1], fw1[1]);
+                        *(uint4*)(frow + 2) = make_u4(fw0[2], fw1[2], fw0[3], fw1[3]);
+                    } else {
+                        DS_UNROLL
+                        for (int kx = 0; kx < 4; kx++)
+                            if (kx < nvalid) { uint2 v; v.x = fw0[kx]; v.y = fw1[kx]; *(uint2*)(frow + kx) = v; }
+                    }
                 } else if (Y < p.o.h) {
                     uint32_t px[4];
                     DS_UNROLL
                     for (int kx = 0; kx < 4; kx++) {
-                        const bool m = f[kx].a != 0;
+                        const bool m = (fw1[kx] >> 16) != 0u;
                         px[kx] = m ? ((uint32_t)sat8i(ob[kx]) | ((uint32_t)sat8i(og[kx]) << 8) | ((uint32_t)sat8i(orr[kx]) << 16) | 0xff000000u) : 0u;
                     }
                     const int nout = imin(nvalid, p.o.w - Xq);

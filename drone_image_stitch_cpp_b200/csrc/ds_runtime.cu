@@ -1250,6 +1250,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     if (idx < 0 || idx > (1 << 20)) return fail(DS_ERR_BAD_ARG, "frame_idx %d out of range", idx);
     if (w <= 0 || h <= 0 || w > 32767 || h > 32767) return fail(DS_ERR_BAD_ARG, "frame size %dx%d (cv::remap needs < 32768)", w, h);
     if (stride < (size_t)w * 3) return fail(DS_ERR_BAD_ARG, "stride %zu < 3*w", stride);
+    if (c->stage_open) return fail(DS_ERR_STATE, "a composite is half done: call ds_composite_stage(c, 1) before uploading");
     int rc;
     if ((rc = set_device(c))) return rc;
     int pl[4];
