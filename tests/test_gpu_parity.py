@@ -77,3 +77,20 @@ def test_cfg2_properties_full_size(cuda_lib):
 
 def test_no_cpu_fallback_symbols(cuda_lib):
     assert b"sm_100a" in cuda_lib.dll.ds_version()
+
+
+def test_cfg4_scale_one_gpu():
+    """BASELINE config 4 at full size on one GPU (600 frames of 5472x3648, 2.7 GP canvas, ~125 GB of HBM): the
+    composite runs and three band handles reproduce its rows bit for bit - indexing beyond 2^31 pixels, tile lists,
+    TMA descriptors. Fresh process (tools/scale_check.py); skipped when the device has less than 140 GB free."""
+    import os, subprocess, sys, json
+    import torch
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 140e9:
+        pytest.skip(f"needs 140 GB of free device memory, {free / 1e9:.0f} GB available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "scale_check.py"), "50", "12"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok"] and res["gigapixels"] > 2.2 and len(res["bands_checked"]) == 3
