@@ -102,6 +102,18 @@ DS_D void apply_gains(const FrameDev& F, int& b, int& g, int& r, int ur, int vr)
         b = sat8i(f2i_rn(f_mul((float)b, gm))); g = sat8i(f2i_rn(f_mul((float)g, gm))); r = sat8i(f2i_rn(f_mul((float)r, gm)));
     }
 }
+// the same with the gain-map value already loaded (gm is ignored without a gain map)
+DS_D void apply_gains_with(const FrameDev& F, int& b, int& g, int& r, float gm) {
+    if (F.has_gain) {
+        b = sat8i(f2i_rn(f_mul((float)b, F.gain[0]))); g = sat8i(f2i_rn(f_mul((float)g, F.gain[1]))); r = sat8i(f2i_rn(f_mul((float)r, F.gain[2])));
+    }
+    if (F.has_cgain) {
+        b = sat8i(d2i_rn(d_mul((double)b, F.cgain[0]))); g = sat8i(d2i_rn(d_mul((double)g, F.cgain[1]))); r = sat8i(d2i_rn(d_mul((double)r, F.cgain[2])));
+    }
+    if (F.gainmap) {
+        b = sat8i(f2i_rn(f_mul((float)b, gm))); g = sat8i(f2i_rn(f_mul((float)g, gm))); r = sat8i(f2i_rn(f_mul((float)r, gm)));
+    }
+}
 
 // A4: cv::remap INTER_LINEAR 8UC3 on the fixed-point coordinate of bbox pixel (ur, vr), then the gains.
 DS_D px8 sample_bilinear(const FrameDev& F, const Coord& c, int ur, int vr) {
@@ -936,7 +948,10 @@ template <bool V> struct BoolTag { static constexpr bool value = V; };
 struct L0Col { float a0, a3, a6; int u; };  // u = bbox column if inside the bbox, else ~(reflected column)
 struct L0Row { float b1, b4, b7; int v; };
 
-template <int T_, bool LEVEL0>
+// AFF ("general"): the fast loop also builds cv::warpAffine (integer) coordinates and takes seam masks and gain maps;
+// a separate instantiation so that the kernel of the headline configuration (plane maps, no per-pixel inputs) keeps
+// its instruction footprint: with AFF = false such tile-frames go through the per-pixel loop.
+template <int T_, bool LEVEL0, bool AFF = false>
 struct MBFastBody {
     // PWS: row pitch of the needed region in smem. Levels >= 1 load it with TMA, whose innermost start
     // coordinate must be 16-byte aligned: the region starts at px0 rounded down to 4 px (up to 3 extra columns).
@@ -1074,7 +1089,8 @@ struct MBFastBody {
             const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
             const int jw = jx1 - jx0, jh = jy1 - jy0;
             const bool border = g.border != 0;
-            const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
+            const bool affine = AFF && LEVEL0 && F.kind == XF_AFFINE;   // cv::warpAffine coordinates (integer tables)
+            const bool proj = !affine && !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
             uint32_t* const G1out = (uint32_t*)F.G[l + 1];
             float* const W1out = F.W[l + 1];
             const int op1 = F.gp[l + 1];   // row pitch of the level-(l+1) arrays
@@ -1087,22 +1103,35 @@ struct MBFastBody {
                 if (i < PWS) {
                     const int u = rx + px0 + imin(i, pw - 1) - F.cx;   // padding columns repeat the last one
                     const int ur = refl(u, F.w, BORDER_REFL);
-                    float U = (float)(F.tlx + ur);
-                    if (F.scale != 1.f) U = f_div(U, F.scale);
-                    const float up = f_sub(U, F.t0);
                     L0Col c;
-                    c.a0 = f_mul(F.k[0], up); c.a3 = f_mul(F.k[3], up); c.a6 = f_mul(F.k[6], up);
+                    if (affine) {
+                        // cv::warpAffine: adelta / bdelta of the column, 10 fractional bits (A6), kept as integer bits
+                        c.a0 = i2f_bits(d2i_rn(d_mul(d_mul(F.inv[0], (double)ur), 1024.0)));
+                        c.a3 = i2f_bits(d2i_rn(d_mul(d_mul(F.inv[3], (double)ur), 1024.0)));
+                        c.a6 = 0.f;
+                    } else {
+                        float U = (float)(F.tlx + ur);
+                        if (F.scale != 1.f) U = f_div(U, F.scale);
+                        const float up = f_sub(U, F.t0);
+                        c.a0 = f_mul(F.k[0], up); c.a3 = f_mul(F.k[3], up); c.a6 = f_mul(F.k[6], up);
+                    }
                     c.u = (unsigned)u < (unsigned)F.w ? u : ~ur;   // >= 0: inside (u == ur); < 0: ~(reflected index)
                     s_col[i] = c;
                 } else {
                     const int yy = i - PWS;
                     const int v = ry + py0 + yy - F.cy;
                     const int vr = refl(v, F.h, BORDER_REFL);
-                    float V = (float)(F.tly + vr);
-                    if (F.scale != 1.f) V = f_div(V, F.scale);
-                    const float vp = f_sub(V, F.t1);
                     L0Row r;
-                    r.b1 = f_mul(F.k[1], vp); r.b4 = f_mul(F.k[4], vp); r.b7 = f_mul(F.k[7], vp);
+                    if (affine) {
+                        r.b1 = i2f_bits(d2i_rn(d_mul(d_add(d_mul(F.inv[1], (double)vr), F.inv[2]), 1024.0)));
+                        r.b4 = i2f_bits(d2i_rn(d_mul(d_add(d_mul(F.inv[4], (double)vr), F.inv[5]), 1024.0)));
+                        r.b7 = 0.f;
+                    } else {
+                        float V = (float)(F.tly + vr);
+                        if (F.scale != 1.f) V = f_div(V, F.scale);
+                        const float vp = f_sub(V, F.t1);
+                        r.b1 = f_mul(F.k[1], vp); r.b4 = f_mul(F.k[4], vp); r.b7 = f_mul(F.k[7], vp);
+                    }
                     r.v = (unsigned)v < (unsigned)F.h ? v : ~vr;
                     s_row[yy] = r;
                 }
@@ -1153,7 +1182,7 @@ struct MBFastBody {
                 // bound every pixel: no border handling, no cvRound patch, nearest mask = "inside the bbox".
                 // `interior`: the region is inside the bbox as well, so the mask is 255 everywhere.
                 bool inbounds = false, interior = false;
-                if (!proj && !seam && !F.gainmap) {
+                if (!proj && (AFF || (!seam && !F.gainmap))) {
                     const int u_lo = rx + px0 - F.cx, u_hi = u_lo + pw - 1, v_lo = ry + py0 - F.cy, v_hi = v_lo + ph - 1;
                     // mirrored index interval [mn, mx] of [lo, hi] on an axis of length n (single reflection only)
                     auto fold = [](int lo, int hi, int n, int& mn, int& mx) {
@@ -1165,7 +1194,21 @@ struct MBFastBody {
                         return true;
                     };
                     int umn = 0, umx = 0, vmn = 0, vmx = 0;
-                    if (fold(u_lo, u_hi, F.w, umn, umx) && fold(v_lo, v_hi, F.h, vmn, vmx)) {
+                    if (affine) {
+                        if (fold(u_lo, u_hi, F.w, umn, umx) && fold(v_lo, v_hi, F.h, vmn, vmx)) {
+                            int xmn = 0x7fffffff, xmx = (int)0x80000000, ymn = 0x7fffffff, ymx = (int)0x80000000;
+                            DS_UNROLL
+                            for (int e = 0; e < 4; e++) {
+                                const double uu = (double)((e & 1) ? umx : umn), vv = (double)((e >> 1) ? vmx : vmn);
+                                const int X = (d2i_rn(d_mul(d_add(d_mul(F.inv[1], vv), F.inv[2]), 1024.0)) + 16 + d2i_rn(d_mul(d_mul(F.inv[0], uu), 1024.0))) >> 5;
+                                const int Y = (d2i_rn(d_mul(d_add(d_mul(F.inv[4], vv), F.inv[5]), 1024.0)) + 16 + d2i_rn(d_mul(d_mul(F.inv[3], uu), 1024.0))) >> 5;
+                                xmn = imin(xmn, X); xmx = imax(xmx, X); ymn = imin(ymn, Y); ymx = imax(ymx, Y);
+                            }
+                            inbounds = (xmn >> 5) >= 1 && (xmx >> 5) <= sw - 3 && (ymn >> 5) >= 1 && (ymx >> 5) <= sh - 3;
+                            interior = inbounds && u_lo >= 0 && u_hi < F.w && v_lo >= 0 && v_hi < F.h;
+                            if (!interior && !(p.flags & 1)) inbounds = false;
+                        }
+                    } else if (fold(u_lo, u_hi, F.w, umn, umx) && fold(v_lo, v_hi, F.h, vmn, vmx)) {
                         float ca0[2], ca3[2], rb1[2], rb4[2];
                         DS_UNROLL
                         for (int e = 0; e < 2; e++) {
@@ -1197,24 +1240,44 @@ struct MBFastBody {
                     const int npx = PWS * ph, last = npx - 1;
                     const int nst = (npx + STEP - 1) / STEP;
                     const SAddr a_col = s_addr(s_col), a_row = s_addr(s_row), a_g0 = s_addr(s_g0);
-                    struct Taps { int ix[UB], iy[UB]; uint32_t p00[UB], p01[UB], p10[UB], p11[UB]; };
-                    auto fetch = [&](int i0, Taps& t) {
+                    // mk / gm: mask byte and gain-map value of the pixel, requested together with the taps (general variant)
+                    struct Taps { int ix[UB], iy[UB]; uint32_t p00[UB], p01[UB], p10[UB], p11[UB]; int mk[UB]; float gm[UB]; };
+                    const float* const gainmap = F.gainmap;
+                    const int gainmap_pitch = F.gainmap_pitch;
+                    auto fetch = [&](int i0, Taps& t, auto aff, auto masked) {   // integral_constant<bool> tags: warpAffine integer coordinates / per-pixel mask
                         DS_UNROLL
                         for (int b = 0; b < UB; b++) {
                             const int i = imin(i0 + b * NT, last);
                             const int yy = i / PWS, xx = i - yy * PWS;
-                            float ca0, ca3, rb1, rb4;
-                            lds_f2(a_col + xx * 16, ca0, ca3);
-                            lds_f2(a_row + yy * 16, rb1, rb4);
-                            const float x = f_add(f_add(ca0, rb1), k2);
-                            const float y = f_add(f_add(ca3, rb4), k5);
+                            if constexpr (decltype(aff)::value) {
+                                uint32_t ad, bd, xr, yr;
+                                lds_u2(a_col + xx * 16, ad, bd);
+                                lds_u2(a_row + yy * 16, xr, yr);
+                                t.ix[b] = ((int)xr + 16 + (int)ad) >> 5; t.iy[b] = ((int)yr + 16 + (int)bd) >> 5;
+                            } else {
+                                float ca0, ca3, rb1, rb4;
+                                lds_f2(a_col + xx * 16, ca0, ca3);
+                                lds_f2(a_row + yy * 16, rb1, rb4);
+                                const float x = f_add(f_add(ca0, rb1), k2);
+                                const float y = f_add(f_add(ca3, rb4), k5);
 #if DS_CUDA
-                            t.ix[b] = __float2int_rn(f_mul(x, 32.f)); t.iy[b] = __float2int_rn(f_mul(y, 32.f));
+                                t.ix[b] = __float2int_rn(f_mul(x, 32.f)); t.iy[b] = __float2int_rn(f_mul(y, 32.f));
 #else
-                            t.ix[b] = f2i_rn(f_mul(x, 32.f)); t.iy[b] = f2i_rn(f_mul(y, 32.f));
+                                t.ix[b] = f2i_rn(f_mul(x, 32.f)); t.iy[b] = f2i_rn(f_mul(y, 32.f));
 #endif
+                            }
                             const uint32_t* r0 = src + ((t.iy[b] >> 5) * pitch + (t.ix[b] >> 5));
                             t.p00[b] = ld_ro(r0); t.p01[b] = ld_ro(r0 + 1); t.p10[b] = ld_ro(r0 + pitch); t.p11[b] = ld_ro(r0 + pitch + 1);
+                            if constexpr (AFF && decltype(masked)::value) {
+                                // mask byte (seam mask inside the bbox, 0 in the gap) and gain-map value at the (mirrored)
+                                // bbox position, in flight with the taps
+                                const int cu = (int)lds_u1(a_col + xx * 16 + 12), rv = (int)lds_u1(a_row + yy * 16 + 12);
+                                const int inside = (cu | rv) >= 0;
+                                t.mk[b] = inside ? 255 : 0;
+                                if (seam && inside) t.mk[b] = (int)ld_ro(seam + (size_t)rv * seam_pitch + cu);
+                                t.gm[b] = 1.f;
+                                if (gainmap) t.gm[b] = ld_ro(gainmap + (size_t)(rv >= 0 ? rv : ~rv) * gainmap_pitch + (cu >= 0 ? cu : ~cu));
+                            }
                         }
                     };
                     auto finish = [&](int i0, const Taps& t, auto masked) {   // masked: integral_constant<bool>
@@ -1228,38 +1291,57 @@ struct MBFastBody {
                             int ob = (dot4u(t0, wb, 0) * wy0 + dot4u(t1, wb, 0) * wy1 + 512) >> 10;
                             int og = (dot4u(t0, wg, 0) * wy0 + dot4u(t1, wg, 0) * wy1 + 512) >> 10;
                             int orr = (dot4u(t0r, wb, 0) * wy0 + dot4u(t1r, wb, 0) * wy1 + 512) >> 10;
-                            if (has_gain) apply_gains(F, ob, og, orr, 0, 0);   // no gain map on this path
                             const int i = i0 + b * NT;
                             uint32_t mbyte = 0xff000000u;
                             if constexpr (decltype(masked)::value) {
-                                // gap of the feed ROI: the pixel is a mirror image, its mask (CONSTANT 0 border) is 0
+                                // the general form: a pixel in the gap of the feed ROI is a mirror image whose mask
+                                // (CONSTANT 0 border) is 0; inside the bbox the seam mask, if any, is the mask; the
+                                // gain map is read at the (mirrored) bbox position
                                 const int ic = imin(i, last);
                                 const int yy = ic / PWS, xx = ic - yy * PWS;
-                                const int inside = ((int)(lds_u1(a_col + xx * 16 + 12) | lds_u1(a_row + yy * 16 + 12)) >= 0) ? 255 : 0;
-                                mbyte = (uint32_t)inside << 24;
-                                if (i < npx && xx < pw) { m_and &= inside; m_or |= inside; }
+                                int m;
+                                if constexpr (AFF) {
+                                    if (has_gain) apply_gains_with(F, ob, og, orr, t.gm[b]);
+                                    m = t.mk[b];
+                                } else {
+                                    const int cu = (int)lds_u1(a_col + xx * 16 + 12), rv = (int)lds_u1(a_row + yy * 16 + 12);
+                                    m = (cu | rv) >= 0 ? 255 : 0;
+                                    if (has_gain) apply_gains(F, ob, og, orr, 0, 0);   // no gain map, no seam mask here
+                                }
+                                mbyte = (uint32_t)m << 24;
+                                if (i < npx && xx < pw) { m_and &= m; m_or |= m; }
+                            } else {
+                                if (has_gain) apply_gains(F, ob, og, orr, 0, 0);   // no gain map in this variant
                             }
                             if (i < npx) sts_u1(a_g0 + i * 4, (uint32_t)ob | ((uint32_t)og << 8) | ((uint32_t)orr << 16) | mbyte);
                         }
                     };
-                    auto pipeline = [&](auto masked) {
+                    auto pipeline = [&](auto masked, auto aff) {
                         Taps A, B;
-                        fetch(tid, A);
+                        fetch(tid, A, aff, masked);
                         int st = 0;
                         for (; st + 2 <= nst; st += 2) {
-                            fetch(tid + (st + 1) * STEP, B);
+                            fetch(tid + (st + 1) * STEP, B, aff, masked);
                             finish(tid + st * STEP, A, masked);
-                            fetch(tid + (st + 2) * STEP, A);   // past the end on the last trip: clamped, unused
+                            fetch(tid + (st + 2) * STEP, A, aff, masked);   // past the end on the last trip: clamped, unused
                             finish(tid + (st + 1) * STEP, B, masked);
                         }
                         if (st < nst) finish(tid + st * STEP, A, masked);
                     };
-                    if (interior) {
-                        pipeline(BoolTag<false>());
+                    const bool plain = interior && !seam && !F.gainmap;   // mask 255 everywhere, no per-pixel inputs
+                    bool done = false;
+                    if constexpr (AFF) {
+                        if (affine) {
+                            if (plain) pipeline(BoolTag<false>(), BoolTag<true>()); else pipeline(BoolTag<true>(), BoolTag<true>());
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        if (plain) pipeline(BoolTag<false>(), BoolTag<false>()); else pipeline(BoolTag<true>(), BoolTag<false>());
+                    }
+                    if (plain) {
                         m_or = 255;   // m_and stays 255: the mask is uniform 255
                         known_uniform = true;
-                    } else {
-                        pipeline(BoolTag<true>());
                     }
                 } else
                 for (int i = tid; i < PWS * ph; i += NT) {
@@ -1267,6 +1349,13 @@ struct MBFastBody {
                     if (xx >= pw) continue;
                     const L0Col c = s_col[xx];
                     const L0Row r = s_row[yy];
+                    bool okx = true, oky = true;
+                    int ix, iy, nx, ny;
+                    if (affine) {
+                        const int xr = f2i_bits(r.b1), yr = f2i_bits(r.b4), ad = f2i_bits(c.a0), bd = f2i_bits(c.a3);
+                        ix = (xr + 16 + ad) >> 5; iy = (yr + 16 + bd) >> 5;
+                        nx = sat16i((xr + 512 + ad) >> 10); ny = sat16i((yr + 512 + bd) >> 10);
+                    } else {
                     float x = f_add(f_add(c.a0, r.b1), k2);
                     float y = f_add(f_add(c.a3, r.b4), k5);
                     if (proj) {
@@ -1276,16 +1365,17 @@ struct MBFastBody {
                     // cvRound: |32 x| >= 2^31 or NaN gives INT_MIN on the oracle's x86 (f2i_rn); below that the
                     // plain conversion is identical. For the nearest mask the patch is not needed: a
                     // saturated coordinate is out of the source either way, NaN is excluded through `ok`.
-                    const bool okx = x < 67108864.f, oky = y < 67108864.f;
+                    okx = x < 67108864.f; oky = y < 67108864.f;
 #if DS_CUDA
-                    int ix = __float2int_rn(f_mul(x, 32.f)), iy = __float2int_rn(f_mul(y, 32.f));
-                    const int nx = __float2int_rn(x), ny = __float2int_rn(y);
+                    ix = __float2int_rn(f_mul(x, 32.f)); iy = __float2int_rn(f_mul(y, 32.f));
+                    nx = __float2int_rn(x); ny = __float2int_rn(y);
 #else
-                    int ix = f2i_rn(f_mul(x, 32.f)), iy = f2i_rn(f_mul(y, 32.f));
-                    const int nx = okx ? f2i_rn(x) : 0, ny = oky ? f2i_rn(y) : 0;
+                    ix = f2i_rn(f_mul(x, 32.f)); iy = f2i_rn(f_mul(y, 32.f));
+                    nx = okx ? f2i_rn(x) : 0; ny = oky ? f2i_rn(y) : 0;
 #endif
                     ix = okx ? ix : (int)0x80000000;
                     iy = oky ? iy : (int)0x80000000;
+                    }
                     const int sx = sat16i(ix >> 5), sy = sat16i(iy >> 5);
                     const int ax = ix & 31, ay = iy & 31;
                     int m = ((c.u | r.v) >= 0 && okx && oky && (unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255 : 0;
@@ -1750,8 +1840,10 @@ DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
 DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 3)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)
 typedef MBFastBody<64, true> MBFastL0;
+typedef MBFastBody<64, true, true> MBFastL0A;
 typedef MBFastBody<32, false> MBFastLN;
 DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
+DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_ln, MBFastLN, 256, MBParams, 4)
 DS_DEFINE_KERNEL(ds_mb_feed_generic, MBBodyLN, 256, MBParams, 1)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 5)

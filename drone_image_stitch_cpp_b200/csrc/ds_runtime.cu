@@ -313,6 +313,7 @@ struct ds_canvas {
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
     bool ln_fast_ok = false;   // fast kernel for levels 1..L-1 (<= 64 frames per tile at every level)
+    bool l0_has_affine = false;   // some frame is AFFINE_F64 or has a seam mask / gain map: level 0 runs the general variant of the fast kernel
     bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
     int feather_R = 0;
     int64_t device_bytes = 0;
@@ -810,9 +811,11 @@ int build_lists(ds_canvas* c) {
             int longest = 0;
             for (int t = 0; t < ntiles; t++) longest = std::max(longest, counts[(size_t)t + 1] - counts[t]);
             if (l == 0) {
-                bool all_plane = true;
-                for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32) all_plane = false;
+                bool all_plane = true;   // the fast level-0 kernel builds plane (float) and warpAffine (integer) coordinates
+                for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32 && f.xf.kind != DS_XF_AFFINE_F64) all_plane = false;
                 c->l0_fast_ok = all_plane && longest <= 64;
+                c->l0_has_affine = false;
+                for (const Frame& f : c->frames) if (f.used && (f.xf.kind == DS_XF_AFFINE_F64 || f.d_seam || f.d_gainmap)) c->l0_has_affine = true;
                 c->ln_fast_ok = true;
             } else if (longest > 64) {
                 c->ln_fast_ok = false;
@@ -973,7 +976,8 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     else ab = abm.A * q * 40.0;
     ab *= (double)count / (double)std::max(pl.n_ids, 1);
     if ((rc = prof_mark(c, st, true, "mb_feed", l, (int64_t)ab))) return rc;
-    if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, count, st, MBFastBody<64, true>::smem_bytes());
+    if (l == 0 && c->L > 0 && c->l0_fast_ok && c->l0_has_affine) rc = launch<MBFastBody<64, true, true>, 512>(mp, count, st, MBFastBody<64, true, true>::smem_bytes());
+    else if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, count, st, MBFastBody<64, true>::smem_bytes());
     else if (l > 0 && l < c->L && c->ln_fast_ok) rc = launch<MBFastBody<32, false>, 256>(mp, count, st, MBFastBody<32, false>::smem_bytes());
     else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, count, st, MBBody<64, true>::smem_bytes());
     else rc = launch<MBBody<32, false>, 256>(mp, count, st, MBBody<32, false>::smem_bytes());
