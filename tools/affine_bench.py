@@ -22,6 +22,14 @@ for A in plan.A:
     M = A.copy(); M[0, 2] -= x0; M[1, 2] -= y0
     xfs.append(CP.affine_transform(M, (x0, y0), (w, h)))
     rois.append((x0, y0, w, h))
+if mode == "plane_proj":
+    # PlaneWarper with a slight perspective (mode C of SURVEY 8(d)): the map divides by z per pixel
+    Rs = []
+    for R in plan.Rs:
+        R = np.array(R, np.float32).copy(); R[2, 0] = 1e-6; R[2, 1] = -1e-6
+        Rs.append(R)
+    xfs = [CP.plane_transform(K, R, plan.scale, affine=False) for K, R in zip(plan.Ks, Rs)]
+    rois = [CP.warp_roi(xf, fw, fh, lib) for xf in xfs]
 if mode == "plane_seam":
     xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
     rois = [CP.warp_roi(xf, fw, fh, lib) for xf in xfs]
@@ -31,7 +39,7 @@ cv = CP.Canvas(roi, "multiband", 5, lib=lib)
 rng = np.random.default_rng(3)
 for i, f in enumerate(frames):
     kw = {}
-    if mode != "affine":
+    if mode not in ("affine", "plane_proj"):
         # a seam mask over the frame's bbox: everything but a diagonal band and the outer 40 px; soft edges for the global stage
         w, h = rois[i][2], rois[i][3]
         yy, xx = np.mgrid[0:h, 0:w]
