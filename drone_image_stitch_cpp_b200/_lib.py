@@ -23,6 +23,7 @@ EXPORTS = [
     "ds_p2p_export", "ds_p2p_connect", "ds_p2p_disconnect", "ds_composite_stage",
     "ds_last_error", "ds_get_info", "ds_version", "ds_debug_get_placement", "ds_debug_get_maps",
     "ds_debug_get_warped", "ds_debug_get_frame_level", "ds_set_profiling", "ds_get_kernel_times",
+    "ds_update_frame_opts", "ds_download_frame_mask",
 ]
 
 
@@ -36,7 +37,7 @@ class ds_transform(C.Structure):
     ]
 
 
-DS_UPLOAD_ASYNC = 1
+DS_UPLOAD_ASYNC, DS_MASK_CONTENT, DS_SEAM_NEAREST, DS_MASK_SOFT = 1, 2, 4, 8
 
 
 class ds_frame_opts(C.Structure):
@@ -44,7 +45,7 @@ class ds_frame_opts(C.Structure):
                 ("seam_lowres", C.c_void_p), ("seam_lowres_w", C.c_int32), ("seam_lowres_h", C.c_int32),
                 ("seam_lowres_stride", C.c_size_t),
                 ("compensator_gain", C.POINTER(C.c_double)), ("gain_map", C.c_void_p), ("gain_map_stride", C.c_size_t),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32), ("soft_sigma", C.c_float)]
 
 
 class ds_canvas_desc(C.Structure):
@@ -117,6 +118,8 @@ class Library:
         d.ds_p2p_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         d.ds_p2p_disconnect.argtypes = [C.c_void_p]
         d.ds_composite_stage.argtypes = [C.c_void_p, C.c_int]
+        d.ds_update_frame_opts.argtypes = [C.c_void_p, C.c_int, C.POINTER(ds_frame_opts)]
+        d.ds_download_frame_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
 
     def check(self, rc):
         if rc != DS_OK:

@@ -5,7 +5,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "ds_runtime.cu")
-DEPS = [os.path.join(_HERE, "csrc", n) for n in ("ds_runtime.cu", "ds_kernels.h", "ds_types.h", "ds_device.h", "ds_geometry.h")]
+DEPS = [os.path.join(_HERE, "csrc", n) for n in ("ds_runtime.cu", "ds_kernels.h", "ds_mask_kernels.h", "ds_types.h", "ds_device.h", "ds_geometry.h")]
 DEPS.append(os.path.join(_HERE, "..", "include", "dronestitch.h"))
 OUT = os.path.join(_HERE, "lib", "libdronestitch_cuda.so")
 

@@ -110,40 +110,52 @@ class Canvas:
         arr = (C.c_int32 * 4)(*[int(v) for v in frame_roi])
         return bool(self.lib.dll.ds_frame_touches_band(C.byref(self.desc), arr))
 
-    def upload(self, idx, img, xf, seam_mask=None, channel_gain=None, seam_lowres=None, compensator_gain=None, gain_map=None,
-               async_=False):
+    @staticmethod
+    def _make_opts(seam_mask=None, channel_gain=None, seam_lowres=None, compensator_gain=None, gain_map=None, async_=False,
+                   content_mask=False, seam_nearest=False, soft_mask=None):
+        """-> (ds_frame_opts or None, buffers to keep alive)."""
+        keep = []
+        if not (async_ or content_mask or seam_nearest or soft_mask is not None or
+                any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map))):
+            return None, keep
+        opts = L.ds_frame_opts()
+        opts.flags = ((L.DS_UPLOAD_ASYNC if async_ else 0) | (L.DS_MASK_CONTENT if content_mask else 0) |
+                      (L.DS_SEAM_NEAREST if seam_nearest else 0) | (L.DS_MASK_SOFT if soft_mask is not None else 0))
+        if soft_mask is not None and soft_mask is not True:
+            opts.soft_sigma = float(soft_mask)
+        if compensator_gain is not None:
+            cg = (C.c_double * 3)(*[float(v) for v in compensator_gain])
+            keep.append(cg)
+            opts.compensator_gain = C.cast(cg, C.POINTER(C.c_double))
+        if gain_map is not None:
+            gm = np.ascontiguousarray(gain_map, np.float32)
+            keep.append(gm)
+            opts.gain_map = gm.ctypes.data
+            opts.gain_map_stride = gm.strides[0]
+        if seam_lowres is not None:
+            sl = np.ascontiguousarray(seam_lowres, np.uint8)
+            keep.append(sl)
+            opts.seam_lowres = sl.ctypes.data
+            opts.seam_lowres_w, opts.seam_lowres_h = sl.shape[1], sl.shape[0]
+            opts.seam_lowres_stride = sl.strides[0]
+        if seam_mask is not None:
+            sm = np.ascontiguousarray(seam_mask, np.uint8)
+            keep.append(sm)
+            opts.seam_mask = sm.ctypes.data
+            opts.seam_mask_stride = sm.strides[0]
+        if channel_gain is not None:
+            g = (C.c_float * 3)(*[float(v) for v in channel_gain])
+            keep.append(g)
+            opts.channel_gain = C.cast(g, C.POINTER(C.c_float))
+        return opts, keep
+
+    def upload(self, idx, img, xf, async_=False, **opt_kw):
         """img: HxWx3 uint8 (numpy; any row stride) or a (ptr, w, h, stride) tuple.
         async_: DS_UPLOAD_ASYNC - `img` (pinned) must stay valid and unchanged until composite() / synchronize() /
-        a full download() has returned."""
-        opts = None
-        keep = []
-        if async_ or any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map)):
-            opts = L.ds_frame_opts()
-            opts.flags = L.DS_UPLOAD_ASYNC if async_ else 0
-            if compensator_gain is not None:
-                cg = (C.c_double * 3)(*[float(v) for v in compensator_gain])
-                keep.append(cg)
-                opts.compensator_gain = C.cast(cg, C.POINTER(C.c_double))
-            if gain_map is not None:
-                gm = np.ascontiguousarray(gain_map, np.float32)
-                keep.append(gm)
-                opts.gain_map = gm.ctypes.data
-                opts.gain_map_stride = gm.strides[0]
-            if seam_lowres is not None:
-                sl = np.ascontiguousarray(seam_lowres, np.uint8)
-                keep.append(sl)
-                opts.seam_lowres = sl.ctypes.data
-                opts.seam_lowres_w, opts.seam_lowres_h = sl.shape[1], sl.shape[0]
-                opts.seam_lowres_stride = sl.strides[0]
-            if seam_mask is not None:
-                sm = np.ascontiguousarray(seam_mask, np.uint8)
-                keep.append(sm)
-                opts.seam_mask = sm.ctypes.data
-                opts.seam_mask_stride = sm.strides[0]
-            if channel_gain is not None:
-                g = (C.c_float * 3)(*[float(v) for v in channel_gain])
-                keep.append(g)
-                opts.channel_gain = C.cast(g, C.POINTER(C.c_float))
+        a full download() has returned.
+        opt_kw (ds_frame_opts): seam_mask, seam_lowres, seam_nearest, channel_gain, compensator_gain, gain_map,
+        content_mask (DS_MASK_CONTENT), soft_mask (DS_MASK_SOFT: True or the sigma)."""
+        opts, keep = self._make_opts(async_=async_, **opt_kw)
         if isinstance(img, tuple):
             ptr, w, h, stride = img
         else:
@@ -153,6 +165,19 @@ class Canvas:
                                                     C.byref(xf), C.byref(opts) if opts is not None else None))
         if async_:
             self._pending.append((img, keep))
+
+    def update_opts(self, idx, **opt_kw):
+        """ds_update_frame_opts: new seam masks / gains / mask flags for a frame whose pixels are already uploaded
+        (the global stage's feed loop, /root/reference/src/stitch_global.cpp:643-660)."""
+        opts, keep = self._make_opts(**opt_kw)
+        self.lib.check(self.lib.dll.ds_update_frame_opts(self._h, int(idx), C.byref(opts) if opts is not None else None))
+
+    def frame_mask(self, idx, which=0):
+        """ds_download_frame_mask: 0 = the mask the blender is fed with, 1 = the content mask (DS_MASK_CONTENT)."""
+        x, y, w, h = self.placement(idx)
+        m = np.empty((h, w), np.uint8)
+        self.lib.check(self.lib.dll.ds_download_frame_mask(self._h, int(idx), int(which), m.ctypes.data, m.strides[0]))
+        return m
 
     def upload_device(self, idx, dev_ptr, w, h, stride, xf):
         self.lib.check(self.lib.dll.ds_upload_frame_device(self._h, int(idx), C.c_void_p(dev_ptr), int(w), int(h),

@@ -1827,6 +1827,8 @@ struct FinalizeL0Body {
     }
 };
 
+#include "ds_mask_kernels.h"
+
 #if DS_CUDA
 typedef MBBody<64, true> MBBodyL0;
 typedef MBBody<32, false> MBBodyLN;
@@ -1836,6 +1838,8 @@ DS_DEFINE_KERNEL(ds_p2p_pull, PullBody, 256, PullParams, 1)
 DS_DEFINE_KERNEL(ds_p2p_signal, SignalBody, 32, SignalParams, 1)
 DS_DEFINE_KERNEL(ds_debug_tap, TapBody, 256, TapParams, 1)
 DS_DEFINE_KERNEL(ds_seam_upsize, SeamUpBody, 256, SeamUpParams, 1)
+DS_DEFINE_KERNEL(ds_mask_prep, MaskPrepBody, 256, MaskPrepParams, 1)
+DS_DEFINE_KERNEL(ds_soft_mask, SoftMaskBody, 256, SoftMaskParams, 3)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
 DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 3)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)

@@ -219,7 +219,8 @@ struct Frame {
     int rx = 0, ry = 0, rw = 0, rh = 0;              // feed ROI rel. to padded canvas origin
     void* d_pyr = nullptr; size_t pyr_cap = 0;       // G/W levels 1..L
     uint32_t* d_mbits = nullptr; size_t mbits_cap = 0;
-    uint8_t* d_seam = nullptr; size_t seam_cap = 0;
+    uint8_t* d_seam = nullptr; size_t seam_cap = 0;        // the frame's mask plane over its bbox (seam / content / soft mask)
+    uint8_t* d_content = nullptr; size_t content_cap = 0;  // DS_MASK_CONTENT: the content mask, kept for ds_download_frame_mask
     float* d_gainmap = nullptr; size_t gainmap_cap = 0;
     FrameDev dev{};
     bool mask_done = false; // FEATHER: mask bit plane built for the current composite
@@ -1248,6 +1249,151 @@ int check_device() {
     return DS_OK;
 }
 
+// cv::getGaussianKernel(n, sigma, CV_32F) (bit-exact variant): values exp(-x^2 / (2 sigma^2)) for the lower half, their
+// sum doubled + the centre's 1, every tap scaled by 1 / sum in double, rounded to float once.
+int gaussian_kernel_f32(double sigma, float* k, int* radius) {
+    const int n = (int)lrint(sigma * 8.0 + 1.0) | 1;   // float depth: cvRound(sigma * 4 * 2 + 1) | 1
+    const int R = n / 2;
+    if (sigma <= 0.0 || R > DS_SOFT_MAXR) return fail(DS_ERR_UNSUPPORTED, "soft_sigma %g needs a kernel of %d taps (supported: sigma in (0, 10])", sigma, n);
+    const double scale2x = -0.125 / (sigma * sigma);
+    double vals[DS_SOFT_MAXR], sum = 0.0;
+    int x = 1 - n;
+    for (int i = 0; i < R; i++, x += 2) { vals[i] = exp((double)(x * x) * scale2x); sum += vals[i]; }
+    sum *= 2.0; sum += 1.0;
+    const double mul = 1.0 / sum;
+    for (int i = 0; i < R; i++) k[i] = k[n - 1 - i] = (float)(vals[i] * mul);
+    k[R] = (float)mul;
+    *radius = R;
+    return DS_OK;
+}
+
+// cv::resize(INTER_NEAREST): source index of every destination column / row.
+void nearest_table(int s_, int d_, int* idx) {
+    const double inv_scale = (double)d_ / (double)s_;
+    const double ifx = 1.0 / inv_scale;
+    for (int v = 0; v < d_; v++) idx[v] = std::min((int)floor((double)v * ifx), s_ - 1);
+}
+
+// Optional per-frame inputs (ds_frame_opts): seam masks, the global stage's content / soft masks, gains.
+// The frame's geometry and source buffer are in place; the pixels may still be on their way (they are waited for only
+// when the content mask reads them).
+int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
+    int rc;
+    const uint32_t fl = opts ? opts->flags : 0u;
+    const bool want_content = (fl & DS_MASK_CONTENT) != 0, want_soft = (fl & DS_MASK_SOFT) != 0;
+    const bool has_low = opts && opts->seam_lowres, has_full = opts && opts->seam_mask && !has_low;
+    const bool nearest = has_low && (fl & DS_SEAM_NEAREST);
+    const size_t plane = (size_t)f.bw * f.bh;
+    uint8_t* d_low = nullptr; int* d_tab = nullptr; uint8_t* d_tmp = nullptr;
+    bool drain = false;
+    auto cleanup = [&](int code) {
+        if (drain) { const int r2 = stream_sync(c->up); if (!code) code = r2; }   // temporaries below are freed: these (rare) paths drain
+        dev_free(d_low); dev_free(d_tab); dev_free(d_tmp);
+        return code;
+    };
+    if (has_low) {
+        const int sw = opts->seam_lowres_w, sh = opts->seam_lowres_h;
+        if (sw <= 0 || sh <= 0) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", sw, sh);
+        const size_t sst = opts->seam_lowres_stride ? opts->seam_lowres_stride : (size_t)sw;
+        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, plane))) return rc;
+        std::vector<int> tab(2 * ((size_t)f.bw + f.bh));
+        if (nearest) {
+            // stitch_global.cpp:649-655: resize(seam_masks[i], warped size, INTER_NEAREST), threshold(> 1)
+            nearest_table(sw, f.bw, tab.data());
+            nearest_table(sh, f.bh, tab.data() + f.bw);
+        } else {
+            // composePanorama: dilate(masks_warped[i]) -> resize(mask_warped.size(), INTER_LINEAR_EXACT) -> AND
+            // coefficient tables in double on the host (OpenCV computes them in softdouble)
+            auto coefs = [](int s_, int d_, int* idx, int* c1) {
+                const double scale = (double)s_ / (double)d_;
+                for (int v = 0; v < d_; v++) {
+                    const double fv = scale * ((double)v + 0.5) - 0.5;
+                    int i = (int)floor(fv);
+                    int k1 = (int)lrint((fv - (double)i) * 256.0);
+                    if (i < 0 || s_ <= 1) { i = 0; k1 = 0; }
+                    if (i >= s_ - 1) { i = s_ - 1; k1 = 0; }
+                    idx[v] = i; c1[v] = k1;
+                }
+            };
+            coefs(sw, f.bw, tab.data(), tab.data() + f.bw);
+            coefs(sh, f.bh, tab.data() + 2 * f.bw, tab.data() + 2 * f.bw + f.bh);
+        }
+        if ((rc = dev_alloc_t(&d_low, (size_t)sw * sh))) return rc;
+        if ((rc = dev_alloc_t(&d_tab, tab.size()))) return cleanup(rc);
+        drain = true;
+        if ((rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->up))) return cleanup(rc);
+        if ((rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->up))) return cleanup(rc);
+        if (!nearest) {
+            SeamUpParams sp{d_low, sw, sh, sw, d_tab, d_tab + f.bw, d_tab + 2 * f.bw, d_tab + 2 * f.bw + f.bh, f.d_seam, f.bw, f.bh};
+            if ((rc = launch<SeamUpBody, 256>(sp, ((long long)plane + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->up, 0))) return cleanup(rc);
+        }
+    } else if (has_full) {
+        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, plane))) return rc;
+        if ((rc = h2d_2d(f.d_seam, (size_t)f.bw, opts->seam_mask, opts->seam_mask_stride ? opts->seam_mask_stride : (size_t)f.bw,
+                         (size_t)f.bw, (size_t)f.bh, c->up))) return rc;
+    } else if (f.d_seam && !want_content && !want_soft) {
+        dev_free(f.d_seam); c->device_bytes -= (int64_t)f.seam_cap; f.d_seam = nullptr; f.seam_cap = 0;
+    }
+    if (!want_content && f.d_content) {
+        dev_free(f.d_content); c->device_bytes -= (int64_t)f.content_cap; f.d_content = nullptr; f.content_cap = 0;
+    }
+    if ((rc = fill_frame_dev(c, f))) return cleanup(rc);
+    if (want_content || want_soft || nearest) {
+        // the global stage's mask chain (ds_mask_kernels.h), on the upload stream behind the copies it reads
+        MaskPrepParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.F = f.dev;
+        mp.want_content = want_content ? 1 : 0;
+        if (nearest) { mp.low = d_low; mp.low_pitch = opts->seam_lowres_w; mp.ix = d_tab; mp.iy = d_tab + f.bw; }
+        else if (has_low || has_full) { mp.seam = f.d_seam; mp.seam_pitch = f.bw; }
+        mp.binarize = (nearest || want_soft) ? 1 : 0;
+        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, plane))) return cleanup(rc);
+        if (want_content) {
+            if ((rc = grow(c, (void**)&f.d_content, &f.content_cap, plane))) return cleanup(rc);
+            // the content mask reads the frame's pixels: bring them in now and queue behind their expansion
+            if (f.partial) return cleanup(fail(DS_ERR_STATE, "frame %d is only partially resident", idx));
+            if (f.pend.left > 0 && (rc = issue_rows(c, idx, 0, f.h - 1))) return cleanup(rc);
+            if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->up, c->ev_chunks))) return cleanup(rc);
+        }
+        mp.content_out = f.d_content;
+        mp.out = f.d_seam;
+        drain = true;
+        if ((rc = launch<MaskPrepBody, 256>(mp, ((long long)plane + MaskPrepBody::PER_BLOCK - 1) / MaskPrepBody::PER_BLOCK, c->up, 0))) return cleanup(rc);
+        if (want_soft) {
+            SoftMaskParams sp;
+            memset(&sp, 0, sizeof(sp));
+            if ((rc = gaussian_kernel_f32(opts->soft_sigma > 0.f ? (double)opts->soft_sigma : 10.0, sp.k, &sp.R))) return cleanup(rc);
+            if ((rc = dev_alloc_t(&d_tmp, plane))) return cleanup(rc);
+            sp.bin = f.d_seam; sp.bin_pitch = f.bw; sp.out = d_tmp; sp.out_pitch = f.bw; sp.w = f.bw; sp.h = f.bh;
+            const long long tiles = (long long)((f.bw + SoftMaskBody::T - 1) / SoftMaskBody::T) * ((f.bh + SoftMaskBody::T - 1) / SoftMaskBody::T);
+            if ((rc = launch<SoftMaskBody, 256>(sp, tiles, c->up, SoftMaskBody::smem_bytes()))) return cleanup(rc);
+            // the blurred plane becomes the frame's mask
+            c->device_bytes += (int64_t)plane - (int64_t)f.seam_cap;
+            std::swap(f.d_seam, d_tmp); f.seam_cap = plane;
+        }
+        f.dev.seam = f.d_seam; f.dev.seam_pitch = f.bw;
+    }
+    if ((rc = cleanup(DS_OK))) return rc;
+    if (opts && opts->gain_map) {
+        const size_t gst = opts->gain_map_stride ? opts->gain_map_stride : (size_t)f.bw * sizeof(float);
+        if ((rc = grow(c, (void**)&f.d_gainmap, &f.gainmap_cap, (size_t)f.bw * f.bh * sizeof(float)))) return rc;
+        if ((rc = h2d_2d(f.d_gainmap, (size_t)f.bw * sizeof(float), opts->gain_map, gst, (size_t)f.bw * sizeof(float), (size_t)f.bh, c->up))) return rc;
+        f.dev.gainmap = f.d_gainmap; f.dev.gainmap_pitch = f.bw;
+    } else if (f.d_gainmap) {
+        dev_free(f.d_gainmap); c->device_bytes -= (int64_t)f.gainmap_cap; f.d_gainmap = nullptr; f.gainmap_cap = 0;
+    }
+    if (opts && opts->channel_gain) {
+        f.dev.has_gain = 1;
+        for (int k = 0; k < 3; k++) f.dev.gain[k] = opts->channel_gain[k];
+    }
+    if (opts && opts->compensator_gain) {
+        f.dev.has_cgain = 1;
+        for (int k = 0; k < 3; k++) f.dev.cgain[k] = opts->compensator_gain[k];
+    }
+    f.dev.any_gain = (f.dev.has_gain || f.dev.has_cgain || f.dev.gainmap) ? 1 : 0;
+    return DS_OK;
+}
+
 int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int h, size_t stride,
               const ds_transform* xf, const ds_frame_opts* opts) {
     if (!c || !bgr || !xf) return fail(DS_ERR_BAD_ARG, "null argument");
@@ -1307,65 +1453,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     } else {
         if ((rc = grow(c, (void**)&f.d_mbits, &f.mbits_cap, (size_t)((f.bw + 31) / 32) * f.bh * sizeof(uint32_t)))) return rc;
     }
-    if (opts && opts->seam_lowres) {
-        // composePanorama: dilate(masks_warped[i]) -> resize(mask_warped.size(), INTER_LINEAR_EXACT) -> AND
-        const int sw = opts->seam_lowres_w, sh = opts->seam_lowres_h;
-        if (sw <= 0 || sh <= 0) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", sw, sh);
-        const size_t sst = opts->seam_lowres_stride ? opts->seam_lowres_stride : (size_t)sw;
-        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, (size_t)f.bw * f.bh))) return rc;
-        // coefficient tables in double on the host (OpenCV computes them in softdouble)
-        std::vector<int> tab(2 * ((size_t)f.bw + f.bh));
-        auto coefs = [](int s_, int d_, int* idx, int* c1) {
-            const double scale = (double)s_ / (double)d_;
-            for (int v = 0; v < d_; v++) {
-                const double fv = scale * ((double)v + 0.5) - 0.5;
-                int i = (int)floor(fv);
-                int k1 = (int)lrint((fv - (double)i) * 256.0);
-                if (i < 0 || s_ <= 1) { i = 0; k1 = 0; }
-                if (i >= s_ - 1) { i = s_ - 1; k1 = 0; }
-                idx[v] = i; c1[v] = k1;
-            }
-        };
-        coefs(sw, f.bw, tab.data(), tab.data() + f.bw);
-        coefs(sh, f.bh, tab.data() + 2 * f.bw, tab.data() + 2 * f.bw + f.bh);
-        uint8_t* d_low = nullptr; int* d_tab = nullptr;
-        if ((rc = dev_alloc_t(&d_low, (size_t)sw * sh))) return rc;
-        if ((rc = dev_alloc_t(&d_tab, tab.size()))) { dev_free(d_low); return rc; }
-        rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->up);
-        if (!rc) rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->up);
-        if (!rc) {
-            SeamUpParams sp{d_low, sw, sh, sw, d_tab, d_tab + f.bw, d_tab + 2 * f.bw, d_tab + 2 * f.bw + f.bh, f.d_seam, f.bw, f.bh};
-            const long long n = (long long)f.bw * f.bh;
-            rc = launch<SeamUpBody, 256>(sp, (n + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->up, 0);
-        }
-        if (!rc) rc = stream_sync(c->up);   // temporaries below are freed: this (rare) path always drains
-        dev_free(d_low); dev_free(d_tab);
-        if (rc) return rc;
-    } else if (opts && opts->seam_mask) {
-        if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, (size_t)f.bw * f.bh))) return rc;
-        if ((rc = h2d_2d(f.d_seam, (size_t)f.bw, opts->seam_mask, opts->seam_mask_stride ? opts->seam_mask_stride : (size_t)f.bw,
-                         (size_t)f.bw, (size_t)f.bh, c->up))) return rc;
-    } else if (f.d_seam) {
-        dev_free(f.d_seam); c->device_bytes -= (int64_t)f.seam_cap; f.d_seam = nullptr; f.seam_cap = 0;
-    }
-    if ((rc = fill_frame_dev(c, f))) return rc;
-    if (opts && opts->gain_map) {
-        const size_t gst = opts->gain_map_stride ? opts->gain_map_stride : (size_t)f.bw * sizeof(float);
-        if ((rc = grow(c, (void**)&f.d_gainmap, &f.gainmap_cap, (size_t)f.bw * f.bh * sizeof(float)))) return rc;
-        if ((rc = h2d_2d(f.d_gainmap, (size_t)f.bw * sizeof(float), opts->gain_map, gst, (size_t)f.bw * sizeof(float), (size_t)f.bh, c->up))) return rc;
-        f.dev.gainmap = f.d_gainmap; f.dev.gainmap_pitch = f.bw;
-    } else if (f.d_gainmap) {
-        dev_free(f.d_gainmap); c->device_bytes -= (int64_t)f.gainmap_cap; f.d_gainmap = nullptr; f.gainmap_cap = 0;
-    }
-    if (opts && opts->channel_gain) {
-        f.dev.has_gain = 1;
-        for (int k = 0; k < 3; k++) f.dev.gain[k] = opts->channel_gain[k];
-    }
-    if (opts && opts->compensator_gain) {
-        f.dev.has_cgain = 1;
-        for (int k = 0; k < 3; k++) f.dev.cgain[k] = opts->compensator_gain[k];
-    }
-    f.dev.any_gain = (f.dev.has_gain || f.dev.has_cgain || f.dev.gainmap) ? 1 : 0;
+    if ((rc = apply_opts(c, f, idx, opts))) return rc;
     if (async) c->async_pending = true;
     else if ((rc = stream_sync(c->up)) || (rc = stream_sync(c->xp))) return rc;
     // same geometry, buffers and gains as before (a new image for the same slot): the launch metadata stands
@@ -1541,7 +1629,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     if (c->dl) cudaStreamSynchronize(c->dl);
 #endif
     for (Frame& f : c->frames) {
-        dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_gainmap);
+        dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_content); dev_free(f.d_gainmap);
     }
     for (int l = 0; l < DS_MAXL; l++) dev_free(c->d_lvl_alloc[l]);
     for (SubBand& sb : c->subs) { ev_drop(sb.done); ev_drop(sb.fed); ev_drop(sb.fed0); }
@@ -1574,6 +1662,54 @@ DS_API int ds_upload_frame(ds_canvas* c, int frame_idx, const uint8_t* bgr, int 
 DS_API int ds_upload_frame_device(ds_canvas* c, int frame_idx, const void* dev_bgr, int w, int h, size_t stride,
                                   const ds_transform* xf, const ds_frame_opts* opts) {
     return do_upload(c, frame_idx, dev_bgr, true, w, h, stride, xf, opts);
+}
+
+DS_API int ds_update_frame_opts(ds_canvas* c, int frame_idx, const ds_frame_opts* opts) {
+    if (!c) return fail(DS_ERR_BAD_ARG, "null canvas");
+    if (frame_idx < 0 || (size_t)frame_idx >= c->frames.size() || !c->frames[(size_t)frame_idx].used)
+        return fail(DS_ERR_BAD_ARG, "frame %d not uploaded", frame_idx);
+    if (c->stage_open) return fail(DS_ERR_STATE, "a composite is half done: call ds_composite_stage(c, 1) first");
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = flush_uploads(c))) return rc;
+    // the frame's planes may still be read by the previous composite
+    if (c->ev_done_valid && (rc = ev_wait(c->up, c->ev_done))) return rc;
+    Frame& f = c->frames[(size_t)frame_idx];
+    const FrameDev before = f.dev;
+    if ((rc = apply_opts(c, f, frame_idx, opts))) return rc;
+    if ((rc = stream_sync(c->up))) return rc;
+    if (memcmp(&before, &f.dev, sizeof(FrameDev)) != 0) c->dirty = true;
+    c->composited = false;
+    return DS_OK;
+}
+
+DS_API int ds_download_frame_mask(ds_canvas* c, int frame_idx, int which, uint8_t* out, size_t stride) {
+    if (!c || !out) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (frame_idx < 0 || (size_t)frame_idx >= c->frames.size() || !c->frames[(size_t)frame_idx].used)
+        return fail(DS_ERR_BAD_ARG, "frame %d not uploaded", frame_idx);
+    if (which != 0 && which != 1) return fail(DS_ERR_BAD_ARG, "which = %d (0: blend mask, 1: content mask)", which);
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = flush_uploads(c))) return rc;
+    Frame& f = c->frames[(size_t)frame_idx];
+    const size_t st = stride ? stride : (size_t)f.bw;
+    if (st < (size_t)f.bw) return fail(DS_ERR_BAD_ARG, "stride %zu < width %d", st, f.bw);
+    if (which == 1) {
+        if (!f.d_content) return fail(DS_ERR_STATE, "frame %d was not uploaded with DS_MASK_CONTENT", frame_idx);
+        if ((rc = d2h_2d(out, st, f.d_content, (size_t)f.bw, (size_t)f.bw, (size_t)f.bh, c->up))) return rc;
+        return stream_sync(c->up);
+    }
+    const size_t plane = (size_t)f.bw * f.bh;
+    uint8_t* d_tmp = nullptr;
+    if ((rc = dev_alloc_t(&d_tmp, plane))) return rc;
+    MaskPrepParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.F = f.dev; mp.seam = f.d_seam; mp.seam_pitch = f.bw; mp.and_nearest = 1; mp.out = d_tmp;
+    rc = launch<MaskPrepBody, 256>(mp, ((long long)plane + MaskPrepBody::PER_BLOCK - 1) / MaskPrepBody::PER_BLOCK, c->up, 0);
+    if (!rc) rc = d2h_2d(out, st, d_tmp, (size_t)f.bw, (size_t)f.bw, (size_t)f.bh, c->up);
+    const int r2 = stream_sync(c->up);
+    dev_free(d_tmp);
+    return rc ? rc : r2;
 }
 
 DS_API int ds_composite_async(ds_canvas* c) {

@@ -113,9 +113,28 @@ typedef struct ds_frame_opts {
      * starting as soon as the frames it reads have arrived, and ds_download_tile copies every slice out as soon
      * as it is final - upload, compute and download overlap. Results are identical. */
     uint32_t flags;
+    /* DS_MASK_SOFT: sigma of buildSoftBlendMask's GaussianBlur; 0 = the reference's 10.0 (stitch_global.cpp:345).
+     * Supported up to 10 (kernel of 81 taps). */
+    float soft_sigma;
 } ds_frame_opts;
 
-enum { DS_UPLOAD_ASYNC = 1u };
+/* ds_frame_opts.flags */
+enum {
+    DS_UPLOAD_ASYNC = 1u,
+    /* The global stage's masks (stitchInterStripsCustom), built on the device:
+     * DS_MASK_CONTENT  buildWarpedContentMask (stitch_global.cpp:353-383): BGR2GRAY > 3 of the source as float 0/1,
+     *                  warped with the frame's own transform (INTER_LINEAR, BORDER_CONSTANT 0), > 0.999 -> 255. It is
+     *                  ANDed into the frame's mask and can be read back with ds_download_frame_mask(.., 1, ..) - the
+     *                  reference hands it to the exposure compensator and the seam finder (:577, :599-607).
+     * DS_SEAM_NEAREST  seam_lowres is brought to the warped bbox by resize(INTER_NEAREST) + threshold(> 1)
+     *                  (:649-655) instead of composePanorama's dilate + INTER_LINEAR_EXACT.
+     * DS_MASK_SOFT     buildSoftBlendMask (:332-351): (seam AND content) > 1 as float 0/1 -> GaussianBlur(sigma,
+     *                  BORDER_REPLICATE) -> * binary -> * 255 -> 8U is the mask the blender is fed with (:657-658).
+     * A frame uploaded with DS_MASK_CONTENT is copied at once even with DS_UPLOAD_ASYNC (the mask reads its pixels). */
+    DS_MASK_CONTENT = 2u,
+    DS_SEAM_NEAREST = 4u,
+    DS_MASK_SOFT = 8u
+};
 
 typedef struct ds_canvas_desc {
     int32_t x, y, width, height; /* canvas ROI = cv::detail::resultRoi(corners, sizes) */
@@ -171,6 +190,17 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out);
  * Re-uploading an index replaces it. */
 DS_API int ds_upload_frame(ds_canvas* c, int frame_idx, const uint8_t* bgr, int w, int h, size_t stride,
                            const ds_transform* xf, const ds_frame_opts* opts);
+
+/* New optional inputs (seam masks, gains, DS_MASK_* flags) for a frame whose pixels are already uploaded: what the
+ * global stage does between its warp loop (stitch_global.cpp:470-486) and its feed loop (:643-660), where exposure
+ * gains and seam masks only exist after the strips were warped. No pixels are transferred; DS_UPLOAD_ASYNC is
+ * ignored. opts == NULL removes every optional input. */
+DS_API int ds_update_frame_opts(ds_canvas* c, int frame_idx, const ds_frame_opts* opts);
+
+/* A frame's 8UC1 mask plane over its warped bbox (size from ds_debug_get_placement / ds_warp_roi):
+ * which = 0: the mask the blender is fed with (nearest-warped 255s AND seam / content / soft mask),
+ * which = 1: the content mask of DS_MASK_CONTENT (warped_masks[i] of the global stage). */
+DS_API int ds_download_frame_mask(ds_canvas* c, int frame_idx, int which, uint8_t* out, size_t stride);
 
 /* Same, but `dev_bgr` is a device pointer (frames already resident in HBM). */
 DS_API int ds_upload_frame_device(ds_canvas* c, int frame_idx, const void* dev_bgr, int w, int h, size_t stride,

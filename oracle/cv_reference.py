@@ -78,3 +78,30 @@ def compose_cv2(frames, Ks, Rs, scale, blend="multiband", bands=5, sharpness=0.0
     if timings is not None:
         timings["seconds"] = time.perf_counter() - t0
     return pano, res_mask, tuple(int(v) for v in roi)
+
+
+# ---- the global stage's mask helpers, through cv2 itself (src/stitch_global.cpp:328-383)
+
+def content_mask_cv2(img, M, dsize):
+    """buildWarpedContentMask."""
+    import cv2
+    gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    _, m8 = cv2.threshold(gray, 3, 255, cv2.THRESH_BINARY)
+    mf = cv2.multiply(m8, 1.0 / 255.0, dtype=cv2.CV_32F)   # convertTo(CV_32F, 1/255): 255 -> exactly 1.0f either way
+    wf = cv2.warpAffine(mf, np.asarray(M, np.float64).reshape(2, 3), dsize, flags=cv2.INTER_LINEAR,
+                        borderMode=cv2.BORDER_CONSTANT, borderValue=0.0)
+    _, mw = cv2.threshold(wf, 0.999, 255.0, cv2.THRESH_BINARY)
+    return mw.astype(np.uint8)
+
+
+def soft_blend_mask_cv2(seam, content, sigma=10.0):
+    """buildSoftBlendMask."""
+    import cv2
+    b = cv2.bitwise_and(seam, content)
+    _, b = cv2.threshold(b, 1.0, 255.0, cv2.THRESH_BINARY)
+    bf = (b > 0).astype(np.float32)                        # convertTo(CV_32F, 1/255) of a 0 / 255 image
+    soft = cv2.GaussianBlur(bf, (0, 0), sigma, None, sigma, cv2.BORDER_REPLICATE)
+    soft = cv2.multiply(soft, bf)
+    # convertTo(CV_8U, 255.0) scales in float32 (cvt_32f); cv2.normalize(MINMAX 0..255) issues exactly that call when the
+    # input spans [0, 1] - here done directly
+    return np.clip(np.rint((soft * np.float32(255.0)).astype(np.float32)), 0, 255).astype(np.uint8)

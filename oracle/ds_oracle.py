@@ -181,6 +181,58 @@ def seam_mask_upsize(mask, dw, dh):
     return out
 
 
+# ---- global-stage masks (src/stitch_global.cpp:328-383, :649-655)
+
+def bgr2gray(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape[:2], np.uint8)
+    lib().orc_bgr2gray(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_size_t(img.strides[0]), _p(out))
+    return out
+
+
+def content_mask(img, M, dw, dh):
+    """buildWarpedContentMask(src_image, affine, dst_size)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    M = np.ascontiguousarray(M, np.float64).reshape(-1)[:6].copy()
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_content_mask(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_size_t(img.strides[0]), _p(M),
+                           C.c_int(dw), C.c_int(dh), _p(out))
+    return out
+
+
+def resize_nearest(mask, dw, dh):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_nearest_u8(_p(mask), C.c_int(mask.shape[1]), C.c_int(mask.shape[0]), C.c_size_t(mask.strides[0]),
+                                C.c_int(dw), C.c_int(dh), _p(out))
+    return out
+
+
+def gaussian_kernel_f32(n, sigma):
+    k = np.empty(n, np.float32)
+    lib().orc_gaussian_kernel_f32(C.c_int(n), C.c_double(sigma), _p(k))
+    return k
+
+
+def soft_blend_mask(seam, content, sigma=10.0):
+    """buildSoftBlendMask(seam_mask, content_mask); either may be None (= all 255)."""
+    ref = seam if seam is not None else content
+    h, w = ref.shape
+    seam = None if seam is None else np.ascontiguousarray(seam, np.uint8)
+    content = None if content is None else np.ascontiguousarray(content, np.uint8)
+    out = np.empty((h, w), np.uint8)
+    lib().orc_soft_blend_mask(_p(seam) if seam is not None else None, C.c_size_t(seam.strides[0] if seam is not None else 0),
+                              _p(content) if content is not None else None,
+                              C.c_size_t(content.strides[0] if content is not None else 0),
+                              C.c_int(w), C.c_int(h), C.c_double(sigma), _p(out))
+    return out
+
+
+def threshold_gt1(mask):
+    """ensureBinaryMask: threshold(mask, 1, 255, THRESH_BINARY)."""
+    return np.where(np.asarray(mask) > 1, 255, 0).astype(np.uint8)
+
+
 def mbb_feed_geometry(roi, bands, tl, size):
     out = np.empty(8, np.int32)
     lib().orc_mbb_feed_geometry(C.c_int(roi[0]), C.c_int(roi[1]), C.c_int(roi[2]), C.c_int(roi[3]), C.c_int(bands),

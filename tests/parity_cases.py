@@ -40,7 +40,15 @@ def oracle_warp(spec):
         warped = np.clip(np.rint(warped.astype(np.float64) * g[None, None, :]), 0, 255).astype(np.uint8)
     if spec.get("gain_map") is not None:      # BlocksGainCompensator::apply: float32 per pixel
         warped = np.clip(np.rint(warped.astype(np.float32) * spec["gain_map"][:, :, None]), 0, 255).astype(np.uint8)
-    if spec.get("seam_lowres") is not None:
+    if spec.get("global_stage"):
+        # stitchInterStripsCustom (stitch_global.cpp:479-486, :643-658): content mask, seam mask resized with
+        # INTER_NEAREST + threshold, soft blend mask; the blender is fed with the soft mask itself
+        content = O.content_mask(img, spec["M"], dw, dh)
+        seam = None
+        if spec.get("seam_lowres") is not None:
+            seam = O.threshold_gt1(O.resize_nearest(spec["seam_lowres"], dw, dh))
+        mask = O.soft_blend_mask(seam, content, spec.get("sigma", 10.0))
+    elif spec.get("seam_lowres") is not None:
         mask = mask & O.seam_mask_upsize(spec["seam_lowres"], mask.shape[1], mask.shape[0])
     elif spec.get("seam") is not None:
         mask = mask & spec["seam"]
@@ -93,8 +101,11 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
         for i, (s, xf) in enumerate(zip(specs, xfs)):
             if band is not None and not cv.touches(rois[i]):
                 continue
+            gs = bool(s.get("global_stage"))
             cv.upload(i, s["img"], xf, seam_mask=s.get("seam"), channel_gain=s.get("gain"), seam_lowres=s.get("seam_lowres"),
-                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"), async_=slice_rows > 0)
+                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"), async_=slice_rows > 0,
+                      content_mask=gs, seam_nearest=gs and s.get("seam_lowres") is not None,
+                      soft_mask=(s.get("sigma", 10.0) if gs else None))
         if slice_rows > 0:
             cv.composite_async()
         else:
@@ -326,6 +337,76 @@ def case_exposure_gains(lib):
     return run_case(lib, specs, "feather", 0)
 
 
+def global_stage_specs(seed=31, n=3, fw=420, fh=300):
+    """Strip panoramas as the global stage sees them: black wedges / holes left by the strip stage, placed by
+    transformedBoundingRect (affine_specs), with a low-resolution seam mask per strip."""
+    specs = affine_specs(seed, n, fw, fh)
+    rng = np.random.default_rng(seed)
+    for i, s in enumerate(specs):
+        img = s["img"].copy()
+        yy, xx = np.mgrid[0:fh, 0:fw]
+        img[(yy < 0.12 * xx - 8 * i) | (yy > fh - 14 + 0.04 * xx)] = 0            # wedges
+        img[fh // 3:fh // 3 + 11, fw // 2:fw // 2 + 37] = rng.integers(0, 5, (11, 37, 3), dtype=np.uint8)   # near-black hole
+        s["img"] = img
+        bw, bh = s["size"]
+        lw, lh = max(4, bw // 7), max(4, bh // 7)
+        m = np.full((lh, lw), 255, np.uint8)
+        yy, xx = np.mgrid[0:lh, 0:lw]
+        if i % 2:
+            m[xx > 0.6 * lw + 0.2 * yy] = 0
+        else:
+            m[xx < 0.35 * lw - 0.1 * yy] = 0
+        m[rng.integers(0, lh), rng.integers(0, lw)] = 1     # a value ensureBinaryMask drops
+        s["seam_lowres"] = m
+        s["global_stage"] = True
+        if i:
+            s["gain"] = (1.0 + 0.04 * i, 0.97, 1.05)
+            s["cgain"] = (0.98, 1.02 + 0.01 * i, 1.0)
+    return specs
+
+
+def case_global_stage_masks(lib):
+    # SURVEY 8(f) rank 2: buildWarpedContentMask + NEAREST seam resize + buildSoftBlendMask on the device, fed to the
+    # multi-band blender like stitchInterStripsCustom does; also the two-step flow of the reference (warp first, masks and
+    # gains once the CPU-side exposure / seam steps are done) through ds_update_frame_opts
+    specs = global_stage_specs()
+    run_case(lib, specs, "multiband", 5, check_taps=False)
+    ow = [oracle_warp(s) for s in specs]
+    roi = O.result_roi([o[0] for o in ow], [(o[1].shape[1], o[1].shape[0]) for o in ow])
+    cv = CP.Canvas(roi, "multiband", 5, lib=lib)
+    for i, s in enumerate(specs):
+        cv.upload(i, s["img"], lib_transform(s), content_mask=True)
+        dw, dh = s["size"]
+        assert np.array_equal(cv.frame_mask(i, 1), O.content_mask(s["img"], s["M"], dw, dh)), f"strip {i}: content mask differs"
+        img, _ = cv.warped(i)
+        assert np.array_equal(img, O.remap_bilinear(s["img"], *O.affine_tables(s["M"], dw, dh), "constant"))
+    for i, s in enumerate(specs):
+        cv.update_opts(i, seam_lowres=s["seam_lowres"], seam_nearest=True, content_mask=True, soft_mask=True,
+                       channel_gain=s.get("gain"), compensator_gain=s.get("cgain"))
+        assert np.array_equal(cv.frame_mask(i, 0), ow[i][2]), f"strip {i}: soft blend mask differs"
+        assert ((ow[i][2] > 0) & (ow[i][2] < 255)).any()
+    cv.composite()
+    pano, mask = cv.download()
+    bl = O.MultiBand(roi, 5)
+    for o in ow:
+        bl.feed(o[1].astype(np.int16), o[2], o[0])
+    ref16, refmask = bl.blend()
+    assert np.array_equal(mask, refmask)
+    assert_blend_parity(pano, O.s16_to_u8(ref16))
+    # dropping the options again gives the plain composite
+    for i in range(len(specs)):
+        cv.update_opts(i)
+    cv.composite()
+    p2, _ = cv.download()
+    plain = [dict(s, global_stage=False, seam_lowres=None, gain=None, cgain=None) for s in specs]
+    cv2_ = CP.Canvas(roi, "multiband", 5, lib=lib)
+    for i, s in enumerate(plain):
+        cv2_.upload(i, s["img"], lib_transform(s))
+    cv2_.composite()
+    assert np.array_equal(p2, cv2_.download()[0])
+    cv.close(); cv2_.close()
+
+
 def case_bands8_and_row_bands(lib):
     # 8 bands (BASELINE config 5's blend depth) on a canvas just large enough, split into 3 row bands
     sv = synth.grid_survey(2, 3, 520, 400, overlap=0.55, seed=95)
@@ -347,6 +428,7 @@ def case_very_wide_canvas(lib):
 
 
 CASES = {
+    "global_stage_masks": case_global_stage_masks,
     "exposure_gains": case_exposure_gains,
     "bands8_and_row_bands": case_bands8_and_row_bands,
     "very_wide_canvas": case_very_wide_canvas,

@@ -147,3 +147,63 @@ def test_gain_apply_semantics():
     gm = (rng.random((120, 160)) * 0.4 + 0.8).astype(np.float32)
     ref = cv2.multiply(img, cv2.merge([gm, gm, gm]), dtype=cv2.CV_8U)
     assert np.array_equal(ref, np.clip(np.rint(img.astype(np.float32) * gm[:, :, None]), 0, 255).astype(np.uint8))
+
+
+# ---- the global stage's masks (src/stitch_global.cpp:328-383, :649-655)
+
+def _strip_like(rng, h, w, holes=True):
+    """A strip panorama stand-in: textured content with black wedges / holes (what autoCrop leaves behind)."""
+    img = rng.integers(8, 256, (h, w, 3), dtype=np.uint8)
+    if holes:
+        yy, xx = np.mgrid[0:h, 0:w]
+        img[(yy < 0.15 * xx - 10) | (yy > h - 12 + 0.05 * xx)] = 0
+        img[h // 3:h // 3 + 17, w // 2:w // 2 + 40] = rng.integers(0, 5, (17, 40, 3), dtype=np.uint8)   # near-black noise
+    return img
+
+
+def test_bgr2gray():
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (211, 317, 3), dtype=np.uint8)
+    img[:40] = rng.integers(0, 9, (40, 317, 3), dtype=np.uint8)
+    assert np.array_equal(O.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_content_mask(seed):
+    rng = np.random.default_rng(100 + seed)
+    sh, sw = 180 + 17 * seed, 260 + 11 * seed
+    img = _strip_like(rng, sh, sw, holes=seed % 3 != 2)
+    ang, s = np.deg2rad(rng.uniform(-25, 25)), rng.uniform(0.8, 1.3)
+    M = np.array([[s * np.cos(ang), -s * np.sin(ang), rng.uniform(-20, 60)], [s * np.sin(ang), s * np.cos(ang), rng.uniform(-20, 60)]])
+    if seed == 4:
+        M = np.array([[1.0, 0, 5.03125], [0, 1.0, 3.03125]])   # fractions of 1/32: single taps of weight 1/1024 decide
+    dw, dh = 390, 310
+    assert np.array_equal(O.content_mask(img, M, dw, dh), CR.content_mask_cv2(img, M, (dw, dh)))
+
+
+@pytest.mark.parametrize("dims", [(37, 29, 400, 330), (123, 77, 1001, 613), (50, 50, 50, 50), (64, 48, 63, 47), (7, 5, 1000, 999)])
+def test_resize_nearest(dims):
+    sw, sh, dw, dh = dims
+    m = np.random.default_rng(sw).integers(0, 2, (sh, sw), dtype=np.uint8) * 255
+    assert np.array_equal(O.resize_nearest(m, dw, dh), cv2.resize(m, (dw, dh), interpolation=cv2.INTER_NEAREST))
+
+
+def test_gaussian_kernel():
+    for sigma in (10.0, 3.0, 7.5, 1.0):
+        n = int(np.rint(sigma * 8 + 1)) | 1
+        assert np.array_equal(O.gaussian_kernel_f32(n, sigma), cv2.getGaussianKernel(n, sigma, cv2.CV_32F).ravel())
+
+
+@pytest.mark.parametrize("hw,sigma", [((300, 421), 10.0), ((257, 256), 10.0), ((90, 77), 10.0), ((33, 500), 10.0), ((640, 37), 10.0),
+                                      ((301, 333), 4.0), ((1200, 1611), 10.0)])
+def test_soft_blend_mask(hw, sigma):
+    h, w = hw
+    rng = np.random.default_rng(h + w)
+    seam = (cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), 25) > 0.5).astype(np.uint8) * 255
+    content = np.full((h, w), 255, np.uint8)
+    content[:, :5] = 0
+    content[h // 2:h // 2 + 9, w // 3:w // 3 + 30] = 0
+    got = O.soft_blend_mask(seam, content, sigma)
+    ref = CR.soft_blend_mask_cv2(seam, content, sigma)
+    assert np.array_equal(got, ref)
+    assert ((got > 0) & (got < 255)).any() and (got == 0).any()
