@@ -234,6 +234,13 @@ class Canvas:
                                                      mask.strides[0] if mask is not None else 0))
         return out, mask
 
+    def auto_crop_rect(self):
+        """ds_auto_crop_rect: the rectangle autoCropBlackBorder (/root/reference/src/stitch_common.cpp:4-27) keeps,
+        (x, y, w, h) relative to the canvas origin; download it with download(x, y, w, h)."""
+        o = (C.c_int32 * 4)()
+        self.lib.check(self.lib.dll.ds_auto_crop_rect(self._h, o))
+        return tuple(o)
+
     def set_profiling(self, on=True):
         self.lib.check(self.lib.dll.ds_set_profiling(self._h, 1 if on else 0))
 

@@ -44,9 +44,9 @@ DS_D int content_mask_value(const FrameDev& F, int u, int v) {
     const int wx1 = c.ax, wx0 = 32 - c.ax, wy1 = c.ay, wy0 = 32 - c.ay;
     int s = 0;
     if (content_tap(F, c.sx, c.sy)) s += wx0 * wy0;
-    if (wx1 * wy0 && content_tap(F, c.sx + 1, c.sy)) s += wx1 * wy0;
-    if (wx0 * wy1 && content_tap(F, c.sx, c.sy + 1)) s += wx0 * wy1;
-    if (wx1 * wy1 && content_tap(F, c.sx + 1, c.sy + 1)) s += wx1 * wy1;
+    if ((wx1 * wy0) != 0 && content_tap(F, c.sx + 1, c.sy)) s += wx1 * wy0;
+    if ((wx0 * wy1) != 0 && content_tap(F, c.sx, c.sy + 1)) s += wx0 * wy1;
+    if ((wx1 * wy1) != 0 && content_tap(F, c.sx + 1, c.sy + 1)) s += wx1 * wy1;
     return s >= 1023 ? 255 : 0;
 }
 
@@ -147,6 +147,39 @@ struct SoftMaskBody {
                 o = sat8i(f2i_rn(f_mul(s, 255.f)));
             }
             p.out[(size_t)y * p.out_pitch + x] = (unsigned char)o;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// autoCropBlackBorder (src/stitch_common.cpp:4-27), device half: BGR2GRAY > 1 of the composited canvas, reduced to
+// the runs of foreground pixels of every row. A block owns one row; run starts and ends are appended to the row's
+// event list (x << 1 | is_end) through an atomic cursor — a handful per row for a mosaic. The host pairs them, labels
+// the 8-connected components of the runs and picks the contour the reference picks (ds_runtime.cu: auto_crop).
+
+struct RowRunsParams {
+    const uint8_t* out; size_t out_pitch; int bpp;   // composited canvas, BGR8 / BGRA8
+    int w, h;
+    int cap;                                         // events per row
+    int* count;                                      // [h] events appended (may exceed cap: overflow)
+    int* events;                                     // [h][cap]
+};
+DS_D int crop_fg(const RowRunsParams& p, const uint8_t* row, int x) {
+    if ((unsigned)x >= (unsigned)p.w) return 0;
+    const uint8_t* q = row + (size_t)x * p.bpp;
+    return (int)((q[0] * 3735u + q[1] * 19235u + q[2] * 9798u + 16384u) >> 15) > 1;
+}
+struct RowRunsBody {
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const RowRunsParams& p, int block, int tid, unsigned char*) {
+        const int y = block;
+        const uint8_t* row = p.out + (size_t)y * p.out_pitch;
+        for (int x = tid; x < p.w; x += NT) {
+            if (!crop_fg(p, row, x)) continue;
+            const int st = !crop_fg(p, row, x - 1), en = !crop_fg(p, row, x + 1);
+            if (st) { const int k = ds_atomic_add(p.count + y, 1); if (k < p.cap) p.events[(size_t)y * p.cap + k] = x << 1; }
+            if (en) { const int k = ds_atomic_add(p.count + y, 1); if (k < p.cap) p.events[(size_t)y * p.cap + k] = (x << 1) | 1; }
         }
     }
 };

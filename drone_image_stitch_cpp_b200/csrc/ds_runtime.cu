@@ -1782,6 +1782,104 @@ DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* o
     return DS_OK;
 }
 
+DS_API int ds_auto_crop_rect(ds_canvas* c, int32_t out_xywh[4]) {
+    if (!c || !out_xywh) return fail(DS_ERR_BAD_ARG, "null argument");
+    if (!c->composited) return fail(DS_ERR_STATE, "ds_auto_crop_rect before ds_composite");
+    const int W = c->desc.width, H = c->desc.height;
+    if (c->band.lo != 0 || c->out_hi < H) return fail(DS_ERR_UNSUPPORTED, "ds_auto_crop_rect needs a whole-canvas handle (this one owns rows [%d,%d))", c->band.lo, c->out_hi);
+    int rc;
+    if ((rc = set_device(c))) return rc;
+    if ((rc = stream_sync(c->stream))) return rc;
+    for (const SubBand& sb : c->subs) if (sb.done && (rc = ev_sync(sb.done))) return rc;
+    const int cap = 64;
+    int* d_count = nullptr; int* d_events = nullptr;
+    if ((rc = dev_alloc_t(&d_count, (size_t)H))) return rc;
+    if ((rc = dev_alloc_t(&d_events, (size_t)H * cap))) { dev_free(d_count); return rc; }
+    std::vector<int> count((size_t)H), events((size_t)H * cap);
+    rc = dev_zero(d_count, (size_t)H * sizeof(int));
+    if (!rc) {
+        RowRunsParams rp{c->d_out, c->out_pitch, c->desc.out_format == DS_OUT_BGRA8 ? 4 : 3, W, H, cap, d_count, d_events};
+        rc = launch<RowRunsBody, 256>(rp, H, c->stream, 0);
+    }
+    if (!rc) rc = d2h(count.data(), d_count, (size_t)H * sizeof(int), c->stream);
+    if (!rc) rc = d2h(events.data(), d_events, (size_t)H * cap * sizeof(int), c->stream);
+    const int r2 = stream_sync(c->stream);
+    dev_free(d_count); dev_free(d_events);
+    if (rc || r2) return rc ? rc : r2;
+    c->launches++;
+    // runs per row, in x order
+    struct Run { int y, s, e, parent; };
+    std::vector<Run> runs;
+    std::vector<int> row_first((size_t)H + 1, 0);
+    for (int y = 0; y < H; y++) {
+        row_first[(size_t)y] = (int)runs.size();
+        const int n = count[(size_t)y];
+        if (n > cap) return fail(DS_ERR_UNSUPPORTED, "row %d of the canvas has more than %d foreground runs: use cv::findContours on the downloaded panorama", y, cap / 2);
+        int* ev = events.data() + (size_t)y * cap;
+        std::sort(ev, ev + n);   // x << 1 | is_end: a one-pixel run sorts as start, end
+        for (int k = 0; k + 1 < n; k += 2) runs.push_back(Run{y, ev[k] >> 1, ev[k + 1] >> 1, (int)runs.size()});
+    }
+    row_first[(size_t)H] = (int)runs.size();
+    if (runs.empty()) { out_xywh[0] = 0; out_xywh[1] = 0; out_xywh[2] = W; out_xywh[3] = H; return DS_OK; }
+    // 8-connected components of the runs (union-find)
+    auto find = [&](int i) { while (runs[(size_t)i].parent != i) { runs[(size_t)i].parent = runs[(size_t)runs[(size_t)i].parent].parent; i = runs[(size_t)i].parent; } return i; };
+    for (int y = 1; y < H; y++) {
+        int a = row_first[(size_t)y - 1];
+        const int a_end = row_first[(size_t)y];
+        for (int b = row_first[(size_t)y]; b < row_first[(size_t)y + 1]; b++) {
+            const Run& rb = runs[(size_t)b];
+            while (a < a_end && runs[(size_t)a].e < rb.s - 1) a++;
+            for (int k = a; k < a_end && runs[(size_t)k].s <= rb.e + 1; k++) {
+                const int ra = find(k), rbb = find(b);
+                if (ra != rbb) runs[(size_t)std::max(ra, rbb)].parent = std::min(ra, rbb);
+            }
+        }
+    }
+    // per component: bounding box and core pixels (foreground with all four 4-neighbours foreground; never on a border)
+    struct Comp { int x0, y0, x1, y1; long long core; };
+    std::vector<Comp> comp(runs.size(), Comp{INT32_MAX, INT32_MAX, -1, -1, 0});
+    auto overlap_rows = [&](int y, int lo, int hi, std::vector<std::pair<int, int>>& out) {
+        out.clear();
+        if (y < 0 || y >= H) return;
+        for (int k = row_first[(size_t)y]; k < row_first[(size_t)y + 1]; k++) {
+            const int s_ = std::max(lo, runs[(size_t)k].s), e_ = std::min(hi, runs[(size_t)k].e);
+            if (s_ <= e_) out.push_back({s_, e_});
+        }
+    };
+    std::vector<std::pair<int, int>> up, dn;
+    for (size_t i = 0; i < runs.size(); i++) {
+        const Run& r = runs[i];
+        Comp& cc = comp[(size_t)find((int)i)];
+        cc.x0 = std::min(cc.x0, r.s); cc.x1 = std::max(cc.x1, r.e);
+        cc.y0 = std::min(cc.y0, r.y); cc.y1 = std::max(cc.y1, r.y);
+        if (r.e - r.s >= 2) {
+            overlap_rows(r.y - 1, r.s + 1, r.e - 1, up);
+            overlap_rows(r.y + 1, r.s + 1, r.e - 1, dn);
+            size_t j = 0;
+            for (const auto& u : up) {
+                while (j < dn.size() && dn[j].second < u.first) j++;
+                for (size_t k = j; k < dn.size() && dn[k].first <= u.second; k++)
+                    cc.core += std::min(u.second, dn[k].second) - std::max(u.first, dn[k].first) + 1;
+            }
+        }
+    }
+    int best = -1;
+    for (size_t i = 0; i < comp.size(); i++)
+        if (comp[i].x1 >= 0 && (best < 0 || comp[i].core > comp[(size_t)best].core)) best = (int)i;
+    // contourArea bounds: Pick's theorem gives area >= interior lattice points - 1 >= core - 1; any contour's area is at
+    // most that of its bounding box of pixel centres
+    const long long best_lo = comp[(size_t)best].core - 1;
+    for (size_t i = 0; i < comp.size(); i++) {
+        if ((int)i == best || comp[i].x1 < 0) continue;
+        const long long hi = (long long)(comp[i].x1 - comp[i].x0) * (comp[i].y1 - comp[i].y0);
+        if (hi >= best_lo)
+            return fail(DS_ERR_UNSUPPORTED, "two foreground regions of comparable size (%lld vs %lld): use cv::findContours on the downloaded panorama", best_lo, hi);
+    }
+    const Comp& b = comp[(size_t)best];
+    out_xywh[0] = b.x0; out_xywh[1] = b.y0; out_xywh[2] = b.x1 - b.x0 + 1; out_xywh[3] = b.y1 - b.y0 + 1;
+    return DS_OK;
+}
+
 DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
     if (!c || !info) return fail(DS_ERR_BAD_ARG, "null argument");
     memset(info, 0, sizeof(*info));

@@ -217,6 +217,17 @@ DS_API int ds_synchronize(ds_canvas* c);
 DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* out, size_t stride,
                             uint8_t* mask_out, size_t mask_stride);
 
+/* autoCropBlackBorder(pano) (src/stitch_common.cpp:4-27; called at src/stitch_app.cpp:213, :262) on the composited
+ * canvas, without moving it to the host: BGR2GRAY > 1, the external contour of largest cv::contourArea, its
+ * boundingRect -> out_xywh (relative to the canvas ROI origin; the whole canvas when nothing is brighter than 1, as the
+ * reference returns the panorama untouched). The caller then downloads just that rectangle with ds_download_tile.
+ * The device reduces the canvas to its per-row foreground runs; the host labels their 8-connected components and
+ * picks the winner by bounds on contourArea that need no contour tracing: core pixels - 1 <= area <= (w-1)(h-1).
+ * When those bounds cannot separate the two best candidates (or a row has more runs than the list holds) the call
+ * returns DS_ERR_UNSUPPORTED and the caller keeps the reference's cv::findContours on the downloaded panorama.
+ * Whole-canvas handles only (no row band). */
+DS_API int ds_auto_crop_rect(ds_canvas* c, int32_t out_xywh[4]);
+
 /* ---- NVLink peer-to-peer halo exchange between row-band handles (one handle per GPU, any process layout) ----
  * Without it a band recomputes the pyramid halo beyond its edges from the frames themselves: no communication,
  * about 9 % extra work per band at 5 bands. With it the level-0 feed (warp + first pyrDown, the bulk of the work)

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <array>
 #include <climits>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -87,6 +88,19 @@ inline ds_transform affineTransform(const double M[6], int corner_x, int corner_
 }
 
 struct Rect { int x = 0, y = 0, width = 0, height = 0; };
+// transformedBoundingRect(size, h) of the global stage (src/stitch_global.cpp:71-98): the four corners (0,0), (w,0),
+// (w,h), (0,h) through the 3x3 double transform; floor(min), ceil(max) - floor(min), at least 1.
+inline Rect transformedBoundingRect(int cols, int rows, const double H[9]) {
+    const double px[4] = {0.0, (double)cols, (double)cols, 0.0}, py[4] = {0.0, 0.0, (double)rows, (double)rows};
+    double min_x = 1.7976931348623157e308, min_y = min_x, max_x = -min_x, max_y = -min_x;
+    for (int i = 0; i < 4; i++) {
+        const double x = H[0] * px[i] + H[1] * py[i] + H[2] * 1.0, y = H[3] * px[i] + H[4] * py[i] + H[5] * 1.0;
+        min_x = std::min(min_x, x); min_y = std::min(min_y, y);
+        max_x = std::max(max_x, x); max_y = std::max(max_y, y);
+    }
+    const int x = (int)std::floor(min_x), y = (int)std::floor(min_y);
+    return Rect{x, y, std::max(1, (int)std::ceil(max_x) - x), std::max(1, (int)std::ceil(max_y) - y)};
+}
 // cv::detail::resultRoi(corners, sizes)
 inline Rect resultRoi(const std::vector<Rect>& placed) {
     int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
@@ -136,6 +150,23 @@ public:
         o.flags |= DS_UPLOAD_ASYNC;
         check(ds_upload_frame(c_, fed_++, img.data, img.cols, img.rows, img.step, &t, &o));
     }
+    // The global stage's feed loop (stitch_global.cpp:643-660) runs after the strips were warped: gains and seam masks
+    // for strip `idx`, fed earlier, without sending its pixels again (ds_update_frame_opts).
+    void update(int idx, const ds_frame_opts* opts) { check(ds_update_frame_opts(c_, idx, opts)); }
+    // warped_masks[idx] (which = 1, needs DS_MASK_CONTENT) or the mask the blender is fed with (which = 0)
+    void frameMask(int idx, int which, Image& out) {
+        int32_t pl[4];
+        check(ds_debug_get_placement(c_, idx, pl));
+        out.create(pl[3], pl[2], 1);
+        check(ds_download_frame_mask(c_, idx, which, out.data.data(), out.step()));
+    }
+    // warped_imgs[idx] / its nearest-warped mask, for the CPU-side exposure and seam steps (stitch_global.cpp:497-630)
+    void warped(int idx, Image& img, Image& mask) {
+        int32_t pl[4];
+        check(ds_debug_get_placement(c_, idx, pl));
+        img.create(pl[3], pl[2], 3); mask.create(pl[3], pl[2], 1);
+        check(ds_debug_get_warped(c_, idx, img.data.data(), mask.data.data()));
+    }
     // blender->blend(result, result_mask); result.convertTo(result, CV_8U)
     void blend(Image& result, Image* result_mask = nullptr) {
         check(ds_composite_async(c_));
@@ -147,6 +178,18 @@ public:
         check(ds_download_tile(c_, 0, y0, roi_.width, y1 - y0, result.data.data(), result.step(),
                                result_mask ? result_mask->data.data() : nullptr, result_mask ? result_mask->step() : 0));
         check(ds_synchronize(c_));
+    }
+    // autoCropBlackBorder(pano) (src/stitch_common.cpp:4-27) decided on the canvas in device memory; throws
+    // ds::Error(DS_ERR_UNSUPPORTED) when the caller should run the reference's findContours on the panorama instead
+    Rect autoCropRect() {
+        int32_t r[4];
+        check(ds_auto_crop_rect(c_, r));
+        return Rect{r[0], r[1], r[2], r[3]};
+    }
+    // pano(rect).clone(): only the kept rectangle crosses PCIe
+    void download(const Rect& r, Image& out) {
+        out.create(r.height, r.width, 3);
+        check(ds_download_tile(c_, r.x, r.y, r.width, r.height, out.data.data(), out.step(), nullptr, 0));
     }
     ds_canvas* handle() const { return c_; }
     const Rect& roi() const { return roi_; }

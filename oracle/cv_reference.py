@@ -105,3 +105,19 @@ def soft_blend_mask_cv2(seam, content, sigma=10.0):
     # convertTo(CV_8U, 255.0) scales in float32 (cvt_32f); cv2.normalize(MINMAX 0..255) issues exactly that call when the
     # input spans [0, 1] - here done directly
     return np.clip(np.rint((soft * np.float32(255.0)).astype(np.float32)), 0, 255).astype(np.uint8)
+
+
+def auto_crop_rect_cv2(pano):
+    """autoCropBlackBorder (src/stitch_common.cpp:4-27) through cv2; -> (x, y, w, h), plus the contour areas."""
+    import cv2
+    gray = cv2.cvtColor(pano, cv2.COLOR_BGR2GRAY)
+    _, th = cv2.threshold(gray, 1, 255, cv2.THRESH_BINARY)
+    contours, _ = cv2.findContours(th, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    if not contours:
+        return (0, 0, pano.shape[1], pano.shape[0]), []
+    areas = [cv2.contourArea(c) for c in contours]
+    best, best_area = cv2.boundingRect(contours[0]), areas[0]
+    for c, a in zip(contours[1:], areas[1:]):
+        if a > best_area:
+            best_area, best = a, cv2.boundingRect(c)
+    return tuple(int(v) for v in best), areas

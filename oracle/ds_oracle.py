@@ -233,6 +233,77 @@ def threshold_gt1(mask):
     return np.where(np.asarray(mask) > 1, 255, 0).astype(np.uint8)
 
 
+# ---- autoCropBlackBorder (src/stitch_common.cpp:4-27)
+
+def _outer_contour(fg, i, j):
+    """Suzuki-Abe border following of the outer border (8-connected foreground) that starts at the raster-first
+    pixel (i, j) of a component; -> list of (x, y). Pure Python: small cases only."""
+    h, w = fg.shape
+    # 8-neighbourhood in clockwise order on the screen (y down): E, SE, S, SW, W, NW, N, NE
+    nb = [(0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1), (-1, 0), (-1, 1)]
+
+    def val(y, x):
+        return 0 <= y < h and 0 <= x < w and fg[y, x]
+
+    def idx(dy, dx):
+        return nb.index((dy, dx))
+
+    # step 3.1: clockwise from the west neighbour
+    k0 = idx(0, -1)
+    first = None
+    for t in range(8):
+        dy, dx = nb[(k0 + t) % 8]
+        if val(i + dy, j + dx):
+            first = (i + dy, j + dx)
+            break
+    if first is None:
+        return [(j, i)]
+    pts = []
+    i2, j2 = first
+    i3, j3 = i, j
+    while True:
+        # step 3.3: counter-clockwise around (i3, j3), starting after (i2, j2)
+        k = idx(i2 - i3, j2 - j3)
+        for t in range(1, 9):
+            dy, dx = nb[(k - t) % 8]
+            if val(i3 + dy, j3 + dx):
+                i4, j4 = i3 + dy, j3 + dx
+                break
+        pts.append((j3, i3))
+        if (i4, j4) == (i, j) and (i3, j3) == first:
+            break
+        i2, j2 = i3, j3
+        i3, j3 = i4, j4
+    return pts
+
+
+def auto_crop_rect(pano):
+    """The rectangle autoCropBlackBorder keeps: BGR2GRAY > 1, external contours (8-connected components not nested in
+    another one's hole are what RETR_EXTERNAL returns; nested ones are smaller than their host and never win), the one of
+    largest contourArea (shoelace over the border pixels; first wins a tie in raster order of the start pixels - OpenCV
+    lists contours in reverse, a tie between distinct maxima is not pinned), its boundingRect. (x, y, w, h)."""
+    from scipy import ndimage
+    gray = bgr2gray(np.ascontiguousarray(pano[:, :, :3]))
+    fg = gray > 1
+    if not fg.any():
+        return (0, 0, pano.shape[1], pano.shape[0])
+    lbl, n = ndimage.label(fg, structure=np.ones((3, 3), int))
+    best, best_area = None, -1.0
+    for k, sl in enumerate(ndimage.find_objects(lbl), start=1):
+        comp = lbl == k
+        ys, xs = np.nonzero(comp[sl])
+        i = int(ys.min())
+        j = int(xs[ys == i].min())
+        pts = _outer_contour(comp, i + sl[0].start, j + sl[1].start)
+        x = np.array([p[0] for p in pts], np.float64)
+        y = np.array([p[1] for p in pts], np.float64)
+        area = abs(0.5 * float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y)))
+        if area > best_area:
+            best_area = area
+            best = (sl[1].start, sl[0].start, sl[1].stop - sl[1].start, sl[0].stop - sl[0].start)
+    return best
+
+
 def mbb_feed_geometry(roi, bands, tl, size):
     out = np.empty(8, np.int32)
     lib().orc_mbb_feed_geometry(C.c_int(roi[0]), C.c_int(roi[1]), C.c_int(roi[2]), C.c_int(roi[3]), C.c_int(bands),

@@ -407,6 +407,67 @@ def case_global_stage_masks(lib):
     cv.close(); cv2_.close()
 
 
+def case_auto_crop(lib):
+    # autoCropBlackBorder's rectangle computed from the canvas in device memory
+    rng = np.random.default_rng(41)
+    sv = synth.grid_survey(2, 2, 300, 220, overlap=0.5, seed=41, rot_deg=12.0)
+    specs = plane_specs(sv)
+    # a small far-away frame: a second external contour that must lose; dark pixels inside the content
+    small = np.ascontiguousarray(specs[0]["img"][:40, :50])
+    R = np.array([[1, 0, 900.0], [0, 1, -60.0], [0, 0, 1]], np.float32)
+    specs.append(dict(kind="plane", img=small, K=np.eye(3, dtype=np.float32), R=R, scale=sv.scale))
+    for s_ in specs[:4]:
+        img = s_["img"].copy()
+        img[rng.integers(0, img.shape[0], 200), rng.integers(0, img.shape[1], 200)] = 0
+        s_["img"] = img
+    for blend, bands in (("multiband", 3), ("feather", 0)):
+        xfs = [lib_transform(s_) for s_ in specs]
+        rois = [CP.warp_roi(xf, s_["img"].shape[1], s_["img"].shape[0], lib) for xf, s_ in zip(xfs, specs)]
+        roi = CP.result_roi(rois)
+        cv = CP.Canvas(roi, blend, bands, lib=lib)
+        for i, (s_, xf) in enumerate(zip(specs, xfs)):
+            cv.upload(i, s_["img"], xf)
+        cv.composite()
+        pano, _ = cv.download()
+        rect = cv.auto_crop_rect()
+        assert rect == O.auto_crop_rect(pano), (rect, O.auto_crop_rect(pano))
+        assert rect[2] < roi[2]   # the far-away frame is cropped off
+        x, y, w, h = rect
+        assert np.array_equal(cv.download(x, y, w, h)[0], pano[y:y + h, x:x + w])   # pano(max_rect).clone()
+        cv.close()
+    # BGRA canvas, a single frame
+    cv = CP.Canvas(rois[0], "multiband", 2, out_format="bgra", lib=lib)
+    cv.upload(0, specs[0]["img"], xfs[0])
+    cv.composite()
+    assert cv.auto_crop_rect() == O.auto_crop_rect(cv.download()[0])
+    cv.close()
+    # two regions of the same size: the bounds cannot tell which contour is larger -> refused, not guessed
+    twins = [dict(specs[0]), dict(specs[0])]
+    twins[1]["R"] = specs[0]["R"].copy(); twins[1]["R"][0, 2] += 700
+    xfs = [lib_transform(s_) for s_ in twins]
+    rois = [CP.warp_roi(xf, 300, 220, lib) for xf in xfs]
+    cv = CP.Canvas(CP.result_roi(rois), "feather", 0, lib=lib)
+    for i in range(2):
+        cv.upload(i, twins[i]["img"], xfs[i])
+    cv.composite()
+    try:
+        cv.auto_crop_rect()
+        raise AssertionError("ambiguous crop was not refused")
+    except L.DroneStitchError as e:
+        assert e.code == L.DS_ERR_UNSUPPORTED
+    cv.close()
+    # row-band handles are refused
+    cb = CP.Canvas(CP.result_roi(rois), "multiband", 2, band=(0, 64), lib=lib)
+    cb.upload(0, twins[0]["img"], xfs[0])
+    cb.composite()
+    try:
+        cb.auto_crop_rect()
+        raise AssertionError("band handle accepted")
+    except L.DroneStitchError as e:
+        assert e.code == L.DS_ERR_UNSUPPORTED
+    cb.close()
+
+
 def case_bands8_and_row_bands(lib):
     # 8 bands (BASELINE config 5's blend depth) on a canvas just large enough, split into 3 row bands
     sv = synth.grid_survey(2, 3, 520, 400, overlap=0.55, seed=95)
@@ -428,6 +489,7 @@ def case_very_wide_canvas(lib):
 
 
 CASES = {
+    "auto_crop": case_auto_crop,
     "global_stage_masks": case_global_stage_masks,
     "exposure_gains": case_exposure_gains,
     "bands8_and_row_bands": case_bands8_and_row_bands,

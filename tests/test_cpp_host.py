@@ -68,6 +68,88 @@ def run_case(exe, tmp_path, blend, bands, work_scale):
     assert np.array_equal(pano, ref)
 
 
+def run_global_stage(exe, tmp_path):
+    """stitchInterStripsCustom's compose half through the C++ header, against the oracle chain."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity_cases import global_stage_specs
+    from helpers import assert_blend_parity
+    specs = global_stage_specs(seed=77, n=3, fw=380, fh=270)
+    rng = np.random.default_rng(77)
+    # global transforms before the canvas shift: what estimatePairAffine chains produce (arbitrary origin)
+    Hs = []
+    for s in specs:
+        Hm = np.eye(3)
+        Hm[:2] = s["M"]
+        Hm[0, 2] += s["corner"][0] - 1234.0
+        Hm[1, 2] += s["corner"][1] + 321.0
+        Hs.append(Hm)
+    gains = [(1.0, 1.0, 1.0)] + [tuple(float(v) for v in rng.uniform(0.9, 1.1, 3)) for _ in specs[1:]]
+    case, out = os.path.join(tmp_path, "g.bin"), os.path.join(tmp_path, "g.out")
+    with open(case, "wb") as f:
+        f.write(b"DSG1")
+        f.write(struct.pack("<ii", len(specs), 5))
+        for s, Hm, g in zip(specs, Hs, gains):
+            img = s["img"]
+            f.write(struct.pack("<ii", img.shape[1], img.shape[0]))
+            f.write(np.ascontiguousarray(Hm, np.float64).tobytes())
+            f.write(np.asarray(g, np.float32).tobytes())
+            f.write(np.ascontiguousarray(img).tobytes())
+            m = s["seam_lowres"]
+            f.write(struct.pack("<ii", m.shape[1], m.shape[0]))
+            f.write(np.ascontiguousarray(m).tobytes())
+    r = subprocess.run([exe, case, out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    # the oracle side, restating :439-486 and :643-666
+    def tbr(w, h, Hm):
+        pts = Hm @ np.array([[0, w, w, 0], [0, 0, h, h], [1, 1, 1, 1]], np.float64)
+        x, y = int(np.floor(pts[0].min())), int(np.floor(pts[1].min()))
+        return x, y, max(1, int(np.ceil(pts[0].max())) - x), max(1, int(np.ceil(pts[1].max())) - y)
+    pre = [tbr(s["img"].shape[1], s["img"].shape[0], Hm) for s, Hm in zip(specs, Hs)]
+    min_x, min_y = min(p[0] for p in pre), min(p[1] for p in pre)
+    raw = open(out, "rb").read()
+    off = 0
+    warped, masks, corners = [], [], []
+    for s, Hm, g in zip(specs, Hs, gains):
+        S = Hm.copy()
+        S[0, 2] += float(-min_x)
+        S[1, 2] += float(-min_y)
+        x, y, bw, bh = tbr(s["img"].shape[1], s["img"].shape[0], S)
+        M = S[:2].copy()
+        M[0, 2] -= float(x)
+        M[1, 2] -= float(y)
+        content = O.content_mask(s["img"], M, bw, bh)
+        got = np.frombuffer(raw, np.uint8, bw * bh, off).reshape(bh, bw)
+        off += bw * bh
+        assert np.array_equal(got, content)
+        wimg = O.remap_bilinear(s["img"], *O.affine_tables(M, bw, bh), "constant")
+        wimg = np.clip(np.rint(wimg.astype(np.float32) * np.asarray(g, np.float32)[None, None, :]), 0, 255).astype(np.uint8)
+        seam = O.threshold_gt1(O.resize_nearest(s["seam_lowres"], bw, bh))
+        warped.append(wimg)
+        masks.append(O.soft_blend_mask(seam, content, 10.0))
+        corners.append((x, y))
+    roi = O.result_roi(corners, [(w.shape[1], w.shape[0]) for w in warped])
+    bl = O.MultiBand(roi, 5)
+    for wimg, m, c in zip(warped, masks, corners):
+        bl.feed(wimg.astype(np.int16), m, c)
+    ref16, refmask = bl.blend()
+    x, y, w, h = struct.unpack("<iiii", raw[off:off + 16])
+    assert (x, y, w, h) == tuple(roi)
+    pano = np.frombuffer(raw, np.uint8, w * h * 3, off + 16).reshape(h, w, 3)
+    mask = np.frombuffer(raw, np.uint8, w * h, off + 16 + w * h * 3).reshape(h, w)
+    assert np.array_equal(mask, refmask)
+    assert_blend_parity(pano, O.s16_to_u8(ref16))
+
+
+def test_cpp_global_stage_emu(emu_lib, tmp_path):
+    run_global_stage(build_driver(emu_lib.path, "emu"), str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cpp_global_stage_gpu(cuda_lib, tmp_path):
+    run_global_stage(build_driver(cuda_lib.path, "cuda"), str(tmp_path))
+
+
 @pytest.mark.parametrize("blend,bands,work_scale", [("multiband", 4, 1.0), ("multiband", 5, 0.5), ("feather", 0, 1.0)])
 def test_cpp_host_emu(emu_lib, tmp_path, blend, bands, work_scale):
     run_case(build_driver(emu_lib.path, "emu"), str(tmp_path), blend, bands, work_scale)

@@ -207,3 +207,40 @@ def test_soft_blend_mask(hw, sigma):
     ref = CR.soft_blend_mask_cv2(seam, content, sigma)
     assert np.array_equal(got, ref)
     assert ((got > 0) & (got < 255)).any() and (got == 0).any()
+
+
+# ---- autoCropBlackBorder (src/stitch_common.cpp:4-27)
+
+def _pano_like(rng, h, w, blobs, speck=0):
+    img = np.zeros((h, w, 3), np.uint8)
+    m = np.zeros((h, w), np.float32)
+    for _ in range(blobs):
+        cy, cx = rng.integers(0, h), rng.integers(0, w)
+        ry, rx = rng.integers(3, max(4, h // 3)), rng.integers(3, max(4, w // 3))
+        yy, xx = np.mgrid[0:h, 0:w]
+        m[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1] = 1
+    img[m > 0] = rng.integers(2, 256, (int((m > 0).sum()), 3), dtype=np.uint8)
+    for _ in range(speck):
+        img[rng.integers(0, h), rng.integers(0, w)] = rng.integers(0, 256, 3)
+    hole = rng.random((h, w)) < 0.02
+    img[hole] = rng.integers(0, 2, (int(hole.sum()), 3), dtype=np.uint8)   # dark pixels inside the content
+    return img
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_auto_crop_rect(seed):
+    rng = np.random.default_rng(900 + seed)
+    h, w = int(rng.integers(20, 90)), int(rng.integers(20, 120))
+    img = _pano_like(rng, h, w, blobs=int(rng.integers(1, 5)), speck=int(rng.integers(0, 6)))
+    rect, areas = CR.auto_crop_rect_cv2(img)
+    srt = sorted(areas)
+    if len(srt) > 1 and srt[-1] == srt[-2]:
+        pytest.skip("tie between two maximal contours: order of cv::findContours decides")
+    assert O.auto_crop_rect(img) == rect
+
+
+def test_auto_crop_rect_empty_and_full():
+    z = np.zeros((17, 23, 3), np.uint8)
+    assert O.auto_crop_rect(z) == CR.auto_crop_rect_cv2(z)[0] == (0, 0, 23, 17)
+    z[:] = 200
+    assert O.auto_crop_rect(z) == CR.auto_crop_rect_cv2(z)[0] == (0, 0, 23, 17)
