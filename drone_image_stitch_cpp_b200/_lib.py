@@ -23,7 +23,7 @@ EXPORTS = [
     "ds_p2p_export", "ds_p2p_connect", "ds_p2p_disconnect", "ds_composite_stage",
     "ds_last_error", "ds_get_info", "ds_version", "ds_debug_get_placement", "ds_debug_get_maps",
     "ds_debug_get_warped", "ds_debug_get_frame_level", "ds_set_profiling", "ds_get_kernel_times",
-    "ds_update_frame_opts", "ds_download_frame_mask", "ds_auto_crop_rect",
+    "ds_update_frame_opts", "ds_download_frame_mask", "ds_auto_crop_rect", "ds_warp_frame",
 ]
 
 
@@ -119,6 +119,8 @@ class Library:
         d.ds_p2p_disconnect.argtypes = [C.c_void_p]
         d.ds_composite_stage.argtypes = [C.c_void_p, C.c_int]
         d.ds_update_frame_opts.argtypes = [C.c_void_p, C.c_int, C.POINTER(ds_frame_opts)]
+        d.ds_warp_frame.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(ds_transform), C.POINTER(C.c_int32),
+                                    C.c_void_p, C.c_void_p]
         d.ds_auto_crop_rect.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         d.ds_download_frame_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
 

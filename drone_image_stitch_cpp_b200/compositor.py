@@ -71,6 +71,20 @@ def result_roi(rois):
     return (x0, y0, x1 - x0, y1 - y0)
 
 
+def warp_frame(img, xf, device=0, lib=None):
+    """ds_warp_frame: one frame warped on its own (the seam-phase warps of composePanorama, a strip's warpAffine).
+    -> (corner (x, y), warped HxWx3 uint8, warped mask HxW uint8)."""
+    lib = lib or L.default_library()
+    assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3 and img.strides[2] == 1 and img.strides[1] == 3
+    pl = (C.c_int32 * 4)()
+    args = (int(device), C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], C.byref(xf), pl)
+    lib.check(lib.dll.ds_warp_frame(*args, None, None))
+    out = np.empty((pl[3], pl[2], 3), np.uint8)
+    mask = np.empty((pl[3], pl[2]), np.uint8)
+    lib.check(lib.dll.ds_warp_frame(*args, out.ctypes.data, mask.ctypes.data))
+    return (pl[0], pl[1]), out, mask
+
+
 class Canvas:
     """One ds_canvas handle (one GPU, one row band)."""
 

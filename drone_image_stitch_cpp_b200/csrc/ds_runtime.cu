@@ -1782,6 +1782,28 @@ DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* o
     return DS_OK;
 }
 
+DS_API int ds_warp_frame(int device, const uint8_t* bgr, int w, int h, size_t stride, const ds_transform* xf,
+                         int32_t out_xywh[4], uint8_t* out_bgr, uint8_t* out_mask) {
+    if (!bgr || !xf || !out_xywh) return fail(DS_ERR_BAD_ARG, "null argument");
+    int rc;
+    if ((rc = ds_warp_roi(xf, w, h, out_xywh))) return rc;
+    if (!out_bgr && !out_mask) return DS_OK;
+    if (!out_bgr || !out_mask) return fail(DS_ERR_BAD_ARG, "out_bgr and out_mask go together");
+    // a scratch handle whose canvas is the frame's own bbox: the warp is the one every composite runs
+    ds_canvas_desc d;
+    memset(&d, 0, sizeof(d));
+    d.x = out_xywh[0]; d.y = out_xywh[1]; d.width = out_xywh[2]; d.height = out_xywh[3];
+    d.blend_mode = DS_BLEND_FEATHER; d.sharpness = 0.02f; d.out_format = DS_OUT_BGR8; d.device = device;
+    ds_canvas* c = nullptr;
+    if ((rc = ds_create_canvas(&d, &c))) return rc;
+    rc = ds_upload_frame(c, 0, bgr, w, h, stride, xf, nullptr);
+    if (!rc) rc = ds_debug_get_warped(c, 0, out_bgr, out_mask);
+    const std::string keep = g_err;
+    ds_destroy_canvas(c);
+    if (rc) g_err = keep;
+    return rc;
+}
+
 DS_API int ds_auto_crop_rect(ds_canvas* c, int32_t out_xywh[4]) {
     if (!c || !out_xywh) return fail(DS_ERR_BAD_ARG, "null argument");
     if (!c->composited) return fail(DS_ERR_STATE, "ds_auto_crop_rect before ds_composite");

@@ -217,6 +217,15 @@ DS_API int ds_synchronize(ds_canvas* c);
 DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* out, size_t stride,
                             uint8_t* mask_out, size_t mask_stride);
 
+/* One frame warped on its own, no canvas: warper->warp(img, K, R, INTER_LINEAR, BORDER_REFLECT, img_warped) and
+ * warper->warp(mask, K, R, INTER_NEAREST, BORDER_CONSTANT, mask_warped) as composePanorama runs them in its seam phase
+ * on the seam-scale images (cameras scaled by seam_work_aspect; called from src/stitch_robust.cpp:256), or
+ * cv::warpAffine of a strip (src/stitch_global.cpp:479-480) - whatever `xf` describes. The results feed the CPU-side
+ * exposure compensator and seam finder. out_xywh = placement (ds_warp_roi); out_bgr (3 * w * h bytes, dense) and
+ * out_mask (w * h bytes) may be NULL to query the placement only. */
+DS_API int ds_warp_frame(int device, const uint8_t* bgr, int w, int h, size_t stride, const ds_transform* xf,
+                         int32_t out_xywh[4], uint8_t* out_bgr, uint8_t* out_mask);
+
 /* autoCropBlackBorder(pano) (src/stitch_common.cpp:4-27; called at src/stitch_app.cpp:213, :262) on the composited
  * canvas, without moving it to the host: BGR2GRAY > 1, the external contour of largest cv::contourArea, its
  * boundingRect -> out_xywh (relative to the canvas ROI origin; the whole canvas when nothing is brighter than 1, as the

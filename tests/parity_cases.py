@@ -407,6 +407,28 @@ def case_global_stage_masks(lib):
     cv.close(); cv2_.close()
 
 
+def case_seam_phase_warps(lib):
+    # the seam-phase warps of composePanorama - seam-scale images (seam_est_resol), cameras scaled by
+    # seam_work_aspect, LINEAR / REFLECT image warp and NEAREST / CONSTANT mask warp - and a strip's warpAffine, each as
+    # one stand-alone call
+    import cv2  # noqa: F401  (only to resize like the registration stage does; cv2 is a test dependency)
+    sv = synth.grid_survey(2, 2, 640, 480, overlap=0.6, seed=55, work_scale=0.6)
+    seam_work_aspect = 0.31
+    for f, K, R in zip(sv.frames, sv.Ks, sv.Rs):
+        small = cv2.resize(f, None, fx=seam_work_aspect, fy=seam_work_aspect, interpolation=cv2.INTER_LINEAR_EXACT)
+        Ks = np.asarray(K, np.float32).copy()
+        Ks[0, 0] *= seam_work_aspect; Ks[1, 1] *= seam_work_aspect; Ks[0, 2] *= seam_work_aspect; Ks[1, 2] *= seam_work_aspect
+        scale = np.float32(sv.scale * seam_work_aspect)
+        o = O.warp_frame(small, Ks, R, scale)
+        corner, img, mask = CP.warp_frame(small, CP.plane_transform(Ks, R, scale), lib=lib)
+        assert corner == tuple(o["corner"])
+        assert np.array_equal(img, o["warped"]) and np.array_equal(mask, o["mask"])
+    for s_ in affine_specs(56):
+        c_, w_, m_, _, _ = oracle_warp(s_)
+        corner, img, mask = CP.warp_frame(s_["img"], lib_transform(s_), lib=lib)
+        assert corner == tuple(c_) and np.array_equal(img, w_) and np.array_equal(mask, m_)
+
+
 def case_auto_crop(lib):
     # autoCropBlackBorder's rectangle computed from the canvas in device memory
     rng = np.random.default_rng(41)
@@ -489,6 +511,7 @@ def case_very_wide_canvas(lib):
 
 
 CASES = {
+    "seam_phase_warps": case_seam_phase_warps,
     "auto_crop": case_auto_crop,
     "global_stage_masks": case_global_stage_masks,
     "exposure_gains": case_exposure_gains,
