@@ -317,6 +317,7 @@ struct ds_canvas {
     bool l0_has_affine = false;   // some frame is AFFINE_F64 or has a seam mask / gain map: level 0 runs the general variant of the fast kernel
     bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
     int feather_R = 0;
+    void* scratch[3] = {nullptr, nullptr, nullptr}; size_t scratch_cap[3] = {0, 0, 0};   // mask chain temporaries (apply_opts), kept between calls
     int64_t device_bytes = 0;
     int64_t h2d_bytes = 0;   // frame bytes copied host -> device so far
     int64_t launches = 0;
@@ -1301,16 +1302,26 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
     const bool has_low = opts && opts->seam_lowres, has_full = opts && opts->seam_mask && !has_low;
     const bool nearest = has_low && (fl & DS_SEAM_NEAREST);
     const size_t plane = (size_t)f.bw * f.bh;
+    SoftMaskParams sp;
+    memset(&sp, 0, sizeof(sp));
+    // arguments are checked before anything about the frame changes
+    if (want_soft && (rc = gaussian_kernel_f32(opts->soft_sigma > 0.f ? (double)opts->soft_sigma : 10.0, sp.k, &sp.R))) return rc;
+    if (has_low && (opts->seam_lowres_w <= 0 || opts->seam_lowres_h <= 0)) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", opts->seam_lowres_w, opts->seam_lowres_h);
+    // temporaries live in the handle's scratch slots (no allocation per call); the caller's buffers are only borrowed, so
+    // these (rare) paths drain the upload stream before returning
     uint8_t* d_low = nullptr; int* d_tab = nullptr; uint8_t* d_tmp = nullptr;
     bool drain = false;
     auto cleanup = [&](int code) {
-        if (drain) { const int r2 = stream_sync(c->up); if (!code) code = r2; }   // temporaries below are freed: these (rare) paths drain
-        dev_free(d_low); dev_free(d_tab); dev_free(d_tmp);
+        if (drain) { const int r2 = stream_sync(c->up); if (!code) code = r2; }
         return code;
+    };
+    auto scratch = [&](int slot, size_t bytes, void** out) {
+        const int r = grow(c, &c->scratch[slot], &c->scratch_cap[slot], bytes);
+        *out = c->scratch[slot];
+        return r;
     };
     if (has_low) {
         const int sw = opts->seam_lowres_w, sh = opts->seam_lowres_h;
-        if (sw <= 0 || sh <= 0) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", sw, sh);
         const size_t sst = opts->seam_lowres_stride ? opts->seam_lowres_stride : (size_t)sw;
         if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, plane))) return rc;
         std::vector<int> tab(2 * ((size_t)f.bw + f.bh));
@@ -1335,8 +1346,8 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
             coefs(sw, f.bw, tab.data(), tab.data() + f.bw);
             coefs(sh, f.bh, tab.data() + 2 * f.bw, tab.data() + 2 * f.bw + f.bh);
         }
-        if ((rc = dev_alloc_t(&d_low, (size_t)sw * sh))) return rc;
-        if ((rc = dev_alloc_t(&d_tab, tab.size()))) return cleanup(rc);
+        if ((rc = scratch(0, (size_t)sw * sh, (void**)&d_low))) return rc;
+        if ((rc = scratch(1, tab.size() * sizeof(int), (void**)&d_tab))) return rc;
         drain = true;
         if ((rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->up))) return cleanup(rc);
         if ((rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->up))) return cleanup(rc);
@@ -1373,20 +1384,15 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
             if ((rc = ev_make(&c->ev_chunks)) || (rc = ev_record(c->ev_chunks, c->xp)) || (rc = ev_wait(c->up, c->ev_chunks))) return cleanup(rc);
         }
         mp.content_out = f.d_content;
-        mp.out = f.d_seam;
+        // with a soft mask to follow, the binary plane goes to scratch and the blurred plane lands in the frame's mask
+        if (want_soft && (rc = scratch(2, plane, (void**)&d_tmp))) return cleanup(rc);
+        mp.out = want_soft ? d_tmp : f.d_seam;
         drain = true;
         if ((rc = launch<MaskPrepBody, 256>(mp, ((long long)plane + MaskPrepBody::PER_BLOCK - 1) / MaskPrepBody::PER_BLOCK, c->up, 0))) return cleanup(rc);
         if (want_soft) {
-            SoftMaskParams sp;
-            memset(&sp, 0, sizeof(sp));
-            if ((rc = gaussian_kernel_f32(opts->soft_sigma > 0.f ? (double)opts->soft_sigma : 10.0, sp.k, &sp.R))) return cleanup(rc);
-            if ((rc = dev_alloc_t(&d_tmp, plane))) return cleanup(rc);
-            sp.bin = f.d_seam; sp.bin_pitch = f.bw; sp.out = d_tmp; sp.out_pitch = f.bw; sp.w = f.bw; sp.h = f.bh;
+            sp.bin = d_tmp; sp.bin_pitch = f.bw; sp.out = f.d_seam; sp.out_pitch = f.bw; sp.w = f.bw; sp.h = f.bh;
             const long long tiles = (long long)((f.bw + SoftMaskBody::T - 1) / SoftMaskBody::T) * ((f.bh + SoftMaskBody::T - 1) / SoftMaskBody::T);
             if ((rc = launch<SoftMaskBody, 256>(sp, tiles, c->up, SoftMaskBody::smem_bytes()))) return cleanup(rc);
-            // the blurred plane becomes the frame's mask
-            c->device_bytes += (int64_t)plane - (int64_t)f.seam_cap;
-            std::swap(f.d_seam, d_tmp); f.seam_cap = plane;
         }
         f.dev.seam = f.d_seam; f.dev.seam_pitch = f.bw;
     }
@@ -1651,6 +1657,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     for (int l = 0; l < DS_MAXL; l++) dev_free(c->d_lvl_alloc[l]);
     for (SubBand& sb : c->subs) { ev_drop(sb.done); ev_drop(sb.fed); ev_drop(sb.fed0); }
     dev_free(c->d_out); dev_free(c->d_mask); dev_free(c->d_meta);
+    for (int k = 0; k < 3; k++) dev_free(c->scratch[k]);
     peer_close(c, 0); peer_close(c, 1);
     dev_free(c->d_flags);
     for (int k = 0; k < ds_canvas::NSLOT; k++) { dev_free(c->d_slot[k]); ev_drop(c->slot_copied[k]); ev_drop(c->slot_free[k]); }

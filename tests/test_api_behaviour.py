@@ -225,3 +225,53 @@ def test_band_partial_upload_emu(emu_lib):
 @pytest.mark.gpu
 def test_band_partial_upload_gpu(cuda_lib):
     _band_partial_upload(cuda_lib)
+
+
+def _widened_api_errors(lib):
+    """Error behaviour of the entry points of SURVEY 8(f): states and arguments are refused with a status, never guessed."""
+    from drone_image_stitch_cpp_b200 import _lib as L
+    import ctypes as C
+    img = synth.orthophoto(120, 160, 3).numpy()
+    M = np.array([[1.0, 0.02, 3.5], [-0.02, 1.0, 2.25]])
+    xf = CP.affine_transform(M, (0, 0), (170, 130))
+    cv = CP.Canvas((0, 0, 170, 130), "multiband", 3, lib=lib)
+
+    def expect(code, fn):
+        with pytest.raises(L.DroneStitchError) as e:
+            fn()
+        assert e.value.code == code, e.value
+
+    expect(L.DS_ERR_BAD_ARG, lambda: cv.update_opts(0, content_mask=True))        # nothing uploaded at index 0
+    cv.upload(0, img, xf)
+    expect(L.DS_ERR_STATE, lambda: cv.frame_mask(0, 1))                           # no DS_MASK_CONTENT on that frame
+    expect(L.DS_ERR_BAD_ARG, lambda: cv.frame_mask(0, 2))
+    expect(L.DS_ERR_UNSUPPORTED, lambda: cv.update_opts(0, soft_mask=12.0))       # kernel wider than 81 taps
+    expect(L.DS_ERR_STATE, lambda: cv.auto_crop_rect())                           # before any composite
+    # a frame without options: mask 0 is the nearest-warped 255s
+    m = cv.frame_mask(0, 0)
+    assert np.array_equal(m, O.affine_nearest_mask(M, 170, 130, 160, 120))
+    # a smaller sigma is accepted and matches the oracle
+    cv.update_opts(0, soft_mask=3.0, content_mask=True)
+    assert np.array_equal(cv.frame_mask(0, 0), O.soft_blend_mask(None, O.content_mask(img, M, 170, 130), 3.0))
+    cv.composite()
+    assert cv.auto_crop_rect() == O.auto_crop_rect(cv.download()[0])
+    # a black canvas is returned whole, like the reference leaves the panorama untouched
+    cv.upload(0, np.zeros_like(img), xf)
+    cv.composite()
+    assert cv.auto_crop_rect() == (0, 0, 170, 130)
+    cv.close()
+    # ds_warp_frame: placement query, argument checks
+    pl = (C.c_int32 * 4)()
+    lib.check(lib.dll.ds_warp_frame(0, C.c_void_p(img.ctypes.data), 160, 120, img.strides[0], C.byref(xf), pl, None, None))
+    assert tuple(pl) == (0, 0, 170, 130)
+    out = np.empty((130, 170, 3), np.uint8)
+    assert lib.dll.ds_warp_frame(0, C.c_void_p(img.ctypes.data), 160, 120, img.strides[0], C.byref(xf), pl, out.ctypes.data, None) == L.DS_ERR_BAD_ARG
+
+
+def test_widened_api_errors_emu(emu_lib):
+    _widened_api_errors(emu_lib)
+
+
+@pytest.mark.gpu
+def test_widened_api_errors_gpu(cuda_lib):
+    _widened_api_errors(cuda_lib)

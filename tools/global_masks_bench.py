@@ -56,6 +56,18 @@ ms_comp = sum(k["ms"] for k in kt)
 
 import cv2
 cv2.setNumThreads(os.cpu_count())
+# autoCropBlackBorder: rectangle decided on the device vs cv2 on the downloaded panorama
+t_crop = []
+for rep in range(3):
+    t0 = time.perf_counter()
+    rect = cv.auto_crop_rect()
+    t_crop.append(time.perf_counter() - t0)
+t0 = time.perf_counter()
+pano, _ = cv.download()
+t_dl = time.perf_counter() - t0
+t0 = time.perf_counter()
+rect_cv, _areas = CR.auto_crop_rect_cv2(pano)
+t_crop_cpu = time.perf_counter() - t0
 t0 = time.perf_counter()
 ref = []
 for i in range(n):
@@ -70,4 +82,6 @@ mp = sum(r[2] * r[3] for r in rois) / 1e6
 print(json.dumps({"strips": n, "strip": [sw, sh], "mask_megapixels": round(mp, 1), "device_masks_ms": round(min(t_masks) * 1e3, 2),
                   "device_masks_MP_per_s": round(mp / min(t_masks), 1), "upload_ms": round(min(t_up) * 1e3, 1),
                   "cv2_masks_ms": round(t_cpu * 1e3, 1), "cv2_threads": os.cpu_count(), "identical_to_cv2": same,
-                  "composite_ms": round(ms_comp, 2), "canvas": [roi[2], roi[3]]}))
+                  "composite_ms": round(ms_comp, 2), "canvas": [roi[2], roi[3]],
+                  "crop_rect": list(rect), "crop_rect_cv2": list(rect_cv), "device_crop_ms": round(min(t_crop) * 1e3, 2),
+                  "cv2_crop_ms": round(t_crop_cpu * 1e3, 1), "full_download_ms": round(t_dl * 1e3, 1)}))
