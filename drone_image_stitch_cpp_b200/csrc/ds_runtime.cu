@@ -679,12 +679,6 @@ int default_pipeline_rows() {
     return v;
 }
 
-bool taper_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DS_PIPELINE_TAPER"); v = (e && atoi(e) == 0) ? 0 : 1; }
-    return v == 1;
-}
-
 // Cuts the handle's rows into slices that run one after the other on the compute stream. Slice b feeds, at every
 // level, the rows between the end of slice b-1 and its own end (band rows + the pyramid halo below them, as
 // plan_rows gives for a band ending there): the per-frame pyramids and the Laplacian levels a slice leaves behind
@@ -725,17 +719,6 @@ void plan_subbands(ds_canvas* c, int rows_per_slice) {
             const int n = std::max(1, (hi - lo + step / 2) / step);
             const int piece = ((hi - lo + n - 1) / n + align - 1) / align * align;
             for (int k = 0; k < n && lo + k * piece < hi; k++) fine.push_back(lo + k * piece);
-        }
-        // (3) taper the end: whatever runs after the last upload chunk has landed is the tail of an end-to-end step,
-        // so the last piece is cut into ever thinner slices (1/3 and 1/6 of a slice) - the one that waits for the
-        // final source rows then has little left to feed, collapse and copy out
-        if (!fine.empty() && taper_enabled()) {
-            const int lo = fine.back();
-            for (int div : {3, 6}) {
-                const int t = std::max(step / div / align * align, align);
-                const int y = band.hi - t;
-                if (y - std::max(lo, fine.back()) >= t && y > fine.back()) fine.push_back(y);
-            }
         }
         fine.push_back(band.hi);
         edges.swap(fine);
