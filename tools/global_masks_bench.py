@@ -11,7 +11,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from drone_image_stitch_cpp_b200 import compositor as CP  # noqa: E402
-from oracle import cv_reference as CR  # noqa: E402  (bench: the CPU reference timed beside the device path)
 
 sw, sh, n = (int(v) for v in (sys.argv[1:4] + ["12000", "4000", "3"][len(sys.argv) - 1:]))
 rng = np.random.default_rng(5)
@@ -56,6 +55,41 @@ ms_comp = sum(k["ms"] for k in kt)
 
 import cv2
 cv2.setNumThreads(os.cpu_count())
+
+
+# The reference's own OpenCV calls (src/stitch_global.cpp:353-383, :332-351; src/stitch_common.cpp:4-27), timed on the host
+def content_mask_cv2(img, M, dsize):
+    gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    _, m8 = cv2.threshold(gray, 3, 255, cv2.THRESH_BINARY)
+    mf = cv2.multiply(m8, 1.0 / 255.0, dtype=cv2.CV_32F)
+    wf = cv2.warpAffine(mf, np.asarray(M, np.float64).reshape(2, 3), dsize, flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0.0)
+    _, mw = cv2.threshold(wf, 0.999, 255.0, cv2.THRESH_BINARY)
+    return mw.astype(np.uint8)
+
+
+def soft_blend_mask_cv2(seam, content, sigma=10.0):
+    b = cv2.bitwise_and(seam, content)
+    _, b = cv2.threshold(b, 1.0, 255.0, cv2.THRESH_BINARY)
+    bf = cv2.multiply(b, 1.0 / 255.0, dtype=cv2.CV_32F)
+    soft = cv2.GaussianBlur(bf, (0, 0), sigma, None, sigma, cv2.BORDER_REPLICATE)
+    soft = cv2.multiply(soft, bf)
+    return np.clip(np.rint(soft * np.float32(255.0)), 0, 255).astype(np.uint8)   # convertTo(CV_8U, 255.0): float32 scaling
+
+
+def auto_crop_rect_cv2(pano):
+    gray = cv2.cvtColor(pano, cv2.COLOR_BGR2GRAY)
+    _, th = cv2.threshold(gray, 1, 255, cv2.THRESH_BINARY)
+    contours, _ = cv2.findContours(th, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    if not contours:
+        return (0, 0, pano.shape[1], pano.shape[0])
+    best, best_area = cv2.boundingRect(contours[0]), cv2.contourArea(contours[0])
+    for c in contours[1:]:
+        a = cv2.contourArea(c)
+        if a > best_area:
+            best_area, best = a, cv2.boundingRect(c)
+    return tuple(int(v) for v in best)
+
+
 # autoCropBlackBorder: rectangle decided on the device vs cv2 on the downloaded panorama
 t_crop = []
 for rep in range(3):
@@ -66,16 +100,16 @@ t0 = time.perf_counter()
 pano, _ = cv.download()
 t_dl = time.perf_counter() - t0
 t0 = time.perf_counter()
-rect_cv, _areas = CR.auto_crop_rect_cv2(pano)
+rect_cv = auto_crop_rect_cv2(pano)
 t_crop_cpu = time.perf_counter() - t0
 t0 = time.perf_counter()
 ref = []
 for i in range(n):
     bw, bh = rois[i][2], rois[i][3]
-    content = CR.content_mask_cv2(strips[i], Ms[i], (bw, bh))
+    content = content_mask_cv2(strips[i], Ms[i], (bw, bh))
     seam = cv2.resize(seams[i], (bw, bh), interpolation=cv2.INTER_NEAREST)
     _, seam = cv2.threshold(seam, 1.0, 255.0, cv2.THRESH_BINARY)
-    ref.append(CR.soft_blend_mask_cv2(seam, content, 10.0))
+    ref.append(soft_blend_mask_cv2(seam, content, 10.0))
 t_cpu = time.perf_counter() - t0
 same = [bool(np.array_equal(a, b)) for a, b in zip(got, ref)]
 mp = sum(r[2] * r[3] for r in rois) / 1e6
