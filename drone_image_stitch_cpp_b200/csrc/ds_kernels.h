@@ -190,9 +190,17 @@ constexpr int ds_al128(int v) { return (v + 127) & ~127; }  // TMA destinations 
 #if DS_CUDA
 // One named __global__ per body (so profiles show ds_mb_feed_l0 etc. instead of one template name).
 template <class Body, int NT> struct KernelOf;
+// Programmatic dependent launch: every kernel first lets the next launch of its stream start being scheduled (its CTAs
+// become resident as this grid's last wave drains) and then waits until the previous grid has completed and its memory
+// is visible. Nothing is read or written before the wait, so the only overlap is launch latency and the wave tail.
+__device__ __forceinline__ void ds_grid_dependency_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 #define DS_DEFINE_KERNEL(kname, Body, NT, P, MINB)                                         \
     __global__ void __launch_bounds__(NT, MINB) kname(const P p) {                         \
         extern __shared__ __align__(128) unsigned char ds_smem[];                           \
+        ds_grid_dependency_sync();                                                          \
         Body::template run<NT>(p, (int)blockIdx.x, (int)threadIdx.x, ds_smem);             \
     }                                                                                      \
     template <> struct KernelOf<Body, NT> { static constexpr void (*fn)(const P) = kname; };
@@ -1722,17 +1730,31 @@ struct CollapseBody {
                 }
             }
             const int nvalid = imin(4, fw - Xq);
+            // the fine pixels of BOTH rows are requested before anything is stored: the stores below may alias the
+            // loads as far as the compiler knows, so a load placed after them would wait for the first row to finish
+            uint4 fv[2][2];
+            bool live[2];
             DS_UNROLL
             for (int dy = 0; dy < 2; dy++) {
                 const int Y = 2 * c1y + dy;
-                if (Y < p.y0 || Y >= p.y1) continue;
+                live[dy] = Y >= p.y0 && Y < p.y1;
+                fv[dy][0] = fv[dy][1] = make_u4(0u, 0u, 0u, 0u);
+                if (live[dy] && nvalid == 4) {
+                    const px16* frow = p.fine + (size_t)Y * fw + Xq;
+                    fv[dy][0] = *(const uint4*)frow; fv[dy][1] = *(const uint4*)(frow + 2);
+                }
+            }
+            DS_UNROLL
+            for (int dy = 0; dy < 2; dy++) {
+                const int Y = 2 * c1y + dy;
+                if (!live[dy]) continue;
                 const bool oddy = dy != 0;
                 // the four fine pixels as words (b | g << 16, r | flag << 16): kept in registers, never as an
                 // addressable array (that would live in local memory)
                 uint32_t fw0[4], fw1[4];
                 px16* frow = p.fine + (size_t)Y * fw + Xq;
                 if (nvalid == 4) {
-                    const uint4 v0 = *(const uint4*)frow, v1 = *(const uint4*)(frow + 2);
+                    const uint4 v0 = fv[dy][0], v1 = fv[dy][1];
                     fw0[0] = v0.x; fw1[0] = v0.y; fw0[1] = v0.z; fw1[1] = v0.w;
                     fw0[2] = v1.x; fw1[2] = v1.y; fw0[3] = v1.z; fw1[3] = v1.w;
                 } else {
@@ -1851,6 +1873,6 @@ DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_ln, MBFastLN, 256, MBParams, 4)
 DS_DEFINE_KERNEL(ds_mb_feed_generic, MBBodyLN, 256, MBParams, 1)
-DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 5)
+DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 4)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)
 #endif

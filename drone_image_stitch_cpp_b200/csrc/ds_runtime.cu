@@ -116,7 +116,21 @@ int launch(const P& p, long long blocks, stream_t s, int smem_bytes) {
         DS_CK(cudaFuncSetAttribute(KernelOf<Body, NT>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured_dev = dev;
     }
-    KernelOf<Body, NT>::fn<<<(unsigned)blocks, NT, smem_bytes, s>>>(p);
+    // programmatic dependent launch (see ds_grid_dependency_sync): DS_PDL=0 falls back to plain stream order
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("DS_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
+    if (pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        DS_CK(cudaLaunchKernelEx(&cfg, KernelOf<Body, NT>::fn, p));
+    } else {
+        KernelOf<Body, NT>::fn<<<(unsigned)blocks, NT, smem_bytes, s>>>(p);
+    }
     DS_CK(cudaGetLastError());
     return DS_OK;
 }
