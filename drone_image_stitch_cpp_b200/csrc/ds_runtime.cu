@@ -1834,7 +1834,7 @@ DS_API int ds_auto_crop_rect(ds_canvas* c, int32_t out_xywh[4]) {
     if ((rc = set_device(c))) return rc;
     if ((rc = stream_sync(c->stream))) return rc;
     for (const SubBand& sb : c->subs) if (sb.done && (rc = ev_sync(sb.done))) return rc;
-    const int cap = 64;
+    const int cap = 256;   // events per row: up to 128 foreground runs (dark specks inside the content split runs)
     int* d_count = nullptr; int* d_events = nullptr;
     if ((rc = dev_alloc_t(&d_count, (size_t)H))) return rc;
     if ((rc = dev_alloc_t(&d_events, (size_t)H * cap))) { dev_free(d_count); return rc; }
