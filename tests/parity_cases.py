@@ -174,6 +174,52 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
     return st
 
 
+def windowed_oracle(frames, Ks, Rs, scale, bands, roi, win):
+    """SURVEY 8(c) P17, the oracle for canvases too large to blend whole on the CPU: the blender is prepared on an aligned
+    window of the canvas (origin a multiple of 2^bands from the canvas origin), every warped frame is cropped to the
+    window, and pixels at least 8 * 2^bands inside the window equal the full-canvas result bit for bit.
+    win = (x, y, w, h) relative to the canvas origin; -> (pano16 -> u8, mask) of the window."""
+    wx, wy, ww, wh = win
+    m = 1 << bands
+    assert wx % m == 0 and wy % m == 0 and ww % m == 0 and wh % m == 0
+    ax, ay = roi[0] + wx, roi[1] + wy
+    bl = O.MultiBand((ax, ay, ww, wh), bands)
+    assert bl.bands == bands
+    for f, K, R in zip(frames, Ks, Rs):
+        w = O.warp_frame(f, K, R, scale)
+        cx, cy = w["corner"]
+        bw, bh = w["size"]
+        x0, y0, x1, y1 = max(cx, ax), max(cy, ay), min(cx + bw, ax + ww), min(cy + bh, ay + wh)
+        if x0 >= x1 or y0 >= y1:
+            continue
+        img = np.ascontiguousarray(w["warped"][y0 - cy:y1 - cy, x0 - cx:x1 - cx]).astype(np.int16)
+        msk = np.ascontiguousarray(w["mask"][y0 - cy:y1 - cy, x0 - cx:x1 - cx])
+        bl.feed(img, msk, (x0, y0))
+    ref16, refmask = bl.blend()
+    return O.s16_to_u8(ref16), refmask
+
+
+def check_window(pano, mask, ref, refmask, win, bands):
+    wx, wy, ww, wh = win
+    g = 8 << bands
+    sl = (slice(wy + g, wy + wh - g), slice(wx + g, wx + ww - g))
+    rs = (slice(g, wh - g), slice(g, ww - g))
+    assert np.array_equal(mask[sl], refmask[rs]), "result mask differs inside the window"
+    return assert_blend_parity(pano[sl], ref[rs])
+
+
+def case_windowed_oracle(lib):
+    # the windowed oracle itself, at a size where the full-canvas oracle exists: both must agree with the library
+    sv = synth.grid_survey(3, 3, 400, 300, overlap=0.6, seed=17, rot_deg=2.0)
+    bands = 3
+    pano, mask, roi = CP.compose_panorama(sv.frames, sv.Ks, sv.Rs, sv.scale, "multiband", bands, lib=lib)
+    full, fullmask, roi2 = O.compose_port(sv.frames, sv.Ks, sv.Rs, sv.scale, "multiband", bands)
+    assert roi == roi2 and np.array_equal(pano, full) and np.array_equal(mask, fullmask)
+    win = (128, 96, 384, 320)
+    ref, refmask = windowed_oracle(sv.frames, sv.Ks, sv.Rs, sv.scale, bands, roi, win)
+    check_window(pano, mask, ref, refmask, win, bands)
+
+
 def plane_specs(sv):
     return [dict(kind="plane", img=f, K=K, R=R, scale=sv.scale) for f, K, R in zip(sv.frames, sv.Ks, sv.Rs)]
 
@@ -511,6 +557,7 @@ def case_very_wide_canvas(lib):
 
 
 CASES = {
+    "windowed_oracle": case_windowed_oracle,
     "seam_phase_warps": case_seam_phase_warps,
     "auto_crop": case_auto_crop,
     "global_stage_masks": case_global_stage_masks,

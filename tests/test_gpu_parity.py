@@ -94,3 +94,65 @@ def test_cfg4_scale_one_gpu():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert res["ok"] and res["gigapixels"] > 2.2 and len(res["bands_checked"]) == 3
+
+
+def _windowed_check(cuda_lib, plan, bands, win_frac=(0.5, 0.5), win_size=(2048, 1536)):
+    """Composite a whole BASELINE-size survey on the GPU (frames cut on the device, handed over by device pointer) and
+    compare an aligned window of the canvas with the windowed oracle: bit-exact at least 8 * 2^bands
+    inside the window."""
+    import torch
+    from drone_image_stitch_cpp_b200 import compositor as CP, synth
+    from parity_cases import windowed_oracle
+    xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
+    rois = [CP.warp_roi(xf, plan.fw, plan.fh, cuda_lib) for xf in xfs]
+    roi = CP.result_roi(rois)
+    m = 1 << bands
+    ww, wh = win_size
+    wx = int((roi[2] - ww) * win_frac[0]) // m * m
+    wy = int((roi[3] - wh) * win_frac[1]) // m * m
+    win = (wx, wy, ww, wh)
+    ortho = synth.orthophoto(plan.ortho_h, plan.ortho_w, plan.seed, "cuda")
+    cv = CP.Canvas(roi, "multiband", bands, lib=cuda_lib)
+    keep = {}
+    for i, xf in enumerate(xfs):
+        fr = synth.cut(plan, [i], "cuda", as_torch=True, ortho=ortho)[0]
+        cv.upload_device(i, fr.data_ptr(), plan.fw, plan.fh, plan.fw * 3, xf)
+        r = rois[i]
+        if r[0] < roi[0] + wx + ww and r[0] + r[2] > roi[0] + wx and r[1] < roi[1] + wy + wh and r[1] + r[3] > roi[1] + wy:
+            keep[i] = fr.cpu().numpy()
+        del fr
+    del ortho
+    torch.cuda.empty_cache()
+    cv.composite()
+    assert cv.info().num_bands == bands
+    tile, tmask = cv.download(wx, wy, ww, wh)
+    cv.close()
+    idx = sorted(keep)
+    assert len(idx) >= 4, "the window should see several overlapping frames"
+    ref, refmask = windowed_oracle([keep[i] for i in idx], [plan.Ks[i] for i in idx], [plan.Rs[i] for i in idx], plan.scale, bands, roi, win)
+    g = 8 << bands
+    assert np.array_equal(tmask[g:wh - g, g:ww - g], refmask[g:wh - g, g:ww - g]), "result mask differs inside the window"
+    from helpers import assert_blend_parity
+    return assert_blend_parity(tile[g:wh - g, g:ww - g], ref[g:wh - g, g:ww - g]), len(idx), roi
+
+
+def test_cfg2_full_size_windowed_oracle(cuda_lib):
+    """BASELINE config 2 at full size (3x3 of 5472x3648, 70 % overlap, 5 bands): the middle of the canvas, where all nine
+    frames overlap, against the windowed oracle."""
+    from drone_image_stitch_cpp_b200 import synth
+    plan = synth.plan_grid(3, 3, 5472, 3648, overlap=0.7, seed=synth.MASTER_SEED)
+    st, n, roi = _windowed_check(cuda_lib, plan, 5)
+    assert n == 9 and st["n_diff"] == 0
+
+
+def test_cfg3_full_size_windowed_oracle(cuda_lib):
+    """BASELINE config 3 at full size: 120 frames of 5472x3648 in three serpentine lines, 0.6 GP canvas about 69 k px
+    wide. A window between the first and the second flight line against the windowed oracle."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip(f"needs 60 GB of free device memory, {free / 1e9:.0f} GB available")
+    from drone_image_stitch_cpp_b200 import synth
+    plan = synth.plan_grid(40, 3, 5472, 3648, overlap=0.7, side_overlap=0.32, seed=synth.MASTER_SEED)
+    st, n, roi = _windowed_check(cuda_lib, plan, 5, win_frac=(0.37, 0.36))
+    assert roi[2] > 65535 and st["n_diff"] == 0
