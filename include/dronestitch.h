@@ -202,7 +202,8 @@ DS_API int ds_update_frame_opts(ds_canvas* c, int frame_idx, const ds_frame_opts
  * which = 1: the content mask of DS_MASK_CONTENT (warped_masks[i] of the global stage). */
 DS_API int ds_download_frame_mask(ds_canvas* c, int frame_idx, int which, uint8_t* out, size_t stride);
 
-/* Same, but `dev_bgr` is a device pointer (frames already resident in HBM). */
+/* Same, but `dev_bgr` is a device pointer (frames already resident in HBM). The library reads it on its own streams:
+ * whatever produced the pixels must have completed (synchronise the producing stream first). */
 DS_API int ds_upload_frame_device(ds_canvas* c, int frame_idx, const void* dev_bgr, int w, int h, size_t stride,
                                   const ds_transform* xf, const ds_frame_opts* opts);
 

@@ -116,6 +116,7 @@ def _windowed_check(cuda_lib, plan, bands, win_frac=(0.5, 0.5), win_size=(2048, 
     keep = {}
     for i, xf in enumerate(xfs):
         fr = synth.cut(plan, [i], "cuda", as_torch=True, ortho=ortho)[0]
+        torch.cuda.synchronize()   # the library reads the pixels on its own streams: they must be complete
         cv.upload_device(i, fr.data_ptr(), plan.fw, plan.fh, plan.fw * 3, xf)
         r = rois[i]
         if r[0] < roi[0] + wx + ww and r[0] + r[2] > roi[0] + wx and r[1] < roi[1] + wy + wh and r[1] + r[3] > roi[1] + wy:
