@@ -79,10 +79,11 @@ def test_no_cpu_fallback_symbols(cuda_lib):
     assert b"sm_100a" in cuda_lib.dll.ds_version()
 
 
-def test_cfg4_scale_one_gpu():
+def test_cfg4_scale_one_gpu(tmp_path):
     """BASELINE config 4 at full size on one GPU (600 frames of 5472x3648, 2.7 GP canvas, ~125 GB of HBM): the
-    composite runs and three band handles reproduce its rows bit for bit - indexing beyond 2^31 pixels, tile lists,
-    TMA descriptors. Fresh process (tools/scale_check.py); skipped when the device has less than 140 GB free."""
+    composite runs, three band handles reproduce its rows bit for bit - indexing beyond 2^31 pixels, tile lists,
+    TMA descriptors - and a window from the middle of the canvas equals the windowed oracle.
+    Fresh process (tools/scale_check.py); skipped when the device has less than 140 GB free."""
     import os, subprocess, sys, json
     import torch
     torch.cuda.empty_cache()
@@ -90,10 +91,36 @@ def test_cfg4_scale_one_gpu():
     if free < 140e9:
         pytest.skip(f"needs 140 GB of free device memory, {free / 1e9:.0f} GB available")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "scale_check.py"), "50", "12"], capture_output=True, text=True, timeout=900)
+    npz = os.path.join(str(tmp_path), "window.npz")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "scale_check.py"), "50", "12", npz], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert res["ok"] and res["gigapixels"] > 2.2 and len(res["bands_checked"]) == 3
+    # the window against the oracle: the frames are seeded noise, regenerated here for the indices the window sees
+    from drone_image_stitch_cpp_b200 import compositor as CP, synth, _lib
+    from parity_cases import windowed_oracle
+    from helpers import assert_blend_parity
+    w = np.load(npz)
+    roi, win = tuple(int(v) for v in w["roi"]), tuple(int(v) for v in w["win"])
+    fw, fh, bands = 5472, 3648, 5
+    plan = synth.plan_grid(50, 12, fw, fh, overlap=0.7, side_overlap=0.32, seed=synth.MASTER_SEED)
+    lib = _lib.default_library()
+    wx, wy, ww, wh = win
+    idx = []
+    for i, (K, R) in enumerate(zip(plan.Ks, plan.Rs)):
+        q = CP.warp_roi(CP.plane_transform(K, R, plan.scale), fw, fh, lib)
+        if q[0] < roi[0] + wx + ww and q[0] + q[2] > roi[0] + wx and q[1] < roi[1] + wy + wh and q[1] + q[3] > roi[1] + wy:
+            idx.append(i)
+    assert len(idx) >= 4
+    frames = []
+    for i in idx:
+        g = torch.Generator(device="cuda").manual_seed(1000 + i)
+        frames.append(torch.randint(0, 256, (fh, fw, 3), dtype=torch.uint8, device="cuda", generator=g).cpu().numpy())
+    ref, refmask = windowed_oracle(frames, [plan.Ks[i] for i in idx], [plan.Rs[i] for i in idx], plan.scale, bands, roi, win)
+    gm = 8 << bands
+    assert np.array_equal(w["mask"][gm:wh - gm, gm:ww - gm], refmask[gm:wh - gm, gm:ww - gm])
+    st = assert_blend_parity(w["tile"][gm:wh - gm, gm:ww - gm], ref[gm:wh - gm, gm:ww - gm])
+    assert st["n_diff"] == 0
 
 
 def _windowed_check(cuda_lib, plan, bands, win_frac=(0.5, 0.5), win_size=(2048, 1536)):

@@ -3,7 +3,9 @@ multi-band 5, canvas ~2.5 GP. Frames are generated on the device (seeded noise: 
 here) and handed over with ds_upload_frame_device. Checks: the composite runs, is idempotent, and three row bands
 computed by separate band handles reproduce the same rows of the big canvas bit for bit (64-bit indexing, tile
 lists and TMA descriptors at > 2^31 pixels). Prints one JSON line.
-usage: python tools/scale_check.py [nx ny]"""
+With a third argument (path), a 2048x1536 window from the middle of the canvas is written there as .npz (tile, mask, win,
+roi) - tests/test_gpu_parity.py compares it with the windowed oracle.
+usage: python tools/scale_check.py [nx ny [window.npz]]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -21,7 +23,9 @@ print("canvas", roi[2], "x", roi[3], "=", roi[2] * roi[3] / 1e9, "GP;", len(xfs)
 
 def frame(i):
     g = torch.Generator(device="cuda").manual_seed(1000 + i)
-    return torch.randint(0, 256, (fh, fw, 3), dtype=torch.uint8, device="cuda", generator=g)
+    f = torch.randint(0, 256, (fh, fw, 3), dtype=torch.uint8, device="cuda", generator=g)
+    torch.cuda.synchronize()   # the library reads the pixels on its own streams
+    return f
 
 
 def fill(cv, which):
@@ -45,6 +49,11 @@ H, m = info.padded_height, 1 << info.num_bands
 res = {"canvas": [roi[2], roi[3]], "gigapixels": roi[2] * roi[3] / 1e9, "frames": len(xfs), "device_GB": info.device_bytes / 1e9,
        "composite_ms": min(ms), "MPps": roi[2] * roi[3] / 1e6 / (min(ms) / 1e3), "upload_s": t_up, "bands_checked": []}
 print(json.dumps(res), flush=True)
+if len(sys.argv) > 3:
+    ww, wh = 2048, 1536
+    wx, wy = (roi[2] - ww) // 2 // m * m, (roi[3] - wh) // 2 // m * m
+    tile, tmask = cv.download(wx, wy, ww, wh)
+    np.savez(sys.argv[3], tile=tile, mask=tmask, win=np.array([wx, wy, ww, wh]), roi=np.array(roi))
 # three row bands of 512 rows: top, across the middle, bottom
 for y0 in (0, (H // 2) // m * m, (roi[3] - 512) // m * m):
     y1 = min(y0 + 512, H)
