@@ -184,3 +184,61 @@ def test_cfg3_full_size_windowed_oracle(cuda_lib):
     plan = synth.plan_grid(40, 3, 5472, 3648, overlap=0.7, side_overlap=0.32, seed=synth.MASTER_SEED)
     st, n, roi = _windowed_check(cuda_lib, plan, 5, win_frac=(0.37, 0.36))
     assert roi[2] > 65535 and st["n_diff"] == 0
+
+
+def test_cfg5_one_band_of_eight_windowed_oracle(cuda_lib):
+    """BASELINE config 5 geometry: 2000 frames of 5472x3648 (25 lines x 80), 8-level multi-band, canvas about 8 GP, cut into
+    eight row bands. One GPU computes ONE of the eight bands exactly as it would in the 8-GPU job (a band handle with the
+    frames that touch the band + its recomputed pyramid halo) and the top of that band is compared with the windowed oracle
+    (margin 8 * 2^8 = 2048 px). Frames are seeded noise generated on the device."""
+    import torch
+    from drone_image_stitch_cpp_b200 import compositor as CP, synth
+    from parity_cases import windowed_oracle
+    from helpers import assert_blend_parity
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 120e9:
+        pytest.skip(f"needs 120 GB of free device memory, {free / 1e9:.0f} GB available")
+    fw, fh, bands = 5472, 3648, 8
+    plan = synth.plan_grid(80, 25, fw, fh, overlap=0.7, side_overlap=0.32, seed=synth.MASTER_SEED)
+    xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
+    rois = [CP.warp_roi(xf, fw, fh, cuda_lib) for xf in xfs]
+    roi = CP.result_roi(rois)
+    assert roi[2] * roi[3] > 7.5e9
+    m = 1 << bands
+    H = (roi[3] + m - 1) // m * m
+    y0, y1 = (H * 3 // 8) // m * m, (H * 4 // 8) // m * m
+    cb = CP.Canvas(roi, "multiband", bands, band=(y0, y1), lib=cuda_lib)
+    assert cb.info().num_bands == bands
+
+    def frame(i):
+        g = torch.Generator(device="cuda").manual_seed(5000 + i)
+        f = torch.randint(0, 256, (fh, fw, 3), dtype=torch.uint8, device="cuda", generator=g)
+        torch.cuda.synchronize()
+        return f
+
+    mine = [i for i in range(len(xfs)) if cb.touches(rois[i])]
+    assert 200 < len(mine) < 1000
+    for i in mine:
+        f = frame(i)
+        cb.upload_device(i, f.data_ptr(), fw, fh, fw * 3, xfs[i])
+        del f
+    cb.composite()
+    info = cb.info()
+    g = 8 << bands
+    ww, wh = 2 * g + 2048, 2 * g + 1024
+    wx, wy = (roi[2] - ww) // 2 // m * m, y0 - g
+    win = (wx, wy, ww, wh)
+    tile, tmask = cb.download(wx + g, y0, 2048, 1024)
+    ms, dev_gb = info.ms_last_composite, info.device_bytes / 1e9
+    cb.close()
+    torch.cuda.empty_cache()
+    idx = [i for i in range(len(xfs)) if rois[i][0] < roi[0] + wx + ww and rois[i][0] + rois[i][2] > roi[0] + wx and
+           rois[i][1] < roi[1] + wy + wh and rois[i][1] + rois[i][3] > roi[1] + wy]
+    assert set(idx) <= set(mine) and len(idx) >= 8
+    frames = [frame(i).cpu().numpy() for i in idx]
+    ref, refmask = windowed_oracle(frames, [plan.Ks[i] for i in idx], [plan.Rs[i] for i in idx], plan.scale, bands, roi, win)
+    assert np.array_equal(tmask, refmask[g:g + 1024, g:g + 2048])
+    st = assert_blend_parity(tile, ref[g:g + 1024, g:g + 2048])
+    assert st["n_diff"] == 0
+    print(f"cfg5 band: {len(mine)} frames, {dev_gb:.1f} GB, composite {ms:.1f} ms, window frames {len(idx)}")
