@@ -45,7 +45,7 @@ class ds_frame_opts(C.Structure):
                 ("seam_lowres", C.c_void_p), ("seam_lowres_w", C.c_int32), ("seam_lowres_h", C.c_int32),
                 ("seam_lowres_stride", C.c_size_t),
                 ("compensator_gain", C.POINTER(C.c_double)), ("gain_map", C.c_void_p), ("gain_map_stride", C.c_size_t),
-                ("flags", C.c_uint32), ("soft_sigma", C.c_float)]
+                ("flags", C.c_uint32), ("soft_sigma", C.c_double)]
 
 
 class ds_canvas_desc(C.Structure):

@@ -1302,7 +1302,7 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
     SoftMaskParams sp;
     memset(&sp, 0, sizeof(sp));
     // arguments are checked before anything about the frame changes
-    if (want_soft && (rc = gaussian_kernel_f32(opts->soft_sigma > 0.f ? (double)opts->soft_sigma : 10.0, sp.k, &sp.R))) return rc;
+    if (want_soft && (rc = gaussian_kernel_f32(opts->soft_sigma > 0.0 ? opts->soft_sigma : 10.0, sp.k, &sp.R))) return rc;
     if (has_low && (opts->seam_lowres_w <= 0 || opts->seam_lowres_h <= 0)) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", opts->seam_lowres_w, opts->seam_lowres_h);
     // temporaries live in the handle's scratch slots (no allocation per call); the caller's buffers are only borrowed, so
     // these (rare) paths drain the upload stream before returning

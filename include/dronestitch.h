@@ -115,7 +115,7 @@ typedef struct ds_frame_opts {
     uint32_t flags;
     /* DS_MASK_SOFT: sigma of buildSoftBlendMask's GaussianBlur; 0 = the reference's 10.0 (stitch_global.cpp:345).
      * Supported up to 10 (kernel of 81 taps). */
-    float soft_sigma;
+    double soft_sigma;   /* double like cv::GaussianBlur's sigmaX: the kernel taps are computed from it in double */
 } ds_frame_opts;
 
 /* ds_frame_opts.flags */
