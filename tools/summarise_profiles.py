@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 launch_csv, rep = sys.argv[1], sys.argv[2]
+PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]   # GB/s, measured copy bandwidth of this pool
 rows = list(csv.reader(open(launch_csv)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 hdr = rows[hi]
@@ -29,10 +30,15 @@ for l in mine[start:]:
 tot = sum(l["gpu__time_duration.sum"] for l in seq)
 out = [dict(kernel=l["name"].split("(")[0], grid=l["grid"], block=l["block"], us=round(l["gpu__time_duration.sum"] / 1e3, 2),
             share=round(l["gpu__time_duration.sum"] / tot, 4), dram_read_MB=round(l["dram__bytes_read.sum"] / 1e6, 1),
-            dram_write_MB=round(l["dram__bytes_write.sum"] / 1e6, 1)) for l in seq]
+            dram_write_MB=round(l["dram__bytes_write.sum"] / 1e6, 1),
+            dram_GBps=round((l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"]) / l["gpu__time_duration.sum"], 1),
+            frac_of_measured_hbm_peak=round((l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"]) / l["gpu__time_duration.sum"] / PEAK, 3))
+       for l in seq]
 json.dump(dict(command="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv "
                        "python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
-               note="one ds_composite of cfg2; per-launch times under ncu are cold-cache / serialised: compare shares",
+               note="one ds_composite of cfg2; per-launch times under ncu are cold-cache / serialised: compare shares. dram_GBps = "
+                    "(dram read + write) / duration of the launch: the REAL traffic rate, against MEASURED_PEAKS.json hbm_gbs "
+                    "(%.1f GB/s; nominal ~8000). The bench line's roofline.achieved uses the algorithmic bytes instead." % PEAK,
                launches=out, total_us=round(tot / 1e3, 1), dram_total_MB=round(sum(o["dram_read_MB"] + o["dram_write_MB"] for o in out), 1)),
           open("profiles/r1_launches_cfg2.json", "w"), indent=1)
 with open("profiles/r1_launches_cfg2.csv", "w") as f:
