@@ -1682,9 +1682,118 @@ struct CollapseBody {
     }
 
     // one pyrUp output from the horizontally filtered rows (A10), plus the fine value, saturated
+    // (vv + 32) >> 6 of 16-bit inputs always fits 16 bits (the taps sum to 64), so pyrUp's cast to short changes nothing.
+    // FINAL: the result is only saturated to 8 bits afterwards, which subsumes the 16-bit saturation of the add.
+    template <bool FINAL>
     DS_DM int up1(int hl, int hc, int hr, bool odd_y, int fine) {
         const int vv = odd_y ? 4 * (hc + hr) : (hl + 6 * hc + hr);
-        return sat16i((int)(short)((vv + 32) >> 6) + fine);
+        const int v = ((vv + 32) >> 6) + fine;
+        return FINAL ? v : sat16i(v);
+    }
+
+    // ---- interior items: no pyrUp border rule applies, four valid fine columns, coarse columns c0-1 .. c0+2 readable as
+    // 8 + 16 + 8 bytes per row. Straight-line arithmetic with the scale factors of the odd taps folded into the final
+    // shifts: with E = l + 6c + r and S = c + r per coarse row (horizontal pass, odd columns would be 4S),
+    //   even column, even row: (E0 + 6 E1 + E2 + 32) >> 6        even column, odd row: (4 (E1 + E2) + 32) >> 6 = (E1 + E2 + 8) >> 4
+    //   odd column,  even row: (4 (S0 + 6 S1 + S2) + 32) >> 6 = (S0 + 6 S1 + S2 + 8) >> 4
+    //   odd column,  odd row:  (16 (S1 + S2) + 32) >> 6 = (S1 + S2 + 2) >> 2          (arithmetic shifts: exact for negatives)
+    DS_DM int sx16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+    template <bool FINAL>
+    DS_DM int fin(int v) {
+#if DS_CUDA
+        if (FINAL) return __vimin_s32_relu(v, 255);   // min(max(v, 0), 255) in one instruction; subsumes the 16-bit saturation
+#endif
+        return FINAL ? sat8i(v) : sat16i(v);
+    }
+    // one channel: v[row][col] coarse values, f[dy][kx] fine values -> o[dy][kx]
+    template <bool FINAL>
+    DS_DM void chan(const int (&v)[3][4], const int (&f)[2][4], int (&o)[2][4]) {
+        int E0[3], E1[3], S0[3], S1[3];
+        DS_UNROLL
+        for (int r = 0; r < 3; r++) {
+            E0[r] = v[r][0] + v[r][2] + 6 * v[r][1]; S0[r] = v[r][1] + v[r][2];
+            E1[r] = v[r][1] + v[r][3] + 6 * v[r][2]; S1[r] = v[r][2] + v[r][3];
+        }
+        o[0][0] = fin<FINAL>(((E0[0] + E0[2] + 32 + 6 * E0[1]) >> 6) + f[0][0]);
+        o[1][0] = fin<FINAL>(((E0[1] + E0[2] + 8) >> 4) + f[1][0]);
+        o[0][1] = fin<FINAL>(((S0[0] + S0[2] + 8 + 6 * S0[1]) >> 4) + f[0][1]);
+        o[1][1] = fin<FINAL>(((S0[1] + S0[2] + 2) >> 2) + f[1][1]);
+        o[0][2] = fin<FINAL>(((E1[0] + E1[2] + 32 + 6 * E1[1]) >> 6) + f[0][2]);
+        o[1][2] = fin<FINAL>(((E1[1] + E1[2] + 8) >> 4) + f[1][2]);
+        o[0][3] = fin<FINAL>(((S1[0] + S1[2] + 8 + 6 * S1[1]) >> 4) + f[0][3]);
+        o[1][3] = fin<FINAL>(((S1[1] + S1[2] + 2) >> 2) + f[1][3]);
+    }
+    template <bool FINAL>
+    DS_DM void item_interior(const CollapseParams& p, int c1y, int Xq) {
+        const int cw = p.cw, fw = p.fw;
+        const px16* cq = p.coarse + (size_t)(c1y - 1) * cw + ((Xq >> 1) - 1);
+        uint32_t w0[3][4], w1[3][4];   // coarse pixels as words: b | g << 16, r | a << 16
+        DS_UNROLL
+        for (int r = 0; r < 3; r++) {
+            const px16* q = cq + (size_t)r * cw;
+            const uint2 a = *(const uint2*)q; const uint4 b = *(const uint4*)(q + 1); const uint2 c = *(const uint2*)(q + 3);
+            w0[r][0] = a.x; w1[r][0] = a.y; w0[r][1] = b.x; w1[r][1] = b.y; w0[r][2] = b.z; w1[r][2] = b.w; w0[r][3] = c.x; w1[r][3] = c.y;
+        }
+        uint32_t g0[2][4], g1[2][4];   // fine pixels, same word layout
+        bool live[2];
+        DS_UNROLL
+        for (int dy = 0; dy < 2; dy++) {
+            const int Y = 2 * c1y + dy;
+            live[dy] = Y >= p.y0 && Y < p.y1;
+            uint4 u0 = make_u4(0u, 0u, 0u, 0u), u1 = u0;
+            if (live[dy]) { const px16* frow = p.fine + (size_t)Y * fw + Xq; u0 = *(const uint4*)frow; u1 = *(const uint4*)(frow + 2); }
+            g0[dy][0] = u0.x; g1[dy][0] = u0.y; g0[dy][1] = u0.z; g1[dy][1] = u0.w;
+            g0[dy][2] = u1.x; g1[dy][2] = u1.y; g0[dy][3] = u1.z; g1[dy][3] = u1.w;
+        }
+        int v[3][4], f[2][4], ob[2][4], og[2][4], orr[2][4];
+        DS_UNROLL
+        for (int r = 0; r < 3; r++) { DS_UNROLL for (int k = 0; k < 4; k++) v[r][k] = sx16(w0[r][k]); }
+        DS_UNROLL
+        for (int dy = 0; dy < 2; dy++) { DS_UNROLL for (int k = 0; k < 4; k++) f[dy][k] = sx16(g0[dy][k]); }
+        chan<FINAL>(v, f, ob);
+        DS_UNROLL
+        for (int r = 0; r < 3; r++) { DS_UNROLL for (int k = 0; k < 4; k++) v[r][k] = (int)w0[r][k] >> 16; }
+        DS_UNROLL
+        for (int dy = 0; dy < 2; dy++) { DS_UNROLL for (int k = 0; k < 4; k++) f[dy][k] = (int)g0[dy][k] >> 16; }
+        chan<FINAL>(v, f, og);
+        DS_UNROLL
+        for (int r = 0; r < 3; r++) { DS_UNROLL for (int k = 0; k < 4; k++) v[r][k] = sx16(w1[r][k]); }
+        DS_UNROLL
+        for (int dy = 0; dy < 2; dy++) { DS_UNROLL for (int k = 0; k < 4; k++) f[dy][k] = sx16(g1[dy][k]); }
+        chan<FINAL>(v, f, orr);
+        DS_UNROLL
+        for (int dy = 0; dy < 2; dy++) {
+            const int Y = 2 * c1y + dy;
+            if (!live[dy]) continue;
+            if (!FINAL) {
+                px16* frow = p.fine + (size_t)Y * fw + Xq;
+                uint32_t a0[4], a1[4];
+                DS_UNROLL
+                for (int k = 0; k < 4; k++) {
+                    a0[k] = ((uint32_t)ob[dy][k] & 0xffffu) | ((uint32_t)og[dy][k] << 16);
+                    a1[k] = ((uint32_t)orr[dy][k] & 0xffffu) | (g1[dy][k] & 0xffff0000u);
+                }
+                *(uint4*)frow = make_u4(a0[0], a1[0], a0[1], a1[1]);
+                *(uint4*)(frow + 2) = make_u4(a0[2], a1[2], a0[3], a1[3]);
+            } else if (Y < p.o.h) {
+                uint32_t px[4];
+                DS_UNROLL
+                for (int k = 0; k < 4; k++) {
+                    const bool m = (g1[dy][k] >> 16) != 0u;
+                    px[k] = m ? ((uint32_t)ob[dy][k] | ((uint32_t)og[dy][k] << 8) | ((uint32_t)orr[dy][k] << 16) | 0xff000000u) : 0u;
+                }
+                if (p.o.fmt == 1) {
+                    *(uint4*)((uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch) + Xq) = make_u4(px[0], px[1], px[2], px[3]);
+                } else {
+                    uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)Xq * 3);
+                    q[0] = (px[0] & 0xffffffu) | (px[1] << 24);
+                    q[1] = ((px[1] >> 8) & 0xffffu) | (px[2] << 16);
+                    q[2] = ((px[2] >> 16) & 0xffu) | (px[3] << 8);
+                    *(uint32_t*)(p.o.mask + (size_t)Y * p.o.mask_pitch + Xq) =
+                        (px[0] >> 24) | ((px[1] >> 24) << 8) | ((px[2] >> 24) << 16) | ((px[3] >> 24) << 24);
+                }
+            }
+        }
     }
 
     template <int NT>
@@ -1702,6 +1811,14 @@ struct CollapseBody {
             if (n <= 0x7fffffffLL) { const unsigned u = (unsigned)idx; rowi = (int)(u / (unsigned)qw); coli = (int)(u - (unsigned)rowi * (unsigned)qw); }
             else { rowi = (int)(idx / qw); coli = (int)(idx - (long long)rowi * qw); }
             const int c1y = m0 + rowi, Xq = coli * 4;
+            {
+                const int c0i = Xq >> 1;
+                if (c0i >= 1 && c0i + 2 <= cw - 1 && c1y >= 1 && c1y + 1 <= chh - 1 && fw - Xq >= 4 && !(cw & 1) && !(fw & 1) &&
+                    (!p.final || Xq + 4 <= p.o.w)) {
+                    if (p.final) item_interior<true>(p, c1y, Xq); else item_interior<false>(p, c1y, Xq);
+                    continue;
+                }
+            }
             // both rows of the pair read coarse rows (l, c, r) around c1y; columns c0-1 .. c0+2 with the pyrUp border rules
             const int ry[3] = {up_l(c1y, chh), c1y, up_r(c1y, chh)};
             const int c0 = Xq >> 1;
@@ -1767,9 +1884,16 @@ struct CollapseBody {
                 int ob[4], og[4], orr[4];
                 DS_UNROLL
                 for (int kx = 0; kx < 4; kx++) {
-                    ob[kx] = up1(hb[0][kx], hb[1][kx], hb[2][kx], oddy, (int)(short)(fw0[kx] & 0xffffu));
-                    og[kx] = up1(hg[0][kx], hg[1][kx], hg[2][kx], oddy, (int)(short)(fw0[kx] >> 16));
-                    orr[kx] = up1(hr[0][kx], hr[1][kx], hr[2][kx], oddy, (int)(short)(fw1[kx] & 0xffffu));
+                    const int fb = (int)(short)(fw0[kx] & 0xffffu), fg = (int)(fw0[kx]) >> 16, fr = (int)(short)(fw1[kx] & 0xffffu);
+                    if (p.final) {
+                        ob[kx] = up1<true>(hb[0][kx], hb[1][kx], hb[2][kx], oddy, fb);
+                        og[kx] = up1<true>(hg[0][kx], hg[1][kx], hg[2][kx], oddy, fg);
+                        orr[kx] = up1<true>(hr[0][kx], hr[1][kx], hr[2][kx], oddy, fr);
+                    } else {
+                        ob[kx] = up1<false>(hb[0][kx], hb[1][kx], hb[2][kx], oddy, fb);
+                        og[kx] = up1<false>(hg[0][kx], hg[1][kx], hg[2][kx], oddy, fg);
+                        orr[kx] = up1<false>(hr[0][kx], hr[1][kx], hr[2][kx], oddy, fr);
+                    }
                 }
                 if (!p.final) {
                     DS_UNROLL
