@@ -11,6 +11,10 @@
 //   A10 pyrUp 16S, A11 MultiBandBlender feed / blend, A12 FeatherBlender.
 #pragma once
 #include "ds_types.h"
+#if !DS_CUDA
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // exact helpers
@@ -1052,6 +1056,37 @@ struct MBFastBody {
             g.border = !(2 * g.gx0 - 2 >= 0 && 2 * g.gx1 + 2 <= g.rw - 1 && 2 * g.gy0 - 2 >= 0 && 2 * g.gy1 + 2 <= g.rh - 1 &&
                          g.jx0 >= 1 && g.jx1 <= n1x - 1 && g.jy0 >= 1 && g.jy1 <= n1y - 1) ? 1 : 0;
             g.pad0 = g.pad1 = 0;
+            if constexpr (!LEVEL0) {
+                // pad0 = "every weight of the needed region is exactly 1", decided from geometry alone: a plane-mapped frame
+                // without per-pixel mask whose level-0 support of the region (radius 2^(l+1) - 2 after l pyrDowns) lies
+                // inside the bbox and maps into the source at its four corners - x(u, v) is monotone in u and in v even in
+                // float arithmetic (the level-0 kernel's interior test), so the corners bound every pixel; the nearest mask
+                // is then 255 throughout, W_0 = 255 * (1 / 255f) = 1 and every pyrDown of all-ones is exactly 1. Such
+                // tile-frames skip the load and the scan of their weight box.
+                if (!g.skip && F.kind == XF_PLANE && !F.seam && F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f) {
+                    const int rl = (2 << l) - 2;
+                    const int u_lo = F.rx + (g.px0 << l) - rl - F.cx, u_hi = F.rx + ((g.px0 + g.pw - 1) << l) + rl - F.cx;
+                    const int v_lo = F.ry + (g.py0 << l) - rl - F.cy, v_hi = F.ry + ((g.py0 + g.ph - 1) << l) + rl - F.cy;
+                    if (u_lo >= 0 && u_hi <= F.w - 1 && v_lo >= 0 && v_hi <= F.h - 1) {
+                        float ca0[2], ca3[2], rb1[2], rb4[2];
+                        DS_UNROLL
+                        for (int e = 0; e < 2; e++) {
+                            float U = (float)(F.tlx + (e ? u_hi : u_lo)), V = (float)(F.tly + (e ? v_hi : v_lo));
+                            if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+                            const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+                            ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
+                            rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
+                        }
+                        float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+                        DS_UNROLL
+                        for (int e = 0; e < 4; e++) {
+                            const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), F.k2one), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), F.k5one);
+                            xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
+                        }
+                        if (xmn >= 0.f && xmx <= (float)(F.src_w - 1) && ymn >= 0.f && ymx <= (float)(F.src_h - 1) && c255 == 1.f) g.pad0 = 1;
+                    }
+                }
+            }
             s_geo[j] = g;
         }
         DS_SYNC();
@@ -1075,9 +1110,9 @@ struct MBFastBody {
             fence_tensormap_acquire(tm);
             fence_tensormap_acquire(tm + 128);
             fence_proxy_async();   // generic-proxy reads of this buffer ended before the last barrier
-            mbar_expect_tx(s_bar + buf, 2 * TMA_BYTES);
+            mbar_expect_tx(s_bar + buf, gg.pad0 ? TMA_BYTES : 2 * TMA_BYTES);
             tma_load_2d(g0_buf(buf), tm, gg.px0, gg.py0, s_bar + buf);
-            tma_load_2d(w_buf(buf), tm + 128, gg.px0, gg.py0, s_bar + buf);
+            if (!gg.pad0) tma_load_2d(w_buf(buf), tm + 128, gg.px0, gg.py0, s_bar + buf);   // weights known to be 1: not loaded
         };
         if (use_tma && tid == 0) { const int j0 = next_live(f_begin); if (j0 < f_end) tma_issue(j0, 0); }
 #endif
@@ -1435,6 +1470,8 @@ struct MBFastBody {
                     float wmn = 1.f, wmx = 0.f;
                     constexpr int Q = PWS / 4;
                     static_assert(PWS % 4 == 0, "rows of the weight box are read as float4");
+                    if (g.pad0) { known_uniform = true; wmx = 1.f; }   // all ones by geometry: the box was not even loaded
+                    else
                     for (int q = tid; q < Q * ph; q += NT) {
                         const int yy = q / Q, x4 = (q - yy * Q) * 4;
                         if (x4 >= pw) continue;
@@ -1465,6 +1502,11 @@ struct MBFastBody {
                     m_and &= (w == 1.f) ? 255 : 0;
                     m_or |= (w != 0.f) ? 255 : 0;
                 }
+#if !DS_CUDA
+                // emulation (tests): the geometric "all ones" claim the TMA path relies on is checked against the data
+                if (g.pad0 && m_and != 255) { fprintf(stderr, "ds emu: level %d tile %d frame %d: weights claimed 1 by geometry are not\n", l, tile, fi); abort(); }
+                if (g.pad0) known_uniform = true;
+#endif
                 }
             }
             const int all255 = (m_and == 255), all0 = (m_or == 0);
