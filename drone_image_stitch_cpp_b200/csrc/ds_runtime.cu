@@ -961,8 +961,13 @@ int prof_mark(ds_canvas* c, stream_t st, bool begin, const char* name, int level
 //   top level      : A/4^L * (20 + 20)
 //   collapse       : C * 17.5 / 4^(l-1) per step into level l-1, minus 2*C for the final uchar4 store
 struct ABModel { double S, A, C; };
+// canvas pixels of the model: the rows this handle owns (a row-band handle composites its band only)
+double ab_canvas_px(const ds_canvas* c) {
+    const int rows = std::max(0, std::min(c->band.hi, c->desc.height) - c->band.lo);
+    return (double)c->desc.width * rows;
+}
 ABModel ab_inputs(const ds_canvas* c) {
-    ABModel m{0, 0, (double)c->desc.width * c->desc.height};
+    ABModel m{0, 0, ab_canvas_px(c)};
     for (const Frame& f : c->frames) if (f.used) { m.S += (double)f.w * f.h; m.A += (double)f.bw * f.bh; }
     return m;
 }
@@ -1937,7 +1942,7 @@ DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
     info->ms_last_composite = c->last_ms;
     info->h2d_bytes_total = c->h2d_bytes;
     // SURVEY.md §8(d) algorithmic-bytes model
-    const double C = (double)c->desc.width * c->desc.height;
+    const double C = ab_canvas_px(c);
     if (c->desc.blend_mode == DS_BLEND_FEATHER) info->algorithmic_bytes = (int64_t)(3.0 * src_px + 4.0 * C);
     else {
         double g = 0, q = 1;
