@@ -61,7 +61,59 @@ def affine_case():
         per_mask=cv2.warpPerspective(full, H, (200, 170), flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT))
 
 
+def global_stage_case():
+    """stitchInterStripsCustom's compose half through cv2 itself (src/stitch_global.cpp:470-486, :643-666 and
+    src/stitch_common.cpp:4-27): warpAffine, buildWarpedContentMask, seam mask NEAREST resize + threshold,
+    buildSoftBlendMask, applyChannelGainInPlace, MultiBandBlender, ->8U, autoCropBlackBorder's rectangle."""
+    rng = np.random.default_rng(55)
+    fw, fh, n, bands = 300, 200, 3, 4
+    ortho = synth.orthophoto(fh * 2 + 100, fw * 2 + 200, 55).numpy()
+    strips, Ms, corners, sizes, seams, gains = [], [], [], [], [], []
+    for i in range(n):
+        th, sc = rng.uniform(-0.12, 0.12), rng.uniform(0.93, 1.07)
+        Hm = np.array([[sc * np.cos(th), -sc * np.sin(th), 30 + i * fw * 0.5], [sc * np.sin(th), sc * np.cos(th), 20 + (i % 2) * fh * 0.35], [0, 0, 1.0]])
+        pts = Hm @ np.array([[0, fw, fw, 0], [0, 0, fh, fh], [1, 1, 1, 1]], np.float64)
+        x0, y0 = int(np.floor(pts[0].min())), int(np.floor(pts[1].min()))
+        bw, bh = max(1, int(np.ceil(pts[0].max())) - x0), max(1, int(np.ceil(pts[1].max())) - y0)
+        M = Hm[:2].copy(); M[0, 2] -= x0; M[1, 2] -= y0
+        img = np.ascontiguousarray(ortho[15 * i:15 * i + fh, 25 * i:25 * i + fw]).copy()
+        yy, xx = np.mgrid[0:fh, 0:fw]
+        img[(yy < 0.1 * xx - 6 * i) | (yy > fh - 10 + 0.03 * xx)] = 0
+        img[60:70, 100:140] = rng.integers(0, 5, (10, 40, 3), dtype=np.uint8)
+        low = np.full((max(4, bh // 6), max(4, bw // 6)), 255, np.uint8)
+        ly, lx = np.mgrid[0:low.shape[0], 0:low.shape[1]]
+        low[(lx > 0.62 * low.shape[1] + 0.15 * ly) if i % 2 == 0 else (lx < 0.3 * low.shape[1] - 0.1 * ly)] = 0
+        low[1, 2] = 1
+        strips.append(img); Ms.append(M); corners.append((x0, y0)); sizes.append((bw, bh)); seams.append(low)
+        gains.append((1.0, 1.0, 1.0) if i == 0 else tuple(float(v) for v in rng.uniform(0.85, 1.2, 3)))
+    x_min, y_min = min(c[0] for c in corners), min(c[1] for c in corners)
+    x_max, y_max = max(c[0] + s_[0] for c, s_ in zip(corners, sizes)), max(c[1] + s_[1] for c, s_ in zip(corners, sizes))
+    blender = cv2.detail_MultiBandBlender(0, bands)
+    blender.prepare((x_min, y_min, x_max - x_min, y_max - y_min))
+    out = {}
+    for i in range(n):
+        warped = cv2.warpAffine(strips[i], Ms[i], sizes[i], flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        content = CR.content_mask_cv2(strips[i], Ms[i], sizes[i])
+        if gains[i] != (1.0, 1.0, 1.0):   # applyChannelGainInPlace: float32 multiply, convertTo(CV_8U)
+            g = np.asarray(gains[i], np.float32)
+            warped = np.clip(np.rint(warped.astype(np.float32) * g[None, None, :]), 0, 255).astype(np.uint8)
+        seam = cv2.resize(seams[i], sizes[i], interpolation=cv2.INTER_NEAREST)
+        _, seam = cv2.threshold(seam, 1.0, 255.0, cv2.THRESH_BINARY)
+        soft = CR.soft_blend_mask_cv2(seam, content, 10.0)
+        blender.feed(warped.astype(np.int16), soft, corners[i])
+        out[f"strip{i}"] = strips[i]; out[f"M{i}"] = Ms[i]; out[f"seam{i}"] = seams[i]
+        out[f"content{i}"] = content; out[f"soft{i}"] = soft; out[f"warped{i}"] = warped
+    res, res_mask = blender.blend(None, None)
+    pano = np.clip(res, 0, 255).astype(np.uint8)
+    rect, _ = CR.auto_crop_rect_cv2(pano)
+    np.savez_compressed(os.path.join(HERE, "global_stage.npz"), n=n, bands=bands, corners=np.array(corners), sizes=np.array(sizes),
+                        gains=np.array(gains, np.float32), pano=pano, mask=res_mask, crop=np.array(rect),
+                        roi=np.array([x_min, y_min, x_max - x_min, y_max - y_min]), cv_version=cv2.__version__, **out)
+    print("global_stage", pano.shape, rect)
+
+
 if __name__ == "__main__":
+    global_stage_case()
     plane_case("compose_mb5", 3, 2, 200, 150, 0.6, 31, 0.4, "multiband", 5)
     plane_case("compose_mb3", 2, 2, 180, 140, 0.5, 32, 1.0, "multiband", 3)
     plane_case("compose_feather", 2, 2, 200, 150, 0.6, 33, 0.37, "feather", 0)
