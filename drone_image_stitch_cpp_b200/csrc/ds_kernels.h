@@ -2039,6 +2039,8 @@ DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_ln, MBFastLN, 256, MBParams, 4)
 DS_DEFINE_KERNEL(ds_mb_feed_generic, MBBodyLN, 256, MBParams, 1)
+typedef MBBody<16, false> MBBodyLN16;
+DS_DEFINE_KERNEL(ds_mb_feed_generic16, MBBodyLN16, 128, MBParams, 1)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 4)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)
 #endif

@@ -428,7 +428,11 @@ void plan_rows(int L, const int* lh, Range band, Range* acc, Range* own) {
     }
 }
 
-int level_tile(int l) { return l == 0 ? 64 : 32; }
+// Tile edge per level: 64 at level 0, 32 above; the top level of a pyramid of 3+ bands runs 16x16 tiles - it has so few
+// pixels that 32x32 tiles leave most SMs idle while each CTA walks its frames serially (cfg2: 63 -> 252 CTAs, 0.039 ->
+// 0.026 ms; at the levels below the extra halo of small tiles costs more than the parallelism gains: level 3 measured
+// 0.050 -> 0.088 ms).
+int level_tile(int l, int L) { return l == 0 ? 64 : ((l == L && L >= 3) ? 16 : 32); }
 
 int fill_frame_dev(ds_canvas* c, Frame& f) {
     FrameDev& d = f.dev;
@@ -1001,6 +1005,7 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     else if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, count, st, MBFastBody<64, true>::smem_bytes());
     else if (l > 0 && l < c->L && c->ln_fast_ok) rc = launch<MBFastBody<32, false>, 256>(mp, count, st, MBFastBody<32, false>::smem_bytes());
     else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, count, st, MBBody<64, true>::smem_bytes());
+    else if (pl.T == 16) rc = launch<MBBody<16, false>, 128>(mp, count, st, MBBody<16, false>::smem_bytes());
     else rc = launch<MBBody<32, false>, 256>(mp, count, st, MBBody<32, false>::smem_bytes());
     if (rc) return rc;
     if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
@@ -1619,7 +1624,7 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
     if (!rc && desc->blend_mode == DS_BLEND_MULTIBAND) {
         for (int l = 0; l <= c->L && !rc; l++) {
             LevelPlan& pl = c->plan[l];
-            pl.T = level_tile(l);
+            pl.T = level_tile(l, c->L);
             pl.tiles_x = (c->lw[l] + pl.T - 1) / pl.T; pl.tiles_y = (c->lh[l] + pl.T - 1) / pl.T;
             pl.own = own[l]; pl.acc = acc[l];
             if (l == 0) c->own0_recompute = own[0];
