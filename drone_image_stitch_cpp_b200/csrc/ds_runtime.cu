@@ -429,7 +429,7 @@ void plan_rows(int L, const int* lh, Range band, Range* acc, Range* own) {
 }
 
 // Tile edge per level: 64 at level 0, 32 above; the top level of a pyramid of 3+ bands runs 16x16 tiles - it has so few
-// pixels that 32x32 tiles leave most SMs idle while each CTA walks its frames serially (cfg2: 63 -> 252 CTAs, 0.039 ->
+// pixels that 32x32 tiles leave most SMs idle while each CTA walks its frames serially (cfg2: 63 -> 234 CTAs, 0.039 ->
 // 0.026 ms; at the levels below the extra halo of small tiles costs more than the parallelism gains: level 3 measured
 // 0.050 -> 0.088 ms).
 int level_tile(int l, int L) { return l == 0 ? 64 : ((l == L && L >= 3) ? 16 : 32); }
