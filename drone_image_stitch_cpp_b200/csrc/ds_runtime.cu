@@ -970,9 +970,16 @@ double ab_canvas_px(const ds_canvas* c) {
     const int rows = std::max(0, std::min(c->band.hi, c->desc.height) - c->band.lo);
     return (double)c->desc.width * rows;
 }
+// share of a frame that falls into the rows this handle owns (1 for a whole-canvas handle): a frame straddling two bands
+// counts once across the handles, and the halo a band recomputes is overhead, not algorithmic work
+double ab_frame_share(const ds_canvas* c, const Frame& f) {
+    const int top = f.corner_y - c->desc.y;
+    const int rows = std::min(top + f.bh, std::min(c->band.hi, c->desc.height)) - std::max(top, c->band.lo);
+    return f.bh > 0 ? (double)std::max(rows, 0) / (double)f.bh : 0.0;
+}
 ABModel ab_inputs(const ds_canvas* c) {
     ABModel m{0, 0, ab_canvas_px(c)};
-    for (const Frame& f : c->frames) if (f.used) { m.S += (double)f.w * f.h; m.A += (double)f.bw * f.bh; }
+    for (const Frame& f : c->frames) if (f.used) { const double k = ab_frame_share(c, f); m.S += k * f.w * f.h; m.A += k * f.bw * f.bh; }
     return m;
 }
 
@@ -1939,7 +1946,7 @@ DS_API int ds_get_info(const ds_canvas* c, ds_canvas_info* info) {
     info->padded_width = c->pw; info->padded_height = c->ph; info->num_bands = c->L;
     int n = 0;
     double src_px = 0, bbox_px = 0;
-    for (const Frame& f : c->frames) if (f.used) { n++; src_px += (double)f.w * f.h; bbox_px += (double)f.bw * f.bh; }
+    for (const Frame& f : c->frames) if (f.used) { n++; const double k = ab_frame_share(c, f); src_px += k * f.w * f.h; bbox_px += k * f.bw * f.bh; }
     info->num_frames = n;
     info->band_y0 = c->band.lo; info->band_y1 = c->band.hi;
     info->device_bytes = c->device_bytes;
