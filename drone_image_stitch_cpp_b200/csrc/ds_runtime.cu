@@ -1366,8 +1366,8 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
         if ((rc = h2d_2d(d_low, (size_t)sw, opts->seam_lowres, sst, (size_t)sw, (size_t)sh, c->up))) return cleanup(rc);
         if ((rc = h2d(d_tab, tab.data(), tab.size() * sizeof(int), c->up))) return cleanup(rc);
         if (!nearest) {
-            SeamUpParams sp{d_low, sw, sh, sw, d_tab, d_tab + f.bw, d_tab + 2 * f.bw, d_tab + 2 * f.bw + f.bh, f.d_seam, f.bw, f.bh};
-            if ((rc = launch<SeamUpBody, 256>(sp, ((long long)plane + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->up, 0))) return cleanup(rc);
+            SeamUpParams up{d_low, sw, sh, sw, d_tab, d_tab + f.bw, d_tab + 2 * f.bw, d_tab + 2 * f.bw + f.bh, f.d_seam, f.bw, f.bh};
+            if ((rc = launch<SeamUpBody, 256>(up, ((long long)plane + SeamUpBody::PER_BLOCK - 1) / SeamUpBody::PER_BLOCK, c->up, 0))) return cleanup(rc);
         }
     } else if (has_full) {
         if ((rc = grow(c, (void**)&f.d_seam, &f.seam_cap, plane))) return rc;
