@@ -484,8 +484,10 @@ struct FeatherBody {
                     const int nk = k_hi - k_lo + 1;
                     const int n = nk * (v_hi - v_lo);
                     int found = 0;
+                    const uint32_t nk_m = div_magic(nk);
                     for (int i = tid; i < n; i += NT) {
-                        const int v = v_lo + i / nk, k = k_lo + i % nk;
+                        const int q_ = div_by(i, nk_m);
+                        const int v = v_lo + q_, k = k_lo + (i - q_ * nk);
                         uint32_t wd = ld_ro(F.mbits + (size_t)v * F.mbits_pitch + k);
                         uint32_t sel = 0xffffffffu;
                         if (k == k_lo) sel &= 0xffffffffu << (u_lo & 31);
@@ -499,8 +501,9 @@ struct FeatherBody {
             const int has_zero = *s_flag;
             if (has_zero) {
                 // 2) expand to bytes: 0 at zero mask pixels, 255 elsewhere (outside bbox = not a source)
+                const uint32_t ww_m = div_magic(ww);
                 for (int i = tid; i < ww * wh; i += NT) {
-                    const int yy = i / ww, xx = i - yy * ww;
+                    const int yy = div_by(i, ww_m), xx = i - yy * ww;
                     const int u = wu0 + xx, v = wv0 + yy;
                     unsigned char d = 255;
                     if ((unsigned)u < (unsigned)F.w && (unsigned)v < (unsigned)F.h) {
