@@ -475,6 +475,34 @@ def case_seam_phase_warps(lib):
         assert corner == tuple(c_) and np.array_equal(img, w_) and np.array_equal(mask, m_)
 
 
+def case_global_stage_edge_sizes(lib):
+    # the mask chain and the crop on degenerate and awkward plane sizes: 1-pixel-wide / -high bboxes, widths around the
+    # 8-column boundary of OpenCV's vector column filter, sizes around the 64-pixel tile of the blur kernel
+    rng = np.random.default_rng(1)
+    img = synth.orthophoto(120, 160, 9).numpy().copy()
+    img[:20, :50] = 0
+    M = np.array([[1.0, 0.03, -3.5], [-0.02, 1.0, -2.25]])
+    for dw, dh in [(1, 1), (1, 40), (40, 1), (2, 2), (7, 200), (8, 200), (9, 200), (200, 3), (65, 65), (64, 64), (63, 129)]:
+        low = (rng.random((max(1, dh // 3), max(1, dw // 3))) > 0.3).astype(np.uint8) * 255
+        cv = CP.Canvas((0, 0, dw, dh), "multiband", 2, lib=lib)
+        cv.upload(0, img, CP.affine_transform(M, (0, 0), (dw, dh)), content_mask=True, seam_lowres=low, seam_nearest=True, soft_mask=10.0)
+        content = O.content_mask(img, M, dw, dh)
+        soft = O.soft_blend_mask(O.threshold_gt1(O.resize_nearest(low, dw, dh)), content, 10.0)
+        assert np.array_equal(cv.frame_mask(0, 1), content), (dw, dh)
+        assert np.array_equal(cv.frame_mask(0, 0), soft), (dw, dh)
+        cv.composite()
+        pano, mask = cv.download()
+        bl = O.MultiBand((0, 0, dw, dh), 2)
+        bl.feed(O.remap_bilinear(img, *O.affine_tables(M, dw, dh), "constant").astype(np.int16), soft, (0, 0))
+        r16, rm = bl.blend()
+        assert np.array_equal(pano, O.s16_to_u8(r16)) and np.array_equal(mask, rm), (dw, dh)
+        try:
+            assert cv.auto_crop_rect() == O.auto_crop_rect(pano), (dw, dh)
+        except L.DroneStitchError as e:
+            assert e.code == L.DS_ERR_UNSUPPORTED
+        cv.close()
+
+
 def case_auto_crop(lib):
     # autoCropBlackBorder's rectangle computed from the canvas in device memory
     rng = np.random.default_rng(41)
@@ -557,6 +585,7 @@ def case_very_wide_canvas(lib):
 
 
 CASES = {
+    "global_stage_edge_sizes": case_global_stage_edge_sizes,
     "windowed_oracle": case_windowed_oracle,
     "seam_phase_warps": case_seam_phase_warps,
     "auto_crop": case_auto_crop,
