@@ -80,6 +80,18 @@ static int global_stage(std::ifstream& f, const char* out_path) {
         out.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
         out.write(reinterpret_cast<const char*>(pano.data.data()), (std::streamsize)pano.data.size());
         out.write(reinterpret_cast<const char*>(mask.data.data()), (std::streamsize)mask.data.size());
+        // autoCropBlackBorder (stitch_app.cpp:262): the rectangle decided on the device, then only that tile downloaded
+        int32_t keep[5] = {0, 0, roi.width, roi.height, 0};
+        try {
+            const ds::Rect r = blender.autoCropRect();
+            keep[0] = r.x; keep[1] = r.y; keep[2] = r.width; keep[3] = r.height; keep[4] = 1;
+        } catch (const ds::Error& e) {
+            if (e.code != DS_ERR_UNSUPPORTED) throw;
+        }
+        out.write(reinterpret_cast<const char*>(keep), sizeof(keep));
+        ds::Image cropped;
+        blender.download(ds::Rect{keep[0], keep[1], keep[2], keep[3]}, cropped);
+        out.write(reinterpret_cast<const char*>(cropped.data.data()), (std::streamsize)cropped.data.size());
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 1;

@@ -139,6 +139,13 @@ def run_global_stage(exe, tmp_path):
     mask = np.frombuffer(raw, np.uint8, w * h, off + 16 + w * h * 3).reshape(h, w)
     assert np.array_equal(mask, refmask)
     assert_blend_parity(pano, O.s16_to_u8(ref16))
+    # the crop: rectangle as the oracle's autoCropBlackBorder picks it (or refused), and pano(rect) downloaded on its own
+    off2 = off + 16 + w * h * 4
+    kx, ky, kw, kh, decided = struct.unpack("<iiiii", raw[off2:off2 + 20])
+    if decided:
+        assert (kx, ky, kw, kh) == O.auto_crop_rect(pano)
+    cropped = np.frombuffer(raw, np.uint8, kw * kh * 3, off2 + 20).reshape(kh, kw, 3)
+    assert np.array_equal(cropped, pano[ky:ky + kh, kx:kx + kw])
 
 
 def test_cpp_global_stage_emu(emu_lib, tmp_path):
