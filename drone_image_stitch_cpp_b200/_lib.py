@@ -24,6 +24,7 @@ EXPORTS = [
     "ds_last_error", "ds_get_info", "ds_version", "ds_debug_get_placement", "ds_debug_get_maps",
     "ds_debug_get_warped", "ds_debug_get_frame_level", "ds_set_profiling", "ds_get_kernel_times",
     "ds_update_frame_opts", "ds_download_frame_mask", "ds_auto_crop_rect", "ds_warp_frame",
+    "ds_global_blend_bands", "ds_plan_row_bands",
 ]
 
 
@@ -123,6 +124,8 @@ class Library:
                                     C.c_void_p, C.c_void_p]
         d.ds_auto_crop_rect.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         d.ds_download_frame_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        d.ds_global_blend_bands.argtypes = [C.c_int, C.c_int, C.c_int]
+        d.ds_plan_row_bands.argtypes = [C.POINTER(ds_canvas_desc), C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32)]
 
     def check(self, rc):
         if rc != DS_OK:

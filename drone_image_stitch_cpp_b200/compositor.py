@@ -71,6 +71,26 @@ def result_roi(rois):
     return (x0, y0, x1 - x0, y1 - y0)
 
 
+def global_blend_bands(canvas_w, canvas_h, configured_bands, lib=None):
+    """Band count of the global stage's blender (/root/reference/src/stitch_global.cpp:632-635)."""
+    lib = lib or L.default_library()
+    return int(lib.dll.ds_global_blend_bands(int(canvas_w), int(canvas_h), int(configured_bands)))
+
+
+def plan_row_bands(roi, rois, n_bands, blend="multiband", bands=5, lib=None):
+    """Row-band edges (ds_plan_row_bands) for `n_bands` handles of one canvas, balanced by the frames' footprints."""
+    lib = lib or L.default_library()
+    d = L.ds_canvas_desc()
+    d.x, d.y, d.width, d.height = [int(v) for v in roi]
+    d.blend_mode = L.DS_BLEND_MULTIBAND if blend == "multiband" else L.DS_BLEND_FEATHER
+    d.num_bands = int(bands)
+    d.sharpness = 0.02
+    flat = (C.c_int32 * (4 * max(len(rois), 1)))(*[int(v) for r in rois for v in r])
+    out = (C.c_int32 * (n_bands + 1))()
+    lib.check(lib.dll.ds_plan_row_bands(C.byref(d), flat, len(rois), int(n_bands), out))
+    return list(out)
+
+
 def warp_frame(img, xf, device=0, lib=None):
     """ds_warp_frame: one frame warped on its own (the seam-phase warps of composePanorama, a strip's warpAffine).
     -> (corner (x, y), warped HxWx3 uint8, warped mask HxW uint8)."""

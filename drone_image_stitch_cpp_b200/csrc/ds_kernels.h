@@ -11,6 +11,7 @@
 //   A10 pyrUp 16S, A11 MultiBandBlender feed / blend, A12 FeatherBlender.
 #pragma once
 #include "ds_types.h"
+#include <type_traits>
 #if !DS_CUDA
 #include <stdio.h>
 #include <stdlib.h>
@@ -185,6 +186,16 @@ DS_D bool pd_h_is_simd(int j, int w, int dw) {
 }
 DS_D bool pd_v_is_simd(int j, int dw) { return j < (dw & ~3); }
 
+#if !DS_CUDA
+// emulation only: how many tile-frames took which level-0 warp path (DS_EMU_STATS=1 prints them at exit)
+static long long g_emu_paths[5];
+static void ds_emu_report() { fprintf(stderr, "[ds emu] level-0 tile-frames: interior %lld, gap %lld, edge %lld, general-fast %lld, per-pixel %lld\n", g_emu_paths[0], g_emu_paths[1], g_emu_paths[2], g_emu_paths[3], g_emu_paths[4]); }
+static inline void ds_emu_count(int k) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DS_EMU_STATS"); on = (e && atoi(e) > 0) ? 1 : 0; if (on) atexit(ds_emu_report); }
+    if (on) { _Pragma("omp atomic") g_emu_paths[k]++; }
+}
+#endif
 constexpr int ds_al16(int v) { return (v + 15) & ~15; }  // every smem section starts 16-B aligned
 constexpr int ds_al128(int v) { return (v + 127) & ~127; }  // TMA destinations need 128 B
 
@@ -960,6 +971,7 @@ DS_D void fence_tensormap_acquire(const void* tmap) {
 // <= 64 frames; longer lists go to the generic kernel).
 
 template <bool V> struct BoolTag { static constexpr bool value = V; };
+template <int V> struct IntTag { static constexpr int value = V; };
 struct L0Col { float a0, a3, a6; int u; };  // u = bbox column if inside the bbox, else ~(reflected column)
 struct L0Row { float b1, b4, b7; int v; };
 
@@ -980,7 +992,8 @@ struct MBFastBody {
     static constexpr int MAXF = 64;                            // frames per tile the packed accumulators allow (host-checked)
     static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
     static constexpr int FDEV_BYTES = (int)((sizeof(FrameDev) + 15) & ~(size_t)15);
-    static constexpr int FDEV_OFF = GEO_OFF + MAXF * 96;      // two FrameDev slots: current frame / prefetch of the next
+    static constexpr int GEO_BYTES = (LEVEL0 && !AFF) ? 112 : 96;   // sizeof(TFGeo)
+    static constexpr int FDEV_OFF = GEO_OFF + MAXF * GEO_BYTES;      // two FrameDev slots: current frame / prefetch of the next
     // levels >= 1: second copy of the G / W boxes so the TMA load of the next frame overlaps this frame's compute
     static constexpr int G0B_OFF = ds_al128(FDEV_OFF + 2 * FDEV_BYTES);   // TMA destinations: 128-B aligned
     static constexpr int W0B_OFF = G0B_OFF + (LEVEL0 ? 0 : G0_BYTES);
@@ -998,6 +1011,73 @@ struct MBFastBody {
         int ph, jx0, jx1, jy0;
         int jy1, border, pad0, pad1;
     };
+    // level 0, plane-only kernel: which warp loop the tile-frame takes (decided once, by the thread that builds its entry)
+    struct alignas(16) TFGeo0 : TFGeo {
+        int mode;         // -1: per-pixel loop; 0 / 1 / 2: v2 loop interior / gap / edge
+        int gap_all0;     // mode 1: the needed region misses the bbox altogether (mask 0 throughout)
+        long long boff;   // modes 0 / 1: byte offset of the biased tap address base from F.src
+    };
+    typedef typename std::conditional<(LEVEL0 && !AFF), TFGeo0, TFGeo>::type Geo;
+    static_assert(sizeof(Geo) == GEO_BYTES, "TFGeo layout");
+    // mirrored index interval [mn, mx] of [lo, hi] on an axis of length n (single reflection only)
+    DS_DM bool fold_range(int lo, int hi, int n, int& mn, int& mx) {
+        if (lo < -n || hi >= 2 * n) return false;
+        mn = lo >= 0 ? imin(lo, n - 1) : (hi >= 0 ? 0 : -hi - 1);
+        mx = hi < n ? imax(hi, 0) : (lo < n ? n - 1 : 2 * n - 1 - lo);
+        if (lo < 0) mx = imax(mx, imin(-lo - 1, n - 1));
+        if (hi >= n) mn = imin(mn, imax(2 * n - 1 - hi, 0));
+        return true;
+    }
+    // Which v2 warp loop a tile-frame of the plane-only kernel can take (see the loop for the modes). The region's bbox
+    // indices (mirrored into the bbox where it lies in the gap of the feed ROI) cover one contiguous interval per axis,
+    // and x(u, v) is monotone in u and in v even in float arithmetic (a chain of monotone roundings), so the values at
+    // the interval ends bound every pixel.
+    DS_DM void classify_plane(const FrameDev& F, TFGeo0& g, int flags) {
+        g.mode = -1; g.gap_all0 = 0; g.boff = 0;
+        const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
+        if (g.skip || proj || F.kind != XF_PLANE || F.seam || F.gainmap || F.any_gain) return;
+        const int sw = F.src_w, sh = F.src_h, pitch = F.src_pitch;
+        if (sw > 32768 || sh > 32768) return;   // the remap tables saturate at 16 bits; the biased rounding needs |32 x| < 2^22
+        const int u_lo = g.rx + g.px0 - F.cx, u_hi = u_lo + g.pw - 1, v_lo = g.ry + g.py0 - F.cy, v_hi = v_lo + g.ph - 1;
+        int umn = 0, umx = 0, vmn = 0, vmx = 0;
+        if (!fold_range(u_lo, u_hi, F.w, umn, umx) || !fold_range(v_lo, v_hi, F.h, vmn, vmx)) return;
+        float ca0[2], ca3[2], rb1[2], rb4[2];
+        DS_UNROLL
+        for (int e = 0; e < 2; e++) {
+            float U = (float)(F.tlx + (e ? umx : umn)), V = (float)(F.tly + (e ? vmx : vmn));
+            if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+            const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+            ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
+            rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
+        }
+        float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+        DS_UNROLL
+        for (int e = 0; e < 4; e++) {
+            const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), F.k2one), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), F.k5one);
+            xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
+        }
+        const bool inbounds = xmn >= 1.f && xmx <= (float)(sw - 3) && ymn >= 1.f && ymx <= (float)(sh - 3);
+        const bool interior = inbounds && u_lo >= 0 && u_hi < F.w && v_lo >= 0 && v_hi < F.h;
+        if (!interior && !(flags & 1)) return;
+        if (inbounds) {
+            // Tap addresses are formed from the biased mantissas directly: with C = bias >> 5,
+            // t = (sy + C) * pitch + (sx + C) mod 2^32 = off + K, and base' = base + 4 * (off_lo - u_lo) makes
+            // base' + 4 * t the tap address as long as u_lo + span does not wrap
+            constexpr int CB = DS_RND_BIAS >> 5;
+            const long long off_lo = (long long)((int)floorf(ymn) - 1) * pitch + ((int)floorf(xmn) - 1);
+            const long long off_hi = (long long)((int)floorf(ymx) + 3) * pitch + ((int)floorf(xmx) + 3);
+            const uint32_t K32 = (uint32_t)CB * (uint32_t)pitch + (uint32_t)CB;
+            const uint32_t u_lo32 = (uint32_t)off_lo + K32;
+            if (off_lo < 0 || (unsigned long long)u_lo32 + (unsigned long long)(off_hi - off_lo) > 0xFFFFFFFFull) return;   // one in ~10^4
+            g.boff = 4 * (off_lo - (long long)u_lo32);
+            g.mode = interior ? 0 : 1;
+            g.gap_all0 = (u_hi < 0 || u_lo >= F.w || v_hi < 0 || v_lo >= F.h) ? 1 : 0;
+        } else if (F.border != BORDER_CONST &&
+                   xmn >= -(float)(sw - 1) && xmx <= (float)(2 * sw - 3) && ymn >= -(float)(sh - 1) && ymx <= (float)(2 * sh - 3) &&
+                   xmx <= 32766.f && ymx <= 32766.f) {
+            g.mode = 2;   // some taps leave the source, but by less than its size: one reflection resolves them
+        }
+    }
 
     // 5-tap [1 4 6 4 1] on packed lanes
     DS_DM uint32_t tap5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a + e + 6u * c + 4u * (b + d); }
@@ -1036,11 +1116,11 @@ struct MBFastBody {
 #endif
         DS_SYNC();
 
-        TFGeo* s_geo = (TFGeo*)(smem + GEO_OFF);
+        Geo* s_geo = (Geo*)(smem + GEO_OFF);
         const int f_begin = p.tile_off[tile], f_end = p.tile_off[tile + 1];
         for (int j = tid; j < f_end - f_begin && j < MAXF; j += NT) {
             const FrameDev& F = p.frames[p.tile_frames[f_begin + j]];
-            TFGeo g;
+            Geo g;
             g.rx = F.rx >> l; g.ry = F.ry >> l; g.rw = F.rw >> l; g.rh = F.rh >> l;
             g.ax0 = imax(X0, g.rx); g.ax1 = imin(X0 + T, g.rx + g.rw);
             g.ay0 = imax(imax(Y0, g.ry), p.own_y0); g.ay1 = imin(imin(Y0 + T, g.ry + g.rh), p.own_y1);
@@ -1090,6 +1170,7 @@ struct MBFastBody {
                     }
                 }
             }
+            if constexpr (LEVEL0 && !AFF) classify_plane(F, g, p.flags);
             s_geo[j] = g;
         }
         DS_SYNC();
@@ -1108,7 +1189,7 @@ struct MBFastBody {
         // the current one is processed (two buffers, two mbarriers)
         auto next_live = [&](int from) { int j = from; while (j < f_end && s_geo[j - f_begin].skip) j++; return j; };
         auto tma_issue = [&](int fi_, int buf) {
-            const TFGeo gg = s_geo[fi_ - f_begin];
+            const Geo gg = s_geo[fi_ - f_begin];
             const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fi_] * DS_MAXL + l) * 2 * 128;
             fence_tensormap_acquire(tm);
             fence_tensormap_acquire(tm + 128);
@@ -1122,27 +1203,33 @@ struct MBFastBody {
         DS_SYNC();
 
         for (int fi = f_begin; fi < f_end; fi++) {
-            const TFGeo g = s_geo[fi - f_begin];
             if (fi + 1 < f_end) stage_frame(fi + 1);   // slot ((fi + 1) & 1) was last read in iteration fi - 1
-            if (g.skip) { DS_SYNC(); continue; }       // block-uniform
             const FrameDev& F = *(const FrameDev*)(smem + FDEV_OFF + (fi & 1) * FDEV_BYTES);
-            const int rx = g.rx, ry = g.ry, rw = g.rw, rh = g.rh;
-            const int ax0 = g.ax0, ax1 = g.ax1, ay0 = g.ay0, ay1 = g.ay1;
-            const int n1x = rw >> 1, n1y = rh >> 1;
-            const int jx0 = g.jx0, jx1 = g.jx1, jy0 = g.jy0, jy1 = g.jy1;
-            const int gx0 = g.gx0, gx1 = g.gx1, gy0 = g.gy0, gy1 = g.gy1;
-            const int px0 = g.px0, py0 = g.py0, pw = g.pw, ph = g.ph;
-            const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
-            const int jw = jx1 - jx0, jh = jy1 - jy0;
-            const bool border = g.border != 0;
+            int m_and = 255, m_or = 0;   // level 0: AND / OR of the mask bytes; levels >= 1: 255 / 0 flags of (w == 1) / (w != 0)
+            int known_votes = -1;        // >= 0: the uniformity of the mask is known without a block-wide vote (bit 0: all 255, bit 1: all 0)
+            // The tile-frame geometry is read from shared memory twice - here and again after the warp loop - so that it
+            // does not stay in registers across the loop: at 64 registers per thread that spilled ~25 values per thread and
+            // tile-frame to local memory, and with 216 of the SM's 228 KB taken by shared memory the L1 does not hold a
+            // CTA's stack (the spill traffic to L2 was as large as the source reads).
+#define DS_TF_LOCALS                                                                     \
+            const int rx = g.rx, ry = g.ry, rw = g.rw, rh = g.rh;                         \
+            const int ax0 = g.ax0, ax1 = g.ax1, ay0 = g.ay0, ay1 = g.ay1;                 \
+            const int n1x = rw >> 1, n1y = rh >> 1;                                       \
+            const int jx0 = g.jx0, jx1 = g.jx1, jy0 = g.jy0, jy1 = g.jy1;                 \
+            const int gx0 = g.gx0, gx1 = g.gx1, gy0 = g.gy0, gy1 = g.gy1;                 \
+            const int px0 = g.px0, py0 = g.py0, pw = g.pw, ph = g.ph;                     \
+            const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;                             \
+            const int jw = jx1 - jx0, jh = jy1 - jy0;                                     \
+            const bool border = g.border != 0;                                            \
+            (void)rx; (void)ry; (void)rw; (void)rh; (void)ax0; (void)ax1; (void)ay0; (void)ay1; (void)n1x; (void)n1y; \
+            (void)jx0; (void)jx1; (void)jy0; (void)jy1; (void)gx0; (void)gy0; (void)px0; (void)py0; (void)pw; (void)ph; \
+            (void)gw; (void)gh; (void)jw; (void)jh; (void)border;
+            if (s_geo[fi - f_begin].skip) { DS_SYNC(); continue; }       // block-uniform
+            {   // ======== first half: tables + phase 1
+            const Geo g = s_geo[fi - f_begin];
+            DS_TF_LOCALS
             const bool affine = AFF && LEVEL0 && F.kind == XF_AFFINE;   // cv::warpAffine coordinates (integer tables)
             const bool proj = !affine && !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
-            uint32_t* const G1out = (uint32_t*)F.G[l + 1];
-            float* const W1out = F.W[l + 1];
-            const int op1 = F.gp[l + 1];   // row pitch of the level-(l+1) arrays
-
-            int m_and = 255, m_or = 0;   // level 0: AND / OR of the mask bytes; levels >= 1: 255 / 0 flags of (w == 1) / (w != 0)
-            bool known_uniform = false;  // the mask is known to be 255 everywhere without a block-wide vote
             if constexpr (LEVEL0) {
             // ---- tables: reflected bbox index + per-column / per-row map terms
             for (int i = tid; i < PWS + ph; i += NT) {
@@ -1187,7 +1274,7 @@ struct MBFastBody {
             // L2 prefetch (TMA) of the source footprint of the NEXT frame of this tile: its descriptor was staged
             // at the top of this iteration and is visible after the barrier above. One thread, fire and forget.
             if (p.tmaps != nullptr && tid == 0 && fi + 1 < f_end) {
-                const TFGeo ng = s_geo[fi + 1 - f_begin];
+                const Geo ng = s_geo[fi + 1 - f_begin];
                 const FrameDev& N = *(const FrameDev*)(smem + FDEV_OFF + ((fi + 1) & 1) * FDEV_BYTES);
                 if (!ng.skip && N.kind == XF_PLANE) {
                     const int u_lo = ng.rx + ng.px0 - N.cx, u_hi = u_lo + ng.pw - 1, v_lo = ng.ry + ng.py0 - N.cy, v_hi = v_lo + ng.ph - 1;
@@ -1228,20 +1315,12 @@ struct MBFastBody {
                 // bound every pixel: no border handling, no cvRound patch, nearest mask = "inside the bbox".
                 // `interior`: the region is inside the bbox as well, so the mask is 255 everywhere.
                 bool inbounds = false, interior = false;
-                if (!proj && (AFF || (!seam && !F.gainmap))) {
+                if constexpr (AFF) {
+                if (!proj) {
                     const int u_lo = rx + px0 - F.cx, u_hi = u_lo + pw - 1, v_lo = ry + py0 - F.cy, v_hi = v_lo + ph - 1;
-                    // mirrored index interval [mn, mx] of [lo, hi] on an axis of length n (single reflection only)
-                    auto fold = [](int lo, int hi, int n, int& mn, int& mx) {
-                        if (lo < -n || hi >= 2 * n) return false;
-                        mn = lo >= 0 ? imin(lo, n - 1) : (hi >= 0 ? 0 : -hi - 1);
-                        mx = hi < n ? imax(hi, 0) : (lo < n ? n - 1 : 2 * n - 1 - lo);
-                        if (lo < 0) mx = imax(mx, imin(-lo - 1, n - 1));
-                        if (hi >= n) mn = imin(mn, imax(2 * n - 1 - hi, 0));
-                        return true;
-                    };
                     int umn = 0, umx = 0, vmn = 0, vmx = 0;
                     if (affine) {
-                        if (fold(u_lo, u_hi, F.w, umn, umx) && fold(v_lo, v_hi, F.h, vmn, vmx)) {
+                        if (fold_range(u_lo, u_hi, F.w, umn, umx) && fold_range(v_lo, v_hi, F.h, vmn, vmx)) {
                             int xmn = 0x7fffffff, xmx = (int)0x80000000, ymn = 0x7fffffff, ymx = (int)0x80000000;
                             DS_UNROLL
                             for (int e = 0; e < 4; e++) {
@@ -1254,7 +1333,7 @@ struct MBFastBody {
                             interior = inbounds && u_lo >= 0 && u_hi < F.w && v_lo >= 0 && v_hi < F.h;
                             if (!interior && !(p.flags & 1)) inbounds = false;
                         }
-                    } else if (fold(u_lo, u_hi, F.w, umn, umx) && fold(v_lo, v_hi, F.h, vmn, vmx)) {
+                    } else if (fold_range(u_lo, u_hi, F.w, umn, umx) && fold_range(v_lo, v_hi, F.h, vmn, vmx)) {
                         float ca0[2], ca3[2], rb1[2], rb4[2];
                         DS_UNROLL
                         for (int e = 0; e < 2; e++) {
@@ -1275,7 +1354,147 @@ struct MBFastBody {
                         if (!interior && !(p.flags & 1)) inbounds = false;
                     }
                 }
-                if (inbounds) {
+                }
+                bool v2_done = false;
+                if constexpr (!AFF) {
+                // ---- v2 warp loop (plane maps without perspective terms, no per-pixel inputs). One thread per region
+                // column: the column's map terms stay in registers, the row's terms come from one broadcast shared
+                // load, so a pixel costs four adds and two fused multiply-adds (cvRound(32 x) as the mantissa of
+                // x * 32 + 1.5 * 2^23: 32 x is exact, the sum rounds once, half to even - cvRound without the XU pipe),
+                // an address, four taps, and the 15-bit bilinear as two-way dot products with 16-bit 2-D weights
+                // ((32-ax)(32-ay) | ax(32-ay) << 16 etc.: dp2a) instead of byte dot products plus a vertical pass.
+                //   MODE 0  region inside the bbox, taps inside the source: mask 255
+                //   MODE 1  region reaches into the gap of the feed ROI (mirrored bbox indices): mask 0 there
+                //   MODE 2  taps may leave the source (BORDER_REFLECT, one reflection), nearest mask per pixel
+                // Tap addresses in modes 0 / 1 are formed from the biased mantissas directly: with C = bias >> 5,
+                // t = (sy + C) * pitch + (sx + C) mod 2^32 = off + K, and base' = base + 4 * (off_lo - u_lo) makes
+                // base' + 4 * t the tap address as long as u_lo + span does not wrap (checked here, per tile-frame).
+                constexpr int CB = DS_RND_BIAS >> 5;
+                const bool v2 = g.mode >= 0;
+                const char* const basep = (const char*)src + g.boff;
+                interior = g.mode == 0; inbounds = g.mode == 0 || g.mode == 1;
+                const bool gap_all0 = g.gap_all0 != 0;
+                if (v2) {
+                    const SAddr a_col = s_addr(s_col), a_row = s_addr(s_row), a_g0 = s_addr(s_g0);
+                    constexpr int NTV = 512, RG = NTV / 64;          // 64 columns x 8 row groups
+                    static_assert((PHM + RG - 1) / RG == 9 && PWS - 64 == 8, "v2 warp loop layout");
+                    struct PX { int bx, by; uint32_t p00, p01, p10, p11; int aux; };
+                    auto fetch = [&](auto mode_tag, float ca0, float ca3, int cu, int r, PX& q) {
+                        constexpr int MODE = decltype(mode_tag)::value;
+                        float rb1, rb4; int rv = 0;
+                        if constexpr (MODE == 0) lds_f2(a_row + r * 16, rb1, rb4);
+                        else { uint32_t w0, w1, w2, w3; lds_u4(a_row + r * 16, w0, w1, w2, w3); rb1 = i2f_bits((int)w0); rb4 = i2f_bits((int)w1); rv = (int)w3; }
+                        const float x = f_add(f_add(ca0, rb1), k2), y = f_add(f_add(ca3, rb4), k5);
+                        q.bx = rnd32_bits(x); q.by = rnd32_bits(y);
+                        if constexpr (MODE != 2) {
+                            const uint32_t t = (uint32_t)(q.by >> 5) * (uint32_t)pitch + (uint32_t)(q.bx >> 5);
+                            const uint32_t* r0 = (const uint32_t*)(basep + 4ull * (unsigned long long)t);
+                            const uint32_t* r1 = (const uint32_t*)(basep + 4ull * (unsigned long long)(t + (uint32_t)pitch));
+                            q.p00 = ld_ro(r0); q.p01 = ld_ro(r0 + 1); q.p10 = ld_ro(r1); q.p11 = ld_ro(r1 + 1);
+                            q.aux = rv;
+                        } else {
+                            const int sx = (q.bx >> 5) - CB, sy = (q.by >> 5) - CB;
+                            // one reflection: p < 0 -> -p - 1, p >= n -> 2n - 1 - p
+                            auto refl1 = [](int p_, int n_) { const int q_ = p_ ^ (p_ >> 31); return imin(q_, 2 * n_ - 1 - q_); };
+                            const int x0 = refl1(sx, sw), x1 = refl1(sx + 1, sw), y0 = refl1(sy, sh), y1 = refl1(sy + 1, sh);
+                            const uint32_t* ra = src + (size_t)y0 * pitch; const uint32_t* rb = src + (size_t)y1 * pitch;
+                            q.p00 = ld_ro(ra + x0); q.p01 = ld_ro(ra + x1); q.p10 = ld_ro(rb + x0); q.p11 = ld_ro(rb + x1);
+                            const int nx = rnd1_bits(x) - DS_RND_BIAS, ny = rnd1_bits(y) - DS_RND_BIAS;
+                            q.aux = ((cu | rv) >= 0 && (unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255 : 0;
+                        }
+                    };
+                    auto finish = [&](auto mode_tag, const PX& q, SAddr dst, bool store, bool count, uint32_t cmask) {
+                        constexpr int MODE = decltype(mode_tag)::value;
+                        const uint32_t ax = (uint32_t)q.bx & 31u, ay = (uint32_t)q.by & 31u;
+                        const uint32_t wxp = ax * 65535u + 32u;                     // (32 - ax) | ax << 16
+                        const uint32_t wbot = wxp * ay, wtop = wxp * 32u - wbot;    // rows weighted by ay / 32 - ay
+                        const uint32_t t0 = byte_perm(q.p00, q.p01, 0x5140), t0r = byte_perm(q.p00, q.p01, 0x6262);
+                        const uint32_t t1 = byte_perm(q.p10, q.p11, 0x5140), t1r = byte_perm(q.p10, q.p11, 0x6262);
+                        // (sum + 2^14) >> 15 of OpenCV's weights * 32 == (sum + 512) >> 10
+                        const uint32_t sb = dot2lo(wbot, t1, dot2lo(wtop, t0, 512u));
+                        const uint32_t sg = dot2hi(wbot, t1, dot2hi(wtop, t0, 512u));
+                        // the mask byte rides in the red accumulator: (s + 512 + (m << 18)) >> 10 == r + (m << 8); every sum,
+                        // shifted left by 6, holds its 8-bit result in byte 2 (and red's mask in byte 3): two byte permutes pack
+                        uint32_t minit;
+                        if constexpr (MODE == 0) minit = 512u + (0xFFu << 18);
+                        else if constexpr (MODE == 1) minit = 512u + ((cmask & ~(uint32_t)(q.aux >> 31)) >> 6);
+                        else minit = 512u + ((uint32_t)q.aux << 18);
+                        const uint32_t sr = dot2lo(wbot, t1r, dot2lo(wtop, t0r, minit));
+                        const uint32_t val = byte_perm(byte_perm(sb << 6, sg << 6, 0x0062), sr << 6, 0x7610);
+                        if constexpr (MODE == 2) { if (count) { m_and &= q.aux; m_or |= q.aux; } }
+                        if (store) sts_u1(dst, val);
+                    };
+                    auto run_v2 = [&](auto mode_tag) {
+                        for (int vt = tid; vt < NTV; vt += NT) {   // a single trip on the GPU (NT == NTV)
+                            {
+                                const int col = vt & 63, rg = vt >> 6;
+                                uint32_t c0, c1, c2, c3;
+                                lds_u4(a_col + col * 16, c0, c1, c2, c3);
+                                const float ca0 = i2f_bits((int)c0), ca3 = i2f_bits((int)c1);
+                                const int cu = (int)c3;
+                                const uint32_t cmask = cu >= 0 ? 0xff000000u : 0u;
+                                const bool count = col < pw;
+                                const SAddr d0 = a_g0 + (rg * PWS + col) * 4;
+                                // rows rg + 8k, k = 0..8, software-pipelined in two register sets of two rows: the taps of
+                                // the next set are requested before this one is interpolated (occupancy is 2 CTAs / SM;
+                                // other warps alone do not cover an L2 round trip)
+                                PX A[2], B[2];
+                                auto row_of = [&](int k) { return imin(rg + RG * k, ph - 1); };
+                                auto fin = [&](const PX& q, int k) {
+                                    const bool live = rg + RG * k < ph;
+                                    finish(mode_tag, q, d0 + k * (RG * PWS * 4), live, live && count, cmask);
+                                };
+                                fetch(mode_tag, ca0, ca3, cu, row_of(0), A[0]); fetch(mode_tag, ca0, ca3, cu, row_of(1), A[1]);
+                                fetch(mode_tag, ca0, ca3, cu, row_of(2), B[0]); fetch(mode_tag, ca0, ca3, cu, row_of(3), B[1]);
+                                fin(A[0], 0); fin(A[1], 1);
+                                fetch(mode_tag, ca0, ca3, cu, row_of(4), A[0]); fetch(mode_tag, ca0, ca3, cu, row_of(5), A[1]);
+                                fin(B[0], 2); fin(B[1], 3);
+                                fetch(mode_tag, ca0, ca3, cu, row_of(6), B[0]); fetch(mode_tag, ca0, ca3, cu, row_of(7), B[1]);
+                                fin(A[0], 4); fin(A[1], 5);
+                                fetch(mode_tag, ca0, ca3, cu, row_of(8), A[0]);
+                                fin(B[0], 6); fin(B[1], 7);
+                                fin(A[0], 8);
+                            }
+                            if (pw > 64) {
+                                // the 8 columns beyond the 64: items of (row, column) over the same virtual threads
+                                PX q[2]; int rr[2], cc[2]; uint32_t cm[2];
+                                DS_UNROLL
+                                for (int j = 0; j < 2; j++) {
+                                    const int e = vt + NTV * j;
+                                    rr[j] = e >> 3; cc[j] = 64 + (e & 7);
+                                    uint32_t c0, c1, c2, c3;
+                                    lds_u4(a_col + cc[j] * 16, c0, c1, c2, c3);
+                                    cm[j] = (int)c3 >= 0 ? 0xff000000u : 0u;
+                                    if (rr[j] < ph || j == 0) fetch(mode_tag, i2f_bits((int)c0), i2f_bits((int)c1), (int)c3, imin(rr[j], ph - 1), q[j]);
+                                }
+                                DS_UNROLL
+                                for (int j = 0; j < 2; j++) {
+                                    const bool live = rr[j] < ph;
+                                    if (live) finish(mode_tag, q[j], a_g0 + (rr[j] * PWS + cc[j]) * 4, true, cc[j] < pw, cm[j]);
+                                }
+                            }
+                        }
+                    };
+#if !DS_CUDA
+                    ds_emu_count(interior ? 0 : (inbounds ? 1 : 2));
+#endif
+                    if (interior) {
+                        run_v2(IntTag<0>());
+                        m_or = 255; known_votes = 1;                 // uniform 255
+                    } else if (inbounds) {
+                        run_v2(IntTag<1>());
+                        known_votes = gap_all0 ? 2 : 0;              // not inside the bbox: never uniform 255
+                    } else {
+                        run_v2(IntTag<2>());
+                    }
+                    v2_done = true;
+                }
+                }
+#if !DS_CUDA
+                if (!v2_done) ds_emu_count(AFF && inbounds ? 3 : 4);
+#endif
+                if (v2_done) {
+                } else if (AFF && inbounds) {
                     // Software-pipelined in two register sets of UB pixels per thread: the taps of stage k+1 are
                     // requested before stage k is interpolated, so the L1 / L2 latency of the gathers hides behind
                     // the arithmetic of the same warp (occupancy is 2 CTAs / SM; other warps alone do not cover it).
@@ -1387,7 +1606,7 @@ struct MBFastBody {
                     }
                     if (plain) {
                         m_or = 255;   // m_and stays 255: the mask is uniform 255
-                        known_uniform = true;
+                        known_votes = 1;
                     }
                 } else
                 for (int i = tid; i < PWS * ph; i += NT) {
@@ -1473,7 +1692,7 @@ struct MBFastBody {
                     float wmn = 1.f, wmx = 0.f;
                     constexpr int Q = PWS / 4;
                     static_assert(PWS % 4 == 0, "rows of the weight box are read as float4");
-                    if (g.pad0) { known_uniform = true; wmx = 1.f; }   // all ones by geometry: the box was not even loaded
+                    if (g.pad0) { known_votes = 1; wmx = 1.f; }   // all ones by geometry: the box was not even loaded
                     else
                     for (int q = tid; q < Q * ph; q += NT) {
                         const int yy = q / Q, x4 = (q - yy * Q) * 4;
@@ -1508,15 +1727,29 @@ struct MBFastBody {
 #if !DS_CUDA
                 // emulation (tests): the geometric "all ones" claim the TMA path relies on is checked against the data
                 if (g.pad0 && m_and != 255) { fprintf(stderr, "ds emu: level %d tile %d frame %d: weights claimed 1 by geometry are not\n", l, tile, fi); abort(); }
-                if (g.pad0) known_uniform = true;
+                if (g.pad0) known_votes = 1;
 #endif
                 }
             }
+            }   // ======== end of the first half
+            {   // ======== second half: votes, pyrDown, Laplacian + accumulate
+            Geo g;
+            {
+                uint32_t gwords[GEO_BYTES / 4];
+                const SAddr ga = s_addr(s_geo + (fi - f_begin));
+                DS_UNROLL
+                for (int k = 0; k < GEO_BYTES / 16; k++) lds_u4(ga + k * 16, gwords[4 * k], gwords[4 * k + 1], gwords[4 * k + 2], gwords[4 * k + 3]);
+                memcpy(&g, gwords, sizeof(g));
+            }
+            DS_TF_LOCALS
+            uint32_t* const G1out = (uint32_t*)F.G[l + 1];
+            float* const W1out = F.W[l + 1];
+            const int op1 = F.gp[l + 1];   // row pitch of the level-(l+1) arrays
             const int all255 = (m_and == 255), all0 = (m_or == 0);
             int uni255, uni0;
-            if (known_uniform) {
+            if (known_votes >= 0) {
                 DS_SYNC();
-                uni255 = (c255 == 1.f); uni0 = 0;
+                uni255 = (known_votes & 1) && (c255 == 1.f); uni0 = (known_votes & 2) != 0;
             } else {
                 // one barrier for both votes: bit 0 = some weight is not 1, bit 1 = some weight is not 0
                 const int bits = block_or_bits((all255 ? 0 : 1) | (all0 ? 0 : 2), s_vote);
@@ -1678,6 +1911,8 @@ struct MBFastBody {
                     }
                 }
             }
+            }   // ======== end of the second half
+#undef DS_TF_LOCALS
             DS_SYNC();
         }
 

@@ -835,7 +835,7 @@ int build_lists(ds_canvas* c) {
                 for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32 && f.xf.kind != DS_XF_AFFINE_F64) all_plane = false;
                 c->l0_fast_ok = all_plane && longest <= 64;
                 c->l0_has_affine = false;
-                for (const Frame& f : c->frames) if (f.used && (f.xf.kind == DS_XF_AFFINE_F64 || f.d_seam || f.d_gainmap)) c->l0_has_affine = true;
+                for (const Frame& f : c->frames) if (f.used && (f.xf.kind == DS_XF_AFFINE_F64 || f.d_seam || f.d_gainmap || f.dev.any_gain)) c->l0_has_affine = true;
                 c->ln_fast_ok = true;
             } else if (longest > 64) {
                 c->ln_fast_ok = false;
@@ -1568,6 +1568,52 @@ DS_API int ds_frame_touches_band(const ds_canvas_desc* desc, const int32_t fr[4]
     }
     y0 = fr[1] - desc->y; y1 = y0 + fr[3];
     return (y0 < band.hi && y1 > band.lo) ? 1 : 0;
+}
+
+DS_API int ds_global_blend_bands(int canvas_w, int canvas_h, int configured_bands) {
+    if (canvas_w <= 0 || canvas_h <= 0) return -1;
+    // std::ceil(std::log2(double(max))) - 1, capped at 12 (stitch_global.cpp:632-634)
+    const int auto_bands = std::min(12, (int)std::ceil(std::log2((double)std::max(canvas_w, canvas_h))) - 1);
+    return std::max(std::max(5, configured_bands), auto_bands);
+}
+
+DS_API int ds_plan_row_bands(const ds_canvas_desc* desc, const int32_t* fr, int n_frames, int n_bands, int32_t* edges) {
+    if (!desc || !edges || n_bands < 1 || n_frames < 0 || (n_frames > 0 && !fr)) return fail(DS_ERR_BAD_ARG, "null / empty argument");
+    ds_canvas_desc d = *desc;
+    d.band_y0 = d.band_y1 = 0;
+    int L, pw, ph, lw[DS_MAXL], lh[DS_MAXL];
+    Range band, acc[DS_MAXL], own[DS_MAXL];
+    int rc = band_plan_from_desc(&d, &L, &pw, &ph, &band, lw, lh, acc, own);
+    if (rc) return rc;
+    const int m = d.blend_mode == DS_BLEND_MULTIBAND ? (1 << L) : FeatherBody::TH;
+    const int nunits = (ph + m - 1) / m;   // rows are handed out in units of m
+    if (n_bands > nunits) return fail(DS_ERR_BAD_ARG, "%d bands for a canvas of %d row units", n_bands, nunits);
+    // work per unit: canvas pixels (collapse, stores) + bbox pixels of every frame crossing it (warp, pyramids, accumulate)
+    std::vector<double> work((size_t)nunits, 0.0);
+    for (int u = 0; u < nunits; u++) work[u] = (double)d.width * std::min(m, ph - u * m);
+    for (int i = 0; i < n_frames; i++) {
+        const int y0 = fr[4 * i + 1] - d.y, y1 = y0 + fr[4 * i + 3], w = fr[4 * i + 2];
+        for (int u = std::max(y0, 0) / m; u < nunits && u * m < y1; u++) {
+            const int a = std::max(y0, u * m), b = std::min(y1, (u + 1) * m);
+            if (b > a) work[u] += 4.0 * (double)w * (b - a);   // a frame pixel costs about four times a bare canvas pixel
+        }
+    }
+    double total = 0;
+    for (double v : work) total += v;
+    edges[0] = 0;
+    double run = 0;
+    int u = 0;
+    for (int k = 1; k < n_bands; k++) {
+        const double target = total * k / n_bands;
+        while (u < nunits && run + work[u] * 0.5 < target) run += work[u++];
+        u = std::max(u, edges[k - 1] / m + 1);            // every band keeps at least one unit ...
+        u = std::min(u, nunits - (n_bands - k));          // ... and leaves one for each band below
+        run = 0;
+        for (int q = 0; q < u; q++) run += work[q];
+        edges[k] = u * m;
+    }
+    edges[n_bands] = ph;
+    return DS_OK;
 }
 
 DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {

@@ -179,6 +179,18 @@ DS_API int ds_warp_roi(const ds_transform* xf, int src_w, int src_h, int32_t out
  * canvas described by `desc` (footprint + multi-band gap + pyramid halo), else 0. */
 DS_API int ds_frame_touches_band(const ds_canvas_desc* desc, const int32_t frame_xywh[4]);
 
+/* Band count of the global stage's blender (src/stitch_global.cpp:632-635):
+ *   auto = min(12, ceil(log2(max(canvas_w, canvas_h))) - 1);  bands = max(max(5, configured), auto).
+ * (ds_create_canvas then crops it like MultiBandBlender::prepare does.) Returns the band count, or -1 for an empty canvas. */
+DS_API int ds_global_blend_bands(int canvas_w, int canvas_h, int configured_bands);
+
+/* Row-band edges for `n_bands` handles of one canvas (one per GPU): edges_out[0] = 0 <= ... <= edges_out[n_bands] =
+ * padded height, interior edges at multiples of 2^bands (feather: of 32), chosen so that every band holds about the
+ * same share of the work - the warped-bbox pixels of the frames (frames_xywh = n_frames x {x, y, w, h} from
+ * ds_warp_roi, absolute coordinates) plus the canvas pixels themselves - instead of the same number of rows: flight
+ * lines overlap, so rows under two lines cost twice the rows under one. */
+DS_API int ds_plan_row_bands(const ds_canvas_desc* desc, const int32_t* frames_xywh, int n_frames, int n_bands, int32_t* edges_out);
+
 /* ---- the four entry points ---- */
 
 /* Replaces blender->prepare(corners, sizes) (stitch_global.cpp:636-638; inside composePanorama). */

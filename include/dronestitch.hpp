@@ -101,6 +101,12 @@ inline Rect transformedBoundingRect(int cols, int rows, const double H[9]) {
     const int x = (int)std::floor(min_x), y = (int)std::floor(min_y);
     return Rect{x, y, std::max(1, (int)std::ceil(max_x) - x), std::max(1, (int)std::ceil(max_y) - y)};
 }
+// Band count of the global stage's blender (src/stitch_global.cpp:632-635): auto = min(12, ceil(log2(max(w, h))) - 1),
+// final = max(max(5, tuning.blend_bands), auto).
+inline int globalBlendBands(int canvas_w, int canvas_h, int configured_bands) {
+    const int auto_blend_bands = std::min(12, static_cast<int>(std::ceil(std::log2(static_cast<double>(std::max(canvas_w, canvas_h))))) - 1);
+    return std::max(std::max(5, configured_bands), auto_blend_bands);
+}
 // cv::detail::resultRoi(corners, sizes)
 inline Rect resultRoi(const std::vector<Rect>& placed) {
     int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;

@@ -53,7 +53,9 @@ static int global_stage(std::ifstream& f, const char* out_path) {
             xf[i] = ds::affineTransform(M, placed[i].x, placed[i].y, placed[i].width, placed[i].height);
         }
         ds::StitchTuning tuning;
-        tuning.blend_bands = bands;
+        // :632-635 band count from the canvas size and the configured value (canvas_w / canvas_h of :455-456)
+        tuning.blend_bands = ds::globalBlendBands(max_x - min_x, max_y - min_y, bands);
+        if (tuning.blend_bands != ds_global_blend_bands(max_x - min_x, max_y - min_y, bands)) throw std::runtime_error("band rule: header and library disagree");
         ds::Blender blender;
         blender.prepare(ds::resultRoi(placed), tuning);
         ds_frame_opts o;

@@ -129,7 +129,11 @@ def run_global_stage(exe, tmp_path):
         masks.append(O.soft_blend_mask(seam, content, 10.0))
         corners.append((x, y))
     roi = O.result_roi(corners, [(w.shape[1], w.shape[0]) for w in warped])
-    bl = O.MultiBand(roi, 5)
+    # stitch_global.cpp:632-635 on canvas_w / canvas_h of :455-456 (configured bands: 5)
+    canvas_w, canvas_h = max(p[0] + p[2] for p in pre) - min_x, max(p[1] + p[3] for p in pre) - min_y
+    final_bands = max(max(5, 5), min(12, int(np.ceil(np.log2(float(max(canvas_w, canvas_h))))) - 1))
+    assert final_bands > 5, "the case should exercise the automatic band count"
+    bl = O.MultiBand(roi, final_bands)
     for wimg, m, c in zip(warped, masks, corners):
         bl.feed(wimg.astype(np.int16), m, c)
     ref16, refmask = bl.blend()
