@@ -989,8 +989,10 @@ struct MBFastBody {
     static constexpr int H_BYTES = ds_al128(PHM * GWS * 8);   // pyrDown H pass; later the float H pass of the weights (PHM * JW * 4)
     static constexpr int ACC_BYTES = T * T * 4;
     static constexpr int COL_BYTES = ds_al128(PWS * 16), ROW_BYTES = ds_al128(PHM * 16);
+    static constexpr int NTAB = LEVEL0 ? 2 : 1;                // level 0: the tables of the next frame are built while this one is processed
+    static constexpr int TAB_BYTES = NTAB * (COL_BYTES + ROW_BYTES);
     static constexpr int MAXF = 64;                            // frames per tile the packed accumulators allow (host-checked)
-    static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES + W0_BYTES;
+    static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + TAB_BYTES + W0_BYTES;
     static constexpr int FDEV_BYTES = (int)((sizeof(FrameDev) + 15) & ~(size_t)15);
     static constexpr int GEO_BYTES = (LEVEL0 && !AFF) ? 112 : 96;   // sizeof(TFGeo)
     static constexpr int FDEV_OFF = GEO_OFF + MAXF * GEO_BYTES;      // two FrameDev slots: current frame / prefetch of the next
@@ -1091,9 +1093,10 @@ struct MBFastBody {
         // accumulators: {B + 65536 R, G} interleaved (one 128-bit access per pixel pair), weight sums apart
         int2* s_acc = (int2*)(smem + G0_BYTES + G1_BYTES + H_BYTES);
         float* s_ws = (float*)(s_acc + T * T);
-        L0Col* s_col = (L0Col*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES);
-        L0Row* s_row = (L0Row*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES);
-        float* s_w = (float*)(smem + G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES);
+        constexpr int TAB_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES;
+        auto col_buf = [&](int b_) { return (L0Col*)(smem + TAB_OFF + (b_ & (NTAB - 1)) * (COL_BYTES + ROW_BYTES)); };
+        auto row_buf = [&](int b_) { return (L0Row*)(smem + TAB_OFF + (b_ & (NTAB - 1)) * (COL_BYTES + ROW_BYTES) + COL_BYTES); };
+        float* s_w = (float*)(smem + TAB_OFF + TAB_BYTES);
         const int l = LEVEL0 ? 0 : p.level;
 
         const int tile = p.tile_ids ? p.tile_ids[block] : block;
@@ -1110,11 +1113,11 @@ struct MBFastBody {
         int tma_cur = 0;
         const bool use_tma = !LEVEL0 && p.tmaps != nullptr;
         if (use_tma && tid == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
-        constexpr int W0A_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + COL_BYTES + ROW_BYTES;
+        constexpr int W0A_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + TAB_BYTES;
         auto g0_buf = [&](int b_) { return (uint32_t*)(smem + (b_ ? G0B_OFF : 0)); };
         auto w_buf = [&](int b_) { return (float*)(smem + (b_ ? W0B_OFF : W0A_OFF)); };
 #endif
-        DS_SYNC();
+        // (no barrier: the accumulators are first touched after several more)
 
         Geo* s_geo = (Geo*)(smem + GEO_OFF);
         const int f_begin = p.tile_off[tile], f_end = p.tile_off[tile + 1];
@@ -1183,6 +1186,83 @@ struct MBFastBody {
             uint4* dstw = (uint4*)(smem + FDEV_OFF + (fi_ & 1) * FDEV_BYTES);
             for (int w = tid; w < (int)(sizeof(FrameDev) / 16); w += NT) dstw[w] = srcw[w];
         };
+        // ---- level-0 tables of one tile-frame: reflected bbox index + per-column / per-row map terms. Built for frame
+        // fi + 1 while frame fi is processed (two buffers), so the warp loop starts without a barrier of its own.
+        auto build_tables = [&](const FrameDev& Fx, int fj) {
+            const Geo gx = s_geo[fj - f_begin];
+            if (gx.skip) return;
+            L0Col* const t_col = col_buf(fj);
+            L0Row* const t_row = row_buf(fj);
+            const bool aff = AFF && LEVEL0 && Fx.kind == XF_AFFINE;
+            for (int i = tid; i < PWS + gx.ph; i += NT) {
+                if (i < PWS) {
+                    const int u = gx.rx + gx.px0 + imin(i, gx.pw - 1) - Fx.cx;   // padding columns repeat the last one
+                    const int ur = refl(u, Fx.w, BORDER_REFL);
+                    L0Col c;
+                    if (aff) {
+                        // cv::warpAffine: adelta / bdelta of the column, 10 fractional bits (A6), kept as integer bits
+                        c.a0 = i2f_bits(d2i_rn(d_mul(d_mul(Fx.inv[0], (double)ur), 1024.0)));
+                        c.a3 = i2f_bits(d2i_rn(d_mul(d_mul(Fx.inv[3], (double)ur), 1024.0)));
+                        c.a6 = 0.f;
+                    } else {
+                        float U = (float)(Fx.tlx + ur);
+                        if (Fx.scale != 1.f) U = f_div(U, Fx.scale);
+                        const float up = f_sub(U, Fx.t0);
+                        c.a0 = f_mul(Fx.k[0], up); c.a3 = f_mul(Fx.k[3], up); c.a6 = f_mul(Fx.k[6], up);
+                    }
+                    c.u = (unsigned)u < (unsigned)Fx.w ? u : ~ur;   // >= 0: inside (u == ur); < 0: ~(reflected index)
+                    t_col[i] = c;
+                } else {
+                    const int yy = i - PWS;
+                    const int v = gx.ry + gx.py0 + yy - Fx.cy;
+                    const int vr = refl(v, Fx.h, BORDER_REFL);
+                    L0Row r;
+                    if (aff) {
+                        r.b1 = i2f_bits(d2i_rn(d_mul(d_add(d_mul(Fx.inv[1], (double)vr), Fx.inv[2]), 1024.0)));
+                        r.b4 = i2f_bits(d2i_rn(d_mul(d_add(d_mul(Fx.inv[4], (double)vr), Fx.inv[5]), 1024.0)));
+                        r.b7 = 0.f;
+                    } else {
+                        float V = (float)(Fx.tly + vr);
+                        if (Fx.scale != 1.f) V = f_div(V, Fx.scale);
+                        const float vp = f_sub(V, Fx.t1);
+                        r.b1 = f_mul(Fx.k[1], vp); r.b4 = f_mul(Fx.k[4], vp); r.b7 = f_mul(Fx.k[7], vp);
+                    }
+                    r.v = (unsigned)v < (unsigned)Fx.h ? v : ~vr;
+                    t_row[yy] = r;
+                }
+            }
+        };
+        // what follows the barrier after a frame's warp loop: tables and L2 prefetch for the next frame of the tile
+        auto prepare_next = [&](int fi) {
+            if (fi + 1 >= f_end) return;
+            const FrameDev& N = *(const FrameDev*)(smem + FDEV_OFF + ((fi + 1) & 1) * FDEV_BYTES);   // staged at the top of iteration fi
+            build_tables(N, fi + 1);
+#if DS_CUDA
+            // L2 prefetch (TMA) of the source footprint of the next frame. One thread, fire and forget.
+            if (p.tmaps != nullptr && tid == 0) {
+                const Geo ng = s_geo[fi + 1 - f_begin];
+                if (!ng.skip && N.kind == XF_PLANE) {
+                    const int u_lo = ng.rx + ng.px0 - N.cx, u_hi = u_lo + ng.pw - 1, v_lo = ng.ry + ng.py0 - N.cy, v_hi = v_lo + ng.ph - 1;
+                    const int ulo = imax(imin(u_lo, N.w - 1), 0), uhi = imax(imin(u_hi, N.w - 1), 0);
+                    const int vlo = imax(imin(v_lo, N.h - 1), 0), vhi = imax(imin(v_hi, N.h - 1), 0);
+                    float xmin = 3.0e38f, ymin = 3.0e38f;
+                    for (int cidx = 0; cidx < 4; cidx++) {
+                        float U = (float)(N.tlx + ((cidx & 1) ? uhi : ulo)), V = (float)(N.tly + ((cidx & 2) ? vhi : vlo));
+                        if (N.scale != 1.f) { U = U / N.scale; V = V / N.scale; }
+                        const float up = U - N.t0, vp = V - N.t1;
+                        xmin = fminf(xmin, N.k[0] * up + N.k[1] * vp + N.k2one);
+                        ymin = fminf(ymin, N.k[3] * up + N.k[4] * vp + N.k5one);
+                    }
+                    if (xmin > -1.0e6f && xmin < 1.0e6f && ymin > -1.0e6f && ymin < 1.0e6f) {
+                        const char* tm = (const char*)p.tmaps + (size_t)p.tile_frames[fi + 1] * DS_MAXL * 2 * 128;   // slot [frame][0][0]: source
+                        fence_tensormap_acquire(tm);
+                        tma_prefetch_l2_2d(tm, ((int)floorf(xmin) - 1) & ~3, (int)floorf(ymin) - 1);
+                    }
+                }
+            }
+#endif
+        };
+        if constexpr (LEVEL0) { if (f_begin < f_end) build_tables(p.frames[p.tile_frames[f_begin]], f_begin); }
         if (f_begin < f_end) stage_frame(f_begin);
 #if DS_CUDA
         // TMA pipeline over the tile's frame list: the boxes of the next non-skipped frame are requested while
@@ -1224,78 +1304,19 @@ struct MBFastBody {
             (void)rx; (void)ry; (void)rw; (void)rh; (void)ax0; (void)ax1; (void)ay0; (void)ay1; (void)n1x; (void)n1y; \
             (void)jx0; (void)jx1; (void)jy0; (void)jy1; (void)gx0; (void)gy0; (void)px0; (void)py0; (void)pw; (void)ph; \
             (void)gw; (void)gh; (void)jw; (void)jh; (void)border;
-            if (s_geo[fi - f_begin].skip) { DS_SYNC(); continue; }       // block-uniform
+            if (s_geo[fi - f_begin].skip) {       // block-uniform
+                DS_SYNC();
+                if constexpr (LEVEL0) { prepare_next(fi); DS_SYNC(); }
+                continue;
+            }
             {   // ======== first half: tables + phase 1
             const Geo g = s_geo[fi - f_begin];
             DS_TF_LOCALS
             const bool affine = AFF && LEVEL0 && F.kind == XF_AFFINE;   // cv::warpAffine coordinates (integer tables)
             const bool proj = !affine && !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
             if constexpr (LEVEL0) {
-            // ---- tables: reflected bbox index + per-column / per-row map terms
-            for (int i = tid; i < PWS + ph; i += NT) {
-                if (i < PWS) {
-                    const int u = rx + px0 + imin(i, pw - 1) - F.cx;   // padding columns repeat the last one
-                    const int ur = refl(u, F.w, BORDER_REFL);
-                    L0Col c;
-                    if (affine) {
-                        // cv::warpAffine: adelta / bdelta of the column, 10 fractional bits (A6), kept as integer bits
-                        c.a0 = i2f_bits(d2i_rn(d_mul(d_mul(F.inv[0], (double)ur), 1024.0)));
-                        c.a3 = i2f_bits(d2i_rn(d_mul(d_mul(F.inv[3], (double)ur), 1024.0)));
-                        c.a6 = 0.f;
-                    } else {
-                        float U = (float)(F.tlx + ur);
-                        if (F.scale != 1.f) U = f_div(U, F.scale);
-                        const float up = f_sub(U, F.t0);
-                        c.a0 = f_mul(F.k[0], up); c.a3 = f_mul(F.k[3], up); c.a6 = f_mul(F.k[6], up);
-                    }
-                    c.u = (unsigned)u < (unsigned)F.w ? u : ~ur;   // >= 0: inside (u == ur); < 0: ~(reflected index)
-                    s_col[i] = c;
-                } else {
-                    const int yy = i - PWS;
-                    const int v = ry + py0 + yy - F.cy;
-                    const int vr = refl(v, F.h, BORDER_REFL);
-                    L0Row r;
-                    if (affine) {
-                        r.b1 = i2f_bits(d2i_rn(d_mul(d_add(d_mul(F.inv[1], (double)vr), F.inv[2]), 1024.0)));
-                        r.b4 = i2f_bits(d2i_rn(d_mul(d_add(d_mul(F.inv[4], (double)vr), F.inv[5]), 1024.0)));
-                        r.b7 = 0.f;
-                    } else {
-                        float V = (float)(F.tly + vr);
-                        if (F.scale != 1.f) V = f_div(V, F.scale);
-                        const float vp = f_sub(V, F.t1);
-                        r.b1 = f_mul(F.k[1], vp); r.b4 = f_mul(F.k[4], vp); r.b7 = f_mul(F.k[7], vp);
-                    }
-                    r.v = (unsigned)v < (unsigned)F.h ? v : ~vr;
-                    s_row[yy] = r;
-                }
-            }
-            DS_SYNC();
-#if DS_CUDA
-            // L2 prefetch (TMA) of the source footprint of the NEXT frame of this tile: its descriptor was staged
-            // at the top of this iteration and is visible after the barrier above. One thread, fire and forget.
-            if (p.tmaps != nullptr && tid == 0 && fi + 1 < f_end) {
-                const Geo ng = s_geo[fi + 1 - f_begin];
-                const FrameDev& N = *(const FrameDev*)(smem + FDEV_OFF + ((fi + 1) & 1) * FDEV_BYTES);
-                if (!ng.skip && N.kind == XF_PLANE) {
-                    const int u_lo = ng.rx + ng.px0 - N.cx, u_hi = u_lo + ng.pw - 1, v_lo = ng.ry + ng.py0 - N.cy, v_hi = v_lo + ng.ph - 1;
-                    const int ulo = imax(imin(u_lo, N.w - 1), 0), uhi = imax(imin(u_hi, N.w - 1), 0);
-                    const int vlo = imax(imin(v_lo, N.h - 1), 0), vhi = imax(imin(v_hi, N.h - 1), 0);
-                    float xmin = 3.0e38f, ymin = 3.0e38f;
-                    for (int cidx = 0; cidx < 4; cidx++) {
-                        float U = (float)(N.tlx + ((cidx & 1) ? uhi : ulo)), V = (float)(N.tly + ((cidx & 2) ? vhi : vlo));
-                        if (N.scale != 1.f) { U = U / N.scale; V = V / N.scale; }
-                        const float up = U - N.t0, vp = V - N.t1;
-                        xmin = fminf(xmin, N.k[0] * up + N.k[1] * vp + N.k2one);
-                        ymin = fminf(ymin, N.k[3] * up + N.k[4] * vp + N.k5one);
-                    }
-                    if (xmin > -1.0e6f && xmin < 1.0e6f && ymin > -1.0e6f && ymin < 1.0e6f) {
-                        const char* tm = (const char*)p.tmaps + (size_t)p.tile_frames[fi + 1] * DS_MAXL * 2 * 128;   // slot [frame][0][0]: source
-                        fence_tensormap_acquire(tm);
-                        tma_prefetch_l2_2d(tm, ((int)floorf(xmin) - 1) & ~3, (int)floorf(ymin) - 1);
-                    }
-                }
-            }
-#endif
+            L0Col* const s_col = col_buf(fi);   // built during the previous frame (or before the loop)
+            L0Row* const s_row = row_buf(fi);
 
             // ---- phase 1: inverse warp of the needed region into s_g0 (b | g<<8 | r<<16 | mask<<24)
             // Frame fields are copied to registers first: F lives in global memory and would otherwise be
@@ -1757,6 +1778,7 @@ struct MBFastBody {
                 uni0 = !(bits & 2);
             }
 
+            if constexpr (LEVEL0) prepare_next(fi);
             // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op
             for (int i = tid; i < ph * GWS; i += NT) {
                 const int yy = i / GWS, gxx = i - yy * GWS;
