@@ -4,12 +4,18 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (OpenCV), rank 0
 
-Workload at N = 1: BASELINE configs[1] — a 3x3 grid of synthetic 5472x3648 drone frames, 70 % overlap,
-multi-band blend with 5 bands. At N > 1 the survey grows to 3 x 3N frames (canvas N times taller) and
-the canvas is cut into N row bands, one per GPU / process (weak scaling, no data-path collective).
+Workload (default): BASELINE configs[3] — ONE 600-frame survey (12 lines x 50 frames of 5472x3648, 70 % forward /
+32 % side overlap, multi-band 5) composited into one 2.7-gigapixel canvas. It is the largest configuration that fits
+one B200 (125 GB of HBM); at N > 1 the SAME canvas is cut into N row bands, one per GPU / process (strong scaling),
+each band holding only the frames that touch it, neighbouring bands handing each other their level-1 pyramid halo
+rows over NVLink P2P (ds_p2p_connect; no collective on the data path — torch.distributed carries the IPC handles
+once, the barrier, and the max-over-ranks of the device time). `--workload cfg2|cfg1|cfg3|small` select the other
+BASELINE configurations; at N = 1 the line also carries `also.cfg2` / `also.cfg1` for continuity with round 1.
 
-A "step" is one ds_composite over the frames resident in HBM (value), or upload of every frame from
-pinned host memory + composite + download of the whole band (e2e).
+A "step" is one ds_composite over the frames resident in HBM (`value`, CUDA events), or the upload of every frame
+from pinned host memory + composite + download of the panorama through the C ABI (`e2e`).
+Every run checks its own output: each rank compares windows at its band edges with the windowed CPU oracle
+(oracle/windowed.py, checker only) and the line carries `parity`; a mismatch exits non-zero.
 """
 import argparse
 import json
@@ -27,25 +33,48 @@ import numpy as np  # noqa: E402
 
 METRIC = "output_canvas_megapixels_per_sec"
 UNIT = "MP/s"
+DTYPE = "u8/int16/f32"
 
 
-def workload_plan(name, n_gpus):
+# ------------------------------------------------------------------------------------------------ workload
+
+def survey(name):
     from drone_image_stitch_cpp_b200 import synth
-    if name == "cfg2":
-        return synth.plan_grid(3, 3, 5472, 3648, overlap=0.7, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
-            (f"cfg2: {n_gpus} flight block(s) of 3x3 frames 5472x3648, 70% overlap, multi-band 5"
-             + ("" if n_gpus == 1 else ", blocks stacked in y with 2% overlap, one block per GPU row band"))
-    if name == "cfg1":
-        return synth.plan_grid(2, 1, 4000, 3000, overlap=0.7, seed=synth.MASTER_SEED, rot_deg=1.5, blocks=n_gpus), "feather", 0, \
-            f"cfg1: {n_gpus} block(s) of 2 frames 4000x3000, feather 0.02"
-    if name == "cfg3":
-        return synth.plan_grid(40, 3, 5472, 3648, overlap=0.7, side_overlap=0.32, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
-            f"cfg3: {n_gpus} block(s) of 3 serpentine lines x 40 frames 5472x3648, 70% forward / 32% side overlap, multi-band 5"
-    if name == "small":
-        return synth.plan_grid(3, 3, 912, 608, overlap=0.7, seed=synth.MASTER_SEED, blocks=n_gpus), "multiband", 5, \
-            f"small: {n_gpus} block(s) of 3x3 frames 912x608, 70% overlap, multi-band 5"
-    raise SystemExit(f"unknown workload {name}")
+    return synth.plan_survey(name)
 
+
+def geometry(plan, lib):
+    from drone_image_stitch_cpp_b200 import compositor as CP
+    xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
+    rois = [CP.warp_roi(xf, plan.fw, plan.fh, lib) for xf in xfs]
+    return xfs, rois, CP.result_roi(rois)
+
+
+def job_config(desc, plan, roi, blend, bands, n_gpus):
+    """The `config` object of the JSON line: a function of the workload and N only, so both arms print the same one."""
+    frame_bytes = plan.fw * plan.fh * 4 * len(plan.A)
+    return {"workload": desc, "canvas": [int(roi[2]), int(roi[3])], "frames": len(plan.A), "frame_size": [plan.fw, plan.fh],
+            "blend": blend, "bands": int(bands), "parallelism": f"row-bands x{n_gpus} of one canvas",
+            "l2": (f"inputs larger than L2 ({frame_bytes / n_gpus / 1e6:.0f} MB of frames per GPU vs 126 MB)" if frame_bytes / n_gpus > 3 * 126e6
+                   else f"L2 flushed between timed composites (a 256 MB buffer is rewritten; the {frame_bytes / n_gpus / 1e6:.0f} MB of frames would fit L2)")}
+
+
+def make_frame(plan, i, device, procedural, ortho_cache):
+    """Frame i as an HxWx3 uint8 torch tensor on `device`."""
+    from drone_image_stitch_cpp_b200 import synth
+    if procedural:
+        return synth.procedural_frame(plan, i, device=device, as_torch=True)
+    if "o" not in ortho_cache:
+        ortho_cache["o"] = synth.orthophoto(plan.ortho_h, plan.ortho_w, plan.seed, device)
+    return synth.cut(plan, [i], device=device, as_torch=True, ortho=ortho_cache["o"])[0]
+
+
+def uses_procedural(plan):
+    # the stored orthophoto (float CHW on the device) is only practical for small canvases
+    return plan.ortho_w * plan.ortho_h > 400e6
+
+
+# ------------------------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread
@@ -114,16 +143,31 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-class CpuReference:
-    """The reference's CPU path (OpenCV via oracle/cv_reference.py, else the C port) on a bounded
-    sample of the workload: the same grid layout / overlap / blend with the frames scaled by an integer
-    divisor so that one compose fits the time budget. Synthetic inputs are generated once (on the GPU
-    when one is present — generation is not part of any timed region)."""
+def dominant_traffic(workload, name, level):
+    """ncu DRAM bytes per launch of the dominant kernel, from the committed capture summary - only if that capture
+    was taken from the kernels this library was built from (source hash recorded beside it)."""
+    tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    try:
+        from drone_image_stitch_cpp_b200 import build
+        d = json.load(open(tp))
+        if d.get("kernel_source_sha16") != build.source_hash():
+            return None, f"capture is of other kernel sources ({d.get('kernel_source_sha16')}), not reported"
+        return d.get(f"{workload}:{name}:{level}"), d.get("capture")
+    except Exception:
+        return None, "no capture summary"
 
-    def __init__(self, plan, blend, bands, budget_s, threads=None):
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+
+class CpuReference:
+    """The reference's CPU path (OpenCV through oracle/cv_reference.py, else the C port) on a bounded sample of the
+    workload at FULL frame size: the first `cols` frames of every flight line (a shorter flight of the same pattern:
+    same overlaps, same frame size, same blend), composited whole. Synthetic frames are generated once, outside the
+    timed region (on the GPU when one is present)."""
+
+    def __init__(self, plan, blend, bands, nx, target_seconds, rate_guess=11.0, threads=None):
         from oracle import cv_reference as CR
         from oracle import ds_oracle as O
-        self.plan, self.blend, self.bands = plan, blend, bands
         self.use_cv = CR.have_cv2()
         cores = os.cpu_count() or 1
         if self.use_cv:
@@ -132,77 +176,92 @@ class CpuReference:
             O.set_threads(threads or cores)
             self.cores = O.get_threads()
         self.kind = "reference" if self.use_cv else "port"
-        self.impl = ("OpenCV (cv2 wheel): AffineWarper + MultiBandBlender/FeatherBlender" if self.use_cv
-                     else "oracle/ds_oracle.c (OpenMP)")
-        self._prepare(6)
-        mp, dt = self.step()                 # calibration + warm-up on 1/36 of the pixels
-        rate = mp / dt
-        div = 6
-        for d in (1, 2, 3, 4, 6):
-            if (mp * 36 / (d * d)) / rate <= budget_s:
-                div = d
-                break
-        if div != 6:
-            self._prepare(div)
-
-    def _prepare(self, div):
-        from drone_image_stitch_cpp_b200 import synth
+        self.impl = ("OpenCV (cv2 wheel): AffineWarper + MultiBandBlender/FeatherBlender" if self.use_cv else "oracle/ds_oracle.c (OpenMP)")
+        self.blend, self.bands, self.plan = blend, bands, plan
+        n = len(plan.A)
+        ny = n // nx
+        # columns so that one compose takes about target_seconds at rate_guess output MP/s
+        stepx = plan.fw * 0.3
+        canvas_h = plan.fh * (1 + 0.68 * (ny - 1)) if ny > 1 else plan.fh
+        want_w = target_seconds * rate_guess * 1e6 / canvas_h
+        cols = int(max(1, min(nx, round((want_w - plan.fw) / stepx) + 1)))
+        self.cols, self.ny, self.nx = cols, ny, nx
+        self.idx = []
+        for jj in range(ny):
+            for i in range(nx):
+                col = i if jj % 2 == 0 else nx - 1 - i    # serpentine flight order (synth.plan_grid)
+                if col < cols:
+                    self.idx.append(jj * nx + i)
         import torch
-        plan = self.plan
-        fw, fh = max(64, plan.fw // div), max(64, plan.fh // div)
-        nx, ny = (3, 3) if self.blend == "multiband" else (2, 1)
-        blocks = max(1, len(plan.A) // (nx * ny))
-        self.p = synth.plan_grid(nx, ny, fw, fh, overlap=0.7, seed=plan.seed, blocks=blocks,
-                                 rot_deg=3.0 if self.blend == "multiband" else 1.5, trans_jit=20.0 / div)
         dev = "cuda" if torch.cuda.is_available() else "cpu"
-        self.frames = synth.cut(self.p, None, dev)
-        self.div = div
+        proc = uses_procedural(plan)
+        cache = {}
+        self.frames = [make_frame(plan, i, dev, proc, cache).cpu().numpy() for i in self.idx]
+        cache.clear()
+        self.Ks = [plan.Ks[i] for i in self.idx]
+        self.Rs = [plan.Rs[i] for i in self.idx]
+        self.last_dt = None
 
     def step(self):
         from oracle import cv_reference as CR
         from oracle import ds_oracle as O
         t0 = time.perf_counter()
         if self.use_cv:
-            pano, _, roi = CR.compose_cv2(self.frames, self.p.Ks, self.p.Rs, self.p.scale, self.blend, self.bands)
+            pano, _, roi = CR.compose_cv2(self.frames, self.Ks, self.Rs, self.plan.scale, self.blend, self.bands)
         else:
-            pano, _, roi = O.compose_port(self.frames, self.p.Ks, self.p.Rs, self.p.scale, self.blend, self.bands)
+            pano, _, roi = O.compose_port(self.frames, self.Ks, self.Rs, self.plan.scale, self.blend, self.bands)
         dt = time.perf_counter() - t0
-        self.last_dt = dt
+        self.last_dt, self.last_roi = dt, roi
         return roi[2] * roi[3] / 1e6, dt
 
     def sample(self):
-        return (f"{len(self.frames)} frames of {self.p.fw}x{self.p.fh} (1/{self.div} linear scale of the workload), "
-                f"{self.impl}, one compose = {self.last_dt:.2f} s")
+        whole = self.cols == self.nx
+        what = ("the whole workload" if whole else
+                f"the first {self.cols} frames of each of the {self.ny} flight lines ({len(self.idx)} of {len(self.plan.A)} frames)")
+        return (f"{what}, full-size {self.plan.fw}x{self.plan.fh} frames, canvas {self.last_roi[2]}x{self.last_roi[3]} = "
+                f"{self.last_roi[2] * self.last_roi[3] / 1e6:.0f} MP, {self.impl}, one compose = {self.last_dt:.2f} s")
+
+
+def grid_nx(name):
+    return {"cfg4": 50, "cfg3": 40, "cfg5": 80, "cfg2": 3, "cfg1": 2, "small": 6}[name]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    plan, blend, bands, desc = workload_plan(args.workload, args.gpus)
+    from drone_image_stitch_cpp_b200 import _lib
+    lib = _lib.default_library()
+    plan, blend, bands, desc = survey(args.workload)
+    xfs, rois, roi = geometry(plan, lib)
     total = args.steps + args.warmup
-    budget = max(1.0, 150.0 / max(total, 1))
-    ref = CpuReference(plan, blend, bands, budget)
-    kind, cores = ref.kind, ref.cores
-    mps, secs = 0.0, 0.0
-    nsteps = 0
+    # one compose of the sample about 45 s (cfg4: 12 lines x 7 frames, 0.5 GP) unless the whole workload is smaller
+    ref = CpuReference(plan, blend, bands, grid_nx(args.workload), target_seconds=45.0)
+    mps, secs, nsteps = 0.0, 0.0, 0
     t_all = time.perf_counter()
+    budget = 200.0
+    warm = min(args.warmup, 1) if ref.cols < ref.nx or plan.fw * plan.fh * len(plan.A) > 100e6 else args.warmup
     for i in range(total):
         mp, dt = ref.step()
-        if i >= args.warmup:
+        if i >= warm:
             mps += mp; secs += dt; nsteps += 1
-        if time.perf_counter() - t_all > 240 and nsteps >= 1:
+        if nsteps >= args.steps:
             break
-    samples = ref.sample()
+        if nsteps >= 1 and time.perf_counter() - t_all + dt > budget:
+            break
     v = mps / secs
+    sample = ref.sample() + f"; {nsteps} timed compose(s) after {warm} warm-up (bounded to {budget:.0f} s)"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps,
-            "warmup": args.warmup, "ms_per_step": secs / nsteps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/int16/f32", "data": "synthetic", "config": {"workload": desc, "sample": samples},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": samples},
+            "warmup": warm, "ms_per_step": secs / nsteps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": DTYPE, "data": "synthetic",
+            "config": job_config(desc, plan, roi, blend, bands, args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
+
+# ------------------------------------------------------------------------------------------------ native arm
 
 def bind_to_gpu_numa_node(idx):
     """Pin this process (and so its pinned host buffers, first-touch) to the CPU cores NVML reports as local to
@@ -216,18 +275,128 @@ def bind_to_gpu_numa_node(idx):
         cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
         allowed = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in allowed]
+        node = None
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return f"{len(cpus)} cores local to GPU {idx}"
+            return {"gpu": idx, "cores": len(cpus), "first_core": min(cpus), "numa_node": node}
     except Exception as e:  # measurement nicety only
-        return f"unbound ({type(e).__name__})"
-    return "unbound"
+        return {"gpu": idx, "unbound": type(e).__name__}
+    return {"gpu": idx, "unbound": "no affinity reported"}
+
+
+class L2Flusher:
+    """Rewrites a buffer twice the size of L2 between timed composites (for workloads whose frames would fit L2)."""
+
+    def __init__(self, device, stream):
+        import torch
+        self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+        self.stream = stream
+
+    def __call__(self):
+        import torch
+        with torch.cuda.stream(self.stream):
+            self.buf.add_(1)
+
+
+def resident_value(cv, steps, warmup, stream, barrier, flush=None):
+    """K timed composites over frames resident in HBM: device time by CUDA events on the canvas stream."""
+    import torch
+    for _ in range(max(warmup, 3)):
+        cv.composite_async()
+    cv.set_profiling(True)
+    barrier()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for k in range(steps):
+        if flush is not None:
+            flush()
+        e0[k].record(stream)
+        cv.composite_async()
+        e1[k].record(stream)
+    barrier()
+    ms = [a.elapsed_time(b) for a, b in zip(e0, e1)]
+    if flush is None:
+        total = e0[0].elapsed_time(e1[-1])     # back to back: one span
+    else:
+        total = float(sum(ms))                  # flushes between the composites are not part of the steps
+    kt = cv.kernel_times()
+    cv.set_profiling(False)
+    return total, kt
+
+
+def quick_workload(name, lib, local, steps=10):
+    """A small single-GPU side measurement for the `also` object (composite-only, frames resident)."""
+    import torch
+    from drone_image_stitch_cpp_b200 import compositor as CP
+    plan, blend, bands, desc = survey(name)
+    xfs, rois, roi = geometry(plan, lib)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        cv = CP.Canvas(roi, blend, bands, out_format="bgr", device=local, stream=stream.cuda_stream, lib=lib)
+        cache = {}
+        for i in range(len(xfs)):
+            f = make_frame(plan, i, f"cuda:{local}", uses_procedural(plan), cache)
+            torch.cuda.synchronize()
+            cv.upload_device(i, f.data_ptr(), plan.fw, plan.fh, plan.fw * 3, xfs[i])
+            del f
+        cache.clear()
+        flush = None
+        if plan.fw * plan.fh * 4 * len(xfs) <= 3 * 126e6:
+            flush = L2Flusher(f"cuda:{local}", stream)
+
+        def barrier():
+            torch.cuda.synchronize()
+        total, kt = resident_value(cv, steps, 3, stream, barrier, flush)
+        ab = int(cv.info().algorithmic_bytes)
+        cv.close()
+    mp = roi[2] * roi[3] / 1e6
+    ms = total / steps
+    peak, _ = hbm_peak()
+    agg = {}
+    for k in kt:
+        agg.setdefault((k["name"], k["level"]), []).append(k["ms"])
+    top = max(agg.items(), key=lambda kv: np.mean(kv[1]))
+    top_ab = next(k["algorithmic_bytes"] for k in kt if (k["name"], k["level"]) == top[0])
+    top_ms = float(np.mean(top[1]))
+    return {"workload": desc, "canvas": [int(roi[2]), int(roi[3])], "value": mp / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+            "steps": steps, "l2": "flushed between composites" if flush is not None else "inputs larger than L2",
+            "whole_step_frac": ab / (ms / 1e3) / 1e9 / peak,
+            "dominant": {"kernel": f"{top[0][0]}[level {top[0][1]}]", "ms_per_launch": top_ms,
+                         "frac": top_ab / (top_ms / 1e3) / 1e9 / peak}}
+
+
+def parity_windows(edges, rank, world, roi, bands, PH):
+    """Windows (x, y, w, h) this rank checks and the canvas rows of its own it compares in each: one window straddling
+    every band edge the rank touches (compared on its side of the edge), or the canvas centre on a single GPU."""
+    m = 1 << bands
+    g = 8 << bands
+    ww = min(2048, (roi[2] // m) * m)
+    wx = max(0, ((roi[2] - ww) // 2) // m * m)
+    half = 768 // m * m if PH >= 4 * 768 else max(g + m, (PH // 4) // m * m)
+    out = []
+
+    def win_at(e):
+        y0 = max(0, e - half)
+        y1 = min(PH, e + half)
+        return (wx, y0, ww, y1 - y0)
+    if world == 1:
+        out.append((win_at((PH // 2) // m * m), None))
+    else:
+        if rank > 0:
+            out.append((win_at(edges[rank]), "below"))          # my rows just below my upper edge
+        if rank < world - 1:
+            out.append((win_at(edges[rank + 1]), "above"))      # my rows just above my lower edge
+    return out, g
 
 
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from drone_image_stitch_cpp_b200 import _lib, compositor as CP, synth
+    from drone_image_stitch_cpp_b200 import _lib, compositor as CP
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,53 +406,80 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (libdronestitch_cuda has no CPU fallback)")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.default_library()
+    t_start = time.perf_counter()
 
-    plan, blend, bands, desc = workload_plan(args.workload, world)
+    def note(msg):
+        if args.verbose and rank == 0:
+            print(f"[bench {time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    # ---------------- side measurements for continuity (single GPU only, before the big canvas takes the memory)
+    also = {}
+    if world == 1 and not args.no_also and args.workload == "cfg4":
+        for name in ("cfg2", "cfg1"):
+            try:
+                also[name] = quick_workload(name, lib, local)
+            except Exception as e:   # never lose the headline over a side measurement
+                also[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            note(f"also.{name} done")
+        torch.cuda.empty_cache()
+
+    plan, blend, bands, desc = survey(args.workload)
     if args.bands is not None and blend == "multiband":
         bands = args.bands
         desc += f" [bands overridden: {bands}]"
-    xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
-    rois = [CP.warp_roi(xf, plan.fw, plan.fh, lib) for xf in xfs]
-    roi = CP.result_roi(rois)
-    # row bands: edges at multiples of 2^bands
+    xfs, rois, roi = geometry(plan, lib)
+    procedural = uses_procedural(plan)
     probe = CP.Canvas(roi, blend, bands, lib=lib, device=local)
     pinfo = probe.info()
     probe.close()
-    PH, m = pinfo.padded_height, 1 << pinfo.num_bands
-    edges = [0] + [((PH * k // world) // m) * m for k in range(1, world)] + [PH]
+    PH, eff_bands = pinfo.padded_height, pinfo.num_bands
+    edges = CP.plan_row_bands(roi, rois, world, blend, bands, lib=lib) if world > 1 else [0, PH]
     band = (edges[rank], edges[rank + 1]) if world > 1 else None
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         cv = CP.Canvas(roi, blend, bands, out_format="bgr", device=local, band=band, stream=stream.cuda_stream, lib=lib)
         mine = [i for i in range(len(xfs)) if band is None or cv.touches(rois[i])]
-        frames_dev = synth.cut(plan, mine, device=f"cuda:{local}", as_torch=True)
-        pinned = []
-        for f in frames_dev:
-            h = torch.empty(f.shape, dtype=torch.uint8, pin_memory=True)
-            h.copy_(f)
-            pinned.append(h)
-        del frames_dev
-        torch.cuda.synchronize()
-        host_np = [p.numpy() for p in pinned]
-        for i, arr in zip(mine, host_np):
-            cv.upload(i, arr, xfs[i])
+        frame_bytes = plan.fw * plan.fh * 3
+        # pinned host copies of this rank's frames (the e2e step uploads them); one allocation, first touched here
+        host_mode = "every frame of the rank in pinned host memory"
+        pool = None
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 1 << 62
+        n_host = len(mine)
+        if n_host * frame_bytes > 0.6 * avail / world or args.host_pool:   # (every rank of the box pins its share)
+            n_host = max(8, min(len(mine), int(args.host_pool or 64)))
+            host_mode = f"a pool of {n_host} pinned frame buffers cycled over the rank's {len(mine)} frames (host memory)"
+        pinned = torch.empty((n_host, plan.fh, plan.fw, 3), dtype=torch.uint8, pin_memory=True)
+        cache = {}
+        for k, i in enumerate(mine):
+            f = make_frame(plan, i, dev, procedural, cache)
+            torch.cuda.synchronize()
+            cv.upload_device(i, f.data_ptr(), plan.fw, plan.fh, plan.fw * 3, xfs[i])
+            if k < n_host:
+                pinned[k].copy_(f)
+            torch.cuda.synchronize()
+            del f
+        cache.clear()
+        host_np = [pinned[k % n_host].numpy() for k in range(len(mine))]
         info = cv.info()
         out_rows = min(info.band_y1, roi[3]) - info.band_y0
-        out_pin = torch.empty((out_rows, roi[2], 3), dtype=torch.uint8, pin_memory=True)
+        out_pin = torch.empty((max(out_rows, 1), roi[2], 3), dtype=torch.uint8, pin_memory=True)
+        note(f"{len(mine)} frames resident, {info.device_bytes / 1e9:.1f} GB of HBM")
 
         # neighbouring bands hand each other the level-1 halo rows over NVLink (no collective on the data path;
-        # torch.distributed only carries the 64-byte IPC handles once, here)
-        # Measured on cfg2 (5 bands, halo of ~280 rows): recomputing the halo costs 0.05-0.18 ms per composite, the
-        # exchange 0.06 ms of pull per edge plus two cross-GPU hand-overs - a wash. From 6 bands up (halo >= 560
-        # rows, doubling per band) the exchange wins, so "auto" connects only then.
-        halo = "recomputed per band (no exchange)"
-        use_p2p = args.p2p == "on" or (args.p2p == "auto" and info.num_bands >= 6)
-        if world > 1 and blend == "multiband" and use_p2p:
+        # torch.distributed only carries the IPC handles once, here)
+        halo = "none (one band)" if world == 1 else "recomputed per band (no exchange)"
+        use_p2p = world > 1 and blend == "multiband" and args.p2p != "off"
+        if use_p2p:
             blobs = [None] * world
             dist.all_gather_object(blobs, cv.p2p_export())
             ok, why = True, ""
@@ -297,7 +493,7 @@ def run_native(args):
             oks = [None] * world
             dist.all_gather_object(oks, (ok, why))
             if all(o[0] for o in oks):
-                halo = "NVLink P2P pull of the level-1 halo rows (ds_p2p_connect), recomputed in the pipelined e2e schedule"
+                halo = "NVLink P2P pull of the level-1 halo rows (ds_p2p_connect); recomputed in the pipelined e2e schedule"
             else:
                 cv.p2p_disconnect()
                 halo = "recomputed per band (P2P unavailable: " + next(o[1] for o in oks if not o[0])[:120] + ")"
@@ -308,36 +504,69 @@ def run_native(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
+        def allmax(x):
+            t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def allsum(xs):
+            t = torch.tensor([float(v) for v in xs], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t)
+            return [float(v) for v in t.tolist()]
+
         # ---------------- value: composite-only, frames resident in HBM
-        for _ in range(max(args.warmup, 3)):
-            cv.composite_async()
-        cv.set_profiling(True)
-        barrier()
+        flush = None
+        if plan.fw * plan.fh * 4 * len(xfs) / world <= 3 * 126e6:
+            flush = L2Flusher(dev, stream)
         clocks = ClockSampler(local)
         clocks.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            cv.composite_async()
-        e1.record(stream)
-        barrier()
+        ms_total, kt = resident_value(cv, args.steps, args.warmup, stream, barrier, flush)
         clk = clocks.stop()
-        ms_total = e0.elapsed_time(e1)
-        kt = cv.kernel_times()
-        cv.set_profiling(False)
         launches = int(cv.info().launches_last_composite) * args.steps
-        t = torch.tensor([ms_total], device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total = allmax(ms_total)
         canvas_mp = roi[2] * roi[3] / 1e6
         value = canvas_mp * args.steps / (ms_total / 1e3)
+        ab_total = int(cv.info().algorithmic_bytes)
+        note(f"value {value:.0f} MP/s ({ms_total / args.steps:.2f} ms per composite)")
+
+        # ---------------- parity: windows at this rank's band edges against the windowed CPU oracle (checker only)
+        parity = {"checked": False}
+        if not args.no_parity and blend == "multiband":
+            from oracle import windowed as W
+            wins, g = parity_windows(edges, rank, world, roi, eff_bands, PH)
+            n_px = n_bad = mx = 0
+            y_lo, y_hi = info.band_y0, min(info.band_y1, roi[3])
+            checked_rows = []
+            for win, side in wins:
+                need = W.frames_touching(rois, roi, win)
+                frames = {}
+                for i in need:
+                    if i in mine and mine.index(i) < n_host:
+                        frames[i] = host_np[mine.index(i)]
+                    else:   # a frame of the neighbouring band (or beyond the host pool): generated again, same function
+                        frames[i] = make_frame(plan, i, dev, procedural, cache).cpu().numpy()
+                cache.clear()
+                ref, refmask = W.compose_window(frames, plan.Ks, plan.Rs, plan.scale, eff_bands, roi, win)
+                ya, yb = max(win[1] + g, y_lo), min(win[1] + win[3] - g, y_hi)
+                if ya >= yb:
+                    continue
+                rows, rmask = cv.download(x=win[0], y=ya, w=win[2], h=yb - ya)
+                a, b, c = W.compare_inside(rows, rmask, ya, ref, refmask, win, eff_bands, x0=win[0])
+                n_px += a; n_bad += b; mx = max(mx, c)
+                checked_rows.append([int(ya), int(yb)])
+            tot = allsum([n_px, n_bad])
+            parity = {"checked": tot[0] > 0, "identical": tot[0] > 0 and tot[1] == 0, "pixels_compared": int(tot[0]),
+                      "pixels_differing": int(tot[1]), "max_abs_diff": int(allmax(mx)),
+                      "how": ("every rank compares 2048-px-wide windows straddling its band edges (its own rows, >= 256 px inside the window) "
+                              "with the windowed CPU oracle (oracle/windowed.py, SURVEY 8(c) P17); bit-exact required"),
+                      "rank0_rows": checked_rows}
+            note(f"parity {parity['identical']} over {parity['pixels_compared']} px")
 
         # ---------------- e2e: upload from pinned host + composite + download, every step
-        e2e_steps = max(2, min(args.steps, 5))
-        # the step's result is the panorama (what composePanorama hands back, stitch_robust.cpp:256); the
-        # result mask stays on the device unless asked for
-        d2h = int(out_pin.numel())
+        e2e_steps = max(2, min(args.steps, 5 if canvas_mp < 500 else 3))
+        d2h = int(out_rows) * int(roi[2]) * 3
 
         def e2e_step():
             # the caller's frames stay valid for the step, so the uploads are queued (DS_UPLOAD_ASYNC), the composite
@@ -346,7 +575,7 @@ def run_native(args):
             for i, arr in zip(mine, host_np):
                 cv.upload(i, arr, xfs[i], async_=True)
             cv.composite_async()
-            cv.download(out=out_pin.numpy(), want_mask=False)
+            cv.download(out=out_pin.numpy()[:max(out_rows, 0)], want_mask=False)
             cv.synchronize()
 
         e2e_step()
@@ -356,17 +585,53 @@ def run_native(args):
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
-        dt = time.perf_counter() - t0
+        dt = allmax(time.perf_counter() - t0)
         # bytes the library actually copied (a row-band handle only pulls the source rows its band reads)
         h2d = (int(cv.info().h2d_bytes_total) - h2d0) // e2e_steps
-        t = torch.tensor([dt], device=f"cuda:{local}")
+        e2e_val = canvas_mp * e2e_steps / dt
+        e2e_ms = dt / e2e_steps * 1e3
+        h2d_all, d2h_all = allsum([h2d, d2h])
+        note(f"e2e {e2e_val:.0f} MP/s ({e2e_ms:.1f} ms per step)")
+
+        # ---------------- the PCIe floor of that step: the same bytes, N ranks at once, pinned memory, no kernels
+        floor_ms = None
+        try:
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            scratch = torch.empty((plan.fh, plan.fw, 3), dtype=torch.uint8, device=dev)
+            dev_out = torch.empty_like(out_pin, device=dev)
+            n_up = max(1, int(round(h2d / frame_bytes)))
+            rem = h2d - (n_up - 1) * frame_bytes if n_up * frame_bytes > h2d else frame_bytes
+
+            def copies():
+                with torch.cuda.stream(s_up):
+                    for k in range(n_up):
+                        src = pinned[k % n_host]
+                        if k == n_up - 1 and rem < frame_bytes:
+                            rows = max(1, rem // (plan.fw * 3))
+                            scratch[:rows].copy_(src[:rows], non_blocking=True)
+                        else:
+                            scratch.copy_(src, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    out_pin.copy_(dev_out, non_blocking=True)
+            copies()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                copies()
+                torch.cuda.synchronize()
+            barrier()
+            floor_ms = allmax(time.perf_counter() - t0) / 2 * 1e3
+            del scratch, dev_out
+        except Exception as e:
+            floor_ms = None
+            note(f"pcie floor failed: {e}")
+
+        affinities = [None] * world
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_val = canvas_mp * e2e_steps / float(t.item())
-        h2d_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(h2d_t)
-        ab_total = int(cv.info().algorithmic_bytes)
+            dist.all_gather_object(affinities, numa)
+        else:
+            affinities = [numa]
+        launches_all = int(allsum([launches])[0])
 
     if rank == 0:
         # dominant kernel = the launch name/level with the largest mean duration
@@ -382,53 +647,62 @@ def run_native(args):
         if rows:
             (name, level), ms, ab = rows[0]
             ach = ab / (ms / 1e3) / 1e9
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-            if os.path.exists(tp):
-                try:
-                    traffic = json.load(open(tp)).get(f"{args.workload}:{name}:{level}")
-                except Exception:
-                    traffic = None
+            traffic, traffic_src = dominant_traffic(args.workload, name, level)
+            step_ms = ms_total / args.steps
             roof = {"bound": "hbm", "kernel": f"{name}[level {level}]", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                    "note": "achieved = SURVEY 8(d) algorithmic bytes / CUDA-event time; the gather formulation moves fewer real bytes "
-                            "(traffic) than the model, the kernel is issue-bound (profiles/README.md)",
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ab,
+                    "note": "rank 0's launches; achieved = SURVEY 8(d) algorithmic bytes of the launch / its CUDA-event time. The gather "
+                            "formulation moves fewer real bytes (traffic) than the model: the kernel is issue-bound (profiles/README.md)",
                     "ms_per_launch": ms,
-                    "whole_step": {"algorithmic_bytes": ab_total, "achieved": ab_total / (ms_total / args.steps / 1e3) / 1e9,
-                                   "frac": ab_total / (ms_total / args.steps / 1e3) / 1e9 / peak},
+                    "whole_step": {"algorithmic_bytes_rank0": ab_total, "achieved": ab_total / (step_ms / 1e3) / 1e9,
+                                   "frac": ab_total / (step_ms / 1e3) / 1e9 / peak, "frac_of_8TBps_nominal": ab_total / (step_ms / 1e3) / 1e9 / 8000.0},
                     "kernels": [{"kernel": f"{k[0]}[{k[1]}]", "ms": m_, "algorithmic_bytes": a_} for k, m_, a_ in rows]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ref = CpuReference(plan, blend, bands, budget_s=25.0)
-            mp, dt = ref.step()
-            cpu = {"value": mp / dt, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.sample()}
+            ref = CpuReference(plan, blend, bands, grid_nx(args.workload), target_seconds=20.0)
+            mp, dt_ = ref.step()
+            cpu = {"value": mp / dt_, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.sample()}
+        cfg = job_config(desc, plan, roi, blend, bands, world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8/int16/f32", "data": "synthetic",
-                "config": {"workload": desc, "canvas": [roi[2], roi[3]], "frames": len(xfs), "bands_per_gpu": 1,
-                           "parallelism": f"row-bands x{world}", "halo": halo, "host_affinity": numa, "l2": "inputs larger than L2 (720 MB of BGRX frames per band)"},
-                "clocks": clk,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_t[0].item()),
-                        "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": e2e_steps},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": DTYPE, "data": "synthetic", "config": cfg,
+                "run": {"halo": halo, "band_edges": [int(e) for e in edges], "frames_rank0": len(mine), "device_GB_rank0": info.device_bytes / 1e9,
+                        "host_frames": host_mode, "host_affinity": affinities,
+                        "frames_from": "procedural orthophoto evaluated per frame (synth.procedural_frame)" if procedural else "stored procedural orthophoto (synth.orthophoto)"},
+                "clocks": clk, "parity": parity,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps,
+                        "ms_per_step": e2e_ms, "pcie_floor_ms": floor_ms,
+                        "frac_of_floor": (floor_ms / e2e_ms) if floor_ms else None,
+                        "floor_how": "the step's host->device and device->host byte counts copied from / to the same pinned buffers on two streams by all ranks at once, no kernels"},
+                "gpu_launches": launches_all, "roofline": roof, "cpu_baseline": cpu}
+        if also:
+            line["also"] = also
         print(json.dumps(line), flush=True)
     cv.close()
+    ok = (not parity.get("checked")) or parity.get("identical")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg1", "cfg3", "small"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg2", "cfg1", "cfg3", "cfg5", "small"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--host-pool", type=int, default=0, help="pinned host frame buffers for the e2e step (0: one per frame if memory allows)")
     ap.add_argument("--bands", type=int, default=None, help="override the workload's multi-band depth (experiments)")
     ap.add_argument("--p2p", default="auto", choices=["auto", "on", "off"],
-                    help="row bands exchange their level-1 halo rows over NVLink (on), recompute them (off), or decide by pyramid depth (auto)")
+                    help="row bands exchange their level-1 halo rows over NVLink (auto / on), or recompute them (off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

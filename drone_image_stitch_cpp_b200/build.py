@@ -16,6 +16,18 @@ NVCC_FLAGS = [
 ]
 
 
+def source_hash():
+    """sha256 (16 hex digits) over the kernel / runtime sources and the build flags: what a built library, a SASS listing
+    or an ncu capture was made from."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(DEPS):
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def nvcc_path():
     p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(p):
@@ -30,6 +42,9 @@ def build_cuda(force=False, verbose=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     subprocess.check_call(cmd)
+    # which sources the shipped binary was built from (the .so is git-ignored but travels to the GPU box)
+    with open(OUT + ".sources", "w") as f:
+        f.write(source_hash() + "\n")
     return OUT
 
 

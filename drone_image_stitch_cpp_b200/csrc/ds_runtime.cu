@@ -13,6 +13,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -219,6 +221,8 @@ bool encode_tile_map(CUtensorMap* m, bool is_float, void* base, int w, int h, in
 }
 #endif
 
+const int DS_MAX_FRAMES = 1 << 16;   // frame slots per handle (the frame table is dense: an index allocates every slot below it)
+
 template <class T>
 int dev_alloc_t(T** p, size_t count) { return dev_alloc((void**)p, count * sizeof(T)); }
 
@@ -290,6 +294,7 @@ struct ds_canvas {
     struct PeerFrame { int idx, ry, rh, rw, gp1; const char* pyr; size_t g_off, w_off; };
     struct Peer {
         bool connected = false;
+        bool same_process = false; uint64_t uid = 0; int gen = 0;   // liveness check of raw pointers
         int* flags = nullptr;            // the neighbour's counter words (peer-mapped)
         Range band{0, 0};
         std::vector<PeerFrame> frames;
@@ -299,7 +304,10 @@ struct ds_canvas {
     int p2p_seq = 0;                     // composites run in exchange mode
     bool exchange = false;               // the launch metadata (and plan[0].own) are those of the exchange mode
     bool exchange_now = false;           // the composite being queued runs in exchange mode
-    bool stage_open = false;             // ds_composite_stage(c, 0) ran, stage 1 is outstanding
+    bool stage_open = false;             // ds_composite_stage(c, 0) ran in exchange mode, its second half is outstanding
+    bool stage1_due = false;             // ds_composite_stage(c, 0) ran (any mode): stage 1 is expected next
+    uint64_t uid = 0;                    // identity in the registry of live handles (same-process peers check each other's generation)
+    int p2p_gen = 0;                     // bumped whenever a per-frame pyramid is reallocated: exported pointers are then stale
     Range own0_recompute{0, 0};          // level-0 feed rows without / with the exchange
     PullSeg* d_segs = nullptr; int n_segs = 0;   // meta arena
     event_t ev_chunks = 0;   // scratch: recorded on xp after the chunks a slice needs
@@ -349,6 +357,16 @@ struct ds_canvas {
 };
 
 namespace {
+
+// Live handles of this process and the generation of their exported pointers: a same-process peer holds raw device
+// pointers into its neighbour's pyramids, so before using them it checks that the neighbour still exists and has not
+// reallocated them since the export.
+std::mutex g_reg_mu;
+std::map<uint64_t, int> g_reg;
+uint64_t g_next_uid = 1;
+void reg_set(ds_canvas* c) { std::lock_guard<std::mutex> lk(g_reg_mu); if (!c->uid) c->uid = g_next_uid++; g_reg[c->uid] = c->p2p_gen; }
+void reg_drop(ds_canvas* c) { std::lock_guard<std::mutex> lk(g_reg_mu); if (c->uid) g_reg.erase(c->uid); }
+bool reg_alive(uint64_t uid, int gen) { std::lock_guard<std::mutex> lk(g_reg_mu); auto it = g_reg.find(uid); return it != g_reg.end() && it->second == gen; }
 
 // DS_TRACE=1 (measurement aid): timestamps on the upload / compute / download streams.
 #if DS_CUDA
@@ -1113,10 +1131,10 @@ int composite_epilogue(ds_canvas* c) {
     return DS_OK;
 }
 
-int launch_signal(ds_canvas* c, int* a, int* b, int value) {
+int launch_signal(ds_canvas* c, stream_t st, int* a, int* b, int value) {
     if (!a && !b) return DS_OK;
     SignalParams sp{a, b, value};
-    int rc = launch<SignalBody, 32>(sp, 1, c->stream, 0);
+    int rc = launch<SignalBody, 32>(sp, 1, st, 0);
     if (!rc) c->launches++;
     return rc;
 }
@@ -1132,7 +1150,7 @@ int composite_exchange_begin(ds_canvas* c, const ABModel& abm) {
         if (c->peer[side].connected && (rc = stream_wait_value(c->stream, c->d_flags + 2 + side, seq - 1))) return rc;
     if ((rc = launch_feed(c, c->stream, 0, sb, abm))) return rc;
     // seen from the neighbour above this handle is the one below: its word [1]; and vice versa
-    return launch_signal(c, c->peer[0].connected ? c->peer[0].flags + 1 : nullptr, c->peer[1].connected ? c->peer[1].flags + 0 : nullptr, seq);
+    return launch_signal(c, c->stream, c->peer[0].connected ? c->peer[0].flags + 1 : nullptr, c->peer[1].connected ? c->peer[1].flags + 0 : nullptr, seq);
 }
 
 // Second half: wait for the neighbours' level-1 rows, pull the halo rows over NVLink, release the neighbours, and
@@ -1151,7 +1169,7 @@ int composite_exchange_finish(ds_canvas* c) {
         if ((rc = prof_mark(c, c->stream, false, nullptr, 0, 0))) return rc;
         c->launches++;
     }
-    if ((rc = launch_signal(c, c->peer[0].connected ? c->peer[0].flags + 3 : nullptr, c->peer[1].connected ? c->peer[1].flags + 2 : nullptr, seq))) return rc;
+    if ((rc = launch_signal(c, c->stream, c->peer[0].connected ? c->peer[0].flags + 3 : nullptr, c->peer[1].connected ? c->peer[1].flags + 2 : nullptr, seq))) return rc;
     for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, c->stream, l, sb, abm))) return rc;
     for (int l = c->L; l >= 1; l--) if ((rc = launch_collapse(c, c->stream, l, sb, abm))) return rc;
     if ((rc = ev_make(&sb.done)) || (rc = ev_record(sb.done, c->stream))) return rc;
@@ -1162,12 +1180,22 @@ int composite_exchange_finish(ds_canvas* c) {
 int run_composite(ds_canvas* c, int stage) {
     int rc;
     if (stage == 1) {
-        if (!c->stage_open) return fail(DS_ERR_STATE, "ds_composite_stage(c, 1) without stage 0");
-        if (c->exchange_now) return composite_exchange_finish(c);
-        c->stage_open = false;   // nothing was left to do
-        return DS_OK;
+        if (!c->stage1_due) return fail(DS_ERR_STATE, "ds_composite_stage(c, 1) without stage 0");
+        if (c->stage_open) {
+            rc = composite_exchange_finish(c);
+            if (!rc) c->stage1_due = false;
+            return rc;
+        }
+        c->stage1_due = false;
+        return DS_OK;   // stage 0 ran the whole composite (no exchange for this handle): nothing was left to do
     }
-    if (c->stage_open) return fail(DS_ERR_STATE, "the previous composite is half done: call ds_composite_stage(c, 1)");
+    if (c->stage_open || c->stage1_due) return fail(DS_ERR_STATE, "the previous composite is half done: call ds_composite_stage(c, 1)");
+    // same-process neighbours: their exported pointers must still be what was exported
+    for (int side = 0; side < 2; side++) {
+        const ds_canvas::Peer& pr = c->peer[side];
+        if (pr.connected && pr.same_process && !reg_alive(pr.uid, pr.gen))
+            return fail(DS_ERR_STATE, "the neighbour %s was destroyed or reallocated its frames: export and connect again", side ? "below" : "above");
+    }
     // pipelined (sliced) when asked for, or when frames are still arriving on the upload stream
     int slice_rows = 0;
     if (c->desc.pipeline_rows > 0) slice_rows = c->desc.pipeline_rows;
@@ -1203,10 +1231,22 @@ int run_composite(ds_canvas* c, int stage) {
 #if DS_CUDA
     DS_CK(cudaEventRecord(c->ev0, c->stream));
 #endif
-    c->stage_open = true;
+    c->stage1_due = (stage == 0);
     if (xmode) {
+        c->stage_open = true;
         if ((rc = composite_exchange_begin(c, abm))) return rc;
         return stage == -1 ? composite_exchange_finish(c) : DS_OK;
+    }
+    // Connected handles that run the recompute schedule this time (row slices, uploads in flight) keep the hand-over
+    // protocol going, so a neighbour that does exchange never waits for nothing: this composite counts, the neighbours'
+    // "pulled" marks of the previous one are waited for before the level-1 rows are overwritten, and after the last
+    // level-0 feed the rows are announced - and, since this handle pulls nothing, released at once.
+    const bool keepalive = c->peer[0].connected || c->peer[1].connected;
+    int ka_seq = 0;
+    if (keepalive) {
+        ka_seq = ++c->p2p_seq;
+        for (int side = 0; side < 2; side++)
+            if (c->peer[side].connected && (rc = stream_wait_value(c->stream, c->d_flags + 2 + side, ka_seq - 1))) return rc;
     }
     // Sliced schedule: the level-0 feeds (the bulk of the work) of all slices run back to back on a low-priority
     // stream; everything else of a slice - its feeds of level >= 1 and its collapse, small launches that are
@@ -1231,6 +1271,10 @@ int run_composite(ds_canvas* c, int stage) {
         }
         if ((rc = launch_feed(c, P, 0, sb, abm))) return rc;
         trace_mark(c, P, "  level-0 feed end, row", sb.rows.hi);
+        if (keepalive && b + 1 == c->subs.size()) {
+            if ((rc = launch_signal(c, P, c->peer[0].connected ? c->peer[0].flags + 1 : nullptr, c->peer[1].connected ? c->peer[1].flags + 0 : nullptr, ka_seq))) return rc;
+            if ((rc = launch_signal(c, P, c->peer[0].connected ? c->peer[0].flags + 3 : nullptr, c->peer[1].connected ? c->peer[1].flags + 2 : nullptr, ka_seq))) return rc;
+        }
         if (two && ((rc = ev_make(&sb.fed0)) || (rc = ev_record(sb.fed0, P)) || (rc = ev_wait(Q, sb.fed0)))) return rc;
         for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, Q, l, sb, abm))) return rc;
         for (int l = c->L; l >= 1; l--) if ((rc = launch_collapse(c, Q, l, sb, abm))) return rc;
@@ -1251,6 +1295,7 @@ struct BlobHeader {
     int32_t device, L, pw, ph, band_lo, band_hi, nframes, pad;
     uint64_t flags_ptr;
     unsigned char flags_handle[64];
+    uint64_t uid; int32_t gen, pad2;
 };
 struct BlobFrame {
     int32_t idx, ry, rh, rw, gp1, pad;
@@ -1434,7 +1479,7 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
 int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int h, size_t stride,
               const ds_transform* xf, const ds_frame_opts* opts) {
     if (!c || !bgr || !xf) return fail(DS_ERR_BAD_ARG, "null argument");
-    if (idx < 0 || idx > (1 << 20)) return fail(DS_ERR_BAD_ARG, "frame_idx %d out of range", idx);
+    if (idx < 0 || idx >= DS_MAX_FRAMES) return fail(DS_ERR_BAD_ARG, "frame_idx %d out of range [0, %d)", idx, DS_MAX_FRAMES);
     if (w <= 0 || h <= 0 || w > 32767 || h > 32767) return fail(DS_ERR_BAD_ARG, "frame size %dx%d (cv::remap needs < 32768)", w, h);
     if (stride < (size_t)w * 3) return fail(DS_ERR_BAD_ARG, "stride %zu < 3*w", stride);
     if (c->stage_open) return fail(DS_ERR_STATE, "a composite is half done: call ds_composite_stage(c, 1) before uploading");
@@ -1442,8 +1487,16 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     if ((rc = set_device(c))) return rc;
     int pl[4];
     if ((rc = placement(xf, w, h, pl))) return rc;
+    // the frame must lie inside the canvas ROI (prepare(resultRoi(corners, sizes)) guarantees it in the reference);
+    // checked before anything of the handle changes, so that a refused upload leaves the previous frame in place
+    if (pl[0] < c->desc.x || pl[1] < c->desc.y || (long long)pl[0] + pl[2] > (long long)c->desc.x + c->desc.width ||
+        (long long)pl[1] + pl[3] > (long long)c->desc.y + c->desc.height)
+        return fail(DS_ERR_BAD_ARG, "frame %d bbox (%d,%d %dx%d) leaves the canvas ROI (%d,%d %dx%d)", idx, pl[0], pl[1],
+                    pl[2], pl[3], c->desc.x, c->desc.y, c->desc.width, c->desc.height);
     if ((size_t)idx >= c->frames.size()) c->frames.resize((size_t)idx + 1);
     Frame& f = c->frames[(size_t)idx];
+    // from here on the frame's state changes: whatever fails below, the launch metadata must be rebuilt
+    struct DirtyOnFailure { ds_canvas* c; bool armed; ~DirtyOnFailure() { if (armed) { c->dirty = true; c->composited = false; } } } guard{c, true};
     const bool async = opts && (opts->flags & DS_UPLOAD_ASYNC);
     const bool was_used = f.used;
     const FrameDev before = f.dev;
@@ -1451,13 +1504,6 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     if (c->ev_done_valid && ((rc = ev_wait(c->up, c->ev_done)) || (rc = ev_wait(c->xp, c->ev_done)))) return rc;
     f.used = true; f.w = w; f.h = h; f.xf = *xf;
     f.corner_x = pl[0]; f.corner_y = pl[1]; f.bw = pl[2]; f.bh = pl[3];
-    // the frame must lie inside the canvas ROI (prepare(resultRoi(corners, sizes)) guarantees it in the reference)
-    if (f.corner_x < c->desc.x || f.corner_y < c->desc.y || f.corner_x + f.bw > c->desc.x + c->desc.width ||
-        f.corner_y + f.bh > c->desc.y + c->desc.height) {
-        f.used = false;
-        return fail(DS_ERR_BAD_ARG, "frame %d bbox (%d,%d %dx%d) leaves the canvas ROI (%d,%d %dx%d)", idx, f.corner_x, f.corner_y,
-                    f.bw, f.bh, c->desc.x, c->desc.y, c->desc.width, c->desc.height);
-    }
     // source: dense BGR rows -> staging slot -> BGRX expansion, in chunks of source rows
     f.pitch = (w + 31) & ~31;
     if ((rc = grow(c, (void**)&f.d_src, &f.src_cap, (size_t)f.pitch * h * sizeof(uint32_t)))) return rc;
@@ -1486,7 +1532,11 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     // blend-mode specific geometry and buffers
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND) {
         dsgeo::feed_roi(c->desc.x, c->desc.y, c->pw, c->ph, c->L, f.corner_x, f.corner_y, f.bw, f.bh, f.rx, f.ry, f.rw, f.rh);
-        if ((rc = grow(c, &f.d_pyr, &f.pyr_cap, pyr_bytes(c, f)))) return rc;
+        {
+            void* const before_pyr = f.d_pyr;
+            if ((rc = grow(c, &f.d_pyr, &f.pyr_cap, pyr_bytes(c, f)))) return rc;
+            if (before_pyr && f.d_pyr != before_pyr) { c->p2p_gen++; reg_set(c); }   // pointers exported earlier are stale now
+        }
     } else {
         if ((rc = grow(c, (void**)&f.d_mbits, &f.mbits_cap, (size_t)((f.bw + 31) / 32) * f.bh * sizeof(uint32_t)))) return rc;
     }
@@ -1494,6 +1544,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
     if (async) c->async_pending = true;
     else if ((rc = stream_sync(c->up)) || (rc = stream_sync(c->xp))) return rc;
     // same geometry, buffers and gains as before (a new image for the same slot): the launch metadata stands
+    guard.armed = false;
     if (!was_used || memcmp(&before, &f.dev, sizeof(FrameDev)) != 0) c->dirty = true;
     c->composited = false;
     return DS_OK;
@@ -1702,6 +1753,7 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
 
 DS_API void ds_destroy_canvas(ds_canvas* c) {
     if (!c) return;
+    reg_drop(c);
     set_device(c);
 #if DS_CUDA
     if (c->up) cudaStreamSynchronize(c->up);
@@ -1829,7 +1881,7 @@ DS_API int ds_composite(ds_canvas* c) {
 DS_API int ds_download_tile(ds_canvas* c, int x, int y, int w, int h, uint8_t* out, size_t stride, uint8_t* mask_out, size_t mask_stride) {
     if (!c || !out) return fail(DS_ERR_BAD_ARG, "null argument");
     if (!c->composited) return fail(DS_ERR_STATE, "ds_download_tile before ds_composite");
-    if (w <= 0 || h <= 0 || x < 0 || x + w > c->desc.width || y < c->band.lo || y + h > c->out_hi)
+    if (w <= 0 || h <= 0 || x < 0 || w > c->desc.width - x || y < c->band.lo || y > c->out_hi || h > c->out_hi - y)
         return fail(DS_ERR_BAD_ARG, "tile (%d,%d %dx%d) outside this handle's rows [%d,%d) x [0,%d)", x, y, w, h, c->band.lo, c->out_hi, c->desc.width);
     const int bpp = c->desc.out_format == DS_OUT_BGRA8 ? 4 : 3;
     if (stride < (size_t)w * bpp) return fail(DS_ERR_BAD_ARG, "stride too small");
@@ -2051,13 +2103,20 @@ DS_API int ds_p2p_export(ds_canvas* c, void* blob, size_t capacity, size_t* size
     *size = need;
     if (!blob) return DS_OK;   // size query
     if (capacity < need) return fail(DS_ERR_BAD_ARG, "blob needs %zu bytes", need);
-    if (!c->d_flags) {
-        if ((rc = dev_alloc_t(&c->d_flags, 64))) return rc;   // own allocation: it gets its own IPC handle
-        if ((rc = dev_zero(c->d_flags, 64 * sizeof(int)))) return rc;
-    }
+    if (c->stage_open) return fail(DS_ERR_STATE, "a composite is half done");
+    // An export starts a new connection epoch: old neighbours are dropped and the hand-over counters restart from zero,
+    // so every handle of the chain exports again before any of them reconnects (ds_p2p_connect checks it).
+    if ((rc = stream_sync(c->stream))) return rc;
+    if (c->peer[0].connected || c->peer[1].connected) c->dirty = true;
+    peer_close(c, 0); peer_close(c, 1);
+    if (!c->d_flags && (rc = dev_alloc_t(&c->d_flags, 64))) return rc;   // own allocation: it gets its own IPC handle
+    if ((rc = dev_zero(c->d_flags, 64 * sizeof(int)))) return rc;
+    c->p2p_seq = 0;
+    reg_set(c);
     BlobHeader h;
     memset(&h, 0, sizeof(h));
-    h.magic = BLOB_MAGIC; h.version = 1; h.pid = (int64_t)getpid();
+    h.magic = BLOB_MAGIC; h.version = 2; h.pid = (int64_t)getpid();
+    h.uid = c->uid; h.gen = c->p2p_gen;
     h.device = c->desc.device; h.L = c->L; h.pw = c->pw; h.ph = c->ph; h.band_lo = c->band.lo; h.band_hi = c->band.hi;
     h.nframes = (int32_t)fr.size();
     h.flags_ptr = (uint64_t)(uintptr_t)c->d_flags;
@@ -2090,7 +2149,7 @@ DS_API int ds_p2p_connect(ds_canvas* c, int side, const void* blob, size_t size)
     if (size < sizeof(BlobHeader)) return fail(DS_ERR_BAD_ARG, "blob too small");
     BlobHeader h;
     memcpy(&h, blob, sizeof(h));
-    if (h.magic != BLOB_MAGIC || h.version != 1 || size < sizeof(BlobHeader) + (size_t)h.nframes * sizeof(BlobFrame))
+    if (h.magic != BLOB_MAGIC || h.version != 2 || size < sizeof(BlobHeader) + (size_t)h.nframes * sizeof(BlobFrame))
         return fail(DS_ERR_BAD_ARG, "not a ds_p2p_export blob");
     if (h.L != c->L || h.pw != c->pw || h.ph != c->ph) return fail(DS_ERR_BAD_ARG, "the neighbour describes a different canvas");
     if (side == 0 ? h.band_hi != c->band.lo : h.band_lo != c->band.hi)
@@ -2102,6 +2161,9 @@ DS_API int ds_p2p_connect(ds_canvas* c, int side, const void* blob, size_t size)
     int rc;
     if ((rc = set_device(c))) return rc;
     if ((rc = stream_sync(c->stream))) return rc;
+    // both ends count composites from the same epoch: this handle must not have composited in exchange mode since its own
+    // last ds_p2p_export (the neighbour's blob is fresh by construction: exporting reset its counters)
+    if (c->p2p_seq != 0) return fail(DS_ERR_STATE, "this handle has composited since its last ds_p2p_export: export again on every handle before reconnecting");
     if (!c->d_flags) {
         if ((rc = dev_alloc_t(&c->d_flags, 64))) return rc;
         if ((rc = dev_zero(c->d_flags, 64 * sizeof(int)))) return rc;
@@ -2109,6 +2171,8 @@ DS_API int ds_p2p_connect(ds_canvas* c, int side, const void* blob, size_t size)
     peer_close(c, side);
     ds_canvas::Peer& pr = c->peer[side];
     const bool same_process = h.pid == (int64_t)getpid();
+    if (same_process && !reg_alive(h.uid, h.gen)) return fail(DS_ERR_STATE, "the exporting handle was destroyed or changed its frames since the export");
+    pr.same_process = same_process; pr.uid = h.uid; pr.gen = h.gen;
     auto map = [&](uint64_t raw, const unsigned char* handle, void** out) -> int {
         if (same_process) {
 #if DS_CUDA

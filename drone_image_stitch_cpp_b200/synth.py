@@ -138,3 +138,82 @@ def grid_survey(nx, ny, fw, fh, overlap=0.7, seed=MASTER_SEED, rot_deg=3.0, scal
                 work_scale=1.0, device="cpu", serpentine=True, side_overlap=None):
     plan = plan_grid(nx, ny, fw, fh, overlap, seed, rot_deg, scale_jit, trans_jit, work_scale, serpentine, side_overlap)
     return Survey(cut(plan, None, device), plan.Ks, plan.Rs, plan.scale, plan.A)
+
+
+# ---------------------------------------------------------------------------------------------
+# Procedural orthophoto for surveys whose canvas is too large to store (BASELINE configs 3-5): the ground colour is a
+# closed-form function of the orthophoto coordinate - a sum of plane waves over eight octaves (fields, roads, texture
+# down to a 3 px period) plus a few hundred soft-edged "parcels" from a hashed lattice - so a frame is evaluated directly
+# at the ortho position of each of its pixels. Same statistics as `orthophoto` (mean ~110, sigma ~45, fine texture of
+# +-10 levels so Laplacian levels are never trivially zero); overlaps are photometrically consistent by construction.
+
+def _wave_bank(seed):
+    rng = np.random.default_rng(int(seed) + 77)
+    waves = []
+    for octave in range(8):
+        period = 1800.0 / (2.3 ** octave)              # 1800 px ... 5.3 px
+        amp = 26.0 * (0.72 ** octave)
+        for _ in range(3):
+            th = rng.uniform(0, 2 * math.pi)
+            k = 2 * math.pi / (period * rng.uniform(0.8, 1.25))
+            waves.append((k * math.cos(th), k * math.sin(th), rng.uniform(0, 2 * math.pi, 3), amp * rng.uniform(0.6, 1.0, 3)))
+    for _ in range(4):                                  # the finest texture: 3-4 px periods, +-4 levels each
+        th = rng.uniform(0, 2 * math.pi)
+        k = 2 * math.pi / rng.uniform(3.0, 4.2)
+        waves.append((k * math.cos(th), k * math.sin(th), rng.uniform(0, 2 * math.pi, 3), np.full(3, 4.0)))
+    return waves
+
+
+_WAVES = {}
+
+
+def procedural_frame(plan, i, device="cpu", as_torch=False):
+    """Frame i of `plan` (HxWx3 uint8 BGR) evaluated from the procedural orthophoto through its ground-truth map A_i."""
+    waves = _WAVES.setdefault(plan.seed, _wave_bank(plan.seed))
+    A = plan.A[i]
+    fw, fh = plan.fw, plan.fh
+    dt = torch.float32
+    ys, xs = torch.meshgrid(torch.arange(fh, device=device, dtype=dt), torch.arange(fw, device=device, dtype=dt), indexing="ij")
+    # ortho coordinates in float64-accurate form: large offsets are folded into the phases per wave
+    ox = float(A[0, 0]) * xs + float(A[0, 1]) * ys
+    oy = float(A[1, 0]) * xs + float(A[1, 1]) * ys
+    tx, ty = float(A[0, 2]), float(A[1, 2])
+    out = torch.full((3, fh, fw), 112.0, device=device, dtype=dt)
+    for kx, ky, ph, amp in waves:
+        base = kx * ox + ky * oy
+        off = math.fmod(kx * tx + ky * ty, 2 * math.pi)
+        for c in range(3):
+            out[c] += float(amp[c]) * torch.sin(base + (off + float(ph[c])))
+    # parcels: a 700 px lattice, each cell tinted by a hash of its index (soft 40 px edges)
+    gx, gy = (ox + tx) / 700.0, (oy + ty) / 700.0
+    cx, cy = torch.floor(gx), torch.floor(gy)
+    hsh = torch.frac(torch.sin(cx * 127.1 + cy * 311.7 + (plan.seed % 1000) * 0.37) * 43758.5453)
+    edge = torch.minimum(torch.minimum(gx - cx, cx + 1 - gx), torch.minimum(gy - cy, cy + 1 - gy)).clamp_(0, 0.06) / 0.06
+    tint = (hsh - 0.5) * 60.0 * edge
+    out[0] += tint * 0.6
+    out[1] += tint
+    out[2] += tint * 0.8
+    img = out.clamp_(0.0, 255.0).round_().to(torch.uint8).permute(1, 2, 0).contiguous()
+    return img if as_torch else img.cpu().numpy()
+
+
+def plan_survey(name, seed=MASTER_SEED):
+    """The BASELINE.json survey layouts: (plan, blend, bands, description)."""
+    fw, fh = 5472, 3648
+    if name == "cfg2":
+        return plan_grid(3, 3, fw, fh, overlap=0.7, seed=seed), "multiband", 5, "cfg2: 3x3 grid of 5472x3648 frames, 70% overlap, multi-band 5"
+    if name == "cfg3":
+        return (plan_grid(40, 3, fw, fh, overlap=0.7, side_overlap=0.32, seed=seed), "multiband", 5,
+                "cfg3: 120-frame serpentine flight, 3 lines x 40 frames of 5472x3648, 70% forward / 32% side overlap, multi-band 5")
+    if name == "cfg4":
+        return (plan_grid(50, 12, fw, fh, overlap=0.7, side_overlap=0.32, seed=seed), "multiband", 5,
+                "cfg4: 600-frame survey, 12 lines x 50 frames of 5472x3648, 70% forward / 32% side overlap, multi-band 5")
+    if name == "cfg5":
+        return (plan_grid(80, 25, fw, fh, overlap=0.7, side_overlap=0.32, seed=seed), "multiband", 8,
+                "cfg5: 2000-frame large-area survey, 25 lines x 80 frames of 5472x3648, 70% forward / 32% side overlap, multi-band 8")
+    if name == "cfg1":
+        return plan_grid(2, 1, 4000, 3000, overlap=0.7, seed=seed, rot_deg=1.5), "feather", 0, "cfg1: 2 frames of 4000x3000, feather 0.02"
+    if name == "small":
+        return (plan_grid(6, 4, 640, 480, overlap=0.7, side_overlap=0.32, seed=seed), "multiband", 5,
+                "small: 4 lines x 6 frames of 640x480 (test-sized stand-in for cfg4), multi-band 5")
+    raise ValueError(f"unknown survey {name}")

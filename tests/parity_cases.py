@@ -218,6 +218,12 @@ def case_windowed_oracle(lib):
     win = (128, 96, 384, 320)
     ref, refmask = windowed_oracle(sv.frames, sv.Ks, sv.Rs, sv.scale, bands, roi, win)
     check_window(pano, mask, ref, refmask, win, bands)
+    # oracle/windowed.py (frames warped only over their part of the window; what bench.py's in-run check uses) is the same oracle
+    from oracle import windowed as W
+    ref2, refmask2 = W.compose_window(sv.frames, sv.Ks, sv.Rs, sv.scale, bands, roi, win)
+    assert np.array_equal(ref2, ref) and np.array_equal(refmask2, refmask)
+    n, bad, mx = W.compare_inside(pano[100:300], mask[100:300], 100, ref2, refmask2, win, bands)
+    assert n > 0 and bad == 0 and mx == 0
 
 
 def plane_specs(sv):
