@@ -46,7 +46,8 @@ class ds_frame_opts(C.Structure):
                 ("seam_lowres", C.c_void_p), ("seam_lowres_w", C.c_int32), ("seam_lowres_h", C.c_int32),
                 ("seam_lowres_stride", C.c_size_t),
                 ("compensator_gain", C.POINTER(C.c_double)), ("gain_map", C.c_void_p), ("gain_map_stride", C.c_size_t),
-                ("flags", C.c_uint32), ("soft_sigma", C.c_double)]
+                ("flags", C.c_uint32), ("soft_sigma", C.c_double),
+                ("gain_blocks", C.c_void_p), ("gain_blocks_w", C.c_int32), ("gain_blocks_h", C.c_int32), ("gain_blocks_stride", C.c_size_t)]
 
 
 class ds_canvas_desc(C.Structure):

@@ -146,11 +146,11 @@ class Canvas:
 
     @staticmethod
     def _make_opts(seam_mask=None, channel_gain=None, seam_lowres=None, compensator_gain=None, gain_map=None, async_=False,
-                   content_mask=False, seam_nearest=False, soft_mask=None):
+                   content_mask=False, seam_nearest=False, soft_mask=None, gain_blocks=None):
         """-> (ds_frame_opts or None, buffers to keep alive)."""
         keep = []
         if not (async_ or content_mask or seam_nearest or soft_mask is not None or
-                any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map))):
+                any(v is not None for v in (seam_mask, channel_gain, seam_lowres, compensator_gain, gain_map, gain_blocks))):
             return None, keep
         opts = L.ds_frame_opts()
         opts.flags = ((L.DS_UPLOAD_ASYNC if async_ else 0) | (L.DS_MASK_CONTENT if content_mask else 0) |
@@ -166,6 +166,12 @@ class Canvas:
             keep.append(gm)
             opts.gain_map = gm.ctypes.data
             opts.gain_map_stride = gm.strides[0]
+        if gain_blocks is not None:
+            gb = np.ascontiguousarray(gain_blocks, np.float32)
+            keep.append(gb)
+            opts.gain_blocks = gb.ctypes.data
+            opts.gain_blocks_w, opts.gain_blocks_h = gb.shape[1], gb.shape[0]
+            opts.gain_blocks_stride = gb.strides[0]
         if seam_lowres is not None:
             sl = np.ascontiguousarray(seam_lowres, np.uint8)
             keep.append(sl)
@@ -187,7 +193,7 @@ class Canvas:
         """img: HxWx3 uint8 (numpy; any row stride) or a (ptr, w, h, stride) tuple.
         async_: DS_UPLOAD_ASYNC - `img` (pinned) must stay valid and unchanged until composite() / synchronize() /
         a full download() has returned.
-        opt_kw (ds_frame_opts): seam_mask, seam_lowres, seam_nearest, channel_gain, compensator_gain, gain_map,
+        opt_kw (ds_frame_opts): seam_mask, seam_lowres, seam_nearest, channel_gain, compensator_gain, gain_map, gain_blocks,
         content_mask (DS_MASK_CONTENT), soft_mask (DS_MASK_SOFT: True or the sigma)."""
         opts, keep = self._make_opts(async_=async_, **opt_kw)
         if isinstance(img, tuple):
@@ -316,8 +322,10 @@ class Canvas:
 
 
 def compose_panorama(images, Ks, Rs, scale, blend="multiband", bands=5, sharpness=0.02, affine=True,
-                     out_format="bgr", device=0, lib=None, return_canvas=False):
+                     out_format="bgr", device=0, lib=None, return_canvas=False, seam_lowres=None):
     """The compose half of stitchWithMode (/root/reference/src/stitch_robust.cpp:255-256).
+    seam_lowres: optional list of the low-resolution seam masks cv::Stitcher holds after seam finding (one per image;
+    dilated, resized with INTER_LINEAR_EXACT and ANDed into the warped mask on the device, as composePanorama does).
     Returns (pano HxWx3 uint8, result_mask HxW uint8, roi (x, y, w, h))."""
     lib = lib or L.default_library()
     xfs = [plane_transform(K, R, scale, affine) for K, R in zip(Ks, Rs)]
@@ -327,7 +335,10 @@ def compose_panorama(images, Ks, Rs, scale, blend="multiband", bands=5, sharpnes
     # the images outlive this call: queue the uploads, let the composite chase them slice by slice, and copy each
     # slice out as it completes (DS_UPLOAD_ASYNC, include/dronestitch.h)
     for i, (im, xf) in enumerate(zip(images, xfs)):
-        cv.upload(i, im, xf, async_=True)
+        if seam_lowres is not None:
+            cv.upload(i, im, xf, async_=True, seam_lowres=seam_lowres[i])
+        else:
+            cv.upload(i, im, xf, async_=True)
     cv.composite_async()
     pano, mask = cv.download()
     cv.synchronize()
@@ -335,3 +346,24 @@ def compose_panorama(images, Ks, Rs, scale, blend="multiband", bands=5, sharpnes
         return pano, mask, roi, cv
     cv.close()
     return pano, mask, roi
+
+
+def compose_panorama_from_stitcher(images, cameras, work_scale, warped_image_scale=None, blend="multiband", bands=5,
+                                   affine=True, seam_lowres=None, lib=None, device=0):
+    """Python twin of ds::composePanorama (include/dronestitch.hpp): what replaces `stitcher->composePanorama(output)`
+    at /root/reference/src/stitch_robust.cpp:256. `cameras` and `work_scale` are what cv::Stitcher holds after
+    estimateTransform (:251) - objects with focal / aspect / ppx / ppy / R like cv::detail::CameraParams;
+    warped_image_scale defaults to the median focal, as cv::Stitcher computes it. Full-resolution compositing
+    (compositing_resol_mpx = -1): the cameras are rescaled by compose_work_aspect = 1 / work_scale."""
+    focals = sorted(float(c.focal) for c in cameras)
+    if warped_image_scale is None:
+        n = len(focals)
+        warped_image_scale = focals[n // 2] if n % 2 == 1 else (focals[n // 2 - 1] + focals[n // 2]) * 0.5
+    cwa = 1.0 / float(work_scale)
+    scale = np.float32(float(np.float32(warped_image_scale)) * cwa)
+    Ks, Rs = [], []
+    for c in cameras:
+        focal, ppx, ppy = float(c.focal) * cwa, float(c.ppx) * cwa, float(c.ppy) * cwa
+        Ks.append(np.array([[focal, 0, ppx], [0, focal * float(c.aspect), ppy], [0, 0, 1]], np.float64).astype(np.float32))
+        Rs.append(np.ascontiguousarray(c.R, np.float32))
+    return compose_panorama(images, Ks, Rs, scale, blend, bands, affine=affine, lib=lib, device=device, seam_lowres=seam_lowres)

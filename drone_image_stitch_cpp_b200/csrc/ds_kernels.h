@@ -2289,6 +2289,7 @@ DS_DEFINE_KERNEL(ds_seam_upsize, SeamUpBody, 256, SeamUpParams, 1)
 DS_DEFINE_KERNEL(ds_mask_prep, MaskPrepBody, 256, MaskPrepParams, 1)
 DS_DEFINE_KERNEL(ds_soft_mask, SoftMaskBody, 256, SoftMaskParams, 3)
 DS_DEFINE_KERNEL(ds_crop_row_runs, RowRunsBody, 256, RowRunsParams, 1)
+DS_DEFINE_KERNEL(ds_gain_resize, GainResizeBody, 256, GainResizeParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
 DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 3)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)

@@ -183,3 +183,37 @@ struct RowRunsBody {
         }
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// BlocksGainCompensator::apply's gain-map upsizing (src/stitch_robust.cpp:209-211): cv::resize(CV_32FC1,
+// INTER_LINEAR) of the compensator's block gain map to the warped bbox, as the declared OpenCV build computes it
+// (oracle: orc_resize_linear_f32, pinned against cv2.resize): per-column / per-row source index and fraction tabulated on
+// the host in double, h = fma(S[x1] - S[x0], a, S[x0]) on both source rows, out = fma(h1 - h0, b, h0).
+struct GainResizeParams {
+    const float* src; int sw, sh, spitch;      // block gain map (device copy), pitch in elements
+    const int* ix; const float* ax;            // per output column
+    const int* iy; const float* ay;            // per output row
+    float* dst; int dw, dh;                    // per-pixel gain plane over the warped bbox
+};
+struct GainResizeBody {
+    static constexpr int PER_BLOCK = 1024;
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const GainResizeParams& p, int block, int tid, unsigned char*) {
+        const long long n = (long long)p.dw * p.dh;
+        for (int it = tid; it < PER_BLOCK; it += NT) {
+            const long long idx = (long long)block * PER_BLOCK + it;
+            if (idx >= n) break;
+            const int y = (int)(idx / p.dw), x = (int)(idx - (long long)y * p.dw);
+            const int x0 = ld_ro(p.ix + x), x1 = imin(x0 + 1, p.sw - 1);
+            const int y0 = ld_ro(p.iy + y), y1 = imin(y0 + 1, p.sh - 1);
+            const float a = ld_ro(p.ax + x), b = ld_ro(p.ay + y);
+            const float* r0 = p.src + (size_t)y0 * p.spitch;
+            const float* r1 = p.src + (size_t)y1 * p.spitch;
+            const float s00 = ld_ro(r0 + x0), s01 = ld_ro(r0 + x1), s10 = ld_ro(r1 + x0), s11 = ld_ro(r1 + x1);
+            const float h0 = f_fma(f_sub(s01, s00), a, s00);
+            const float h1 = f_fma(f_sub(s11, s10), a, s10);
+            p.dst[idx] = f_fma(f_sub(h1, h0), b, h0);
+        }
+    }
+};

@@ -1366,6 +1366,10 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
     // arguments are checked before anything about the frame changes
     if (want_soft && (rc = gaussian_kernel_f32(opts->soft_sigma > 0.0 ? opts->soft_sigma : 10.0, sp.k, &sp.R))) return rc;
     if (has_low && (opts->seam_lowres_w <= 0 || opts->seam_lowres_h <= 0)) return fail(DS_ERR_BAD_ARG, "seam_lowres size %dx%d", opts->seam_lowres_w, opts->seam_lowres_h);
+    if (opts && opts->gain_blocks && (opts->gain_blocks_w <= 0 || opts->gain_blocks_h <= 0)) return fail(DS_ERR_BAD_ARG, "gain_blocks size %dx%d", opts->gain_blocks_w, opts->gain_blocks_h);
+    // a block map with a single row or column (a frame under 33 px) takes another code path inside cv::resize that is not pinned
+    if (opts && opts->gain_blocks && (opts->gain_blocks_w == 1 || opts->gain_blocks_h == 1))
+        return fail(DS_ERR_UNSUPPORTED, "gain_blocks %dx%d: single-row / single-column block maps are not supported, pass the resized map as gain_map", opts->gain_blocks_w, opts->gain_blocks_h);
     // temporaries live in the handle's scratch slots (no allocation per call); the caller's buffers are only borrowed, so
     // these (rare) paths drain the upload stream before returning
     uint8_t* d_low = nullptr; int* d_tab = nullptr; uint8_t* d_tmp = nullptr;
@@ -1456,7 +1460,39 @@ int apply_opts(ds_canvas* c, Frame& f, int idx, const ds_frame_opts* opts) {
         f.dev.seam = f.d_seam; f.dev.seam_pitch = f.bw;
     }
     if ((rc = cleanup(DS_OK))) return rc;
-    if (opts && opts->gain_map) {
+    if (opts && opts->gain_blocks) {
+        // BlocksGainCompensator::apply: resize(gain_maps_[i], image size, INTER_LINEAR) on the device (fractions in double here)
+        const int gw = opts->gain_blocks_w, gh = opts->gain_blocks_h;
+        const size_t gst = opts->gain_blocks_stride ? opts->gain_blocks_stride : (size_t)gw * sizeof(float);
+        if ((rc = grow(c, (void**)&f.d_gainmap, &f.gainmap_cap, (size_t)f.bw * f.bh * sizeof(float)))) return rc;
+        std::vector<int> tab(2 * ((size_t)f.bw + f.bh));   // ix | ax (float bits) | iy | ay
+        auto coefs = [](int s_, int d_, int* idx, int* frac_bits) {
+            const double scale = (double)s_ / (double)d_;
+            for (int v = 0; v < d_; v++) {
+                const double fv = ((double)v + 0.5) * scale - 0.5;
+                int i = (int)floor(fv);
+                float fr = (float)(fv - (double)i);
+                if (i < 0) { i = 0; fr = 0.f; }
+                if (i >= s_ - 1) { i = s_ - 1; fr = 0.f; }
+                idx[v] = i; memcpy(&frac_bits[v], &fr, 4);
+            }
+        };
+        coefs(gw, f.bw, tab.data(), tab.data() + f.bw);
+        coefs(gh, f.bh, tab.data() + 2 * f.bw, tab.data() + 2 * f.bw + f.bh);
+        float* d_blocks = nullptr; int* d_gtab = nullptr;
+        if ((rc = grow(c, &c->scratch[0], &c->scratch_cap[0], (size_t)gw * gh * sizeof(float)))) return rc;
+        if ((rc = grow(c, &c->scratch[1], &c->scratch_cap[1], tab.size() * sizeof(int)))) return rc;
+        d_blocks = (float*)c->scratch[0]; d_gtab = (int*)c->scratch[1];
+        if ((rc = h2d_2d(d_blocks, (size_t)gw * sizeof(float), opts->gain_blocks, gst, (size_t)gw * sizeof(float), (size_t)gh, c->up))) return rc;
+        if ((rc = h2d(d_gtab, tab.data(), tab.size() * sizeof(int), c->up))) { stream_sync(c->up); return rc; }
+        GainResizeParams gp{d_blocks, gw, gh, gw, d_gtab, (const float*)(d_gtab + f.bw), d_gtab + 2 * f.bw, (const float*)(d_gtab + 2 * f.bw + f.bh),
+                            f.d_gainmap, f.bw, f.bh};
+        const long long n = (long long)f.bw * f.bh;
+        rc = launch<GainResizeBody, 256>(gp, (n + GainResizeBody::PER_BLOCK - 1) / GainResizeBody::PER_BLOCK, c->up, 0);
+        const int rs = stream_sync(c->up);   // the caller's block map and the host tables are only borrowed
+        if (rc || rs) return rc ? rc : rs;
+        f.dev.gainmap = f.d_gainmap; f.dev.gainmap_pitch = f.bw;
+    } else if (opts && opts->gain_map) {
         const size_t gst = opts->gain_map_stride ? opts->gain_map_stride : (size_t)f.bw * sizeof(float);
         if ((rc = grow(c, (void**)&f.d_gainmap, &f.gainmap_cap, (size_t)f.bw * f.bh * sizeof(float)))) return rc;
         if ((rc = h2d_2d(f.d_gainmap, (size_t)f.bw * sizeof(float), opts->gain_map, gst, (size_t)f.bw * sizeof(float), (size_t)f.bh, c->up))) return rc;

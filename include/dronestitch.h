@@ -116,6 +116,14 @@ typedef struct ds_frame_opts {
     /* DS_MASK_SOFT: sigma of buildSoftBlendMask's GaussianBlur; 0 = the reference's 10.0 (stitch_global.cpp:345).
      * Supported up to 10 (kernel of 81 taps). */
     double soft_sigma;   /* double like cv::GaussianBlur's sigmaX: the kernel taps are computed from it in double */
+    /* BlocksGainCompensator::apply as the reference configures it (stitch_robust.cpp:209-211), from the compensator's own
+     * block gain map (gain_maps_[i], CV_32F, one value per 32x32 block of the seam-scale frame): the library resizes it to
+     * the warped bbox on the device exactly like cv::resize(INTER_LINEAR) does for CV_32FC1 - fractions in double,
+     * fused multiply-adds - and applies sat_u8(rint(float(p) * g)) last. Overrides gain_map when non-NULL. Block maps with
+     * a single row or column (frames under 33 px) are refused with DS_ERR_UNSUPPORTED (cv::resize treats them differently). */
+    const float* gain_blocks;
+    int32_t gain_blocks_w, gain_blocks_h;
+    size_t gain_blocks_stride; /* bytes; 0 = dense */
 } ds_frame_opts;
 
 /* ds_frame_opts.flags */

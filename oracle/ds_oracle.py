@@ -181,6 +181,15 @@ def seam_mask_upsize(mask, dw, dh):
     return out
 
 
+def resize_linear_f32(src, dw, dh):
+    """cv::resize(CV_32FC1, INTER_LINEAR) of the declared OpenCV build: BlocksGainCompensator::apply's gain-map upsizing."""
+    src = np.ascontiguousarray(src, np.float32)
+    sh, sw = src.shape
+    out = np.empty((dh, dw), np.float32)
+    lib().orc_resize_linear_f32(_p(src), C.c_int(sw), C.c_int(sh), C.c_size_t(src.strides[0] // 4), C.c_int(dw), C.c_int(dh), _p(out))
+    return out
+
+
 # ---- global-stage masks (src/stitch_global.cpp:328-383, :649-655)
 
 def bgr2gray(img):

@@ -40,6 +40,9 @@ def oracle_warp(spec):
         warped = np.clip(np.rint(warped.astype(np.float64) * g[None, None, :]), 0, 255).astype(np.uint8)
     if spec.get("gain_map") is not None:      # BlocksGainCompensator::apply: float32 per pixel
         warped = np.clip(np.rint(warped.astype(np.float32) * spec["gain_map"][:, :, None]), 0, 255).astype(np.uint8)
+    if spec.get("gain_blocks") is not None:   # the same from the compensator's block map: resize(INTER_LINEAR) to the bbox first
+        gm = O.resize_linear_f32(spec["gain_blocks"], warped.shape[1], warped.shape[0])
+        warped = np.clip(np.rint(warped.astype(np.float32) * gm[:, :, None]), 0, 255).astype(np.uint8)
     if spec.get("global_stage"):
         # stitchInterStripsCustom (stitch_global.cpp:479-486, :643-658): content mask, seam mask resized with
         # INTER_NEAREST + threshold, soft blend mask; the blender is fed with the soft mask itself
@@ -103,7 +106,7 @@ def run_case(lib, specs, blend, bands, check_taps=True, out_format="bgr", band_s
                 continue
             gs = bool(s.get("global_stage"))
             cv.upload(i, s["img"], xf, seam_mask=s.get("seam"), channel_gain=s.get("gain"), seam_lowres=s.get("seam_lowres"),
-                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"), async_=slice_rows > 0,
+                      compensator_gain=s.get("cgain"), gain_map=s.get("gain_map"), gain_blocks=s.get("gain_blocks"), async_=slice_rows > 0,
                       content_mask=gs, seam_nearest=gs and s.get("seam_lowres") is not None,
                       soft_mask=(s.get("sigma", 10.0) if gs else None))
         if slice_rows > 0:
@@ -386,7 +389,15 @@ def case_exposure_gains(lib):
         if i == 0:
             s["gain"] = (1.07, 0.93, 1.21)
     run_case(lib, specs, "multiband", 3)
-    return run_case(lib, specs, "feather", 0)
+    run_case(lib, specs, "feather", 0)
+    # BlocksGainCompensator as the reference configures it (stitch_robust.cpp:209-211): the compensator's 32x32-block gain
+    # maps go in as they are, the f32 INTER_LINEAR resize to the warped size happens on the device
+    for i, s in enumerate(specs):
+        s.pop("gain_map", None)
+        o = O.warp_frame(s["img"], s["K"], s["R"], s["scale"])
+        bw, bh = o["size"]
+        s["gain_blocks"] = (rng.random(((bh + 31) // 32, (bw + 31) // 32)) * 0.6 + 0.7).astype(np.float32)
+    return run_case(lib, specs, "multiband", 3)
 
 
 def global_stage_specs(seed=31, n=3, fw=420, fh=300):

@@ -244,3 +244,38 @@ def test_auto_crop_rect_empty_and_full():
     assert O.auto_crop_rect(z) == CR.auto_crop_rect_cv2(z)[0] == (0, 0, 23, 17)
     z[:] = 200
     assert O.auto_crop_rect(z) == CR.auto_crop_rect_cv2(z)[0] == (0, 0, 23, 17)
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(23, 17, 731, 540), (171, 114, 1368, 912), (9, 7, 280, 210), (40, 30, 40, 30), (5, 3, 161, 97),
+                                          (2, 2, 64, 64), (2, 3, 20, 20), (60, 45, 1900, 1430)])
+def test_resize_linear_f32(sw, sh, dw, dh):
+    """cv::resize(CV_32FC1, INTER_LINEAR) - the gain-map upsizing of BlocksGainCompensator::apply
+    (/root/reference/src/stitch_robust.cpp:209-211) - pinned bit for bit (round-1 left it with the caller). Maps with a
+    single row or column (frames under 33 px in one dimension) take another path inside OpenCV and are not pinned: the
+    library refuses them (DS_ERR_UNSUPPORTED) and the caller passes the resized map as gain_map."""
+    rng = np.random.default_rng(sw * 1000 + dh)
+    src = (1.0 + 0.3 * rng.standard_normal((sh, sw))).astype(np.float32)
+    ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    got = O.resize_linear_f32(src, dw, dh)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_blocks_gain_apply_chain():
+    """BlocksGainCompensator.apply == sat_u8(rint(img * resize_linear_f32(gain blocks))), through the
+    real compensator: feed it two overlapping images, read its gain maps back, apply, and restate."""
+    rng = np.random.default_rng(5)
+    h, w = 200, 300
+    base = rng.integers(30, 200, (h, w, 3)).astype(np.uint8)
+    imgs = [base.copy(), np.clip(base.astype(np.float32) * 1.25, 0, 255).astype(np.uint8)]
+    masks = [np.full((h, w), 255, np.uint8), np.full((h, w), 255, np.uint8)]
+    comp = cv2.detail_BlocksGainCompensator(32, 32)
+    comp.feed([(0, 0), (0, 0)], imgs, masks)
+    maps = comp.getMatGains()
+    for i in range(2):
+        gm = np.asarray(maps[i].get() if hasattr(maps[i], "get") else maps[i], np.float32)
+        assert gm.shape == ((h + 31) // 32, (w + 31) // 32)
+        want = imgs[i].copy()
+        comp.apply(i, (0, 0), want, masks[i])
+        full = O.resize_linear_f32(gm, w, h)
+        got = np.clip(np.rint(imgs[i].astype(np.float32) * full[:, :, None]), 0, 255).astype(np.uint8)
+        assert np.array_equal(got, want)

@@ -11,7 +11,7 @@ from drone_image_stitch_cpp_b200 import compositor as CP
 from drone_image_stitch_cpp_b200 import synth
 
 
-def _exchange(lib, bands, nbands, ny=5, fw=200, fh=180, seed=51, steps=2):
+def _exchange(lib, bands, nbands, ny=5, fw=200, fh=180, seed=51, steps=2, devices=(0,)):
     sv = synth.grid_survey(2, ny, fw, fh, overlap=0.45, seed=seed, work_scale=0.5)
     xfs = [CP.plane_transform(K, R, sv.scale) for K, R in zip(sv.Ks, sv.Rs)]
     rois = [CP.warp_roi(xf, fw, fh, lib) for xf in xfs]
@@ -27,7 +27,7 @@ def _exchange(lib, bands, nbands, ny=5, fw=200, fh=180, seed=51, steps=2):
     edges = [e for e in edges if e < roi[3]] + [H]
     handles = []
     for y0, y1 in zip(edges[:-1], edges[1:]):
-        cb = CP.Canvas(roi, "multiband", bands, band=(y0, y1), lib=lib)
+        cb = CP.Canvas(roi, "multiband", bands, band=(y0, y1), lib=lib, device=devices[len(handles) % len(devices)])
         for i, (f, xf) in enumerate(zip(sv.frames, xfs)):
             if cb.touches(rois[i]):
                 cb.upload(i, f, xf)
@@ -111,3 +111,15 @@ def test_exchange_refuses_thin_bands(emu_lib):
 def test_exchange_gpu_one_device(cuda_lib, bands, nbands):
     # one process, one device, several handles: stream-ordered counters, plain pointers
     _exchange(cuda_lib, bands, nbands, ny=6, fw=400, fh=360)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bands,nbands", [(3, 4), (5, 2)])
+def test_exchange_gpu_two_devices(cuda_lib, bands, nbands):
+    """Neighbouring bands on DIFFERENT GPUs of one process: the halo rows cross NVLink (peer access enabled by
+    ds_p2p_connect), the hand-over counters live in the other device's memory. Skips on a single-GPU box; the
+    multi-process form (cudaIpc handles, one process per GPU) is checked inside every bench.py --gpus N run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _exchange(cuda_lib, bands, nbands, ny=6, fw=400, fh=360, devices=(0, 1))
