@@ -188,8 +188,8 @@ DS_D bool pd_v_is_simd(int j, int dw) { return j < (dw & ~3); }
 
 #if !DS_CUDA
 // emulation only: how many tile-frames took which level-0 warp path (DS_EMU_STATS=1 prints them at exit)
-static long long g_emu_paths[5];
-static void ds_emu_report() { fprintf(stderr, "[ds emu] level-0 tile-frames: interior %lld, gap %lld, edge %lld, general-fast %lld, per-pixel %lld\n", g_emu_paths[0], g_emu_paths[1], g_emu_paths[2], g_emu_paths[3], g_emu_paths[4]); }
+static long long g_emu_paths[6];
+static void ds_emu_report() { fprintf(stderr, "[ds emu] level-0 tile-frames: interior %lld, gap %lld, edge %lld, general-fast %lld, per-pixel %lld; taps from the source box %lld\n", g_emu_paths[0], g_emu_paths[1], g_emu_paths[2], g_emu_paths[3], g_emu_paths[4], g_emu_paths[5]); }
 static inline void ds_emu_count(int k) {
     static int on = -1;
     if (on < 0) { const char* e = getenv("DS_EMU_STATS"); on = (e && atoi(e) > 0) ? 1 : 0; if (on) atexit(ds_emu_report); }
@@ -986,15 +986,24 @@ struct MBFastBody {
     static constexpr int W0_BYTES = LEVEL0 ? 0 : ds_al128(PHM * PWS * 4);   // W_l of the needed region (levels >= 1)
     static constexpr int G0_BYTES = ds_al128(PHM * PWS * 4);
     static constexpr int G1_BYTES = ds_al128(GWS * GWS * 8);
-    static constexpr int H_BYTES = ds_al128(PHM * GWS * 8);   // pyrDown H pass; later the float H pass of the weights (PHM * JW * 4)
+    // level 0, plane-only kernel: the source footprint of a tile-frame (the box the inverse map of the 71 x 71 region
+    // fits in for rotations up to ~3 degrees) is brought into shared memory by one TMA tile load and the bilinear taps
+    // are read from there. The box shares its buffer with the pyrDown H pass: it is free from the end of a frame's
+    // vertical pass to the next frame's horizontal pass, which is when the next frame's box is in flight.
+    static constexpr bool HAS_BOX = LEVEL0 && !AFF;
+    // (the innermost start coordinate of a TMA tile must be 16-byte aligned: the box starts at a multiple of 4 pixels, up
+    // to 3 columns left of the footprint)
+    static constexpr int BOXW = 84, BOXH = 80, BOX_BYTES = BOXW * BOXH * 4;
+    static constexpr int H_ONLY_BYTES = ds_al128(PHM * GWS * 8);   // pyrDown H pass; later the float H pass of the weights (PHM * JW * 4)
+    static constexpr int H_BYTES = (HAS_BOX && BOX_BYTES > H_ONLY_BYTES) ? ds_al128(BOX_BYTES) : H_ONLY_BYTES;
     static constexpr int ACC_BYTES = T * T * 4;
     static constexpr int COL_BYTES = ds_al128(PWS * 16), ROW_BYTES = ds_al128(PHM * 16);
     static constexpr int NTAB = LEVEL0 ? 2 : 1;                // level 0: the tables of the next frame are built while this one is processed
     static constexpr int TAB_BYTES = NTAB * (COL_BYTES + ROW_BYTES);
-    static constexpr int MAXF = 64;                            // frames per tile the packed accumulators allow (host-checked)
+    static constexpr int MAXF = LEVEL0 ? 24 : 64;              // frames per tile of the fast kernels (host-checked; the packed accumulators allow 64)
     static constexpr int GEO_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + TAB_BYTES + W0_BYTES;
     static constexpr int FDEV_BYTES = (int)((sizeof(FrameDev) + 15) & ~(size_t)15);
-    static constexpr int GEO_BYTES = (LEVEL0 && !AFF) ? 112 : 96;   // sizeof(TFGeo)
+    static constexpr int GEO_BYTES = (LEVEL0 && !AFF) ? 128 : 96;   // sizeof(TFGeo)
     static constexpr int FDEV_OFF = GEO_OFF + MAXF * GEO_BYTES;      // two FrameDev slots: current frame / prefetch of the next
     // levels >= 1: second copy of the G / W boxes so the TMA load of the next frame overlaps this frame's compute
     static constexpr int G0B_OFF = ds_al128(FDEV_OFF + 2 * FDEV_BYTES);   // TMA destinations: 128-B aligned
@@ -1018,6 +1027,8 @@ struct MBFastBody {
         int mode;         // -1: per-pixel loop; 0 / 1 / 2: v2 loop interior / gap / edge
         int gap_all0;     // mode 1: the needed region misses the bbox altogether (mask 0 throughout)
         long long boff;   // modes 0 / 1: byte offset of the biased tap address base from F.src
+        int box;          // modes 0 / 1: the footprint fits the shared-memory box whose origin in the source is (bx0, by0)
+        int bx0, by0, pad2;
     };
     typedef typename std::conditional<(LEVEL0 && !AFF), TFGeo0, TFGeo>::type Geo;
     static_assert(sizeof(Geo) == GEO_BYTES, "TFGeo layout");
@@ -1035,7 +1046,7 @@ struct MBFastBody {
     // and x(u, v) is monotone in u and in v even in float arithmetic (a chain of monotone roundings), so the values at
     // the interval ends bound every pixel.
     DS_DM void classify_plane(const FrameDev& F, TFGeo0& g, int flags) {
-        g.mode = -1; g.gap_all0 = 0; g.boff = 0;
+        g.mode = -1; g.gap_all0 = 0; g.boff = 0; g.box = 0; g.bx0 = g.by0 = g.pad2 = 0;
         const bool proj = !(F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f);
         if (g.skip || proj || F.kind != XF_PLANE || F.seam || F.gainmap || F.any_gain) return;
         const int sw = F.src_w, sh = F.src_h, pitch = F.src_pitch;
@@ -1073,6 +1084,9 @@ struct MBFastBody {
             if (off_lo < 0 || (unsigned long long)u_lo32 + (unsigned long long)(off_hi - off_lo) > 0xFFFFFFFFull) return;   // one in ~10^4
             g.boff = 4 * (off_lo - (long long)u_lo32);
             g.mode = interior ? 0 : 1;
+            // taps: columns floor(xmn) - 1 .. floor(xmx) + 2, rows likewise
+            g.bx0 = ((int)floorf(xmn) - 1) & ~3; g.by0 = (int)floorf(ymn) - 1;
+            g.box = ((flags & 2) && (int)floorf(xmx) + 2 - g.bx0 < BOXW && (int)floorf(ymx) + 2 - g.by0 < BOXH) ? 1 : 0;
             g.gap_all0 = (u_hi < 0 || u_lo >= F.w || v_hi < 0 || v_lo >= F.h) ? 1 : 0;
         } else if (F.border != BORDER_CONST &&
                    xmn >= -(float)(sw - 1) && xmx <= (float)(2 * sw - 3) && ymn >= -(float)(sh - 1) && ymx <= (float)(2 * sh - 3) &&
@@ -1106,6 +1120,7 @@ struct MBFastBody {
 
         for (int i = tid; i < T * T; i += NT) { s_acc[i] = make_i2(0, 0); s_ws[i] = 0.f; }
         int* const s_vote = (int*)(smem + MBAR_OFF + 16);   // block-wide OR of the uniformity bits (block_or_bits)
+        uint32_t box_phase = 0u;                            // level 0: parity of the source-box barrier
         if (tid == 0) *s_vote = 0;
 #if DS_CUDA
         unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);   // two barriers, one per box buffer
@@ -1113,6 +1128,7 @@ struct MBFastBody {
         int tma_cur = 0;
         const bool use_tma = !LEVEL0 && p.tmaps != nullptr;
         if (use_tma && tid == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
+        if (HAS_BOX && (p.flags & 2) && tid == 0) mbar_init(s_bar, 1);   // level 0: one barrier, the source box
         constexpr int W0A_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + TAB_BYTES;
         auto g0_buf = [&](int b_) { return (uint32_t*)(smem + (b_ ? G0B_OFF : 0)); };
         auto w_buf = [&](int b_) { return (float*)(smem + (b_ ? W0B_OFF : W0A_OFF)); };
@@ -1232,6 +1248,32 @@ struct MBFastBody {
                 }
             }
         };
+        // Source box of tile-frame fj into the H buffer (free at the call sites: see the layout comment). One thread issues
+        // the TMA tile load (out-of-image parts are zero-filled and never read); the emulator copies.
+        auto issue_box = [&](int fj) {
+            if constexpr (HAS_BOX) {
+                if (fj >= f_end) return;
+                const Geo gx = s_geo[fj - f_begin];
+                if (gx.skip || !gx.box) return;
+#if DS_CUDA
+                if (tid == 0) {
+                    const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fj] * DS_MAXL * 2 + 1) * 128;   // slot [frame][0][1]
+                    fence_tensormap_acquire(tm);
+                    fence_proxy_async();   // generic-proxy accesses of the buffer ended before the last barrier
+                    mbar_expect_tx(s_bar, (uint32_t)BOX_BYTES);
+                    tma_load_2d(smem + G0_BYTES + G1_BYTES, tm, gx.bx0, gx.by0, s_bar);
+                }
+#else
+                const FrameDev& Fx = p.frames[p.tile_frames[fj]];
+                uint32_t* box = (uint32_t*)(smem + G0_BYTES + G1_BYTES);
+                for (int i = tid; i < BOXW * BOXH; i += NT) {
+                    const int by = i / BOXW, bx = i - by * BOXW;
+                    const int sx = gx.bx0 + bx, sy = gx.by0 + by;
+                    box[i] = ((unsigned)sx < (unsigned)Fx.src_w && (unsigned)sy < (unsigned)Fx.src_h) ? Fx.src[(size_t)sy * Fx.src_pitch + sx] : 0u;
+                }
+#endif
+            }
+        };
         // what follows the barrier after a frame's warp loop: tables and L2 prefetch for the next frame of the tile
         auto prepare_next = [&](int fi) {
             if (fi + 1 >= f_end) return;
@@ -1241,7 +1283,9 @@ struct MBFastBody {
             // L2 prefetch (TMA) of the source footprint of the next frame. One thread, fire and forget.
             if (p.tmaps != nullptr && tid == 0) {
                 const Geo ng = s_geo[fi + 1 - f_begin];
-                if (!ng.skip && N.kind == XF_PLANE) {
+                bool boxed = false;
+                if constexpr (HAS_BOX) boxed = ng.box != 0;   // its footprint comes in as a box anyway
+                if (!ng.skip && !boxed && N.kind == XF_PLANE) {
                     const int u_lo = ng.rx + ng.px0 - N.cx, u_hi = u_lo + ng.pw - 1, v_lo = ng.ry + ng.py0 - N.cy, v_hi = v_lo + ng.ph - 1;
                     const int ulo = imax(imin(u_lo, N.w - 1), 0), uhi = imax(imin(u_hi, N.w - 1), 0);
                     const int vlo = imax(imin(v_lo, N.h - 1), 0), vhi = imax(imin(v_hi, N.h - 1), 0);
@@ -1262,7 +1306,7 @@ struct MBFastBody {
             }
 #endif
         };
-        if constexpr (LEVEL0) { if (f_begin < f_end) build_tables(p.frames[p.tile_frames[f_begin]], f_begin); }
+        if constexpr (LEVEL0) { if (f_begin < f_end) { build_tables(p.frames[p.tile_frames[f_begin]], f_begin); issue_box(f_begin); } }
         if (f_begin < f_end) stage_frame(f_begin);
 #if DS_CUDA
         // TMA pipeline over the tile's frame list: the boxes of the next non-skipped frame are requested while
@@ -1306,7 +1350,7 @@ struct MBFastBody {
             (void)gw; (void)gh; (void)jw; (void)jh; (void)border;
             if (s_geo[fi - f_begin].skip) {       // block-uniform
                 DS_SYNC();
-                if constexpr (LEVEL0) { prepare_next(fi); DS_SYNC(); }
+                if constexpr (LEVEL0) { prepare_next(fi); issue_box(fi + 1); DS_SYNC(); }
                 continue;
             }
             {   // ======== first half: tables + phase 1
@@ -1398,16 +1442,39 @@ struct MBFastBody {
                 if (v2) {
                     const SAddr a_col = s_addr(s_col), a_row = s_addr(s_row), a_g0 = s_addr(s_g0);
                     constexpr int NTV = 512, RG = NTV / 64;          // 64 columns x 8 row groups
-                    static_assert((PHM + RG - 1) / RG == 9 && PWS - 64 == 8, "v2 warp loop layout");
+                    static_assert((PHM + RG - 1) / RG == 9 && PWS - 64 == 8 && 7 * PHM <= NTV, "v2 warp loop layout");
                     struct PX { int bx, by; uint32_t p00, p01, p10, p11; int aux; };
+                    // modes 0 / 1 with the footprint in the shared-memory box: the biased tap offset is taken against the
+                    // box origin (all 32-bit, wrap-around is harmless: the final shared address is exact)
+                    const bool boxed = HAS_BOX && g.box != 0;
+                    const uint32_t boxK = (uint32_t)(CB + g.by0) * (uint32_t)BOXW + (uint32_t)(CB + g.bx0);
+#if DS_CUDA
+                    const SAddr a_boxb = s_addr(smem + G0_BYTES + G1_BYTES) - 4u * boxK;   // shared addresses are 32-bit: the bias folds in
+                    auto box_addr = [&](uint32_t t) { return a_boxb + 4u * t; };
+#else
+                    unsigned char* const a_box0 = smem + G0_BYTES + G1_BYTES;
+                    auto box_addr = [&](uint32_t t) { return a_box0 + (ptrdiff_t)(int32_t)(4u * (t - boxK)); };
+#endif
+                    if (boxed) {
+#if DS_CUDA
+                        mbar_wait(s_bar, box_phase);
+#endif
+                        box_phase ^= 1u;
+                    }
                     auto fetch = [&](auto mode_tag, float ca0, float ca3, int cu, int r, PX& q) {
-                        constexpr int MODE = decltype(mode_tag)::value;
+                        constexpr int MODE = decltype(mode_tag)::value / 4;
+                        constexpr bool BOXED = (decltype(mode_tag)::value & 1) != 0;
                         float rb1, rb4; int rv = 0;
                         if constexpr (MODE == 0) lds_f2(a_row + r * 16, rb1, rb4);
                         else { uint32_t w0, w1, w2, w3; lds_u4(a_row + r * 16, w0, w1, w2, w3); rb1 = i2f_bits((int)w0); rb4 = i2f_bits((int)w1); rv = (int)w3; }
                         const float x = f_add(f_add(ca0, rb1), k2), y = f_add(f_add(ca3, rb4), k5);
                         q.bx = rnd32_bits(x); q.by = rnd32_bits(y);
-                        if constexpr (MODE != 2) {
+                        if constexpr (MODE != 2 && BOXED) {
+                            const uint32_t t = (uint32_t)(q.by >> 5) * (uint32_t)BOXW + (uint32_t)(q.bx >> 5);
+                            const SAddr a = box_addr(t);
+                            q.p00 = lds_u1(a); q.p01 = lds_u1(a + 4); q.p10 = lds_u1(a + BOXW * 4); q.p11 = lds_u1(a + BOXW * 4 + 4);
+                            q.aux = rv;
+                        } else if constexpr (MODE != 2) {
                             const uint32_t t = (uint32_t)(q.by >> 5) * (uint32_t)pitch + (uint32_t)(q.bx >> 5);
                             const uint32_t* r0 = (const uint32_t*)(basep + 4ull * (unsigned long long)t);
                             const uint32_t* r1 = (const uint32_t*)(basep + 4ull * (unsigned long long)(t + (uint32_t)pitch));
@@ -1425,7 +1492,7 @@ struct MBFastBody {
                         }
                     };
                     auto finish = [&](auto mode_tag, const PX& q, SAddr dst, bool store, bool count, uint32_t cmask) {
-                        constexpr int MODE = decltype(mode_tag)::value;
+                        constexpr int MODE = decltype(mode_tag)::value / 4;
                         const uint32_t ax = (uint32_t)q.bx & 31u, ay = (uint32_t)q.by & 31u;
                         const uint32_t wxp = ax * 65535u + 32u;                     // (32 - ax) | ax << 16
                         const uint32_t wbot = wxp * ay, wtop = wxp * 32u - wbot;    // rows weighted by ay / 32 - ay
@@ -1472,41 +1539,33 @@ struct MBFastBody {
                                 fin(B[0], 2); fin(B[1], 3);
                                 fetch(mode_tag, ca0, ca3, cu, row_of(6), B[0]); fetch(mode_tag, ca0, ca3, cu, row_of(7), B[1]);
                                 fin(A[0], 4); fin(A[1], 5);
+                                // the tenth pixel of the thread: one of the 7 x 71 pixels of the columns beyond the 64th
+                                // (497 items over the 512 threads), in flight together with row 8
+                                const int er = vt / 7, ec = 64 + (vt - er * 7);
+                                const bool elive = er < ph && ec < pw;
+                                uint32_t e0, e1, e2, e3;
+                                lds_u4(a_col + ec * 16, e0, e1, e2, e3);
                                 fetch(mode_tag, ca0, ca3, cu, row_of(8), A[0]);
+                                fetch(mode_tag, i2f_bits((int)e0), i2f_bits((int)e1), (int)e3, imin(er, ph - 1), A[1]);
                                 fin(B[0], 6); fin(B[1], 7);
                                 fin(A[0], 8);
-                            }
-                            if (pw > 64) {
-                                // the 8 columns beyond the 64: items of (row, column) over the same virtual threads
-                                PX q[2]; int rr[2], cc[2]; uint32_t cm[2];
-                                DS_UNROLL
-                                for (int j = 0; j < 2; j++) {
-                                    const int e = vt + NTV * j;
-                                    rr[j] = e >> 3; cc[j] = 64 + (e & 7);
-                                    uint32_t c0, c1, c2, c3;
-                                    lds_u4(a_col + cc[j] * 16, c0, c1, c2, c3);
-                                    cm[j] = (int)c3 >= 0 ? 0xff000000u : 0u;
-                                    if (rr[j] < ph || j == 0) fetch(mode_tag, i2f_bits((int)c0), i2f_bits((int)c1), (int)c3, imin(rr[j], ph - 1), q[j]);
-                                }
-                                DS_UNROLL
-                                for (int j = 0; j < 2; j++) {
-                                    const bool live = rr[j] < ph;
-                                    if (live) finish(mode_tag, q[j], a_g0 + (rr[j] * PWS + cc[j]) * 4, true, cc[j] < pw, cm[j]);
-                                }
+                                finish(mode_tag, A[1], a_g0 + (imin(er, ph - 1) * PWS + ec) * 4, elive, elive, (int)e3 >= 0 ? 0xff000000u : 0u);
                             }
                         }
                     };
 #if !DS_CUDA
                     ds_emu_count(interior ? 0 : (inbounds ? 1 : 2));
+                    if (boxed) ds_emu_count(5);
 #endif
+                    // tag = 4 * mode + (taps from the shared-memory box)
                     if (interior) {
-                        run_v2(IntTag<0>());
+                        if (boxed) run_v2(IntTag<1>()); else run_v2(IntTag<0>());
                         m_or = 255; known_votes = 1;                 // uniform 255
                     } else if (inbounds) {
-                        run_v2(IntTag<1>());
+                        if (boxed) run_v2(IntTag<5>()); else run_v2(IntTag<4>());
                         known_votes = gap_all0 ? 2 : 0;              // not inside the bbox: never uniform 255
                     } else {
-                        run_v2(IntTag<2>());
+                        run_v2(IntTag<8>());
                     }
                     v2_done = true;
                 }
@@ -1857,7 +1916,10 @@ struct MBFastBody {
                                                          : pd_scalar(t[0], t[1], t[2], t[3], t[4]);
                     W1out[(size_t)jy * op1 + j] = f_mul(v, 1.f / 256.f);
                 }
+                if constexpr (HAS_BOX) DS_SYNC();   // the float H pass shares the buffer the next frame's box is loaded into
             }
+            // the next frame's source box comes in while this frame's Laplacians are accumulated (the H buffer is free now)
+            issue_box(fi + 1);
 
             // ---- phase 3: lap = G_0 - pyrUp(G_1), weighted accumulate, one 2x2 quad per item
             if (!uni0) {

@@ -851,7 +851,7 @@ int build_lists(ds_canvas* c) {
             if (l == 0) {
                 bool all_plane = true;   // the fast level-0 kernel builds plane (float) and warpAffine (integer) coordinates
                 for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32 && f.xf.kind != DS_XF_AFFINE_F64) all_plane = false;
-                c->l0_fast_ok = all_plane && longest <= 64;
+                c->l0_fast_ok = all_plane && longest <= MBFastBody<64, true>::MAXF;
                 c->l0_has_affine = false;
                 for (const Frame& f : c->frames) if (f.used && (f.xf.kind == DS_XF_AFFINE_F64 || f.d_seam || f.d_gainmap || f.dev.any_gain)) c->l0_has_affine = true;
                 c->ln_fast_ok = true;
@@ -903,7 +903,9 @@ int build_lists(ds_canvas* c) {
             if (!f.used) continue;
             // slot [frame][0][0]: the BGRX source, box = footprint of a 71x71 tile region under a few degrees of
             // rotation (L2 prefetch only: correctness never depends on it)
-            ok = encode_tile_map(&tm[(i * DS_MAXL) * 2], false, f.d_src, f.w, f.h, f.pitch, 96, 88);
+            ok = encode_tile_map(&tm[(i * DS_MAXL) * 2], false, f.d_src, f.w, f.h, f.pitch, 96, 88) &&
+                 // slot [frame][0][1]: the same source with the box the level-0 kernel loads into shared memory
+                 encode_tile_map(&tm[(i * DS_MAXL) * 2 + 1], false, f.d_src, f.w, f.h, f.pitch, MBFastBody<64, true>::BOXW, MBFastBody<64, true>::BOXH);
             for (int l = 1; l < c->L && ok; l++) {
                 const int w = f.rw >> l, h = f.rh >> l;
                 ok = encode_tile_map(&tm[(i * DS_MAXL + l) * 2], false, f.dev.G[l], w, h, f.dev.gp[l], MBFastBody<32, false>::PWS, MBFastBody<32, false>::PHM) &&
@@ -1018,7 +1020,12 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     mp.own_y0 = own.lo; mp.own_y1 = own.hi;
     mp.tmaps = c->tmaps_ok ? c->d_tmaps : nullptr;
     static const bool gap_fast = !(getenv("DS_GAP_FAST") && atoi(getenv("DS_GAP_FAST")) == 0);
-    mp.flags = gap_fast ? 1 : 0;
+    // bit 1: source footprints staged in shared memory by TMA box loads (needs the tensor maps; DS_SRC_BOX=0 turns it off)
+    static const bool src_box = !(getenv("DS_SRC_BOX") && atoi(getenv("DS_SRC_BOX")) == 0);
+    mp.flags = (gap_fast ? 1 : 0) | ((src_box && mp.tmaps) ? 2 : 0);
+#if !DS_CUDA
+    if (src_box) mp.flags |= 2;   // the emulator stages the boxes with a plain copy loop
+#endif
     const double q = 1.0 / (double)(1ull << (2 * l));
     double ab;
     if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
