@@ -711,6 +711,7 @@ struct MBParams {
     const FrameDev* frames;
     const int* tile_off; const int* tile_frames;  // CSR: frames per tile of this level
     const int* tile_ids;                           // tiles this launch processes (NULL: block == tile)
+    const int4* tile_rec;                          // per launched tile {tile, list begin, list end, first frame}: one load instead of three dependent ones
     int tiles_x;
     int level, L;
     px16* dst; int dst_w, dst_h;  // normalised Laplacian level of the padded canvas
@@ -1113,7 +1114,8 @@ struct MBFastBody {
         float* s_w = (float*)(smem + TAB_OFF + TAB_BYTES);
         const int l = LEVEL0 ? 0 : p.level;
 
-        const int tile = p.tile_ids ? p.tile_ids[block] : block;
+        const int4 rec = ld_ro(p.tile_rec + block);
+        const int tile = rec.x;
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int X0 = tx * T, Y0 = ty * T;
         const float c255 = f_mul(255.f, 1.f / 255.f);
@@ -1136,9 +1138,20 @@ struct MBFastBody {
         // (no barrier: the accumulators are first touched after several more)
 
         Geo* s_geo = (Geo*)(smem + GEO_OFF);
-        const int f_begin = p.tile_off[tile], f_end = p.tile_off[tile + 1];
+        const int f_begin = rec.y, f_end = rec.z;
+        // Frame descriptors are staged in shared memory: slot (fi & 1) holds frame fi, and while it is being
+        // processed the first threads prefetch frame fi + 1 into the other slot (visible after the barriers
+        // every iteration ends with). Keeps the dependent global loads off the per-tile-frame critical path.
+        auto stage_frame_at = [&](int frame_idx, int fi_) {
+            const uint4* srcw = (const uint4*)(p.frames + frame_idx);
+            uint4* dstw = (uint4*)(smem + FDEV_OFF + (fi_ & 1) * FDEV_BYTES);
+            // the last warps copy: the first ones build the tile-frame geometry at the same time
+            for (int w = NT - 1 - tid; w < (int)(sizeof(FrameDev) / 16); w += NT) dstw[w] = srcw[w];
+        };
+        auto stage_frame = [&](int fi_) { stage_frame_at(p.tile_frames[fi_], fi_); };
+        if (f_begin < f_end) stage_frame_at(rec.w, f_begin);   // the first frame's index came with the tile record
         for (int j = tid; j < f_end - f_begin && j < MAXF; j += NT) {
-            const FrameDev& F = p.frames[p.tile_frames[f_begin + j]];
+            const FrameDev& F = p.frames[j == 0 ? rec.w : p.tile_frames[f_begin + j]];
             Geo g;
             g.rx = F.rx >> l; g.ry = F.ry >> l; g.rw = F.rw >> l; g.rh = F.rh >> l;
             g.ax0 = imax(X0, g.rx); g.ax1 = imin(X0 + T, g.rx + g.rw);
@@ -1194,14 +1207,6 @@ struct MBFastBody {
         }
         DS_SYNC();
 
-        // Frame descriptors are staged in shared memory: slot (fi & 1) holds frame fi, and while it is being
-        // processed the first threads prefetch frame fi + 1 into the other slot (visible after the barriers
-        // every iteration ends with). Keeps the dependent global loads off the per-tile-frame critical path.
-        auto stage_frame = [&](int fi_) {
-            const uint4* srcw = (const uint4*)(p.frames + p.tile_frames[fi_]);
-            uint4* dstw = (uint4*)(smem + FDEV_OFF + (fi_ & 1) * FDEV_BYTES);
-            for (int w = tid; w < (int)(sizeof(FrameDev) / 16); w += NT) dstw[w] = srcw[w];
-        };
         // ---- level-0 tables of one tile-frame: reflected bbox index + per-column / per-row map terms. Built for frame
         // fi + 1 while frame fi is processed (two buffers), so the warp loop starts without a barrier of its own.
         auto build_tables = [&](const FrameDev& Fx, int fj) {
@@ -1306,8 +1311,9 @@ struct MBFastBody {
             }
 #endif
         };
-        if constexpr (LEVEL0) { if (f_begin < f_end) { build_tables(p.frames[p.tile_frames[f_begin]], f_begin); issue_box(f_begin); } }
-        if (f_begin < f_end) stage_frame(f_begin);
+        if constexpr (LEVEL0) {
+            if (f_begin < f_end) { build_tables(*(const FrameDev*)(smem + FDEV_OFF + (f_begin & 1) * FDEV_BYTES), f_begin); issue_box(f_begin); }
+        }
 #if DS_CUDA
         // TMA pipeline over the tile's frame list: the boxes of the next non-skipped frame are requested while
         // the current one is processed (two buffers, two mbarriers)

@@ -257,6 +257,7 @@ struct LevelPlan {
     Range own{0, 0};   // rows of this level whose tiles run (production + accumulation)
     Range acc{0, 0};   // rows whose dst is written / consumed by the collapse
     int* d_off = nullptr; int* d_fr = nullptr; int* d_ids = nullptr;   // inside the canvas meta arena
+    int* d_rec = nullptr;   // per launched tile id: {tile, first and one-past-last entry of its frame list, first frame}
     int n_ids = 0;
 };
 
@@ -807,8 +808,8 @@ int build_lists(ds_canvas* c) {
     const bool mb = c->desc.blend_mode == DS_BLEND_MULTIBAND;
     const int nl = mb ? c->L + 1 : 1;
     MetaBuilder mbd;
-    size_t off_off[DS_MAXL], fr_off[DS_MAXL], ids_off[DS_MAXL];
-    std::vector<int> counts, off, fr, ids;
+    size_t off_off[DS_MAXL], fr_off[DS_MAXL], ids_off[DS_MAXL], rec_off[DS_MAXL];
+    std::vector<int> counts, off, fr, ids, recs;
     for (int l = 0; l < nl; l++) {
         LevelPlan& pl = c->plan[l];
         const int TW = mb ? pl.T : FeatherBody::TW, TH = mb ? pl.T : FeatherBody::TH;
@@ -880,6 +881,14 @@ int build_lists(ds_canvas* c) {
         off_off[l] = mbd.add(counts.data(), counts.size() * sizeof(int));
         fr_off[l] = mbd.add(fr.data(), fr.size() * sizeof(int));
         ids_off[l] = mbd.add(ids.data(), ids.size() * sizeof(int));
+        // one 16-byte record per launched tile: what a CTA otherwise finds through three dependent loads
+        recs.resize(ids.size() * 4);
+        for (size_t k = 0; k < ids.size(); k++) {
+            const int t = ids[k];
+            recs[4 * k] = t; recs[4 * k + 1] = counts[t]; recs[4 * k + 2] = counts[(size_t)t + 1];
+            recs[4 * k + 3] = counts[(size_t)t + 1] > counts[t] ? fr[(size_t)counts[t]] : -1;
+        }
+        rec_off[l] = mbd.add(recs.data(), recs.size() * sizeof(int));
     }
     // frame descriptors
     std::vector<FrameDev> fd(c->frames.size());
@@ -939,6 +948,7 @@ int build_lists(ds_canvas* c) {
         c->plan[l].d_off = (int*)(base + off_off[l]);
         c->plan[l].d_fr = (int*)(base + fr_off[l]);
         c->plan[l].d_ids = (int*)(base + ids_off[l]);
+        c->plan[l].d_rec = (int*)(base + rec_off[l]);
     }
     c->d_frames = (FrameDev*)(base + frames_off);
     c->d_segs = (PullSeg*)(base + segs_off); c->n_segs = (int)segs.size();
@@ -1014,6 +1024,7 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     const Range acc = meet(own, pl.acc);   // every row that runs also writes its dst (if this handle stores it)
     MBParams mp;
     mp.frames = c->d_frames; mp.tile_off = pl.d_off; mp.tile_frames = pl.d_fr; mp.tile_ids = pl.d_ids + first;
+    mp.tile_rec = (const int4*)(pl.d_rec + 4 * (size_t)first);
     mp.tiles_x = pl.tiles_x; mp.level = l; mp.L = c->L;
     mp.dst = c->d_lvl[l]; mp.dst_w = c->lw[l]; mp.dst_h = c->lh[l];
     mp.acc_y0 = acc.lo; mp.acc_y1 = acc.hi;
