@@ -436,6 +436,160 @@ struct MaskBitsBody {
     }
 };
 
+// The same bit plane for plane-mapped frames without a seam mask, one THREAD per 32-pixel word: along a bbox row the
+// backward map is monotone in each source coordinate (also in float arithmetic: a chain of monotone roundings), so when
+// both end pixels of the word map into the source every pixel between them does - two coordinate evaluations settle
+// 32 pixels. Only the words that straddle the edge of the warped source evaluate every pixel.
+struct MaskBitsRowParams {
+    const FrameDev* frames; int frame;
+    uint32_t* bits;
+};
+struct MaskBitsRowBody {
+    static constexpr int PER_BLOCK = 256;
+    static int smem_bytes() { return 0; }
+    static bool eligible(const FrameDev& F) {   // host side
+        return F.kind == XF_PLANE && !F.seam && F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f;
+    }
+    template <int NT>
+    DS_DM void run(const MaskBitsRowParams& p, int block, int tid, unsigned char*) {
+        const FrameDev& F = p.frames[p.frame];
+        const long long nwords = (long long)F.mbits_pitch * F.h;
+        for (int it = tid; it < PER_BLOCK; it += NT) {
+            const long long word = (long long)block * PER_BLOCK + it;
+            if (word >= nwords) break;
+            const int v = (int)(word / F.mbits_pitch), k = (int)(word - (long long)v * F.mbits_pitch);
+            const int u0 = k * 32, u1 = imin(u0 + 31, F.w - 1);
+            // out codes of the two end pixels: left / right / above / below the source (nearest-neighbour coordinates)
+            auto code = [&](int u) {
+                float U = (float)(F.tlx + u), V = (float)(F.tly + v);
+                if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+                const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+                const float x = f_add(f_add(f_mul(F.k[0], up), f_mul(F.k[1], vp)), F.k2one);
+                const float y = f_add(f_add(f_mul(F.k[3], up), f_mul(F.k[4], vp)), F.k5one);
+                const int nx = sat16i(f2i_rn(x)), ny = sat16i(f2i_rn(y));   // as eval_coord
+                return (nx < 0 ? 1 : 0) | (nx >= F.src_w ? 2 : 0) | (ny < 0 ? 4 : 0) | (ny >= F.src_h ? 8 : 0);
+            };
+            const int c0 = code(u0), c1 = code(u1);
+            uint32_t b = 0xffffffffu;   // tail bits (u >= w) stay set: they never act as zeros
+            if (c0 & c1) {
+                // both ends beyond the same side of the source: so is everything between them
+                b = (u1 - u0 == 31) ? 0u : ~((1u << (u1 - u0 + 1)) - 1u);
+            } else if (c0 | c1) {
+                for (int u = u0; u <= u1; u++)
+                    if (code(u) != 0) b &= ~(1u << (u - u0));
+            }
+            p.bits[word] = b;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FEATHER step 1b: L1 distance of every bbox pixel to the nearest zero of the frame's warped mask, capped at 255 and
+// exact below the feather radius R (R * sharpness >= 1, so farther pixels have weight 1 anyway) - cv::distanceTransform
+// (DIST_L1, 3x3) as createWeightMap uses it (A12): zeros are sources only inside the image. Once per frame instead of
+// once per canvas tile. One block = a strip of 256 columns x 96 rows:
+//   (0) the bit window of the strip +- R is staged in shared memory; a window without a zero writes 255s and is done;
+//   (a) horizontal distance of every window pixel from the row's bits alone: the nearest zero bit at or left of it
+//       (count leading zeros of the inverted 64-bit window ending at the pixel) and at or right of it (trailing zeros);
+//   (b) separable min-plus: one thread per column sweeps down and up over the window rows.
+struct FeatherDistParams {
+    const FrameDev* frames; int frame;
+    uint8_t* dist;    // == frames[frame].dist (non-const view)
+    int R;
+};
+struct FeatherDistBody {
+    static constexpr int SW = 256, SH = 96, RMAX = 64;
+    static constexpr int WIN_ROWS = SH + 2 * RMAX;
+    static constexpr int WORDS = SW / 32 + 2 + 2 + 1;   // bit words per window row: two words (64 px >= RMAX) either side + spill
+    static constexpr int H_BYTES = WIN_ROWS * SW, B_BYTES = WIN_ROWS * WORDS * 4;
+    static int smem_bytes() { return H_BYTES + B_BYTES + 16; }
+    static long long blocks(const FrameDev& F) { return (long long)((F.w + SW - 1) / SW) * ((F.h + SH - 1) / SH); }
+    template <int NT>
+    DS_DM void run(const FeatherDistParams& p, int block, int tid, unsigned char* smem) {
+        const FrameDev& F = p.frames[p.frame];
+        unsigned char* s_h = smem;
+        uint32_t* s_b = (uint32_t*)(smem + H_BYTES);
+        int* s_flag = (int*)(smem + H_BYTES + B_BYTES);
+        const int nbx = (F.w + SW - 1) / SW;
+        const int by = block / nbx, bx = block - by * nbx;
+        const int x0 = bx * SW, y0 = by * SH, R = p.R;
+        const int wy0 = y0 - R, wrows = SH + 2 * R;
+        const int k0 = (x0 >> 5) - 2;                      // first bit word of the window rows (may be negative)
+        if (tid == 0) *s_flag = 0;
+        DS_SYNC();
+        // (0) stage the bits: outside the bbox there are no zeros
+        int found = 0;
+        for (int i = tid; i < wrows * WORDS; i += NT) {
+            const int r = i / WORDS, kk = i - r * WORDS;
+            const int v = wy0 + r, k = k0 + kk;
+            uint32_t wd = 0xffffffffu;
+            if ((unsigned)v < (unsigned)F.h && (unsigned)k < (unsigned)F.mbits_pitch) wd = ld_ro(F.mbits + (size_t)v * F.mbits_pitch + k);
+            s_b[i] = wd;
+            if (wd != 0xffffffffu) found = 1;
+        }
+        if (found) *s_flag = 1;   // benign race: all writers store 1
+        DS_SYNC();
+        const int ow = imin(SW, F.w - x0), oh = imin(SH, F.h - y0);
+        if (!*s_flag) {
+            for (int i = tid; i < oh * (SW / 4); i += NT) {
+                const int r = i / (SW / 4), c4 = (i - r * (SW / 4)) * 4;
+                if (c4 >= ow) continue;
+                uint8_t* q = p.dist + (size_t)(y0 + r) * F.dist_pitch + x0 + c4;   // dist_pitch and x0 are multiples of 4
+                *(uint32_t*)q = 0xffffffffu;
+            }
+            return;
+        }
+        // (a) horizontal distances. Pixel u sits in word (u >> 5) - k0 of its staged row, bit u & 31.
+        for (int i = tid; i < wrows * SW; i += NT) {
+            const int r = i / SW, c = i - r * SW;
+            const int u = x0 + c;
+            const uint32_t* row = s_b + r * WORDS;
+            const int kk = (u >> 5) - k0, b = u & 31;   // kk >= 2
+            const uint32_t wm2 = row[kk - 2], wm1 = row[kk - 1], w0 = row[kk], wp1 = row[kk + 1], wp2 = row[kk + 2];
+            // pixels u-63 .. u as a 64-bit window with pixel u in bit 63; u .. u+63 with pixel u in bit 0
+            const uint32_t l_lo = ~funnel_r(wm2, wm1, b + 1), l_hi = ~funnel_r(wm1, w0, b + 1);
+            const uint32_t r_lo = ~funnel_r(w0, wp1, b), r_hi = ~funnel_r(wp1, wp2, b);
+            int dl = l_hi ? clz32(l_hi) : (l_lo ? 32 + clz32(l_lo) : 255);
+            int dr = r_lo ? ctz32(r_lo) : (r_hi ? 32 + ctz32(r_hi) : 255);
+            s_h[i] = (unsigned char)imin(dl, dr);
+        }
+        DS_SYNC();
+        // (b) vertical min-plus sweeps, one column per thread
+        // (eight rows per trip: the loads of a trip are issued before its stores, so only the two-instruction min-plus
+        // recurrence is serial)
+        for (int c = tid; c < SW; c += NT) {
+            int d = 255;
+            for (int r0 = 0; r0 < wrows; r0 += 8) {
+                int v[8];
+                DS_UNROLL
+                for (int j = 0; j < 8; j++) v[j] = (int)s_h[imin(r0 + j, wrows - 1) * SW + c];
+                DS_UNROLL
+                for (int j = 0; j < 8; j++) { d = imin(imin(d + 1, 255), v[j]); v[j] = d; }
+                DS_UNROLL
+                for (int j = 0; j < 8; j++) if (r0 + j < wrows) s_h[(r0 + j) * SW + c] = (unsigned char)v[j];
+            }
+            d = 255;
+            for (int r0 = wrows - 1; r0 >= 0; r0 -= 8) {
+                int v[8];
+                DS_UNROLL
+                for (int j = 0; j < 8; j++) v[j] = (int)s_h[imax(r0 - j, 0) * SW + c];
+                DS_UNROLL
+                for (int j = 0; j < 8; j++) { d = imin(imin(d + 1, 255), v[j]); v[j] = d; }
+                DS_UNROLL
+                for (int j = 0; j < 8; j++) if (r0 - j >= 0) s_h[(r0 - j) * SW + c] = (unsigned char)v[j];
+            }
+        }
+        DS_SYNC();
+        for (int i = tid; i < oh * (SW / 4); i += NT) {
+            const int r = i / (SW / 4), c4 = (i - r * (SW / 4)) * 4;
+            if (c4 >= ow) continue;
+            const unsigned char* hrow = s_h + (r + R) * SW + c4;
+            uint8_t* q = p.dist + (size_t)(y0 + r) * F.dist_pitch + x0 + c4;
+            *(uint32_t*)q = (uint32_t)hrow[0] | ((uint32_t)hrow[1] << 8) | ((uint32_t)hrow[2] << 16) | ((uint32_t)hrow[3] << 24);
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // FEATHER step 2: one canvas tile gathers every frame that covers it, in feed order:
 //   w = min(L1dist(mask) * sharpness, 1); acc += trunc(pix * w); wsum += w
@@ -461,20 +615,16 @@ struct FeatherParams {
 
 struct FeatherBody {
     static constexpr int TW = 64, TH = 32, RMAX = 64;
-    static constexpr int D_BYTES = ((TW + 2 * RMAX) * (TH + 2 * RMAX) + 16 + 15) & ~15;
-    static int smem_bytes() { return D_BYTES + (TW + TH) * 8; }
+    static int smem_bytes() { return (TW + TH) * 8 + TW * TH * 4; }
     template <int NT>
     DS_DM void run(const FeatherParams& p, int block, int tid, unsigned char* smem) {
         constexpr int PPT = TW * TH / NT;
         const int tile = p.tile_ids ? p.tile_ids[block] : block;
-        unsigned char* s_d = smem + 16;
-        int* s_flag = (int*)smem;
-        float2* s_cx = (float2*)(smem + D_BYTES);   // per tile column: k0*u', k3*u'
+        float2* s_cx = (float2*)smem;               // per tile column: k0*u', k3*u'
         float2* s_ry = s_cx + TW;                   // per tile row:    k1*v', k4*v'
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int X0 = tx * TW, Y0 = ty * TH;
         const int R = p.R;
-        const int ww = TW + 2 * R, wh = TH + 2 * R;
         int acc[PPT][3];
         float ws[PPT];
         DS_UNROLL
@@ -482,79 +632,8 @@ struct FeatherBody {
 
         for (int fi = p.tile_off[tile]; fi < p.tile_off[tile + 1]; fi++) {
             const FrameDev& F = p.frames[p.tile_frames[fi]];
-            // window in bbox coordinates
-            const int wu0 = X0 - R - F.cx, wv0 = Y0 - R - F.cy;
-            if (tid == 0) *s_flag = 0;
-            DS_SYNC();
-            // 1) any zero bit inside window ∩ bbox ?
-            {
-                const int u_lo = imax(wu0, 0), u_hi = imin(wu0 + ww, F.w);  // [u_lo, u_hi)
-                const int v_lo = imax(wv0, 0), v_hi = imin(wv0 + wh, F.h);
-                if (u_lo < u_hi && v_lo < v_hi) {
-                    const int k_lo = u_lo >> 5, k_hi = (u_hi - 1) >> 5;
-                    const int nk = k_hi - k_lo + 1;
-                    const int n = nk * (v_hi - v_lo);
-                    int found = 0;
-                    const uint32_t nk_m = div_magic(nk);
-                    for (int i = tid; i < n; i += NT) {
-                        const int q_ = div_by(i, nk_m);
-                        const int v = v_lo + q_, k = k_lo + (i - q_ * nk);
-                        uint32_t wd = ld_ro(F.mbits + (size_t)v * F.mbits_pitch + k);
-                        uint32_t sel = 0xffffffffu;
-                        if (k == k_lo) sel &= 0xffffffffu << (u_lo & 31);
-                        if (k == k_hi) sel &= 0xffffffffu >> (31 - ((u_hi - 1) & 31));
-                        if ((~wd) & sel) found = 1;
-                    }
-                    if (found) *s_flag = 1;  // benign race: all writers store 1
-                }
-            }
-            DS_SYNC();
-            const int has_zero = *s_flag;
-            if (has_zero) {
-                // 2) expand to bytes: 0 at zero mask pixels, 255 elsewhere (outside bbox = not a source)
-                const uint32_t ww_m = div_magic(ww);
-                for (int i = tid; i < ww * wh; i += NT) {
-                    const int yy = div_by(i, ww_m), xx = i - yy * ww;
-                    const int u = wu0 + xx, v = wv0 + yy;
-                    unsigned char d = 255;
-                    if ((unsigned)u < (unsigned)F.w && (unsigned)v < (unsigned)F.h) {
-                        const uint32_t wd = ld_ro(F.mbits + (size_t)v * F.mbits_pitch + (u >> 5));
-                        d = ((wd >> (u & 31)) & 1u) ? 255 : 0;
-                    }
-                    s_d[i] = d;
-                }
-                DS_SYNC();
-                // horizontal min-plus sweeps, one row per thread
-                for (int yy = tid; yy < wh; yy += NT) {
-                    unsigned char* row = s_d + yy * ww;
-                    int d = 255;
-                    for (int xx = 0; xx < ww; xx++) { d = row[xx] == 0 ? 0 : imin(d + 1, 255); row[xx] = (unsigned char)d; }
-                    d = 255;
-                    for (int xx = ww - 1; xx >= 0; xx--) {
-                        d = row[xx] == 0 ? 0 : imin(d + 1, 255);
-                        if (d < row[xx]) row[xx] = (unsigned char)d;
-                    }
-                }
-                DS_SYNC();
-                // vertical sweeps over the tile's own columns
-                for (int xx = R + tid; xx < R + TW; xx += NT) {
-                    int d = 255;
-                    for (int yy = 0; yy < wh; yy++) {
-                        d = imin(d + 1, 255);
-                        const int g = s_d[yy * ww + xx];
-                        if (g < d) d = g;
-                        s_d[yy * ww + xx] = (unsigned char)d;
-                    }
-                    d = 255;
-                    for (int yy = wh - 1; yy >= 0; yy--) {
-                        d = imin(d + 1, 255);
-                        const int g = s_d[yy * ww + xx];
-                        if (g < d) d = g;
-                        s_d[yy * ww + xx] = (unsigned char)d;
-                    }
-                }
-                DS_SYNC();
-            }
+            const uint8_t* const dist = F.dist;
+            const int dpitch = F.dist_pitch;
             // 3) sample + accumulate
             // Interior tile-frames (tile inside the bbox, its four corners at least a pixel inside the source;
             // the plane map is monotone in u and in v, so the corners bound every pixel): border-free loop
@@ -600,12 +679,13 @@ struct FeatherBody {
                 constexpr int UB = PPT < 4 ? PPT : 4;   // pixels in flight per thread
                 DS_UNROLL
                 for (int k0 = 0; k0 < PPT; k0 += UB) {
-                    int ix[UB], iy[UB];
+                    int ix[UB], iy[UB], dd[UB];
                     uint32_t p00[UB], p01[UB], p10[UB], p11[UB];
                     DS_UNROLL
                     for (int b = 0; b < UB; b++) {
                         const int pidx = tid + (k0 + b) * NT;
                         const int yy = pidx / TW, xx = pidx - yy * TW;
+                        dd[b] = (int)ld_ro(dist + (size_t)(Y0 + yy - F.cy) * dpitch + (X0 + xx - F.cx));
                         const float2 c = s_cx[xx], r = s_ry[yy];
                         const float x = f_add(f_add(c.x, r.x), k2);
                         const float y = f_add(f_add(c.y, r.y), k5);
@@ -623,11 +703,12 @@ struct FeatherBody {
                         const int pidx = tid + k * NT;
                         const int yy = pidx / TW, xx = pidx - yy * TW;
                         float wgt = 1.f;
-                        if (has_zero) {
-                            const int d = s_d[(yy + R) * ww + (xx + R)];
+                        {
+                            const int d = dd[b];
                             if (d == 0) continue;
                             if (d < R) { wgt = f_mul((float)d, p.sharpness); if (wgt > 1.f) wgt = 1.f; }
                         }
+                        (void)yy; (void)xx;
                         const int ax = ix[b] & 31, ay = iy[b] & 31;
                         const uint32_t wb = (uint32_t)(32 - ax) | ((uint32_t)ax << 8), wg = wb << 16;
                         const uint32_t t0 = byte_perm(p00[b], p01[b], 0x5140), t0r = byte_perm(p00[b], p01[b], 0x6262);
@@ -655,8 +736,8 @@ struct FeatherBody {
                 const int u = X0 + xx - F.cx, v = Y0 + yy - F.cy;
                 if ((unsigned)u >= (unsigned)F.w || (unsigned)v >= (unsigned)F.h) continue;
                 float wgt = 1.f;
-                if (has_zero) {
-                    const int d = s_d[(yy + R) * ww + (xx + R)];
+                {
+                    const int d = (int)ld_ro(dist + (size_t)v * dpitch + u);
                     if (d == 0) continue;
                     if (d < R) { wgt = f_mul((float)d, p.sharpness); if (wgt > 1.f) wgt = 1.f; }
                 }
@@ -670,27 +751,49 @@ struct FeatherBody {
             }
             DS_SYNC();
         }
-        // normalise + store
+        // normalise into a shared tile of packed pixels (b | g << 8 | r << 16 | mask << 24), then store it with 4-pixel
+        // accesses: 12 BGR bytes as three words + one mask word, or one 16-byte BGRA store
+        uint32_t* s_out = (uint32_t*)(smem + (TW + TH) * 8);
         DS_UNROLL
         for (int k = 0; k < PPT; k++) {
             const int pidx = tid + k * NT;
-            const int yy = pidx / TW, xx = pidx - yy * TW;
-            const int X = X0 + xx, Y = Y0 + yy;
-            if (X >= p.o.w || Y >= p.o.h || Y < p.row0 || Y >= p.row1) continue;
             const float den = f_add(ws[k], 1e-5f);
             const int m = ws[k] > 1e-5f;
             int o[3];
+            DS_UNROLL
             for (int ch = 0; ch < 3; ch++) {
-                const int v16 = (int)(short)f2i_rz(f_div((float)(short)acc[k][ch], den));
+                const short a16 = (short)acc[k][ch];
+                // 0 / den == 0 exactly: skips the division for untouched pixels
+                const int v16 = a16 ? (int)(short)f2i_rz(f_div((float)a16, den)) : 0;
                 o[ch] = m ? sat8i(v16) : 0;
             }
+            s_out[pidx] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | (m ? 0xff000000u : 0u);
+        }
+        DS_SYNC();
+        for (int i = tid; i < TW * TH / 4; i += NT) {
+            const int yy = i / (TW / 4), x4 = (i - yy * (TW / 4)) * 4;
+            const int X = X0 + x4, Y = Y0 + yy;
+            if (X >= p.o.w || Y >= p.o.h || Y < p.row0 || Y >= p.row1) continue;
+            const uint4 px = *(const uint4*)(s_out + yy * TW + x4);
+            const int nout = imin(4, p.o.w - X);
             if (p.o.fmt == 1) {
-                uint32_t pk = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | (m ? 0xff000000u : 0u);
-                *(uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 4) = pk;
+                uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch) + X;
+                if (nout == 4) *(uint4*)q = px;
+                else { const uint32_t v[4] = {px.x, px.y, px.z, px.w}; for (int k = 0; k < nout; k++) q[k] = v[k]; }
+            } else if (nout == 4) {
+                // X is a multiple of 4 and the pitches are multiples of 256: aligned words
+                uint32_t* q = (uint32_t*)(p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 3);
+                q[0] = (px.x & 0xffffffu) | (px.y << 24);
+                q[1] = ((px.y >> 8) & 0xffffu) | (px.z << 16);
+                q[2] = ((px.z >> 16) & 0xffu) | (px.w << 8);
+                *(uint32_t*)(p.o.mask + (size_t)Y * p.o.mask_pitch + X) = (px.x >> 24) | ((px.y >> 24) << 8) | ((px.z >> 24) << 16) | ((px.w >> 24) << 24);
             } else {
-                uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)X * 3;
-                q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
-                p.o.mask[(size_t)Y * p.o.mask_pitch + X] = m ? 255 : 0;
+                const uint32_t v[4] = {px.x, px.y, px.z, px.w};
+                for (int k = 0; k < nout; k++) {
+                    uint8_t* q = p.o.out + (size_t)Y * p.o.out_pitch + (size_t)(X + k) * 3;
+                    q[0] = (uint8_t)v[k]; q[1] = (uint8_t)(v[k] >> 8); q[2] = (uint8_t)(v[k] >> 16);
+                    p.o.mask[(size_t)Y * p.o.mask_pitch + X + k] = (uint8_t)(v[k] >> 24);
+                }
             }
         }
     }
@@ -2359,7 +2462,9 @@ DS_DEFINE_KERNEL(ds_soft_mask, SoftMaskBody, 256, SoftMaskParams, 3)
 DS_DEFINE_KERNEL(ds_crop_row_runs, RowRunsBody, 256, RowRunsParams, 1)
 DS_DEFINE_KERNEL(ds_gain_resize, GainResizeBody, 256, GainResizeParams, 1)
 DS_DEFINE_KERNEL(ds_feather_mask_bits, MaskBitsBody, 256, MaskBitsParams, 1)
-DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 3)
+DS_DEFINE_KERNEL(ds_feather_mask_rows, MaskBitsRowBody, 256, MaskBitsRowParams, 1)
+DS_DEFINE_KERNEL(ds_feather_dist, FeatherDistBody, 256, FeatherDistParams, 1)
+DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 4)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)
 typedef MBFastBody<64, true> MBFastL0;
 typedef MBFastBody<64, true, true> MBFastL0A;

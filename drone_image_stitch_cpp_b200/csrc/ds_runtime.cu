@@ -237,6 +237,7 @@ struct Frame {
     int rx = 0, ry = 0, rw = 0, rh = 0;              // feed ROI rel. to padded canvas origin
     void* d_pyr = nullptr; size_t pyr_cap = 0;       // G/W levels 1..L
     uint32_t* d_mbits = nullptr; size_t mbits_cap = 0;
+    uint8_t* d_dist = nullptr; size_t dist_cap = 0;   // FEATHER: L1 distance plane of the warped mask over the bbox
     uint8_t* d_seam = nullptr; size_t seam_cap = 0;        // the frame's mask plane over its bbox (seam / content / soft mask)
     uint8_t* d_content = nullptr; size_t content_cap = 0;  // DS_MASK_CONTENT: the content mask, kept for ds_download_frame_mask
     float* d_gainmap = nullptr; size_t gainmap_cap = 0;
@@ -484,6 +485,7 @@ int fill_frame_dev(ds_canvas* c, Frame& f) {
         }
     }
     d.mbits = f.d_mbits; d.mbits_pitch = (f.bw + 31) / 32;
+    d.dist = f.d_dist; d.dist_pitch = (f.bw + 15) & ~15;
     d.seam = f.d_seam; d.seam_pitch = f.bw;
     return DS_OK;
 }
@@ -1100,10 +1102,23 @@ int launch_feather(ds_canvas* c, stream_t st, const SubBand& sb, const ABModel& 
         Frame& f = c->frames[i];
         if (!f.used || f.mask_done) continue;
         if (f.dev.cy >= ty1 * TH || f.dev.cy + f.bh <= ty0 * TH) continue;
-        MaskBitsParams mp{c->d_frames, (int)i, f.d_mbits};
         const long long nwords = (long long)f.dev.mbits_pitch * f.bh;
         if ((rc = prof_mark(c, st, true, "feather_mask", -1, 0))) return rc;
-        if ((rc = launch<MaskBitsBody, 256>(mp, (nwords + MaskBitsBody::WORDS_PER_BLOCK - 1) / MaskBitsBody::WORDS_PER_BLOCK, st, 0))) return rc;
+        if (MaskBitsRowBody::eligible(f.dev)) {
+            // plane maps without a seam mask: one thread per 32-pixel word, two coordinate evaluations in the interior
+            MaskBitsRowParams mp{c->d_frames, (int)i, f.d_mbits};
+            rc = launch<MaskBitsRowBody, 256>(mp, (nwords + MaskBitsRowBody::PER_BLOCK - 1) / MaskBitsRowBody::PER_BLOCK, st, 0);
+        } else {
+            MaskBitsParams mp{c->d_frames, (int)i, f.d_mbits};
+            rc = launch<MaskBitsBody, 256>(mp, (nwords + MaskBitsBody::WORDS_PER_BLOCK - 1) / MaskBitsBody::WORDS_PER_BLOCK, st, 0);
+        }
+        if (rc) return rc;
+        if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
+        c->launches++;
+        // L1 distance to the nearest zero of that mask, once per frame (the blend kernel reads it per pixel)
+        FeatherDistParams dp{c->d_frames, (int)i, f.d_dist, c->feather_R};
+        if ((rc = prof_mark(c, st, true, "feather_dist", -1, 0))) return rc;
+        if ((rc = launch<FeatherDistBody, 256>(dp, FeatherDistBody::blocks(f.dev), st, FeatherDistBody::smem_bytes()))) return rc;
         if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
         c->launches++;
         f.mask_done = true;
@@ -1593,6 +1608,7 @@ int do_upload(ds_canvas* c, int idx, const void* bgr, bool on_device, int w, int
         }
     } else {
         if ((rc = grow(c, (void**)&f.d_mbits, &f.mbits_cap, (size_t)((f.bw + 31) / 32) * f.bh * sizeof(uint32_t)))) return rc;
+        if ((rc = grow(c, (void**)&f.d_dist, &f.dist_cap, (size_t)((f.bw + 15) & ~15) * f.bh))) return rc;
     }
     if ((rc = apply_opts(c, f, idx, opts))) return rc;
     if (async) c->async_pending = true;
@@ -1818,7 +1834,7 @@ DS_API void ds_destroy_canvas(ds_canvas* c) {
     if (c->dl) cudaStreamSynchronize(c->dl);
 #endif
     for (Frame& f : c->frames) {
-        dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_seam); dev_free(f.d_content); dev_free(f.d_gainmap);
+        dev_free(f.d_src); dev_free(f.d_pyr); dev_free(f.d_mbits); dev_free(f.d_dist); dev_free(f.d_seam); dev_free(f.d_content); dev_free(f.d_gainmap);
     }
     for (int l = 0; l < DS_MAXL; l++) dev_free(c->d_lvl_alloc[l]);
     for (SubBand& sb : c->subs) { ev_drop(sb.done); ev_drop(sb.fed); ev_drop(sb.fed0); }

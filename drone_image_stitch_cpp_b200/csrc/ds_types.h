@@ -35,6 +35,8 @@ struct alignas(16) FrameDev {
     const float* gainmap;   // BlocksGainCompensator::apply: per-pixel float32 gain over the bbox (stitch_robust.cpp:209-211)
     int gainmap_pitch;
     int any_gain;           // has_gain | has_cgain | (gainmap != 0)
+    const uint8_t* dist;    // FEATHER: min(L1 distance to the nearest zero of the warped mask, 255) over the bbox, exact below the radius
+    int dist_pitch;
 };
 
 struct Coord {
