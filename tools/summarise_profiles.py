@@ -1,12 +1,17 @@
 """Turns the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
-usage: python tools/summarise_profiles.py gpurun_out/launches_r1.csv gpurun_out/prof_r1g.ncu-rep"""
+usage: python tools/summarise_profiles.py <tag> <launches.csv> <sources-hash-file> [<kernel>=<file.ncu-rep> ...]
+  tag                round tag of the output names (r2 -> profiles/r2_launches_cfg2.json ...)
+  sources-hash-file  the .so.sources file copied from the GPU box next to the capture (hash of the kernel sources the
+                     captured library was built from); bench.py only reports roofline.traffic when it matches its own build"""
 import collections
 import csv
 import json
 import subprocess
 import sys
 
-launch_csv, rep = sys.argv[1], sys.argv[2]
+tag, launch_csv, hash_file = sys.argv[1], sys.argv[2], sys.argv[3]
+reps = [a.split("=", 1) for a in sys.argv[4:]]
+SHA = open(hash_file).read().strip()
 PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]   # GB/s, measured copy bandwidth of this pool
 rows = list(csv.reader(open(launch_csv)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -35,26 +40,25 @@ out = [dict(kernel=l["name"].split("(")[0], grid=l["grid"], block=l["block"], us
             frac_of_measured_hbm_peak=round((l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"]) / l["gpu__time_duration.sum"] / PEAK, 3))
        for l in seq]
 json.dump(dict(command="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv "
-                       "python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
+                       "python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline --no-parity",
+               kernel_source_sha16=SHA,
                note="one ds_composite of cfg2; per-launch times under ncu are cold-cache / serialised: compare shares. dram_GBps = "
                     "(dram read + write) / duration of the launch: the REAL traffic rate, against MEASURED_PEAKS.json hbm_gbs "
                     "(%.1f GB/s; nominal ~8000). The bench line's roofline.achieved uses the algorithmic bytes instead." % PEAK,
                launches=out, total_us=round(tot / 1e3, 1), dram_total_MB=round(sum(o["dram_read_MB"] + o["dram_write_MB"] for o in out), 1)),
-          open("profiles/r1_launches_cfg2.json", "w"), indent=1)
-with open("profiles/r1_launches_cfg2.csv", "w") as f:
+          open(f"profiles/{tag}_launches_cfg2.json", "w"), indent=1)
+with open(f"profiles/{tag}_launches_cfg2.csv", "w") as f:
     f.write("idx,kernel,grid,block,time_ns,dram_read_bytes,dram_write_bytes\n")
     for i, l in enumerate(mine):
         f.write(f"{i},{l['name'].split('(')[0]},\"{l['grid']}\",\"{l['block']}\",{l['gpu__time_duration.sum']:.0f},"
                 f"{l['dram__bytes_read.sum']:.0f},{l['dram__bytes_write.sum']:.0f}\n")
-json.dump({"cfg2:mb_feed:0": int(seq[0]["dram__bytes_read.sum"] + seq[0]["dram__bytes_write.sum"])},
+json.dump({"cfg2:mb_feed:0": int(seq[0]["dram__bytes_read.sum"] + seq[0]["dram__bytes_write.sum"]), "kernel_source_sha16": SHA,
+           "capture": f"profiles/{tag}_launches_cfg2.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum of one ds_mb_feed_l0 launch, cfg2)"},
           open("profiles/dominant_kernel_traffic.json", "w"))
 for o in out:
     print(o)
 print("total us", tot / 1e3)
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h, units, r = rr[0], rr[1], rr[2]
 keys = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -71,8 +75,14 @@ keys = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "lau
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
-summ = {k: (r[h.index(k)] + " " + units[h.index(k)]).strip() for k in keys if k in h}
-json.dump(summ, open("profiles/r1_ds_mb_feed_l0_ncu_full.json", "w"), indent=1)
-for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-          "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__shared_mem_per_block_dynamic"):
-    print(k, summ.get(k))
+for kname, rep in reps:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, units, r = rr[0], rr[1], rr[2]
+    summ = {k: (r[h.index(k)] + " " + units[h.index(k)]).strip() for k in keys if k in h}
+    summ["kernel_source_sha16"] = SHA
+    json.dump(summ, open(f"profiles/{tag}_{kname}_ncu_full.json", "w"), indent=1)
+    print(kname)
+    for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+              "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__shared_mem_per_block_dynamic", "launch__registers_per_thread"):
+        print("  ", k, summ.get(k))
