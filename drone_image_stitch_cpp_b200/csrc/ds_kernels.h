@@ -820,7 +820,7 @@ struct MBParams {
     px16* dst; int dst_w, dst_h;  // normalised Laplacian level of the padded canvas
     int acc_y0, acc_y1;           // rows of this level whose dst the band's collapse reads (dst written only there)
     int own_y0, own_y1;           // even-aligned rows of this level the handle processes at all
-    const void* tmaps;            // CUtensorMap[frame][DS_MAXL][2] (G, W) for the TMA tile loads of levels >= 1, or NULL
+    const void* tmaps;            // CUtensorMap[frame][2] over the frame sources (level 0: L2 prefetch box, shared-memory box), or NULL
     int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI
 };
 
@@ -1365,7 +1365,7 @@ struct MBFastBody {
                 if (gx.skip || !gx.box) return;
 #if DS_CUDA
                 if (tid == 0) {
-                    const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fj] * DS_MAXL * 2 + 1) * 128;   // slot [frame][0][1]
+                    const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fj] * 2 + 1) * 128;   // slot [frame][1]: source, shared-memory box
                     fence_tensormap_acquire(tm);
                     fence_proxy_async();   // generic-proxy accesses of the buffer ended before the last barrier
                     mbar_expect_tx(s_bar, (uint32_t)BOX_BYTES);
@@ -1406,7 +1406,7 @@ struct MBFastBody {
                         ymin = fminf(ymin, N.k[3] * up + N.k[4] * vp + N.k5one);
                     }
                     if (xmin > -1.0e6f && xmin < 1.0e6f && ymin > -1.0e6f && ymin < 1.0e6f) {
-                        const char* tm = (const char*)p.tmaps + (size_t)p.tile_frames[fi + 1] * DS_MAXL * 2 * 128;   // slot [frame][0][0]: source
+                        const char* tm = (const char*)p.tmaps + (size_t)p.tile_frames[fi + 1] * 2 * 128;   // slot [frame][0]: source, L2 prefetch box
                         fence_tensormap_acquire(tm);
                         tma_prefetch_l2_2d(tm, ((int)floorf(xmin) - 1) & ~3, (int)floorf(ymin) - 1);
                     }
@@ -2135,6 +2135,306 @@ struct MBFastBody {
 };
 
 // ---------------------------------------------------------------------------------------------
+// MULTIBAND, levels >= 1, streaming formulation. The per-frame pyramids are plain planes in HBM, so above level 0
+// nothing has to be staged tile by tile:
+//   ds_mb_pyrdown  G_{l+1} = pyrDown16S(G_l), W_{l+1} = pyrDownF32(W_l) of every frame, each output computed once
+//                  (no tile halo), 2 x 2 outputs per thread from a 7 x 7 register window, no shared memory;
+//   ds_mb_accum    a canvas tile of level l walks its frames in feed order; every thread owns one 2 x 2 quad and keeps
+//                  its Laplacian and weight sums in registers: lap = G_l - pyrUp(G_{l+1}) straight from the planes
+//                  (neighbouring threads share the taps through L1), acc += trunc(lap * W_l); no barrier inside the
+//                  frame loop; normalised level written once.
+// Same arithmetic as MBBody (A8 - A11); the tile-based kernels spent 4 barriers and a 39 x 39 halo region per 32 x 32
+// tile-frame on this (level 1 of cfg2: 287 M warp instructions, 0.38 ms).
+
+struct PyrParams {
+    const FrameDev* frames; int nframes;
+    int level;            // input level l (>= 1); output level l + 1
+    int txmax, R;         // CTAs per frame: txmax column blocks x R row blocks (first row block = the frame's first needed row)
+    int own_y0, own_y1;   // canvas rows of level l + 1 to produce
+};
+struct PyrDownBody {
+    static constexpr int BW = 32, BH = 16, NTH = 128;   // outputs per CTA; one thread = 2 x 2 outputs
+    static int smem_bytes() { return 0; }
+    template <int NT>
+    DS_DM void run(const PyrParams& p, int block, int tid, unsigned char*) {
+        const int per = p.txmax * p.R;
+        const int fslot = block / per, rem = block - fslot * per;
+        const int byr = rem / p.txmax, bx = rem - byr * p.txmax;
+        const FrameDev& F = p.frames[fslot];
+        const int l = p.level;
+        const int w_in = F.rw >> l, h_in = F.rh >> l, w_out = w_in >> 1, h_out = h_in >> 1;
+        const int ry1 = F.ry >> (l + 1);
+        const int jlo = imax(p.own_y0 - ry1, 0), jhi = imin(p.own_y1 - ry1, h_out);
+        if (jlo >= jhi) return;   // unused slot (rw == rh == 0) or a frame outside the rows
+        const int by = jlo / BH + byr;
+        if (by * BH >= jhi || bx * BW >= w_out) return;
+        const uint32_t* const Gin = (const uint32_t*)F.G[l];
+        const float* const Win = F.W[l];
+        uint32_t* const Gout = (uint32_t*)F.G[l + 1];
+        float* const Wout = F.W[l + 1];
+        const int ip = F.gp[l], op = F.gp[l + 1];
+        for (int t = tid; t < NTH; t += NT) {
+            const int tx = t & 15, ty = t >> 4;
+            const int jx = bx * BW + 2 * tx, jy = by * BH + 2 * ty;   // first of the thread's 2 x 2 outputs
+            if (jx >= w_out || jy >= jhi || jy + 1 < jlo) continue;
+            const int c0 = 2 * jx - 2, r0 = 2 * jy - 2;               // 7 x 7 input window
+            const bool interior = c0 >= 0 && c0 + 6 <= w_in - 1 && r0 >= 0 && r0 + 6 <= h_in - 1;
+            int rows[7], cols[7];
+            DS_UNROLL
+            for (int k = 0; k < 7; k++) { rows[k] = interior ? r0 + k : refl101(r0 + k, h_in); cols[k] = interior ? c0 + k : refl101(c0 + k, w_in); }
+            // ---- G: separable [1 4 6 4 1] on packed lanes (B | R << 16, G); the vertical sums are order-free integers
+            uint32_t vbr[2][2] = {{0u, 0u}, {0u, 0u}}, vg[2][2] = {{0u, 0u}, {0u, 0u}};
+            float hw[7][2];
+            DS_UNROLL
+            for (int k = 0; k < 7; k++) {
+                uint32_t q[7]; float w[7];
+                const uint32_t* gr = Gin + (size_t)rows[k] * ip;
+                const float* wr = Win + (size_t)rows[k] * ip;
+                if (interior) {
+                    // c0 = 2 mod 4 and rows are 16-byte aligned: 8 + 16 + 4 bytes
+                    const uint2 a = ld_ro((const uint2*)(gr + c0)); const uint4 b = ld_ro((const uint4*)(gr + c0 + 2)); const uint32_t c = ld_ro(gr + c0 + 6);
+                    q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = b.z; q[5] = b.w; q[6] = c;
+                    const float2 fa = ld_ro((const float2*)(wr + c0)); const float4 fb = ld_ro((const float4*)(wr + c0 + 2)); const float fc = ld_ro(wr + c0 + 6);
+                    w[0] = fa.x; w[1] = fa.y; w[2] = fb.x; w[3] = fb.y; w[4] = fb.z; w[5] = fb.w; w[6] = fc;
+                } else {
+                    DS_UNROLL
+                    for (int c = 0; c < 7; c++) { q[c] = ld_ro(gr + cols[c]); w[c] = ld_ro(wr + cols[c]); }
+                }
+                uint32_t br[7], gg[7];
+                DS_UNROLL
+                for (int c = 0; c < 7; c++) { br[c] = byte_perm(q[c], 0, 0x4240); gg[c] = byte_perm(q[c], 0, 0x4441); }
+                DS_UNROLL
+                for (int o = 0; o < 2; o++) {
+                    const uint32_t hbr = br[2 * o] + br[2 * o + 4] + 6u * br[2 * o + 2] + 4u * (br[2 * o + 1] + br[2 * o + 3]);
+                    const uint32_t hg = gg[2 * o] + gg[2 * o + 4] + 6u * gg[2 * o + 2] + 4u * (gg[2 * o + 1] + gg[2 * o + 3]);
+                    // input row k is tap k of output row 0 and tap k - 2 of output row 1
+                    const uint32_t k0 = (k == 0 || k == 4) ? 1u : ((k == 1 || k == 3) ? 4u : (k == 2 ? 6u : 0u));
+                    const uint32_t k1 = (k == 2 || k == 6) ? 1u : ((k == 3 || k == 5) ? 4u : (k == 4 ? 6u : 0u));
+                    if (k <= 4) { vbr[0][o] += k0 * hbr; vg[0][o] += k0 * hg; }
+                    if (k >= 2) { vbr[1][o] += k1 * hbr; vg[1][o] += k1 * hg; }
+                    // weights: horizontal pass in the op order of the column's class (A9)
+                    const int j = jx + o;
+                    hw[k][o] = pd_h_is_simd(j, w_in, w_out) ? pd_h_simd(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4])
+                                                            : pd_scalar(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4]);
+                }
+            }
+            DS_UNROLL
+            for (int dy = 0; dy < 2; dy++) {
+                const int y = jy + dy;
+                if (y < jlo || y >= jhi) continue;
+                uint32_t go[2]; float wo[2];
+                DS_UNROLL
+                for (int o = 0; o < 2; o++) {
+                    const uint32_t obr = ((vbr[dy][o] + 0x00800080u) >> 8) & 0x00FF00FFu, og = ((vg[dy][o] + 0x80u) >> 8) & 0xFFu;
+                    go[o] = byte_perm(obr, og, 0x5240);
+                    const float t0 = hw[2 * dy][o], t1 = hw[2 * dy + 1][o], t2 = hw[2 * dy + 2][o], t3 = hw[2 * dy + 3][o], t4 = hw[2 * dy + 4][o];
+                    const float v = pd_v_is_simd(jx + o, w_out) ? pd_v_simd(t0, t1, t2, t3, t4) : pd_scalar(t0, t1, t2, t3, t4);
+                    wo[o] = f_mul(v, 1.f / 256.f);
+                }
+                uint32_t* gq = Gout + (size_t)y * op + jx;
+                float* wq = Wout + (size_t)y * op + jx;
+                if (jx + 1 < w_out) {   // jx is even and the pitch a multiple of 4: 8-byte aligned pairs
+                    uint2 gv; gv.x = go[0]; gv.y = go[1]; *(uint2*)gq = gv;
+                    float2 wv; wv.x = wo[0]; wv.y = wo[1]; *(float2*)wq = wv;
+                } else { gq[0] = go[0]; wq[0] = wo[0]; }
+            }
+        }
+    }
+};
+
+struct AccumBody {
+    static constexpr int TW = 32, TH = 16, NQ = 128;   // one thread = one 2 x 2 quad
+    static constexpr int GCH = 32;                     // frames whose geometry is staged at a time
+    struct alignas(16) AGeo {
+        const uint32_t* G; const float* W;
+        const uint32_t* G1; int gp, gp1;
+        int rx, ry, n1x, n1y;
+        int ax0, ax1, ay0, ay1;
+        int skip, ones, pad0, pad1;
+    };
+    static int smem_bytes() { return GCH * (int)sizeof(AGeo); }
+    struct U2 { uint32_t br, g; };
+    DS_DM U2 split(uint32_t v) { U2 o; o.br = byte_perm(v, 0, 0x4240); o.g = byte_perm(v, 0, 0x4441); return o; }
+
+    // tile x frame geometry, by one thread
+    DS_DM void make_geo(const MBParams& p, const FrameDev& F, int X0, int Y0, bool top, AGeo& g) {
+        const int l = p.level;
+        const int rx = F.rx >> l, ry = F.ry >> l, rw = F.rw >> l, rh = F.rh >> l;
+        g.G = (const uint32_t*)F.G[l]; g.W = F.W[l]; g.G1 = top ? nullptr : (const uint32_t*)F.G[l + 1];
+        g.gp = F.gp[l]; g.gp1 = top ? 0 : F.gp[l + 1];
+        g.rx = rx; g.ry = ry; g.n1x = rw >> 1; g.n1y = rh >> 1;
+        g.ax0 = imax(X0, rx); g.ax1 = imin(X0 + TW, rx + rw);
+        // below the top level the ROI is even-aligned and quads are whole: rows rounded out to quads (the store filters)
+        const int a0 = top ? p.acc_y0 : (p.acc_y0 & ~1), a1 = top ? p.acc_y1 : ((p.acc_y1 + 1) & ~1);
+        g.ay0 = imax(imax(Y0, ry), a0); g.ay1 = imin(imin(Y0 + TH, ry + rh), a1);
+        g.skip = (g.ax0 >= g.ax1 || g.ay0 >= g.ay1) ? 1 : 0;
+        g.ones = 0; g.pad0 = g.pad1 = 0;
+        // "every weight of the tile-frame is exactly 1", from geometry alone: a plane-mapped frame without per-pixel mask
+        // whose level-0 support of the region (radius 2^(l+1) - 2 after l pyrDowns) lies inside the bbox and maps into the
+        // source at its four corners - x(u, v) is monotone in u and in v even in float arithmetic, so the corners bound
+        // every pixel; the nearest mask is then 255 throughout, W_0 = 255 * (1 / 255f) = 1 and every pyrDown of ones is 1.
+        if (!g.skip && F.kind == XF_PLANE && !F.seam && F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f && f_mul(255.f, 1.f / 255.f) == 1.f) {
+            const int rl = (2 << l) - 2;
+            const int u_lo = F.rx + ((g.ax0 - rx) << l) - rl - F.cx, u_hi = F.rx + ((g.ax1 - 1 - rx) << l) + rl - F.cx;
+            const int v_lo = F.ry + ((g.ay0 - ry) << l) - rl - F.cy, v_hi = F.ry + ((g.ay1 - 1 - ry) << l) + rl - F.cy;
+            if (u_lo >= 0 && u_hi <= F.w - 1 && v_lo >= 0 && v_hi <= F.h - 1) {
+                float ca0[2], ca3[2], rb1[2], rb4[2];
+                DS_UNROLL
+                for (int e = 0; e < 2; e++) {
+                    float U = (float)(F.tlx + (e ? u_hi : u_lo)), V = (float)(F.tly + (e ? v_hi : v_lo));
+                    if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+                    const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+                    ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
+                    rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
+                }
+                float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+                DS_UNROLL
+                for (int e = 0; e < 4; e++) {
+                    const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), F.k2one), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), F.k5one);
+                    xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
+                }
+                if (xmn >= 0.f && xmx <= (float)(F.src_w - 1) && ymn >= 0.f && ymx <= (float)(F.src_h - 1)) g.ones = 1;
+            }
+        }
+    }
+
+    template <int NT>
+    DS_DM void run(const MBParams& p, int block, int tid, unsigned char* smem) {
+        constexpr int K = NQ / NT;   // quads per thread: 1 on the GPU; the emulator's single thread holds them all
+        AGeo* s_geo = (AGeo*)smem;
+        const int4 rec = ld_ro(p.tile_rec + block);
+        const int tile = rec.x, f_begin = rec.y, f_end = rec.z;
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int X0 = tx * TW, Y0 = ty * TH;
+        const bool top = p.level == p.L;
+        int ab[K][4], ag[K][4], ar[K][4]; float ws[K][4];
+        DS_UNROLL
+        for (int k = 0; k < K; k++) { DS_UNROLL for (int i = 0; i < 4; i++) { ab[k][i] = ag[k][i] = ar[k][i] = 0; ws[k][i] = 0.f; } }
+        for (int base = f_begin; base < f_end; base += GCH) {
+            const int n = imin(GCH, f_end - base);
+            if (base > f_begin) DS_SYNC();   // everyone is done with the previous chunk's entries
+            for (int j = tid; j < n; j += NT) make_geo(p, p.frames[(base + j == f_begin) ? rec.w : p.tile_frames[base + j]], X0, Y0, top, s_geo[j]);
+            DS_SYNC();
+            DS_UNROLL
+            for (int k = 0; k < K; k++) {
+                const int q = tid + k * NT;
+                const int X = X0 + 2 * (q & 15), Y = Y0 + 2 * (q >> 4);
+                for (int j = 0; j < n; j++) {
+                    const AGeo& g = s_geo[j];
+                    if (g.skip) continue;
+                    if (top) {
+                        // the top level accumulates G_L itself; its ROI need not be even-aligned: per pixel
+                        DS_UNROLL
+                        for (int i = 0; i < 4; i++) {
+                            const int Xp = X + (i & 1), Yp = Y + (i >> 1);
+                            if (Xp < g.ax0 || Xp >= g.ax1 || Yp < g.ay0 || Yp >= g.ay1) continue;
+                            const size_t gi = (size_t)(Yp - g.ry) * g.gp + (Xp - g.rx);
+                            const uint32_t v = ld_ro(g.G + gi);
+                            const float wv = ld_ro(g.W + gi);
+#if !DS_CUDA
+                            if (g.ones && wv != 1.f) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
+#endif
+                            ab[k][i] += (int)(short)f2i_rz(f_mul((float)(v & 255u), wv));
+                            ag[k][i] += (int)(short)f2i_rz(f_mul((float)((v >> 8) & 255u), wv));
+                            ar[k][i] += (int)(short)f2i_rz(f_mul((float)((v >> 16) & 255u), wv));
+                            ws[k][i] = f_add(ws[k][i], wv);
+                        }
+                        continue;
+                    }
+                    if (X < g.ax0 || X >= g.ax1 || Y < g.ay0 || Y >= g.ay1) continue;
+                    const int ox = X - g.rx, oy = Y - g.ry;   // even
+                    const int c1x = ox >> 1, c1y = oy >> 1;
+                    const int ixl = up_l(c1x, g.n1x), ixr = up_r(c1x, g.n1x), iyl = up_l(c1y, g.n1y), iyr = up_r(c1y, g.n1y);
+                    const uint32_t* ra = g.G1 + (size_t)iyl * g.gp1; const uint32_t* rb = g.G1 + (size_t)c1y * g.gp1; const uint32_t* rd = g.G1 + (size_t)iyr * g.gp1;
+                    const uint32_t* g0p = g.G + (size_t)oy * g.gp + ox;
+                    // every load of the quad is requested before the first use
+                    const uint32_t wa0 = ld_ro(ra + ixl), wa1 = ld_ro(ra + c1x), wa2 = ld_ro(ra + ixr);
+                    const uint32_t wb0 = ld_ro(rb + ixl), wb1 = ld_ro(rb + c1x), wb2 = ld_ro(rb + ixr);
+                    const uint32_t wd0 = ld_ro(rd + ixl), wd1 = ld_ro(rd + c1x), wd2 = ld_ro(rd + ixr);
+                    const uint2 gr0 = ld_ro((const uint2*)g0p), gr1 = ld_ro((const uint2*)(g0p + g.gp));
+                    float2 wr0, wr1; wr0.x = wr0.y = wr1.x = wr1.y = 1.f;
+                    if (!g.ones) { const float* wp = g.W + (size_t)oy * g.gp + ox; wr0 = ld_ro((const float2*)wp); wr1 = ld_ro((const float2*)(wp + g.gp)); }
+#if !DS_CUDA
+                    if (g.ones) {
+                        const float* wp = g.W + (size_t)oy * g.gp + ox;
+                        if (wp[0] != 1.f || wp[1] != 1.f || wp[g.gp] != 1.f || wp[g.gp + 1] != 1.f) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
+                    }
+#endif
+                    const U2 a0 = split(wa0), a1 = split(wa1), a2 = split(wa2), b0 = split(wb0), b1 = split(wb1), b2 = split(wb2), d0 = split(wd0), d1 = split(wd1), d2 = split(wd2);
+                    // pyrUp (A10) on packed lanes. horizontal: even = l + 6c + r, odd = 4(c + r), on rows l / c / r
+                    const uint32_t El_br = a0.br + 6u * a1.br + a2.br, Ol_br = 4u * (a1.br + a2.br);
+                    const uint32_t Ec_br = b0.br + 6u * b1.br + b2.br, Oc_br = 4u * (b1.br + b2.br);
+                    const uint32_t Er_br = d0.br + 6u * d1.br + d2.br, Or_br = 4u * (d1.br + d2.br);
+                    const uint32_t El_g = a0.g + 6u * a1.g + a2.g, Ol_g = 4u * (a1.g + a2.g);
+                    const uint32_t Ec_g = b0.g + 6u * b1.g + b2.g, Oc_g = 4u * (b1.g + b2.g);
+                    const uint32_t Er_g = d0.g + 6u * d1.g + d2.g, Or_g = 4u * (d1.g + d2.g);
+                    // vertical + (v + 32) >> 6; index = 2 dy + dx
+                    uint32_t up_br[4], up_g[4];
+                    up_br[0] = ((El_br + 6u * Ec_br + Er_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_br[1] = ((Ol_br + 6u * Oc_br + Or_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_br[2] = ((4u * (Ec_br + Er_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_br[3] = ((4u * (Oc_br + Or_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    up_g[0] = ((El_g + 6u * Ec_g + Er_g + 0x20u) >> 6) & 0x3FFu;
+                    up_g[1] = ((Ol_g + 6u * Oc_g + Or_g + 0x20u) >> 6) & 0x3FFu;
+                    up_g[2] = ((4u * (Ec_g + Er_g) + 0x20u) >> 6) & 0x3FFu;
+                    up_g[3] = ((4u * (Oc_g + Or_g) + 0x20u) >> 6) & 0x3FFu;
+                    const uint32_t g0v[4] = {gr0.x, gr0.y, gr1.x, gr1.y};
+                    const float wv4[4] = {wr0.x, wr0.y, wr1.x, wr1.y};
+                    DS_UNROLL
+                    for (int i = 0; i < 4; i++) {
+                        const U2 gv = split(g0v[i]);
+                        const int lb = (int)(gv.br & 0xFFFFu) - (int)(up_br[i] & 0xFFFFu);
+                        const int lr = (int)(gv.br >> 16) - (int)(up_br[i] >> 16);
+                        const int lg = (int)gv.g - (int)up_g[i];
+                        if (g.ones) {   // trunc(lap * 1) == lap
+                            ab[k][i] += lb; ag[k][i] += lg; ar[k][i] += lr;
+                            ws[k][i] = f_add(ws[k][i], 1.f);
+                        } else {
+                            const float wv = wv4[i];
+                            ab[k][i] += (int)(short)f2i_rz(f_mul((float)lb, wv));
+                            ag[k][i] += (int)(short)f2i_rz(f_mul((float)lg, wv));
+                            ar[k][i] += (int)(short)f2i_rz(f_mul((float)lr, wv));
+                            ws[k][i] = f_add(ws[k][i], wv);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- normalise and store (the sums wrap to 16 bits like the reference's short accumulators)
+        DS_UNROLL
+        for (int k = 0; k < K; k++) {
+            const int q = tid + k * NT;
+            const int X = X0 + 2 * (q & 15), Y = Y0 + 2 * (q >> 4);
+            DS_UNROLL
+            for (int dy = 0; dy < 2; dy++) {
+                const int Yp = Y + dy;
+                if (Yp >= p.dst_h || Yp < p.acc_y0 || Yp >= p.acc_y1) continue;
+                uint32_t w0[2], w1[2];
+                DS_UNROLL
+                for (int dx = 0; dx < 2; dx++) {
+                    const int i = 2 * dy + dx;
+                    const float wsum = ws[k][i];
+                    const float den = f_add(wsum, 1e-5f);
+                    const short nb = (short)ab[k][i], ng = (short)ag[k][i], nr = (short)ar[k][i];
+                    // 0 / den == 0 exactly; skipping it keeps the IEEE division off its special-operand slow path
+                    const int vb = nb ? (int)(short)f2i_rz(f_div((float)nb, den)) : 0;
+                    const int vg = ng ? (int)(short)f2i_rz(f_div((float)ng, den)) : 0;
+                    const int vr = nr ? (int)(short)f2i_rz(f_div((float)nr, den)) : 0;
+                    w0[dx] = ((uint32_t)vb & 0xffffu) | ((uint32_t)vg << 16);
+                    w1[dx] = ((uint32_t)vr & 0xffffu) | (wsum > 1e-5f ? 0x10000u : 0u);
+                }
+                px16* q16 = p.dst + (size_t)Yp * p.dst_w + X;
+                if (X + 1 < p.dst_w && !(p.dst_w & 1)) *(uint4*)q16 = make_u4(w0[0], w1[0], w0[1], w1[1]);   // X even, even pitch: 16-byte aligned
+                else {
+                    if (X < p.dst_w) { uint2 v; v.x = w0[0]; v.y = w1[0]; *(uint2*)q16 = v; }
+                    if (X + 1 < p.dst_w) { uint2 v; v.x = w0[1]; v.y = w1[1]; *(uint2*)(q16 + 1) = v; }
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // MULTIBAND collapse of one level: fine = sat(pyrUp(coarse) + fine). The last step (fine = level 0)
 // also crops to the unpadded canvas, applies the result mask and saturates to 8U (A11 blend).
 // Each work item is 4 horizontally adjacent fine pixels.
@@ -2450,7 +2750,6 @@ struct FinalizeL0Body {
 
 #if DS_CUDA
 typedef MBBody<64, true> MBBodyL0;
-typedef MBBody<32, false> MBBodyLN;
 DS_DEFINE_KERNEL(ds_expand_bgrx, ExpandBody, 256, ExpandParams, 1)
 DS_DEFINE_KERNEL(ds_meta_copy, MetaCopyBody, 256, MetaCopyParams, 1)
 DS_DEFINE_KERNEL(ds_p2p_pull, PullBody, 256, PullParams, 1)
@@ -2468,13 +2767,10 @@ DS_DEFINE_KERNEL(ds_feather_blend, FeatherBody, 256, FeatherParams, 4)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_generic, MBBodyL0, 512, MBParams, 2)
 typedef MBFastBody<64, true> MBFastL0;
 typedef MBFastBody<64, true, true> MBFastL0A;
-typedef MBFastBody<32, false> MBFastLN;
 DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
-DS_DEFINE_KERNEL(ds_mb_feed_ln, MBFastLN, 256, MBParams, 4)
-DS_DEFINE_KERNEL(ds_mb_feed_generic, MBBodyLN, 256, MBParams, 1)
-typedef MBBody<16, false> MBBodyLN16;
-DS_DEFINE_KERNEL(ds_mb_feed_generic16, MBBodyLN16, 128, MBParams, 1)
+DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 4)
+DS_DEFINE_KERNEL(ds_mb_accum, AccumBody, 128, MBParams, 4)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 4)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)
 #endif

@@ -254,8 +254,8 @@ struct Frame {
 };
 
 struct LevelPlan {
-    int T = 0, tiles_x = 0, tiles_y = 0;
-    Range own{0, 0};   // rows of this level whose tiles run (production + accumulation)
+    int TW = 0, TH = 0, tiles_x = 0, tiles_y = 0;   // tile of the level's gather kernel
+    Range own{0, 0};   // level 0: rows whose tiles run; levels >= 1: rows of the per-frame G_l / W_l planes this handle produces (or pulls)
     Range acc{0, 0};   // rows whose dst is written / consumed by the collapse
     int* d_off = nullptr; int* d_fr = nullptr; int* d_ids = nullptr;   // inside the canvas meta arena
     int* d_rec = nullptr;   // per launched tile id: {tile, first and one-past-last entry of its frame list, first frame}
@@ -265,8 +265,8 @@ struct LevelPlan {
 // One internally pipelined slice of the handle's rows (DESIGN.md "Upload / compute / download pipeline").
 struct SubBand {
     Range rows{0, 0};          // level-0 output rows
-    Range own[DS_MAXL];        // feed rows per level: [previous slice's end, this slice's end) - nothing is recomputed
-    Range coll[DS_MAXL];       // rows of level l the collapse into level l finalises in this slice
+    Range own[DS_MAXL];        // level 0: feed rows; level l >= 1: rows of G_l / W_l produced - [previous slice's end, this slice's end), nothing is recomputed
+    Range coll[DS_MAXL];       // rows of level l accumulated (l >= 1) and finalised by the collapse into level l in this slice
     int ids_first[DS_MAXL], ids_count[DS_MAXL];   // the slice's run of LevelPlan::d_ids per level (heaviest tiles first)
     event_t fed0 = 0;          // recorded after the slice's level-0 feed
     event_t fed = 0;           // (unused)
@@ -333,11 +333,10 @@ struct ds_canvas {
     int out_hi = 0;
     std::vector<Frame> frames;
     FrameDev* d_frames = nullptr;                    // inside the meta arena
-    void* d_tmaps = nullptr;                         // CUtensorMap[frame][DS_MAXL][2], levels 1..L-1 (meta arena)
+    void* d_tmaps = nullptr;                         // CUtensorMap[frame][2] over the frame sources (meta arena)
     bool tmaps_ok = false;
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
-    bool ln_fast_ok = false;   // fast kernel for levels 1..L-1 (<= 64 frames per tile at every level)
     bool l0_has_affine = false;   // some frame is AFFINE_F64 or has a seam mask / gain map: level 0 runs the general variant of the fast kernel
     bool l0_fast_ok = false;   // level-0 fast kernel applicable (all frames PLANE_F32, <= 64 frames per tile)
     int feather_R = 0;
@@ -430,8 +429,10 @@ Range clip(Range r, int n) { return Range{std::max(r.lo, 0), std::min(r.hi, n)};
 Range meet(Range a, Range b) { return Range{std::max(a.lo, b.lo), std::max(std::max(a.lo, b.lo), std::min(a.hi, b.hi))}; }
 
 // Row plan of a band (see DESIGN.md "Row bands"): which rows of every level this handle must
-// accumulate (acc = what the collapse reads) and which tile rows must run (own) so that the
-// per-frame pyramids it reads are locally produced — no inter-band exchange needed.
+// accumulate (acc = what the collapse reads), which rows of the per-frame planes G_l / W_l (l >= 1) it must hold
+// (own[l]) and which level-0 tile rows must run (own[0]) so that all of them are locally produced — no inter-band
+// exchange needed. ds_mb_accum at level l reads G_l over acc[l] and G_{l+1} over acc[l+1] (the pyrUp taps, by the
+// definition of acc); ds_mb_pyrdown reads G_l rows [2a - 2, 2b] to produce G_{l+1} rows [a, b).
 void plan_rows(int L, const int* lh, Range band, Range* acc, Range* own) {
     acc[0] = band;
     for (int l = 1; l <= L; l++) {
@@ -439,20 +440,23 @@ void plan_rows(int L, const int* lh, Range band, Range* acc, Range* own) {
         acc[l] = clip(r, lh[l]);
     }
     own[L] = acc[L];
-    for (int l = L - 1; l >= 0; l--) {
-        // level l+1 phase 1 reads G_{l+1} rows [own.lo - 4, own.hi + 3); they are produced by level-l rows 2x
-        Range need{2 * (own[l + 1].lo - 4), 2 * (own[l + 1].hi + 3)};
-        Range r{std::min(acc[l].lo, need.lo), std::max(acc[l].hi, need.hi)};
+    for (int l = L - 1; l >= 1; l--) {
+        Range need{2 * own[l + 1].lo - 2, 2 * own[l + 1].hi + 1};
+        own[l] = clip(Range{std::min(acc[l].lo, need.lo), std::max(acc[l].hi, need.hi)}, lh[l]);
+    }
+    if (L >= 1) {
+        // level-0 tile rows [a, b) (even) produce G_1 rows [a / 2, b / 2)
+        Range r{std::min(acc[0].lo, 2 * own[1].lo), std::max(acc[0].hi, 2 * own[1].hi)};
         r.lo &= ~1; r.hi = (r.hi + 1) & ~1;
-        own[l] = clip(r, lh[l]);
+        own[0] = clip(r, lh[0]);
+    } else {
+        own[0] = acc[0];
     }
 }
 
-// Tile edge per level: 64 at level 0, 32 above; the top level of a pyramid of 3+ bands runs 16x16 tiles - it has so few
-// pixels that 32x32 tiles leave most SMs idle while each CTA walks its frames serially (cfg2: 63 -> 234 CTAs, 0.039 ->
-// 0.026 ms; at the levels below the extra halo of small tiles costs more than the parallelism gains: level 3 measured
-// 0.050 -> 0.088 ms).
-int level_tile(int l, int L) { return l == 0 ? 64 : ((l == L && L >= 3) ? 16 : 32); }
+// Tiles of the gather kernels: 64 x 64 at level 0 (ds_mb_feed_l0), 32 x 16 above (ds_mb_accum, one 2 x 2 quad per thread).
+int level_tile_w(int l) { return l == 0 ? 64 : AccumBody::TW; }
+int level_tile_h(int l) { return l == 0 ? 64 : AccumBody::TH; }
 
 int fill_frame_dev(ds_canvas* c, Frame& f) {
     FrameDev& d = f.dev;
@@ -656,8 +660,8 @@ int issue_for_slice(ds_canvas* c, const SubBand& sb, stream_t waiter) {
 Range pulled_rows(const ds_canvas* c, int side) {
     const Range own1 = c->plan[1].own;
     const int b_lo = c->band.lo >> 1, b_hi = std::min(c->band.hi >> 1, c->lh[1]);
-    if (side == 0) return Range{std::max(own1.lo - 4, 0), b_lo};
-    return Range{b_hi, std::min(own1.hi + 3, c->lh[1])};
+    if (side == 0) return Range{std::max(own1.lo, 0), b_lo};
+    return Range{b_hi, std::min(own1.hi, c->lh[1])};
 }
 
 // Can the next composite exchange halos instead of recomputing them?
@@ -814,10 +818,11 @@ int build_lists(ds_canvas* c) {
     std::vector<int> counts, off, fr, ids, recs;
     for (int l = 0; l < nl; l++) {
         LevelPlan& pl = c->plan[l];
-        const int TW = mb ? pl.T : FeatherBody::TW, TH = mb ? pl.T : FeatherBody::TH;
+        const int TW = mb ? pl.TW : FeatherBody::TW, TH = mb ? pl.TH : FeatherBody::TH;
         const int ntiles = pl.tiles_x * pl.tiles_y;
         counts.assign((size_t)ntiles + 1, 0);
-        const int ty_lo = pl.own.lo / TH, ty_hi = (pl.own.hi + TH - 1) / TH;  // tile rows that run
+        const Range run = (mb && l >= 1) ? pl.acc : pl.own;   // rows whose tiles run
+        const int ty_lo = run.lo / TH, ty_hi = (run.hi + TH - 1) / TH;
         auto frame_rect = [&](const Frame& f, int& x0, int& y0, int& x1, int& y1) {
             if (mb) { x0 = f.rx >> l; y0 = f.ry >> l; x1 = x0 + (f.rw >> l); y1 = y0 + (f.rh >> l); }
             else { x0 = f.dev.cx; y0 = f.dev.cy; x1 = x0 + f.bw; y1 = y0 + f.bh; }
@@ -857,16 +862,13 @@ int build_lists(ds_canvas* c) {
                 c->l0_fast_ok = all_plane && longest <= MBFastBody<64, true>::MAXF;
                 c->l0_has_affine = false;
                 for (const Frame& f : c->frames) if (f.used && (f.xf.kind == DS_XF_AFFINE_F64 || f.d_seam || f.d_gainmap || f.dev.any_gain)) c->l0_has_affine = true;
-                c->ln_fast_ok = true;
-            } else if (longest > 64) {
-                c->ln_fast_ok = false;
             }
         }
         // tiles to run, per slice: every tile in the slice's tile rows (empty ones still write zeros), the ones with
         // the most frames first - blocks are dispatched in id order, so the launch drains on its cheapest tiles
         ids.clear();
         for (SubBand& sb : c->subs) {
-            const Range rows = mb ? sb.own[l] : meet(sb.rows, pl.own);
+            const Range rows = mb ? (l >= 1 ? sb.coll[l] : sb.own[l]) : meet(sb.rows, pl.own);
             sb.ids_first[l] = (int)ids.size();
             if (rows.lo < rows.hi) {
                 const int ty0 = rows.lo / TH, ty1 = (rows.hi + TH - 1) / TH;
@@ -905,23 +907,18 @@ int build_lists(ds_canvas* c) {
     c->tmaps_ok = false;
 #if DS_CUDA
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L >= 1 && !c->frames.empty()) {
-        // TMA descriptors for the box-shaped tile loads of the fast level-l kernel (MBFastBody<32,false>)
-        std::vector<CUtensorMap> tm(c->frames.size() * DS_MAXL * 2);
+        // TMA descriptors of the frame sources (level-0 kernel: shared-memory box loads and L2 prefetches)
+        std::vector<CUtensorMap> tm(c->frames.size() * 2);
         memset(tm.data(), 0, tm.size() * sizeof(CUtensorMap));
         bool ok = true;
         for (size_t i = 0; i < c->frames.size() && ok; i++) {
             const Frame& f = c->frames[i];
             if (!f.used) continue;
-            // slot [frame][0][0]: the BGRX source, box = footprint of a 71x71 tile region under a few degrees of
+            // slot [frame][0]: the BGRX source, box = footprint of a 71x71 tile region under a few degrees of
             // rotation (L2 prefetch only: correctness never depends on it)
-            ok = encode_tile_map(&tm[(i * DS_MAXL) * 2], false, f.d_src, f.w, f.h, f.pitch, 96, 88) &&
-                 // slot [frame][0][1]: the same source with the box the level-0 kernel loads into shared memory
-                 encode_tile_map(&tm[(i * DS_MAXL) * 2 + 1], false, f.d_src, f.w, f.h, f.pitch, MBFastBody<64, true>::BOXW, MBFastBody<64, true>::BOXH);
-            for (int l = 1; l < c->L && ok; l++) {
-                const int w = f.rw >> l, h = f.rh >> l;
-                ok = encode_tile_map(&tm[(i * DS_MAXL + l) * 2], false, f.dev.G[l], w, h, f.dev.gp[l], MBFastBody<32, false>::PWS, MBFastBody<32, false>::PHM) &&
-                     encode_tile_map(&tm[(i * DS_MAXL + l) * 2 + 1], true, f.dev.W[l], w, h, f.dev.gp[l], MBFastBody<32, false>::PWS, MBFastBody<32, false>::PHM);
-            }
+            ok = encode_tile_map(&tm[i * 2], false, f.d_src, f.w, f.h, f.pitch, 96, 88) &&
+                 // slot [frame][1]: the same source with the box the level-0 kernel loads into shared memory
+                 encode_tile_map(&tm[i * 2 + 1], false, f.d_src, f.w, f.h, f.pitch, MBFastBody<64, true>::BOXW, MBFastBody<64, true>::BOXH);
         }
         if (ok) {
             tmaps_off = mbd.add(tm.data(), tm.size() * sizeof(CUtensorMap));
@@ -1020,10 +1017,12 @@ ABModel ab_inputs(const ds_canvas* c) {
 int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABModel& abm) {
     int rc;
     LevelPlan& pl = c->plan[l];
-    const Range own = sb.own[l];
+    // level 0: the tile rows that run (every row that runs also writes its dst, if this handle stores it);
+    // levels >= 1: the rows of the level this slice accumulates and finalises
+    const Range own = l == 0 ? sb.own[0] : sb.coll[l];
     if (own.lo >= own.hi) return DS_OK;
     const int first = sb.ids_first[l], count = sb.ids_count[l];
-    const Range acc = meet(own, pl.acc);   // every row that runs also writes its dst (if this handle stores it)
+    const Range acc = meet(own, pl.acc);
     MBParams mp;
     mp.frames = c->d_frames; mp.tile_off = pl.d_off; mp.tile_frames = pl.d_fr; mp.tile_ids = pl.d_ids + first;
     mp.tile_rec = (const int4*)(pl.d_rec + 4 * (size_t)first);
@@ -1041,20 +1040,51 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
 #endif
     const double q = 1.0 / (double)(1ull << (2 * l));
     double ab;
+    // (levels >= 1: the model's "read G, W twice" is split between ds_mb_pyrdown, which reads them once, and this launch)
     if (l == 0) ab = 3.0 * abm.S + abm.A * (c->L > 0 ? 22.5 : 20.0);
-    else if (l < c->L) ab = abm.A * q * (40.0 + 2.5);
+    else if (l < c->L) ab = abm.A * q * 30.0;
     else ab = abm.A * q * 40.0;
     ab *= (double)count / (double)std::max(pl.n_ids, 1);
-    if ((rc = prof_mark(c, st, true, "mb_feed", l, (int64_t)ab))) return rc;
+    if ((rc = prof_mark(c, st, true, l == 0 ? "mb_feed" : "mb_accum", l, (int64_t)ab))) return rc;
     if (l == 0 && c->L > 0 && c->l0_fast_ok && c->l0_has_affine) rc = launch<MBFastBody<64, true, true>, 512>(mp, count, st, MBFastBody<64, true, true>::smem_bytes());
     else if (l == 0 && c->L > 0 && c->l0_fast_ok) rc = launch<MBFastBody<64, true>, 512>(mp, count, st, MBFastBody<64, true>::smem_bytes());
-    else if (l > 0 && l < c->L && c->ln_fast_ok) rc = launch<MBFastBody<32, false>, 256>(mp, count, st, MBFastBody<32, false>::smem_bytes());
     else if (l == 0) rc = launch<MBBody<64, true>, 512>(mp, count, st, MBBody<64, true>::smem_bytes());
-    else if (pl.T == 16) rc = launch<MBBody<16, false>, 128>(mp, count, st, MBBody<16, false>::smem_bytes());
-    else rc = launch<MBBody<32, false>, 256>(mp, count, st, MBBody<32, false>::smem_bytes());
+    else rc = launch<AccumBody, 128>(mp, count, st, AccumBody::smem_bytes());
     if (rc) return rc;
     if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
     c->launches++;
+    return DS_OK;
+}
+
+// G_{l+1} / W_{l+1} = pyrDown(G_l / W_l) of every frame, over the rows of level l + 1 this slice produces
+int launch_pyrdown(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABModel& abm) {
+    int rc;
+    const Range rows = sb.own[l + 1];
+    if (rows.lo >= rows.hi || c->frames.empty()) return DS_OK;
+    // CTAs per frame: the column blocks of the widest plane x the row blocks a frame can have inside the rows
+    int wmax = 0, hmax = 0;
+    for (const Frame& f : c->frames) if (f.used) { wmax = std::max(wmax, f.rw >> (l + 1)); hmax = std::max(hmax, f.rh >> (l + 1)); }
+    if (wmax <= 0 || hmax <= 0) return DS_OK;
+    PyrParams pp;
+    pp.frames = c->d_frames; pp.nframes = (int)c->frames.size(); pp.level = l;
+    pp.txmax = (wmax + PyrDownBody::BW - 1) / PyrDownBody::BW;
+    pp.R = (std::min(rows.hi - rows.lo, hmax) + PyrDownBody::BH - 1) / PyrDownBody::BH + 1;   // + 1: the first needed row is anywhere in its block
+    pp.own_y0 = rows.lo; pp.own_y1 = rows.hi;
+    const double q = 1.0 / (double)(1ull << (2 * l));
+    const Range all = c->plan[l + 1].own;
+    const double ab = abm.A * q * 12.5 * (double)(rows.hi - rows.lo) / (double)std::max(all.hi - all.lo, 1);
+    if ((rc = prof_mark(c, st, true, "mb_pyrdown", l, (int64_t)ab))) return rc;
+    if ((rc = launch<PyrDownBody, 128>(pp, (long long)pp.nframes * pp.txmax * pp.R, st, 0))) return rc;
+    if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
+    c->launches++;
+    return DS_OK;
+}
+
+// levels 1 .. L of one slice: every per-frame plane first (each reads the one below), then the accumulations
+int launch_upper_levels(ds_canvas* c, stream_t st, const SubBand& sb, const ABModel& abm) {
+    int rc;
+    for (int l = 1; l < c->L; l++) if ((rc = launch_pyrdown(c, st, l, sb, abm))) return rc;
+    for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, st, l, sb, abm))) return rc;
     return DS_OK;
 }
 
@@ -1203,7 +1233,7 @@ int composite_exchange_finish(ds_canvas* c) {
         c->launches++;
     }
     if ((rc = launch_signal(c, c->stream, c->peer[0].connected ? c->peer[0].flags + 3 : nullptr, c->peer[1].connected ? c->peer[1].flags + 2 : nullptr, seq))) return rc;
-    for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, c->stream, l, sb, abm))) return rc;
+    if ((rc = launch_upper_levels(c, c->stream, sb, abm))) return rc;
     for (int l = c->L; l >= 1; l--) if ((rc = launch_collapse(c, c->stream, l, sb, abm))) return rc;
     if ((rc = ev_make(&sb.done)) || (rc = ev_record(sb.done, c->stream))) return rc;
     return composite_epilogue(c);
@@ -1309,7 +1339,7 @@ int run_composite(ds_canvas* c, int stage) {
             if ((rc = launch_signal(c, P, c->peer[0].connected ? c->peer[0].flags + 3 : nullptr, c->peer[1].connected ? c->peer[1].flags + 2 : nullptr, ka_seq))) return rc;
         }
         if (two && ((rc = ev_make(&sb.fed0)) || (rc = ev_record(sb.fed0, P)) || (rc = ev_wait(Q, sb.fed0)))) return rc;
-        for (int l = 1; l <= c->L; l++) if ((rc = launch_feed(c, Q, l, sb, abm))) return rc;
+        if ((rc = launch_upper_levels(c, Q, sb, abm))) return rc;
         for (int l = c->L; l >= 1; l--) if ((rc = launch_collapse(c, Q, l, sb, abm))) return rc;
         if (c->L == 0 && (rc = launch_finalize_l0(c, Q, sb))) return rc;
         if ((rc = ev_make(&sb.done)) || (rc = ev_record(sb.done, Q))) return rc;
@@ -1798,8 +1828,8 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
     if (!rc && desc->blend_mode == DS_BLEND_MULTIBAND) {
         for (int l = 0; l <= c->L && !rc; l++) {
             LevelPlan& pl = c->plan[l];
-            pl.T = level_tile(l, c->L);
-            pl.tiles_x = (c->lw[l] + pl.T - 1) / pl.T; pl.tiles_y = (c->lh[l] + pl.T - 1) / pl.T;
+            pl.TW = level_tile_w(l); pl.TH = level_tile_h(l);
+            pl.tiles_x = (c->lw[l] + pl.TW - 1) / pl.TW; pl.tiles_y = (c->lh[l] + pl.TH - 1) / pl.TH;
             pl.own = own[l]; pl.acc = acc[l];
             if (l == 0) c->own0_recompute = own[0];
             // rows stored: what the collapse touches (acc) — the feed writes only those
@@ -1811,7 +1841,7 @@ DS_API int ds_create_canvas(const ds_canvas_desc* desc, ds_canvas** out) {
         }
     } else if (!rc) {
         LevelPlan& pl = c->plan[0];
-        pl.T = 0;
+        pl.TW = pl.TH = 0;
         pl.tiles_x = (desc->width + FeatherBody::TW - 1) / FeatherBody::TW;
         pl.tiles_y = (desc->height + FeatherBody::TH - 1) / FeatherBody::TH;
         pl.own = Range{c->band.lo, c->out_hi}; pl.acc = pl.own;

@@ -76,3 +76,20 @@ if len(sys.argv) > 5:
     print("---- by phase")
     for k2, c in out.most_common():
         print(f"{100*c/tot:5.1f}% inst {100*outs[k2]/max(ts,1):5.1f}% smp  {k2}")
+    # positional attribution: an instruction whose line is outside every named range (inlined helpers in other files
+    # or at the top of ds_kernels.h) belongs to the phase of the nearest earlier instruction that has one
+    pos = collections.Counter()
+    poss = collections.Counter()
+    curp = "prologue"
+    for k in range(n):
+        f, ln = seq[k][0] if seq[k][0] else ("", 0)
+        if f == "ds_kernels.h":
+            for nm, lo, hi2 in rng:
+                if lo <= ln <= hi2:
+                    curp = nm
+                    break
+        pos[curp] += inst[k][1]
+        poss[curp] += inst[k][2]
+    print("---- by phase, positional")
+    for k2, c in pos.most_common():
+        print(f"{100*c/tot:5.1f}% inst {100*poss[k2]/max(ts,1):5.1f}% smp  {c/1e6:8.1f} M  {k2}")
