@@ -1074,6 +1074,19 @@ DS_D void fence_tensormap_acquire(const void* tmap) {
 // acc lanes: B + 65536 * R in one int (exact while |sum| < 2^15, guaranteed by the host for tiles with
 // <= 64 frames; longer lists go to the generic kernel).
 
+// Normalised Laplacian pixel of a destination level (A11 blend): trunc(sum / (wsum + 1e-5)) per channel, flag = wsum >
+// 1e-5, as the two words of a px16 (b | g << 16, r | flag << 16). The three quotients share the reciprocal refinement
+// (div_by_rcp); the sums are taken modulo 2^16 like the reference's short accumulators.
+DS_D void norm_px(int sb, int sg, int sr, float wsum, uint32_t& w0, uint32_t& w1) {
+    const float den = f_add(wsum, 1e-5f);
+    const float r = rcp_refined(den);
+    const int vb = (int)(short)f2i_rz(div_by_rcp((float)(short)sb, den, r));
+    const int vg = (int)(short)f2i_rz(div_by_rcp((float)(short)sg, den, r));
+    const int vr = (int)(short)f2i_rz(div_by_rcp((float)(short)sr, den, r));
+    w0 = ((uint32_t)vb & 0xffffu) | ((uint32_t)vg << 16);
+    w1 = ((uint32_t)vr & 0xffffu) | (wsum > 1e-5f ? 0x10000u : 0u);
+}
+
 template <bool V> struct BoolTag { static constexpr bool value = V; };
 template <int V> struct IntTag { static constexpr int value = V; };
 struct L0Col { float a0, a3, a6; int u; };  // u = bbox column if inside the bbox, else ~(reflected column)
@@ -2118,18 +2131,9 @@ struct MBFastBody {
             const int abr = av.x;
             const int sb = (int)(short)(abr & 0xFFFF);
             const int sr = (abr - sb) >> 16;
-            const int sg = av.y;
-            const float wsum = s_ws[i];
-            const float den = f_add(wsum, 1e-5f);
-            px16 o;
-            // 0 / den == 0 exactly; skipping it keeps the IEEE division off its special-operand slow path
-            // (zero Laplacian sums are the common case in smooth regions)
-            const short nb = (short)sb, ng = (short)sg, nr = (short)sr;
-            o.b = nb ? (short)f2i_rz(f_div((float)nb, den)) : (short)0;
-            o.g = ng ? (short)f2i_rz(f_div((float)ng, den)) : (short)0;
-            o.r = nr ? (short)f2i_rz(f_div((float)nr, den)) : (short)0;
-            o.a = (short)(wsum > 1e-5f ? 1 : 0);
-            p.dst[(size_t)Y * p.dst_w + X] = o;
+            uint2 o;
+            norm_px(sb, av.y, sr, s_ws[i], o.x, o.y);
+            *(uint2*)(p.dst + (size_t)Y * p.dst_w + X) = o;
         }
     }
 };
@@ -2145,6 +2149,36 @@ struct MBFastBody {
 //                  frame loop; normalised level written once.
 // Same arithmetic as MBBody (A8 - A11); the tile-based kernels spent 4 barriers and a 39 x 39 halo region per 32 x 32
 // tile-frame on this (level 1 of cfg2: 287 M warp instructions, 0.38 ms).
+
+// "Every weight W_l over the pixels [x0, x1] x [y0, y1] (level-l coordinates relative to the frame's feed ROI) is exactly
+// 1", from geometry alone: a plane-mapped frame without per-pixel mask whose level-0 support of the region (radius
+// 2^(l+1) - 2 after l pyrDowns) lies inside the bbox and maps into the source at its four corners - x(u, v) is monotone
+// in u and in v even in float arithmetic (a chain of monotone roundings), so the corners bound every pixel; the nearest
+// mask is then 255 throughout, W_0 = 255 * (1 / 255f) = 1 and every pyrDown of ones is exactly 1. The emulator checks
+// every claim against the data.
+DS_D bool weights_all_ones(const FrameDev& F, int l, int x0, int x1, int y0, int y1) {
+    if (!(F.kind == XF_PLANE && !F.seam && F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f && f_mul(255.f, 1.f / 255.f) == 1.f)) return false;
+    const int rl = (2 << l) - 2;
+    const int u_lo = F.rx + (x0 << l) - rl - F.cx, u_hi = F.rx + (x1 << l) + rl - F.cx;
+    const int v_lo = F.ry + (y0 << l) - rl - F.cy, v_hi = F.ry + (y1 << l) + rl - F.cy;
+    if (!(u_lo >= 0 && u_hi <= F.w - 1 && v_lo >= 0 && v_hi <= F.h - 1)) return false;
+    float ca0[2], ca3[2], rb1[2], rb4[2];
+    DS_UNROLL
+    for (int e = 0; e < 2; e++) {
+        float U = (float)(F.tlx + (e ? u_hi : u_lo)), V = (float)(F.tly + (e ? v_hi : v_lo));
+        if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
+        const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
+        ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
+        rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
+    }
+    float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+    DS_UNROLL
+    for (int e = 0; e < 4; e++) {
+        const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), F.k2one), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), F.k5one);
+        xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
+    }
+    return xmn >= 0.f && xmx <= (float)(F.src_w - 1) && ymn >= 0.f && ymx <= (float)(F.src_h - 1);
+}
 
 struct PyrParams {
     const FrameDev* frames; int nframes;
@@ -2173,6 +2207,8 @@ struct PyrDownBody {
         uint32_t* const Gout = (uint32_t*)F.G[l + 1];
         float* const Wout = F.W[l + 1];
         const int ip = F.gp[l], op = F.gp[l + 1];
+        // the CTA's outputs all have weight 1 by geometry: W_l is not even read
+        const bool ones = weights_all_ones(F, l + 1, bx * BW, imin(bx * BW + BW, w_out) - 1, imax(by * BH, jlo), imin(by * BH + BH, jhi) - 1);
         for (int t = tid; t < NTH; t += NT) {
             const int tx = t & 15, ty = t >> 4;
             const int jx = bx * BW + 2 * tx, jy = by * BH + 2 * ty;   // first of the thread's 2 x 2 outputs
@@ -2187,18 +2223,20 @@ struct PyrDownBody {
             float hw[7][2];
             DS_UNROLL
             for (int k = 0; k < 7; k++) {
-                uint32_t q[7]; float w[7];
+                uint32_t q[7]; float w[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 const uint32_t* gr = Gin + (size_t)rows[k] * ip;
                 const float* wr = Win + (size_t)rows[k] * ip;
                 if (interior) {
                     // c0 = 2 mod 4 and rows are 16-byte aligned: 8 + 16 + 4 bytes
                     const uint2 a = ld_ro((const uint2*)(gr + c0)); const uint4 b = ld_ro((const uint4*)(gr + c0 + 2)); const uint32_t c = ld_ro(gr + c0 + 6);
                     q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = b.z; q[5] = b.w; q[6] = c;
-                    const float2 fa = ld_ro((const float2*)(wr + c0)); const float4 fb = ld_ro((const float4*)(wr + c0 + 2)); const float fc = ld_ro(wr + c0 + 6);
-                    w[0] = fa.x; w[1] = fa.y; w[2] = fb.x; w[3] = fb.y; w[4] = fb.z; w[5] = fb.w; w[6] = fc;
+                    if (!ones || !DS_CUDA) {
+                        const float2 fa = ld_ro((const float2*)(wr + c0)); const float4 fb = ld_ro((const float4*)(wr + c0 + 2)); const float fc = ld_ro(wr + c0 + 6);
+                        w[0] = fa.x; w[1] = fa.y; w[2] = fb.x; w[3] = fb.y; w[4] = fb.z; w[5] = fb.w; w[6] = fc;
+                    }
                 } else {
                     DS_UNROLL
-                    for (int c = 0; c < 7; c++) { q[c] = ld_ro(gr + cols[c]); w[c] = ld_ro(wr + cols[c]); }
+                    for (int c = 0; c < 7; c++) { q[c] = ld_ro(gr + cols[c]); if (!ones || !DS_CUDA) w[c] = ld_ro(wr + cols[c]); }
                 }
                 uint32_t br[7], gg[7];
                 DS_UNROLL
@@ -2214,7 +2252,7 @@ struct PyrDownBody {
                     if (k >= 2) { vbr[1][o] += k1 * hbr; vg[1][o] += k1 * hg; }
                     // weights: horizontal pass in the op order of the column's class (A9)
                     const int j = jx + o;
-                    hw[k][o] = pd_h_is_simd(j, w_in, w_out) ? pd_h_simd(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4])
+                    if (!ones || !DS_CUDA) hw[k][o] = pd_h_is_simd(j, w_in, w_out) ? pd_h_simd(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4])
                                                             : pd_scalar(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4]);
                 }
             }
@@ -2227,9 +2265,13 @@ struct PyrDownBody {
                 for (int o = 0; o < 2; o++) {
                     const uint32_t obr = ((vbr[dy][o] + 0x00800080u) >> 8) & 0x00FF00FFu, og = ((vg[dy][o] + 0x80u) >> 8) & 0xFFu;
                     go[o] = byte_perm(obr, og, 0x5240);
+                    if (ones && DS_CUDA) { wo[o] = 1.f; continue; }
                     const float t0 = hw[2 * dy][o], t1 = hw[2 * dy + 1][o], t2 = hw[2 * dy + 2][o], t3 = hw[2 * dy + 3][o], t4 = hw[2 * dy + 4][o];
                     const float v = pd_v_is_simd(jx + o, w_out) ? pd_v_simd(t0, t1, t2, t3, t4) : pd_scalar(t0, t1, t2, t3, t4);
                     wo[o] = f_mul(v, 1.f / 256.f);
+#if !DS_CUDA
+                    if (ones && wo[o] != 1.f && jx + o < w_out) { fprintf(stderr, "ds emu: pyrdown level %d frame %d: weights claimed 1 by geometry are not\n", l, fslot); abort(); }
+#endif
                 }
                 uint32_t* gq = Gout + (size_t)y * op + jx;
                 float* wq = Wout + (size_t)y * op + jx;
@@ -2244,58 +2286,39 @@ struct PyrDownBody {
 
 struct AccumBody {
     static constexpr int TW = 32, TH = 16, NQ = 128;   // one thread = one 2 x 2 quad
-    static constexpr int GCH = 32;                     // frames whose geometry is staged at a time
+    static constexpr int GCH = 32;                     // frames whose geometry is staged at a time; also the span of the packed sums
+    // tile x frame geometry: built by one thread, read by all. Pointers are pre-offset to the tile origin (they may point
+    // outside the plane; the quads inside the frame's ROI add what brings them back in).
     struct alignas(16) AGeo {
-        const uint32_t* G; const float* W;
-        const uint32_t* G1; int gp, gp1;
-        int rx, ry, n1x, n1y;
-        int ax0, ax1, ay0, ay1;
-        int skip, ones, pad0, pad1;
+        const uint32_t* G; const float* W;   // level l at ROI-relative (X0 - rx, Y0 - ry)
+        const uint32_t* G1; int gp, gp1;     // level l + 1 at ((X0 - rx) / 2, (Y0 - ry) / 2); row pitches
+        int x0, nx, y0, ny;                  // the tile's part inside the ROI and the rows: tile-relative quads (top level: pixels)
+        int c1x0, c1y0, n1x, n1y;            // level-(l+1) coordinate of the tile origin in the frame, plane size (pyrUp border rules)
+        int skip, ones, border, pad;
     };
     static int smem_bytes() { return GCH * (int)sizeof(AGeo); }
     struct U2 { uint32_t br, g; };
     DS_DM U2 split(uint32_t v) { U2 o; o.br = byte_perm(v, 0, 0x4240); o.g = byte_perm(v, 0, 0x4441); return o; }
 
-    // tile x frame geometry, by one thread
     DS_DM void make_geo(const MBParams& p, const FrameDev& F, int X0, int Y0, bool top, AGeo& g) {
         const int l = p.level;
         const int rx = F.rx >> l, ry = F.ry >> l, rw = F.rw >> l, rh = F.rh >> l;
-        g.G = (const uint32_t*)F.G[l]; g.W = F.W[l]; g.G1 = top ? nullptr : (const uint32_t*)F.G[l + 1];
-        g.gp = F.gp[l]; g.gp1 = top ? 0 : F.gp[l + 1];
-        g.rx = rx; g.ry = ry; g.n1x = rw >> 1; g.n1y = rh >> 1;
-        g.ax0 = imax(X0, rx); g.ax1 = imin(X0 + TW, rx + rw);
+        const int ax0 = imax(X0, rx), ax1 = imin(X0 + TW, rx + rw);
         // below the top level the ROI is even-aligned and quads are whole: rows rounded out to quads (the store filters)
         const int a0 = top ? p.acc_y0 : (p.acc_y0 & ~1), a1 = top ? p.acc_y1 : ((p.acc_y1 + 1) & ~1);
-        g.ay0 = imax(imax(Y0, ry), a0); g.ay1 = imin(imin(Y0 + TH, ry + rh), a1);
-        g.skip = (g.ax0 >= g.ax1 || g.ay0 >= g.ay1) ? 1 : 0;
-        g.ones = 0; g.pad0 = g.pad1 = 0;
-        // "every weight of the tile-frame is exactly 1", from geometry alone: a plane-mapped frame without per-pixel mask
-        // whose level-0 support of the region (radius 2^(l+1) - 2 after l pyrDowns) lies inside the bbox and maps into the
-        // source at its four corners - x(u, v) is monotone in u and in v even in float arithmetic, so the corners bound
-        // every pixel; the nearest mask is then 255 throughout, W_0 = 255 * (1 / 255f) = 1 and every pyrDown of ones is 1.
-        if (!g.skip && F.kind == XF_PLANE && !F.seam && F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f && f_mul(255.f, 1.f / 255.f) == 1.f) {
-            const int rl = (2 << l) - 2;
-            const int u_lo = F.rx + ((g.ax0 - rx) << l) - rl - F.cx, u_hi = F.rx + ((g.ax1 - 1 - rx) << l) + rl - F.cx;
-            const int v_lo = F.ry + ((g.ay0 - ry) << l) - rl - F.cy, v_hi = F.ry + ((g.ay1 - 1 - ry) << l) + rl - F.cy;
-            if (u_lo >= 0 && u_hi <= F.w - 1 && v_lo >= 0 && v_hi <= F.h - 1) {
-                float ca0[2], ca3[2], rb1[2], rb4[2];
-                DS_UNROLL
-                for (int e = 0; e < 2; e++) {
-                    float U = (float)(F.tlx + (e ? u_hi : u_lo)), V = (float)(F.tly + (e ? v_hi : v_lo));
-                    if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
-                    const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
-                    ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
-                    rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
-                }
-                float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
-                DS_UNROLL
-                for (int e = 0; e < 4; e++) {
-                    const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), F.k2one), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), F.k5one);
-                    xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
-                }
-                if (xmn >= 0.f && xmx <= (float)(F.src_w - 1) && ymn >= 0.f && ymx <= (float)(F.src_h - 1)) g.ones = 1;
-            }
-        }
+        const int ay0 = imax(imax(Y0, ry), a0), ay1 = imin(imin(Y0 + TH, ry + rh), a1);
+        g.skip = (ax0 >= ax1 || ay0 >= ay1) ? 1 : 0;
+        g.gp = F.gp[l]; g.gp1 = top ? 0 : F.gp[l + 1];
+        const long long o0 = (long long)(Y0 - ry) * g.gp + (X0 - rx);
+        g.G = (const uint32_t*)F.G[l] + o0; g.W = F.W[l] + o0;
+        g.c1x0 = (X0 - rx) >> 1; g.c1y0 = (Y0 - ry) >> 1; g.n1x = rw >> 1; g.n1y = rh >> 1;
+        g.G1 = top ? nullptr : (const uint32_t*)F.G[l + 1] + ((long long)g.c1y0 * g.gp1 + g.c1x0);
+        const int sh = top ? 0 : 1;
+        g.x0 = (ax0 - X0) >> sh; g.nx = (ax1 - ax0) >> sh; g.y0 = (ay0 - Y0) >> sh; g.ny = (ay1 - ay0) >> sh;
+        // does any quad of the part tap beyond the level-(l+1) plane (pyrUp border rules)?
+        g.border = (((ax0 - rx) >> 1) < 1 || ((ax1 - 1 - rx) >> 1) + 1 > g.n1x - 1 || ((ay0 - ry) >> 1) < 1 || ((ay1 - 1 - ry) >> 1) + 1 > g.n1y - 1) ? 1 : 0;
+        g.ones = 0; g.pad = 0;
+        if (!g.skip && weights_all_ones(F, l, ax0 - rx, ax1 - 1 - rx, ay0 - ry, ay1 - 1 - ry)) g.ones = 1;
     }
 
     template <int NT>
@@ -2307,9 +2330,11 @@ struct AccumBody {
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int X0 = tx * TW, Y0 = ty * TH;
         const bool top = p.level == p.L;
-        int ab[K][4], ag[K][4], ar[K][4]; float ws[K][4];
+        // per pixel: packed sums B + 65536 R and G of the current chunk of frames (exact while |sum B| < 2^15: a chunk is 32
+        // frames of |lap| <= 255), folded into wide sums after every chunk; weight sum in feed order
+        int pbr[K][4], pg[K][4], sB[K][4], sR[K][4]; float ws[K][4];
         DS_UNROLL
-        for (int k = 0; k < K; k++) { DS_UNROLL for (int i = 0; i < 4; i++) { ab[k][i] = ag[k][i] = ar[k][i] = 0; ws[k][i] = 0.f; } }
+        for (int k = 0; k < K; k++) { DS_UNROLL for (int i = 0; i < 4; i++) { pbr[k][i] = pg[k][i] = sB[k][i] = sR[k][i] = 0; ws[k][i] = 0.f; } }
         for (int base = f_begin; base < f_end; base += GCH) {
             const int n = imin(GCH, f_end - base);
             if (base > f_begin) DS_SYNC();   // everyone is done with the previous chunk's entries
@@ -2318,7 +2343,7 @@ struct AccumBody {
             DS_UNROLL
             for (int k = 0; k < K; k++) {
                 const int q = tid + k * NT;
-                const int X = X0 + 2 * (q & 15), Y = Y0 + 2 * (q >> 4);
+                const int qx = q & 15, qy = q >> 4;
                 for (int j = 0; j < n; j++) {
                     const AGeo& g = s_geo[j];
                     if (g.skip) continue;
@@ -2326,37 +2351,45 @@ struct AccumBody {
                         // the top level accumulates G_L itself; its ROI need not be even-aligned: per pixel
                         DS_UNROLL
                         for (int i = 0; i < 4; i++) {
-                            const int Xp = X + (i & 1), Yp = Y + (i >> 1);
-                            if (Xp < g.ax0 || Xp >= g.ax1 || Yp < g.ay0 || Yp >= g.ay1) continue;
-                            const size_t gi = (size_t)(Yp - g.ry) * g.gp + (Xp - g.rx);
+                            const int xp = 2 * qx + (i & 1), yp = 2 * qy + (i >> 1);
+                            if ((unsigned)(xp - g.x0) >= (unsigned)g.nx || (unsigned)(yp - g.y0) >= (unsigned)g.ny) continue;
+                            const int gi = yp * g.gp + xp;
                             const uint32_t v = ld_ro(g.G + gi);
                             const float wv = ld_ro(g.W + gi);
 #if !DS_CUDA
                             if (g.ones && wv != 1.f) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
 #endif
-                            ab[k][i] += (int)(short)f2i_rz(f_mul((float)(v & 255u), wv));
-                            ag[k][i] += (int)(short)f2i_rz(f_mul((float)((v >> 8) & 255u), wv));
-                            ar[k][i] += (int)(short)f2i_rz(f_mul((float)((v >> 16) & 255u), wv));
+                            const int tb = (int)(short)f2i_rz(f_mul((float)(v & 255u), wv)), tg = (int)(short)f2i_rz(f_mul((float)((v >> 8) & 255u), wv));
+                            const int tr = (int)(short)f2i_rz(f_mul((float)((v >> 16) & 255u), wv));
+                            pbr[k][i] += tb + tr * 65536; pg[k][i] += tg;
                             ws[k][i] = f_add(ws[k][i], wv);
                         }
                         continue;
                     }
-                    if (X < g.ax0 || X >= g.ax1 || Y < g.ay0 || Y >= g.ay1) continue;
-                    const int ox = X - g.rx, oy = Y - g.ry;   // even
-                    const int c1x = ox >> 1, c1y = oy >> 1;
-                    const int ixl = up_l(c1x, g.n1x), ixr = up_r(c1x, g.n1x), iyl = up_l(c1y, g.n1y), iyr = up_r(c1y, g.n1y);
-                    const uint32_t* ra = g.G1 + (size_t)iyl * g.gp1; const uint32_t* rb = g.G1 + (size_t)c1y * g.gp1; const uint32_t* rd = g.G1 + (size_t)iyr * g.gp1;
-                    const uint32_t* g0p = g.G + (size_t)oy * g.gp + ox;
+                    if ((unsigned)(qx - g.x0) >= (unsigned)g.nx || (unsigned)(qy - g.y0) >= (unsigned)g.ny) continue;
+                    const uint32_t* const g0p = g.G + (2 * qy * g.gp + 2 * qx);
+                    const uint32_t* const c = g.G1 + (qy * g.gp1 + qx);
                     // every load of the quad is requested before the first use
-                    const uint32_t wa0 = ld_ro(ra + ixl), wa1 = ld_ro(ra + c1x), wa2 = ld_ro(ra + ixr);
-                    const uint32_t wb0 = ld_ro(rb + ixl), wb1 = ld_ro(rb + c1x), wb2 = ld_ro(rb + ixr);
-                    const uint32_t wd0 = ld_ro(rd + ixl), wd1 = ld_ro(rd + c1x), wd2 = ld_ro(rd + ixr);
+                    uint32_t wa0, wa1, wa2, wb0, wb1, wb2, wd0, wd1, wd2;
+                    if (!g.border) {
+                        const uint32_t* const ca = c - g.gp1; const uint32_t* const cd = c + g.gp1;
+                        wa0 = ld_ro(ca - 1); wa1 = ld_ro(ca); wa2 = ld_ro(ca + 1);
+                        wb0 = ld_ro(c - 1); wb1 = ld_ro(c); wb2 = ld_ro(c + 1);
+                        wd0 = ld_ro(cd - 1); wd1 = ld_ro(cd); wd2 = ld_ro(cd + 1);
+                    } else {
+                        const int c1x = g.c1x0 + qx, c1y = g.c1y0 + qy;
+                        const int dxl = up_l(c1x, g.n1x) - c1x, dxr = up_r(c1x, g.n1x) - c1x;
+                        const uint32_t* const ca = c + (up_l(c1y, g.n1y) - c1y) * g.gp1; const uint32_t* const cd = c + (up_r(c1y, g.n1y) - c1y) * g.gp1;
+                        wa0 = ld_ro(ca + dxl); wa1 = ld_ro(ca); wa2 = ld_ro(ca + dxr);
+                        wb0 = ld_ro(c + dxl); wb1 = ld_ro(c); wb2 = ld_ro(c + dxr);
+                        wd0 = ld_ro(cd + dxl); wd1 = ld_ro(cd); wd2 = ld_ro(cd + dxr);
+                    }
                     const uint2 gr0 = ld_ro((const uint2*)g0p), gr1 = ld_ro((const uint2*)(g0p + g.gp));
                     float2 wr0, wr1; wr0.x = wr0.y = wr1.x = wr1.y = 1.f;
-                    if (!g.ones) { const float* wp = g.W + (size_t)oy * g.gp + ox; wr0 = ld_ro((const float2*)wp); wr1 = ld_ro((const float2*)(wp + g.gp)); }
+                    if (!g.ones) { const float* wp = g.W + (2 * qy * g.gp + 2 * qx); wr0 = ld_ro((const float2*)wp); wr1 = ld_ro((const float2*)(wp + g.gp)); }
 #if !DS_CUDA
                     if (g.ones) {
-                        const float* wp = g.W + (size_t)oy * g.gp + ox;
+                        const float* wp = g.W + (2 * qy * g.gp + 2 * qx);
                         if (wp[0] != 1.f || wp[1] != 1.f || wp[g.gp] != 1.f || wp[g.gp + 1] != 1.f) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
                     }
 #endif
@@ -2383,24 +2416,33 @@ struct AccumBody {
                     DS_UNROLL
                     for (int i = 0; i < 4; i++) {
                         const U2 gv = split(g0v[i]);
-                        const int lb = (int)(gv.br & 0xFFFFu) - (int)(up_br[i] & 0xFFFFu);
-                        const int lr = (int)(gv.br >> 16) - (int)(up_br[i] >> 16);
-                        const int lg = (int)gv.g - (int)up_g[i];
-                        if (g.ones) {   // trunc(lap * 1) == lap
-                            ab[k][i] += lb; ag[k][i] += lg; ar[k][i] += lr;
+                        if (g.ones) {
+                            // trunc(lap * 1) == lap, and lap_b + 65536 * lap_r == gbr - up_br as plain integers
+                            pbr[k][i] += (int)(gv.br - up_br[i]);
+                            pg[k][i] += (int)gv.g - (int)up_g[i];
                             ws[k][i] = f_add(ws[k][i], 1.f);
                         } else {
                             const float wv = wv4[i];
-                            ab[k][i] += (int)(short)f2i_rz(f_mul((float)lb, wv));
-                            ag[k][i] += (int)(short)f2i_rz(f_mul((float)lg, wv));
-                            ar[k][i] += (int)(short)f2i_rz(f_mul((float)lr, wv));
+                            const int lb = (int)(gv.br & 0xFFFFu) - (int)(up_br[i] & 0xFFFFu);
+                            const int lr = (int)(gv.br >> 16) - (int)(up_br[i] >> 16);
+                            const int lg = (int)gv.g - (int)up_g[i];
+                            const int tb = (int)(short)f2i_rz(f_mul((float)lb, wv)), tr = (int)(short)f2i_rz(f_mul((float)lr, wv));
+                            pbr[k][i] += tb + tr * 65536;
+                            pg[k][i] += (int)(short)f2i_rz(f_mul((float)lg, wv));
                             ws[k][i] = f_add(ws[k][i], wv);
                         }
                     }
                 }
+                // fold the chunk's packed sums into the wide ones
+                DS_UNROLL
+                for (int i = 0; i < 4; i++) {
+                    const int cb = (int)(short)(pbr[k][i] & 0xFFFF);
+                    sB[k][i] += cb; sR[k][i] += (pbr[k][i] - cb) >> 16;
+                    pbr[k][i] = 0;
+                }
             }
         }
-        // ---- normalise and store (the sums wrap to 16 bits like the reference's short accumulators)
+        // ---- normalise and store
         DS_UNROLL
         for (int k = 0; k < K; k++) {
             const int q = tid + k * NT;
@@ -2411,18 +2453,7 @@ struct AccumBody {
                 if (Yp >= p.dst_h || Yp < p.acc_y0 || Yp >= p.acc_y1) continue;
                 uint32_t w0[2], w1[2];
                 DS_UNROLL
-                for (int dx = 0; dx < 2; dx++) {
-                    const int i = 2 * dy + dx;
-                    const float wsum = ws[k][i];
-                    const float den = f_add(wsum, 1e-5f);
-                    const short nb = (short)ab[k][i], ng = (short)ag[k][i], nr = (short)ar[k][i];
-                    // 0 / den == 0 exactly; skipping it keeps the IEEE division off its special-operand slow path
-                    const int vb = nb ? (int)(short)f2i_rz(f_div((float)nb, den)) : 0;
-                    const int vg = ng ? (int)(short)f2i_rz(f_div((float)ng, den)) : 0;
-                    const int vr = nr ? (int)(short)f2i_rz(f_div((float)nr, den)) : 0;
-                    w0[dx] = ((uint32_t)vb & 0xffffu) | ((uint32_t)vg << 16);
-                    w1[dx] = ((uint32_t)vr & 0xffffu) | (wsum > 1e-5f ? 0x10000u : 0u);
-                }
+                for (int dx = 0; dx < 2; dx++) { const int i = 2 * dy + dx; norm_px(sB[k][i], pg[k][i], sR[k][i], ws[k][i], w0[dx], w1[dx]); }
                 px16* q16 = p.dst + (size_t)Yp * p.dst_w + X;
                 if (X + 1 < p.dst_w && !(p.dst_w & 1)) *(uint4*)q16 = make_u4(w0[0], w1[0], w0[1], w1[1]);   // X even, even pitch: 16-byte aligned
                 else {
@@ -2769,8 +2800,8 @@ typedef MBFastBody<64, true> MBFastL0;
 typedef MBFastBody<64, true, true> MBFastL0A;
 DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
-DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 4)
-DS_DEFINE_KERNEL(ds_mb_accum, AccumBody, 128, MBParams, 4)
+DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 8)
+DS_DEFINE_KERNEL(ds_mb_accum, AccumBody, 128, MBParams, 8)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 4)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)
 #endif

@@ -48,7 +48,7 @@ src = {}
 for (f, ln), c in agg.most_common(top):
     if f not in src:
         try:
-            src[f] = open("/root/repo/drone_image_stitch_cpp_b200/csrc/" + f).read().split("\n")
+            src[f] = open(__import__("os").environ.get("LINEPROF_SRC", "/root/repo/drone_image_stitch_cpp_b200/csrc/") + f).read().split("\n")
         except Exception:
             src[f] = []
     text = src[f][ln - 1].strip()[:90] if src[f] and ln <= len(src[f]) else ""
