@@ -2184,16 +2184,28 @@ struct PyrParams {
     const FrameDev* frames; int nframes;
     int level;            // input level l (>= 1); output level l + 1
     int txmax, R;         // CTAs per frame: txmax column blocks x R row blocks (first row block = the frame's first needed row)
+    uint32_t m_per, m_tx; // floor(2^32 / (txmax * R)), floor(2^32 / txmax): block index decode without divisions
     int own_y0, own_y1;   // canvas rows of level l + 1 to produce
 };
 struct PyrDownBody {
-    static constexpr int BW = 32, BH = 16, NTH = 128;   // outputs per CTA; one thread = 2 x 2 outputs
+    // One CTA = 32 x 64 outputs; one thread = a strip of 2 columns x 8 rows, marched down two output rows at a time: of
+    // the seven input rows a 2 x 2 output block reads, three were filtered horizontally for the block above.
+    static constexpr int BW = 32, STRIP = 8, BH = 8 * STRIP, NTH = 128;
     static int smem_bytes() { return 0; }
+    struct HRow { uint32_t br[2], g[2]; float w[2]; };   // horizontally filtered input row at the thread's two output columns
+    // q = i / d with m = floor(2^32 / d): the estimate is at most 2 short
+    DS_DM int div_m(int i, int d, uint32_t m) {
+        int q = (int)(((unsigned long long)(uint32_t)i * m) >> 32);
+        int r = i - q * d;
+        if (r >= d) { q++; r -= d; }
+        if (r >= d) q++;
+        return q;
+    }
     template <int NT>
     DS_DM void run(const PyrParams& p, int block, int tid, unsigned char*) {
         const int per = p.txmax * p.R;
-        const int fslot = block / per, rem = block - fslot * per;
-        const int byr = rem / p.txmax, bx = rem - byr * p.txmax;
+        const int fslot = div_m(block, per, p.m_per), rem = block - fslot * per;
+        const int byr = div_m(rem, p.txmax, p.m_tx), bx = rem - byr * p.txmax;
         const FrameDev& F = p.frames[fslot];
         const int l = p.level;
         const int w_in = F.rw >> l, h_in = F.rh >> l, w_out = w_in >> 1, h_out = h_in >> 1;
@@ -2209,69 +2221,71 @@ struct PyrDownBody {
         const int ip = F.gp[l], op = F.gp[l + 1];
         // the CTA's outputs all have weight 1 by geometry: W_l is not even read
         const bool ones = weights_all_ones(F, l + 1, bx * BW, imin(bx * BW + BW, w_out) - 1, imax(by * BH, jlo), imin(by * BH + BH, jhi) - 1);
+        const bool need_w = !ones || !DS_CUDA;   // (the emulator computes them anyway and checks the claim)
         for (int t = tid; t < NTH; t += NT) {
             const int tx = t & 15, ty = t >> 4;
-            const int jx = bx * BW + 2 * tx, jy = by * BH + 2 * ty;   // first of the thread's 2 x 2 outputs
-            if (jx >= w_out || jy >= jhi || jy + 1 < jlo) continue;
-            const int c0 = 2 * jx - 2, r0 = 2 * jy - 2;               // 7 x 7 input window
-            const bool interior = c0 >= 0 && c0 + 6 <= w_in - 1 && r0 >= 0 && r0 + 6 <= h_in - 1;
-            int rows[7], cols[7];
+            const int jx = bx * BW + 2 * tx, jy0 = by * BH + ty * STRIP;   // the strip's first output
+            if (jx >= w_out || jy0 >= jhi || jy0 + STRIP <= jlo) continue;
+            const int c0 = 2 * jx - 2;                                     // seven input columns from c0
+            const bool xin = c0 >= 0 && c0 + 6 <= w_in - 1;
+            int cols[7];
             DS_UNROLL
-            for (int k = 0; k < 7; k++) { rows[k] = interior ? r0 + k : refl101(r0 + k, h_in); cols[k] = interior ? c0 + k : refl101(c0 + k, w_in); }
-            // ---- G: separable [1 4 6 4 1] on packed lanes (B | R << 16, G); the vertical sums are order-free integers
-            uint32_t vbr[2][2] = {{0u, 0u}, {0u, 0u}}, vg[2][2] = {{0u, 0u}, {0u, 0u}};
-            float hw[7][2];
-            DS_UNROLL
-            for (int k = 0; k < 7; k++) {
+            for (int k = 0; k < 7; k++) cols[k] = xin ? c0 + k : refl101(c0 + k, w_in);
+            const bool hs0 = pd_h_is_simd(jx, w_in, w_out), hs1 = pd_h_is_simd(jx + 1, w_in, w_out);
+            const bool vs0 = pd_v_is_simd(jx, w_out), vs1 = pd_v_is_simd(jx + 1, w_out);
+            // input row r (reflected into the plane, BORDER_REFLECT_101) filtered horizontally: [1 4 6 4 1] on packed lanes
+            // (B | R << 16, G); the weights in the op order of each column's class (A9)
+            auto hrow = [&](int r, HRow& h) {
+                const int rr = refl101(r, h_in);
+                const uint32_t* gr = Gin + (size_t)rr * ip;
+                const float* wr = Win + (size_t)rr * ip;
                 uint32_t q[7]; float w[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                const uint32_t* gr = Gin + (size_t)rows[k] * ip;
-                const float* wr = Win + (size_t)rows[k] * ip;
-                if (interior) {
+                if (xin) {
                     // c0 = 2 mod 4 and rows are 16-byte aligned: 8 + 16 + 4 bytes
                     const uint2 a = ld_ro((const uint2*)(gr + c0)); const uint4 b = ld_ro((const uint4*)(gr + c0 + 2)); const uint32_t c = ld_ro(gr + c0 + 6);
                     q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = b.z; q[5] = b.w; q[6] = c;
-                    if (!ones || !DS_CUDA) {
+                    if (need_w) {
                         const float2 fa = ld_ro((const float2*)(wr + c0)); const float4 fb = ld_ro((const float4*)(wr + c0 + 2)); const float fc = ld_ro(wr + c0 + 6);
                         w[0] = fa.x; w[1] = fa.y; w[2] = fb.x; w[3] = fb.y; w[4] = fb.z; w[5] = fb.w; w[6] = fc;
                     }
                 } else {
                     DS_UNROLL
-                    for (int c = 0; c < 7; c++) { q[c] = ld_ro(gr + cols[c]); if (!ones || !DS_CUDA) w[c] = ld_ro(wr + cols[c]); }
+                    for (int c = 0; c < 7; c++) { q[c] = ld_ro(gr + cols[c]); if (need_w) w[c] = ld_ro(wr + cols[c]); }
                 }
                 uint32_t br[7], gg[7];
                 DS_UNROLL
                 for (int c = 0; c < 7; c++) { br[c] = byte_perm(q[c], 0, 0x4240); gg[c] = byte_perm(q[c], 0, 0x4441); }
                 DS_UNROLL
                 for (int o = 0; o < 2; o++) {
-                    const uint32_t hbr = br[2 * o] + br[2 * o + 4] + 6u * br[2 * o + 2] + 4u * (br[2 * o + 1] + br[2 * o + 3]);
-                    const uint32_t hg = gg[2 * o] + gg[2 * o + 4] + 6u * gg[2 * o + 2] + 4u * (gg[2 * o + 1] + gg[2 * o + 3]);
-                    // input row k is tap k of output row 0 and tap k - 2 of output row 1
-                    const uint32_t k0 = (k == 0 || k == 4) ? 1u : ((k == 1 || k == 3) ? 4u : (k == 2 ? 6u : 0u));
-                    const uint32_t k1 = (k == 2 || k == 6) ? 1u : ((k == 3 || k == 5) ? 4u : (k == 4 ? 6u : 0u));
-                    if (k <= 4) { vbr[0][o] += k0 * hbr; vg[0][o] += k0 * hg; }
-                    if (k >= 2) { vbr[1][o] += k1 * hbr; vg[1][o] += k1 * hg; }
-                    // weights: horizontal pass in the op order of the column's class (A9)
-                    const int j = jx + o;
-                    if (!ones || !DS_CUDA) hw[k][o] = pd_h_is_simd(j, w_in, w_out) ? pd_h_simd(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4])
-                                                            : pd_scalar(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4]);
+                    h.br[o] = br[2 * o] + br[2 * o + 4] + 6u * br[2 * o + 2] + 4u * (br[2 * o + 1] + br[2 * o + 3]);
+                    h.g[o] = gg[2 * o] + gg[2 * o + 4] + 6u * gg[2 * o + 2] + 4u * (gg[2 * o + 1] + gg[2 * o + 3]);
+                    h.w[o] = 0.f;
+                    if (need_w) {
+                        const bool hs = o ? hs1 : hs0;
+                        h.w[o] = hs ? pd_h_simd(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4])
+                                    : pd_scalar(w[2 * o], w[2 * o + 1], w[2 * o + 2], w[2 * o + 3], w[2 * o + 4]);
+                    }
                 }
-            }
-            DS_UNROLL
-            for (int dy = 0; dy < 2; dy++) {
-                const int y = jy + dy;
-                if (y < jlo || y >= jhi) continue;
+            };
+            // output row y from five filtered rows
+            auto emit = [&](int y, const HRow& a, const HRow& b, const HRow& c, const HRow& d, const HRow& e) {
+                if (y < jlo || y >= jhi) return;
                 uint32_t go[2]; float wo[2];
                 DS_UNROLL
                 for (int o = 0; o < 2; o++) {
-                    const uint32_t obr = ((vbr[dy][o] + 0x00800080u) >> 8) & 0x00FF00FFu, og = ((vg[dy][o] + 0x80u) >> 8) & 0xFFu;
+                    const uint32_t vbr = a.br[o] + e.br[o] + 6u * c.br[o] + 4u * (b.br[o] + d.br[o]);
+                    const uint32_t vg = a.g[o] + e.g[o] + 6u * c.g[o] + 4u * (b.g[o] + d.g[o]);
+                    const uint32_t obr = ((vbr + 0x00800080u) >> 8) & 0x00FF00FFu, og = ((vg + 0x80u) >> 8) & 0xFFu;
                     go[o] = byte_perm(obr, og, 0x5240);
-                    if (ones && DS_CUDA) { wo[o] = 1.f; continue; }
-                    const float t0 = hw[2 * dy][o], t1 = hw[2 * dy + 1][o], t2 = hw[2 * dy + 2][o], t3 = hw[2 * dy + 3][o], t4 = hw[2 * dy + 4][o];
-                    const float v = pd_v_is_simd(jx + o, w_out) ? pd_v_simd(t0, t1, t2, t3, t4) : pd_scalar(t0, t1, t2, t3, t4);
-                    wo[o] = f_mul(v, 1.f / 256.f);
+                    wo[o] = 1.f;
+                    if (need_w) {
+                        const bool vs = o ? vs1 : vs0;
+                        const float v = vs ? pd_v_simd(a.w[o], b.w[o], c.w[o], d.w[o], e.w[o]) : pd_scalar(a.w[o], b.w[o], c.w[o], d.w[o], e.w[o]);
+                        wo[o] = f_mul(v, 1.f / 256.f);
 #if !DS_CUDA
-                    if (ones && wo[o] != 1.f && jx + o < w_out) { fprintf(stderr, "ds emu: pyrdown level %d frame %d: weights claimed 1 by geometry are not\n", l, fslot); abort(); }
+                        if (ones && wo[o] != 1.f && jx + o < w_out) { fprintf(stderr, "ds emu: pyrdown level %d frame %d: weights claimed 1 by geometry are not\n", l, fslot); abort(); }
 #endif
+                    }
                 }
                 uint32_t* gq = Gout + (size_t)y * op + jx;
                 float* wq = Wout + (size_t)y * op + jx;
@@ -2279,6 +2293,18 @@ struct PyrDownBody {
                     uint2 gv; gv.x = go[0]; gv.y = go[1]; *(uint2*)gq = gv;
                     float2 wv; wv.x = wo[0]; wv.y = wo[1]; *(float2*)wq = wv;
                 } else { gq[0] = go[0]; wq[0] = wo[0]; }
+            };
+            HRow h0, h1, h2, h3, h4, h5, h6;
+            int r0 = 2 * jy0 - 2;
+            hrow(r0, h0); hrow(r0 + 1, h1); hrow(r0 + 2, h2);
+            DS_UNROLL
+            for (int s = 0; s < STRIP / 2; s++) {
+                const int y = jy0 + 2 * s;
+                if (y >= jhi) break;
+                hrow(r0 + 3, h3); hrow(r0 + 4, h4); hrow(r0 + 5, h5); hrow(r0 + 6, h6);
+                emit(y, h0, h1, h2, h3, h4);
+                emit(y + 1, h2, h3, h4, h5, h6);
+                h0 = h4; h1 = h5; h2 = h6; r0 += 4;
             }
         }
     }
@@ -2800,7 +2826,7 @@ typedef MBFastBody<64, true> MBFastL0;
 typedef MBFastBody<64, true, true> MBFastL0A;
 DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
-DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 8)
+DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 6)
 DS_DEFINE_KERNEL(ds_mb_accum, AccumBody, 128, MBParams, 8)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 4)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)

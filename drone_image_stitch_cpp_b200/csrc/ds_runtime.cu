@@ -1069,6 +1069,9 @@ int launch_pyrdown(ds_canvas* c, stream_t st, int l, const SubBand& sb, const AB
     pp.frames = c->d_frames; pp.nframes = (int)c->frames.size(); pp.level = l;
     pp.txmax = (wmax + PyrDownBody::BW - 1) / PyrDownBody::BW;
     pp.R = (std::min(rows.hi - rows.lo, hmax) + PyrDownBody::BH - 1) / PyrDownBody::BH + 1;   // + 1: the first needed row is anywhere in its block
+    pp.m_per = (uint32_t)(0x100000000ull / (uint32_t)(pp.txmax * pp.R)); pp.m_tx = (uint32_t)(0x100000000ull / (uint32_t)pp.txmax);
+    if (pp.txmax * pp.R == 1) pp.m_per = 0xffffffffu;
+    if (pp.txmax == 1) pp.m_tx = 0xffffffffu;
     pp.own_y0 = rows.lo; pp.own_y1 = rows.hi;
     const double q = 1.0 / (double)(1ull << (2 * l));
     const Range all = c->plan[l + 1].own;
