@@ -821,7 +821,8 @@ struct MBParams {
     int acc_y0, acc_y1;           // rows of this level whose dst the band's collapse reads (dst written only there)
     int own_y0, own_y1;           // even-aligned rows of this level the handle processes at all
     const void* tmaps;            // CUtensorMap[frame][2] over the frame sources (level 0: L2 prefetch box, shared-memory box), or NULL
-    int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI
+    int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI; bit 1: level-0 source boxes; bit 2: ds_mb_accum ring
+    const void* lmaps; int lstride;   // CUtensorMap[frame][lstride][AccumBody::LM_N] over the per-frame G_l / W_l planes (levels 1 .. L), or NULL
 };
 
 template <int T, bool LEVEL0>
@@ -1056,6 +1057,27 @@ DS_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::
 // descriptors live in global memory (one per frame and level): acquire them for the tensormap proxy before use
 DS_D void fence_tensormap_acquire(const void* tmap) {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+DS_D void fence_proxy_async_smem() { fence_proxy_async(); }
+// One bw x bh box of a pitched plane of 4-byte elements into shared memory (TMA tile load, completion on `bar`); elements
+// outside the plane arrive as zeros. The emulator copies.
+// (The descriptors were written by an earlier grid - ds_meta_copy - so no tensormap-proxy fence is needed here.)
+DS_D void box_load(void* dst, const void* tmap, const void*, int, int, int, int x0, int y0, int, int, void* bar) {
+    tma_load_2d(dst, tmap, x0, y0, bar);
+}
+#else
+DS_D void mbar_init(void*, int) {}
+DS_D void mbar_expect_tx(void*, uint32_t) {}
+DS_D void mbar_wait(void*, uint32_t) {}
+DS_D void fence_proxy_async_smem() {}
+DS_D void box_load(void* dst, const void*, const void* plane, int w, int h, int pitch, int x0, int y0, int bw, int bh, void*) {
+    uint32_t* d = (uint32_t*)dst;
+    const uint32_t* s = (const uint32_t*)plane;
+    for (int y = 0; y < bh; y++)
+        for (int x = 0; x < bw; x++) {
+            const int sx = x0 + x, sy = y0 + y;
+            d[y * bw + x] = ((unsigned)sx < (unsigned)w && (unsigned)sy < (unsigned)h) ? s[(size_t)sy * pitch + sx] : 0u;
+        }
 }
 #endif
 
@@ -2313,6 +2335,14 @@ struct PyrDownBody {
 struct AccumBody {
     static constexpr int TW = 32, TH = 16, NQ = 128;   // one thread = one 2 x 2 quad
     static constexpr int GCH = 32;                     // frames whose geometry is staged at a time; also the span of the packed sums
+    // Shared-memory ring (below the top level, when the tensor maps exist): the boxes of up to NST frames of the tile's list
+    // are in flight at once - G_l and W_l of the tile (36 x 16: the innermost start of a TMA box must be 16-byte aligned, so
+    // up to 3 extra columns on the left) and G_{l+1} of the tile / 2 + its pyrUp ring (24 x 10) - each stage completing on
+    // its own mbarrier. Loads in flight no longer cost registers, and the taps become shared-memory reads at fixed offsets.
+    static constexpr int NST = 4, GBW = 36, GBH = TH, CBW = 24, CBH = TH / 2 + 2;
+    static constexpr int GBOX = GBW * GBH * 4, CBOX = CBW * CBH * 4;
+    static constexpr int STAGE_BYTES = 2 * GBOX + ds_al128(CBOX);
+    static constexpr int LM_G = 0, LM_W = 1, LM_C = 2, LM_PG = 3, LM_PW = 4, LM_N = 5;   // tensor maps per frame and level (MBParams::lmaps)
     // tile x frame geometry: built by one thread, read by all. Pointers are pre-offset to the tile origin (they may point
     // outside the plane; the quads inside the frame's ROI add what brings them back in).
     struct alignas(16) AGeo {
@@ -2320,13 +2350,17 @@ struct AccumBody {
         const uint32_t* G1; int gp, gp1;     // level l + 1 at ((X0 - rx) / 2, (Y0 - ry) / 2); row pitches
         int x0, nx, y0, ny;                  // the tile's part inside the ROI and the rows: tile-relative quads (top level: pixels)
         int c1x0, c1y0, n1x, n1y;            // level-(l+1) coordinate of the tile origin in the frame, plane size (pyrUp border rules)
-        int skip, ones, border, pad;
+        int skip, ones, border, frame;
+        int gbx, gby, cbx, cby;              // ring: box origins in the level-l / level-(l+1) plane
+        int goff, coff, pad0, pad1;          // ring: element offset of the tile origin inside the G / W box and the coarse box
     };
-    static int smem_bytes() { return GCH * (int)sizeof(AGeo); }
+    static constexpr int GEO_BYTES = GCH * (int)sizeof(AGeo), RING_OFF = ds_al128(GEO_BYTES);
+    static int smem_bytes() { return RING_OFF + NST * STAGE_BYTES + 64; }
     struct U2 { uint32_t br, g; };
     DS_DM U2 split(uint32_t v) { U2 o; o.br = byte_perm(v, 0, 0x4240); o.g = byte_perm(v, 0, 0x4441); return o; }
 
-    DS_DM void make_geo(const MBParams& p, const FrameDev& F, int X0, int Y0, bool top, AGeo& g) {
+    DS_DM void make_geo(const MBParams& p, int frame, int X0, int Y0, bool top, AGeo& g) {
+        const FrameDev& F = p.frames[frame];
         const int l = p.level;
         const int rx = F.rx >> l, ry = F.ry >> l, rw = F.rw >> l, rh = F.rh >> l;
         const int ax0 = imax(X0, rx), ax1 = imin(X0 + TW, rx + rw);
@@ -2334,6 +2368,7 @@ struct AccumBody {
         const int a0 = top ? p.acc_y0 : (p.acc_y0 & ~1), a1 = top ? p.acc_y1 : ((p.acc_y1 + 1) & ~1);
         const int ay0 = imax(imax(Y0, ry), a0), ay1 = imin(imin(Y0 + TH, ry + rh), a1);
         g.skip = (ax0 >= ax1 || ay0 >= ay1) ? 1 : 0;
+        g.frame = frame;
         g.gp = F.gp[l]; g.gp1 = top ? 0 : F.gp[l + 1];
         const long long o0 = (long long)(Y0 - ry) * g.gp + (X0 - rx);
         g.G = (const uint32_t*)F.G[l] + o0; g.W = F.W[l] + o0;
@@ -2343,36 +2378,122 @@ struct AccumBody {
         g.x0 = (ax0 - X0) >> sh; g.nx = (ax1 - ax0) >> sh; g.y0 = (ay0 - Y0) >> sh; g.ny = (ay1 - ay0) >> sh;
         // does any quad of the part tap beyond the level-(l+1) plane (pyrUp border rules)?
         g.border = (((ax0 - rx) >> 1) < 1 || ((ax1 - 1 - rx) >> 1) + 1 > g.n1x - 1 || ((ay0 - ry) >> 1) < 1 || ((ay1 - 1 - ry) >> 1) + 1 > g.n1y - 1) ? 1 : 0;
-        g.ones = 0; g.pad = 0;
+        g.ones = 0; g.pad0 = g.pad1 = 0;
         if (!g.skip && weights_all_ones(F, l, ax0 - rx, ax1 - 1 - rx, ay0 - ry, ay1 - 1 - ry)) g.ones = 1;
+        // ring boxes: origins clamped into the plane (whatever lies left of / above it belongs to no active quad)
+        g.gbx = imax(X0 - rx, 0) & ~3; g.gby = imax(Y0 - ry, 0);
+        g.goff = (Y0 - ry - g.gby) * GBW + (X0 - rx - g.gbx);
+        g.cbx = imax(g.c1x0 - 1, 0) & ~3; g.cby = imax(g.c1y0 - 1, 0);
+        g.coff = (g.c1y0 - g.cby) * CBW + (g.c1x0 - g.cbx);
+    }
+
+    // pyrUp of the 3 x 3 coarse neighbourhood (A10, packed lanes) and the weighted Laplacians of the quad
+    DS_DM void quad(const uint32_t (&cw)[9], const uint32_t (&g0v)[4], const float (&wv4)[4], bool ones, int (&pbr)[4], int (&pg)[4], float (&ws)[4]) {
+        const U2 a0 = split(cw[0]), a1 = split(cw[1]), a2 = split(cw[2]), b0 = split(cw[3]), b1 = split(cw[4]), b2 = split(cw[5]), d0 = split(cw[6]), d1 = split(cw[7]), d2 = split(cw[8]);
+        // horizontal: even = l + 6c + r, odd = 4(c + r), on rows l / c / r
+        const uint32_t El_br = a0.br + 6u * a1.br + a2.br, Ol_br = 4u * (a1.br + a2.br);
+        const uint32_t Ec_br = b0.br + 6u * b1.br + b2.br, Oc_br = 4u * (b1.br + b2.br);
+        const uint32_t Er_br = d0.br + 6u * d1.br + d2.br, Or_br = 4u * (d1.br + d2.br);
+        const uint32_t El_g = a0.g + 6u * a1.g + a2.g, Ol_g = 4u * (a1.g + a2.g);
+        const uint32_t Ec_g = b0.g + 6u * b1.g + b2.g, Oc_g = 4u * (b1.g + b2.g);
+        const uint32_t Er_g = d0.g + 6u * d1.g + d2.g, Or_g = 4u * (d1.g + d2.g);
+        // vertical + (v + 32) >> 6; index = 2 dy + dx
+        uint32_t up_br[4], up_g[4];
+        up_br[0] = ((El_br + 6u * Ec_br + Er_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+        up_br[1] = ((Ol_br + 6u * Oc_br + Or_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+        up_br[2] = ((4u * (Ec_br + Er_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+        up_br[3] = ((4u * (Oc_br + Or_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+        up_g[0] = ((El_g + 6u * Ec_g + Er_g + 0x20u) >> 6) & 0x3FFu;
+        up_g[1] = ((Ol_g + 6u * Oc_g + Or_g + 0x20u) >> 6) & 0x3FFu;
+        up_g[2] = ((4u * (Ec_g + Er_g) + 0x20u) >> 6) & 0x3FFu;
+        up_g[3] = ((4u * (Oc_g + Or_g) + 0x20u) >> 6) & 0x3FFu;
+        DS_UNROLL
+        for (int i = 0; i < 4; i++) {
+            const U2 gv = split(g0v[i]);
+            if (ones) {
+                // trunc(lap * 1) == lap, and lap_b + 65536 * lap_r == gbr - up_br as plain integers
+                pbr[i] += (int)(gv.br - up_br[i]);
+                pg[i] += (int)gv.g - (int)up_g[i];
+                ws[i] = f_add(ws[i], 1.f);
+            } else {
+                const float wv = wv4[i];
+                const int lb = (int)(gv.br & 0xFFFFu) - (int)(up_br[i] & 0xFFFFu);
+                const int lr = (int)(gv.br >> 16) - (int)(up_br[i] >> 16);
+                const int lg = (int)gv.g - (int)up_g[i];
+                const int tb = (int)(short)f2i_rz(f_mul((float)lb, wv)), tr = (int)(short)f2i_rz(f_mul((float)lr, wv));
+                pbr[i] += tb + tr * 65536;
+                pg[i] += (int)(short)f2i_rz(f_mul((float)lg, wv));
+                ws[i] = f_add(ws[i], wv);
+            }
+        }
     }
 
     template <int NT>
     DS_DM void run(const MBParams& p, int block, int tid, unsigned char* smem) {
         constexpr int K = NQ / NT;   // quads per thread: 1 on the GPU; the emulator's single thread holds them all
         AGeo* s_geo = (AGeo*)smem;
+        unsigned char* const s_ring = smem + RING_OFF;
+        unsigned long long* const s_bar = (unsigned long long*)(s_ring + NST * STAGE_BYTES);
         const int4 rec = ld_ro(p.tile_rec + block);
         const int tile = rec.x, f_begin = rec.y, f_end = rec.z;
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int X0 = tx * TW, Y0 = ty * TH;
         const bool top = p.level == p.L;
+        const bool ring = !top && (p.flags & 4) && (p.lmaps != nullptr || !DS_CUDA);
+        if (ring && tid == 0) { for (int s = 0; s < NST; s++) mbar_init(s_bar + s, 1); }   // visible after the first barrier below
         // per pixel: packed sums B + 65536 R and G of the current chunk of frames (exact while |sum B| < 2^15: a chunk is 32
         // frames of |lap| <= 255), folded into wide sums after every chunk; weight sum in feed order
         int pbr[K][4], pg[K][4], sB[K][4], sR[K][4]; float ws[K][4];
         DS_UNROLL
         for (int k = 0; k < K; k++) { DS_UNROLL for (int i = 0; i < 4; i++) { pbr[k][i] = pg[k][i] = sB[k][i] = sR[k][i] = 0; ws[k][i] = 0.f; } }
+        int m_issue = 0, m_use = 0;   // live (non-skipped) tile-frames issued into / consumed from the ring so far
         for (int base = f_begin; base < f_end; base += GCH) {
             const int n = imin(GCH, f_end - base);
             if (base > f_begin) DS_SYNC();   // everyone is done with the previous chunk's entries
-            for (int j = tid; j < n; j += NT) make_geo(p, p.frames[(base + j == f_begin) ? rec.w : p.tile_frames[base + j]], X0, Y0, top, s_geo[j]);
+            for (int j = tid; j < n; j += NT) make_geo(p, (base + j == f_begin) ? rec.w : p.tile_frames[base + j], X0, Y0, top, s_geo[j]);
             DS_SYNC();
-            DS_UNROLL
-            for (int k = 0; k < K; k++) {
-                const int q = tid + k * NT;
-                const int qx = q & 15, qy = q >> 4;
-                for (int j = 0; j < n; j++) {
-                    const AGeo& g = s_geo[j];
-                    if (g.skip) continue;
+            int jn = 0;   // next entry to look at for the ring
+            // every thread follows the ring's bookkeeping (block-uniform); thread 0 issues the loads
+            auto issue_next = [&]() {
+                while (jn < n && s_geo[jn].skip) jn++;
+                if (jn >= n) return false;
+                if (tid == 0) {
+                    const AGeo& g = s_geo[jn];
+                    const int s = m_issue % NST;
+                    unsigned char* st = s_ring + s * STAGE_BYTES;
+                    const char* lm = (const char*)((uintptr_t)p.lmaps + ((size_t)g.frame * p.lstride + p.level) * (LM_N * 128));
+                    const char* lc = (const char*)((uintptr_t)p.lmaps + ((size_t)g.frame * p.lstride + p.level + 1) * (LM_N * 128));
+#if DS_CUDA
+                    const void* pG = nullptr; const void* pW = nullptr; const void* pC = nullptr;   // the tensor maps know the planes
+                    const int pw_ = 0, ph_ = 0;
+#else
+                    const FrameDev& F = p.frames[g.frame];
+                    const void* pG = F.G[p.level]; const void* pW = F.W[p.level]; const void* pC = F.G[p.level + 1];
+                    const int pw_ = F.rw >> p.level, ph_ = F.rh >> p.level;
+#endif
+                    if (m_issue >= NST) fence_proxy_async_smem();   // the stage's previous contents were read through the generic proxy
+                    mbar_expect_tx(s_bar + s, (uint32_t)(GBOX + CBOX + (g.ones ? 0 : GBOX)));
+                    box_load(st, lm + LM_G * 128, pG, pw_, ph_, g.gp, g.gbx, g.gby, GBW, GBH, s_bar + s);
+                    if (!g.ones || !DS_CUDA) box_load(st + GBOX, lm + LM_W * 128, pW, pw_, ph_, g.gp, g.gbx, g.gby, GBW, GBH, s_bar + s);
+                    box_load(st + 2 * GBOX, lc + LM_C * 128, pC, g.n1x, g.n1y, g.gp1, g.cbx, g.cby, CBW, CBH, s_bar + s);
+                }
+                m_issue++; jn++;
+                return true;
+            };
+            if (ring) { for (int s = 0; s < NST; s++) if (!issue_next()) break; }
+            for (int j = 0; j < n; j++) {
+                const AGeo& g = s_geo[j];
+                if (g.skip) continue;   // block-uniform
+                const unsigned char* st = nullptr;
+                if (ring) {
+                    const int s = m_use % NST;
+                    st = s_ring + s * STAGE_BYTES;
+                    mbar_wait(s_bar + s, (uint32_t)((m_use / NST) & 1));
+                }
+                DS_UNROLL
+                for (int k = 0; k < K; k++) {
+                    const int q = tid + k * NT;
+                    const int qx = q & 15, qy = q >> 4;
                     if (top) {
                         // the top level accumulates G_L itself; its ROI need not be even-aligned: per pixel
                         DS_UNROLL
@@ -2393,73 +2514,53 @@ struct AccumBody {
                         continue;
                     }
                     if ((unsigned)(qx - g.x0) >= (unsigned)g.nx || (unsigned)(qy - g.y0) >= (unsigned)g.ny) continue;
-                    const uint32_t* const g0p = g.G + (2 * qy * g.gp + 2 * qx);
-                    const uint32_t* const c = g.G1 + (qy * g.gp1 + qx);
-                    // every load of the quad is requested before the first use
-                    uint32_t wa0, wa1, wa2, wb0, wb1, wb2, wd0, wd1, wd2;
-                    if (!g.border) {
-                        const uint32_t* const ca = c - g.gp1; const uint32_t* const cd = c + g.gp1;
-                        wa0 = ld_ro(ca - 1); wa1 = ld_ro(ca); wa2 = ld_ro(ca + 1);
-                        wb0 = ld_ro(c - 1); wb1 = ld_ro(c); wb2 = ld_ro(c + 1);
-                        wd0 = ld_ro(cd - 1); wd1 = ld_ro(cd); wd2 = ld_ro(cd + 1);
-                    } else {
+                    uint32_t cw[9], g0v[4]; float wv4[4] = {1.f, 1.f, 1.f, 1.f};
+                    int dxl = -1, dxr = 1, dyl = -1, dyr = 1;   // pyrUp neighbours, relative to the quad's coarse pixel
+                    if (g.border) {
                         const int c1x = g.c1x0 + qx, c1y = g.c1y0 + qy;
-                        const int dxl = up_l(c1x, g.n1x) - c1x, dxr = up_r(c1x, g.n1x) - c1x;
-                        const uint32_t* const ca = c + (up_l(c1y, g.n1y) - c1y) * g.gp1; const uint32_t* const cd = c + (up_r(c1y, g.n1y) - c1y) * g.gp1;
-                        wa0 = ld_ro(ca + dxl); wa1 = ld_ro(ca); wa2 = ld_ro(ca + dxr);
-                        wb0 = ld_ro(c + dxl); wb1 = ld_ro(c); wb2 = ld_ro(c + dxr);
-                        wd0 = ld_ro(cd + dxl); wd1 = ld_ro(cd); wd2 = ld_ro(cd + dxr);
+                        dxl = up_l(c1x, g.n1x) - c1x; dxr = up_r(c1x, g.n1x) - c1x; dyl = up_l(c1y, g.n1y) - c1y; dyr = up_r(c1y, g.n1y) - c1y;
                     }
-                    const uint2 gr0 = ld_ro((const uint2*)g0p), gr1 = ld_ro((const uint2*)(g0p + g.gp));
-                    float2 wr0, wr1; wr0.x = wr0.y = wr1.x = wr1.y = 1.f;
-                    if (!g.ones) { const float* wp = g.W + (2 * qy * g.gp + 2 * qx); wr0 = ld_ro((const float2*)wp); wr1 = ld_ro((const float2*)(wp + g.gp)); }
-#if !DS_CUDA
-                    if (g.ones) {
-                        const float* wp = g.W + (2 * qy * g.gp + 2 * qx);
-                        if (wp[0] != 1.f || wp[1] != 1.f || wp[g.gp] != 1.f || wp[g.gp + 1] != 1.f) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
-                    }
-#endif
-                    const U2 a0 = split(wa0), a1 = split(wa1), a2 = split(wa2), b0 = split(wb0), b1 = split(wb1), b2 = split(wb2), d0 = split(wd0), d1 = split(wd1), d2 = split(wd2);
-                    // pyrUp (A10) on packed lanes. horizontal: even = l + 6c + r, odd = 4(c + r), on rows l / c / r
-                    const uint32_t El_br = a0.br + 6u * a1.br + a2.br, Ol_br = 4u * (a1.br + a2.br);
-                    const uint32_t Ec_br = b0.br + 6u * b1.br + b2.br, Oc_br = 4u * (b1.br + b2.br);
-                    const uint32_t Er_br = d0.br + 6u * d1.br + d2.br, Or_br = 4u * (d1.br + d2.br);
-                    const uint32_t El_g = a0.g + 6u * a1.g + a2.g, Ol_g = 4u * (a1.g + a2.g);
-                    const uint32_t Ec_g = b0.g + 6u * b1.g + b2.g, Oc_g = 4u * (b1.g + b2.g);
-                    const uint32_t Er_g = d0.g + 6u * d1.g + d2.g, Or_g = 4u * (d1.g + d2.g);
-                    // vertical + (v + 32) >> 6; index = 2 dy + dx
-                    uint32_t up_br[4], up_g[4];
-                    up_br[0] = ((El_br + 6u * Ec_br + Er_br + 0x00200020u) >> 6) & 0x03FF03FFu;
-                    up_br[1] = ((Ol_br + 6u * Oc_br + Or_br + 0x00200020u) >> 6) & 0x03FF03FFu;
-                    up_br[2] = ((4u * (Ec_br + Er_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
-                    up_br[3] = ((4u * (Oc_br + Or_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
-                    up_g[0] = ((El_g + 6u * Ec_g + Er_g + 0x20u) >> 6) & 0x3FFu;
-                    up_g[1] = ((Ol_g + 6u * Oc_g + Or_g + 0x20u) >> 6) & 0x3FFu;
-                    up_g[2] = ((4u * (Ec_g + Er_g) + 0x20u) >> 6) & 0x3FFu;
-                    up_g[3] = ((4u * (Oc_g + Or_g) + 0x20u) >> 6) & 0x3FFu;
-                    const uint32_t g0v[4] = {gr0.x, gr0.y, gr1.x, gr1.y};
-                    const float wv4[4] = {wr0.x, wr0.y, wr1.x, wr1.y};
-                    DS_UNROLL
-                    for (int i = 0; i < 4; i++) {
-                        const U2 gv = split(g0v[i]);
-                        if (g.ones) {
-                            // trunc(lap * 1) == lap, and lap_b + 65536 * lap_r == gbr - up_br as plain integers
-                            pbr[k][i] += (int)(gv.br - up_br[i]);
-                            pg[k][i] += (int)gv.g - (int)up_g[i];
-                            ws[k][i] = f_add(ws[k][i], 1.f);
-                        } else {
-                            const float wv = wv4[i];
-                            const int lb = (int)(gv.br & 0xFFFFu) - (int)(up_br[i] & 0xFFFFu);
-                            const int lr = (int)(gv.br >> 16) - (int)(up_br[i] >> 16);
-                            const int lg = (int)gv.g - (int)up_g[i];
-                            const int tb = (int)(short)f2i_rz(f_mul((float)lb, wv)), tr = (int)(short)f2i_rz(f_mul((float)lr, wv));
-                            pbr[k][i] += tb + tr * 65536;
-                            pg[k][i] += (int)(short)f2i_rz(f_mul((float)lg, wv));
-                            ws[k][i] = f_add(ws[k][i], wv);
+                    if (ring) {
+                        const SAddr ag = s_addr(st) + 4 * (g.goff + 2 * qy * GBW + 2 * qx);
+                        const SAddr ac = s_addr(st + 2 * GBOX) + 4 * (g.coff + qy * CBW + qx);
+                        const SAddr aa = ac + 4 * CBW * dyl, ad = ac + 4 * CBW * dyr;
+                        cw[0] = lds_u1(aa + 4 * dxl); cw[1] = lds_u1(aa); cw[2] = lds_u1(aa + 4 * dxr);
+                        cw[3] = lds_u1(ac + 4 * dxl); cw[4] = lds_u1(ac); cw[5] = lds_u1(ac + 4 * dxr);
+                        cw[6] = lds_u1(ad + 4 * dxl); cw[7] = lds_u1(ad); cw[8] = lds_u1(ad + 4 * dxr);
+                        lds_u2(ag, g0v[0], g0v[1]); lds_u2(ag + 4 * GBW, g0v[2], g0v[3]);
+                        if (!g.ones || !DS_CUDA) { lds_f2(ag + GBOX, wv4[0], wv4[1]); lds_f2(ag + GBOX + 4 * GBW, wv4[2], wv4[3]); }
+                    } else {
+                        const uint32_t* const g0p = g.G + (2 * qy * g.gp + 2 * qx);
+                        const uint32_t* const c = g.G1 + (qy * g.gp1 + qx);
+                        const uint32_t* const ca = c + dyl * g.gp1; const uint32_t* const cd = c + dyr * g.gp1;
+                        // every load of the quad is requested before the first use
+                        cw[0] = ld_ro(ca + dxl); cw[1] = ld_ro(ca); cw[2] = ld_ro(ca + dxr);
+                        cw[3] = ld_ro(c + dxl); cw[4] = ld_ro(c); cw[5] = ld_ro(c + dxr);
+                        cw[6] = ld_ro(cd + dxl); cw[7] = ld_ro(cd); cw[8] = ld_ro(cd + dxr);
+                        const uint2 gr0 = ld_ro((const uint2*)g0p), gr1 = ld_ro((const uint2*)(g0p + g.gp));
+                        g0v[0] = gr0.x; g0v[1] = gr0.y; g0v[2] = gr1.x; g0v[3] = gr1.y;
+                        if (!g.ones || !DS_CUDA) {
+                            const float* wp = g.W + (2 * qy * g.gp + 2 * qx);
+                            const float2 wr0 = ld_ro((const float2*)wp), wr1 = ld_ro((const float2*)(wp + g.gp));
+                            wv4[0] = wr0.x; wv4[1] = wr0.y; wv4[2] = wr1.x; wv4[3] = wr1.y;
                         }
                     }
+#if !DS_CUDA
+                    if (g.ones && (wv4[0] != 1.f || wv4[1] != 1.f || wv4[2] != 1.f || wv4[3] != 1.f)) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
+#endif
+                    quad(cw, g0v, wv4, g.ones != 0, pbr[k], pg[k], ws[k]);
                 }
-                // fold the chunk's packed sums into the wide ones
+                if (ring) {
+                    m_use++;
+                    // refill the stage just consumed, if the chunk has more live entries (block-uniform decision)
+                    int jp = jn;
+                    while (jp < n && s_geo[jp].skip) jp++;
+                    if (jp < n) { DS_SYNC(); issue_next(); }
+                }
+            }
+            // fold the chunk's packed sums into the wide ones
+            DS_UNROLL
+            for (int k = 0; k < K; k++) {
                 DS_UNROLL
                 for (int i = 0; i < 4; i++) {
                     const int cb = (int)(short)(pbr[k][i] & 0xFFFF);

@@ -335,6 +335,7 @@ struct ds_canvas {
     FrameDev* d_frames = nullptr;                    // inside the meta arena
     void* d_tmaps = nullptr;                         // CUtensorMap[frame][2] over the frame sources (meta arena)
     bool tmaps_ok = false;
+    void* d_lmaps = nullptr;                         // CUtensorMap[frame][L + 1][AccumBody::LM_N] over the per-frame G_l / W_l planes (meta arena)
     LevelPlan plan[DS_MAXL];   // multiband: one per level; feather: plan[0]
     bool dirty = true;
     bool l0_has_affine = false;   // some frame is AFFINE_F64 or has a seam mask / gain map: level 0 runs the general variant of the fast kernel
@@ -903,7 +904,8 @@ int build_lists(ds_canvas* c) {
     std::vector<PullSeg> segs;
     if (c->exchange) { int rcs = build_pull_segments(c, segs); if (rcs) return rcs; }
     const size_t segs_off = mbd.add(segs.data(), segs.size() * sizeof(PullSeg));
-    size_t tmaps_off = 0;
+    size_t tmaps_off = 0, lmaps_off = 0;
+    bool lmaps_ok = false;
     c->tmaps_ok = false;
 #if DS_CUDA
     if (c->desc.blend_mode == DS_BLEND_MULTIBAND && c->L >= 1 && !c->frames.empty()) {
@@ -923,6 +925,24 @@ int build_lists(ds_canvas* c) {
         if (ok) {
             tmaps_off = mbd.add(tm.data(), tm.size() * sizeof(CUtensorMap));
             c->tmaps_ok = true;
+        }
+        // ... and of the per-frame planes G_l / W_l, l = 1 .. L, with the boxes ds_mb_accum stages in its shared-memory ring
+        if (ok) {
+            const size_t ls = (size_t)c->L + 1;
+            std::vector<CUtensorMap> lm(c->frames.size() * ls * AccumBody::LM_N);
+            memset(lm.data(), 0, lm.size() * sizeof(CUtensorMap));
+            for (size_t i = 0; i < c->frames.size() && ok; i++) {
+                const Frame& f = c->frames[i];
+                if (!f.used) continue;
+                for (int l = 1; l <= c->L && ok; l++) {
+                    const int w = f.rw >> l, h = f.rh >> l;
+                    CUtensorMap* m = &lm[(i * ls + l) * AccumBody::LM_N];
+                    ok = encode_tile_map(m + AccumBody::LM_G, false, f.dev.G[l], w, h, f.dev.gp[l], AccumBody::GBW, AccumBody::GBH) &&
+                         encode_tile_map(m + AccumBody::LM_W, true, f.dev.W[l], w, h, f.dev.gp[l], AccumBody::GBW, AccumBody::GBH) &&
+                         encode_tile_map(m + AccumBody::LM_C, false, f.dev.G[l], w, h, f.dev.gp[l], AccumBody::CBW, AccumBody::CBH);
+                }
+            }
+            if (ok) { lmaps_off = mbd.add(lm.data(), lm.size() * sizeof(CUtensorMap)); lmaps_ok = true; }
         }
     }
 #endif
@@ -952,6 +972,7 @@ int build_lists(ds_canvas* c) {
     c->d_frames = (FrameDev*)(base + frames_off);
     c->d_segs = (PullSeg*)(base + segs_off); c->n_segs = (int)segs.size();
     c->d_tmaps = c->tmaps_ok ? (void*)(base + tmaps_off) : nullptr;
+    c->d_lmaps = lmaps_ok ? (void*)(base + lmaps_off) : nullptr;
     c->dirty = false;
     return DS_OK;
 }
@@ -1035,8 +1056,13 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     // bit 1: source footprints staged in shared memory by TMA box loads (needs the tensor maps; DS_SRC_BOX=0 turns it off)
     static const bool src_box = !(getenv("DS_SRC_BOX") && atoi(getenv("DS_SRC_BOX")) == 0);
     mp.flags = (gap_fast ? 1 : 0) | ((src_box && mp.tmaps) ? 2 : 0);
+    // bit 2: ds_mb_accum brings the planes in through its shared-memory ring of TMA boxes (DS_ACC_RING=0: direct loads)
+    static const bool acc_ring = !(getenv("DS_ACC_RING") && atoi(getenv("DS_ACC_RING")) == 0);
+    mp.lmaps = c->d_lmaps; mp.lstride = c->L + 1;
+    if (acc_ring && mp.lmaps) mp.flags |= 4;
 #if !DS_CUDA
     if (src_box) mp.flags |= 2;   // the emulator stages the boxes with a plain copy loop
+    if (acc_ring) mp.flags |= 4;
 #endif
     const double q = 1.0 / (double)(1ull << (2 * l));
     double ab;
