@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(_HERE, "lib", "libdronestitch_cuda.so")
+# DS_LIB_VARIANT (development aid): a differently configured build of the same sources, tools/build_variant.py
+CUDA_LIB_PATH = os.path.join(_HERE, "lib", "libdronestitch_cuda%s.so" % (("_" + os.environ["DS_LIB_VARIANT"]) if os.environ.get("DS_LIB_VARIANT") else ""))
 
 DS_OK = 0
 DS_ERR_BAD_ARG, DS_ERR_OOM, DS_ERR_CUDA, DS_ERR_P2P_UNAVAILABLE, DS_ERR_STATE, DS_ERR_NO_DEVICE, DS_ERR_UNSUPPORTED = range(1, 8)

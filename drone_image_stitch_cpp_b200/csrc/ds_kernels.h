@@ -1982,49 +1982,98 @@ struct MBFastBody {
             }
 
             if constexpr (LEVEL0) prepare_next(fi);
-            // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op
-            for (int i = tid; i < ph * GWS; i += NT) {
-                const int yy = i / GWS, gxx = i - yy * GWS;
-                if (gxx >= gw) continue;
-                const int c0 = 2 * (gx0 + gxx) - 2;
-                uint32_t q[5];
-                if (!border) {
-                    const uint32_t* s = s_g0 + yy * PWS + (c0 - px0);
+            // ---- phase 2a: G_1 = pyrDown16S, separable, two channels per op. Away from the ROI border an item is a PAIR of
+            // horizontally adjacent outputs: the seven (horizontal pass) / two x five (vertical pass) inputs come in 16-byte
+            // shared loads and are split into lanes once.
+            if (!border && (GWS & 1) == 0) {
+                const SAddr a_g0 = s_addr(s_g0), a_h = s_addr(s_h), a_g1 = s_addr(s_g1); (void)a_g1;
+                constexpr int HP = GWS / 2;   // pairs per row
+                for (int i = tid; i < ph * HP; i += NT) {
+                    const int yy = i / HP, pj = i - yy * HP;
+                    // px0 == 2 gx0 - 2: the pair's window starts at region column 4 pj (16-byte aligned, 8 columns inside the pitch)
+                    uint32_t q[8];
+                    lds_u4(a_g0 + 4 * (yy * PWS + 4 * pj), q[0], q[1], q[2], q[3]);
+                    lds_u4(a_g0 + 4 * (yy * PWS + 4 * pj) + 16, q[4], q[5], q[6], q[7]);
+                    uint32_t br[7], gg[7];
                     DS_UNROLL
-                    for (int t = 0; t < 5; t++) q[t] = s[t];
-                } else {
-                    DS_UNROLL
-                    for (int t = 0; t < 5; t++) q[t] = s_g0[yy * PWS + (refl101(c0 + t, rw) - px0)];
+                    for (int t = 0; t < 7; t++) { br[t] = byte_perm(q[t], 0, 0x4240); gg[t] = byte_perm(q[t], 0, 0x4341); }
+                    const uint32_t h0br = tap5(br[0], br[1], br[2], br[3], br[4]), h0g = tap5(gg[0], gg[1], gg[2], gg[3], gg[4]);
+                    const uint32_t h1br = tap5(br[2], br[3], br[4], br[5], br[6]), h1g = tap5(gg[2], gg[3], gg[4], gg[5], gg[6]);
+#if DS_CUDA
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_h + 8 * (yy * GWS + 2 * pj)), "r"(h0br), "r"(h0g), "r"(h1br), "r"(h1g) : "memory");
+#else
+                    U2 h0, h1; h0.br = h0br; h0.g = h0g; h1.br = h1br; h1.g = h1g;
+                    s_h[yy * GWS + 2 * pj] = h0; s_h[yy * GWS + 2 * pj + 1] = h1;
+#endif
                 }
-                U2 h;
-                h.br = tap5(byte_perm(q[0], 0, 0x4240), byte_perm(q[1], 0, 0x4240), byte_perm(q[2], 0, 0x4240),
-                            byte_perm(q[3], 0, 0x4240), byte_perm(q[4], 0, 0x4240));
-                h.g = tap5(byte_perm(q[0], 0, 0x4341), byte_perm(q[1], 0, 0x4341), byte_perm(q[2], 0, 0x4341),
-                           byte_perm(q[3], 0, 0x4341), byte_perm(q[4], 0, 0x4341));
-                s_h[i] = h;
-            }
-            DS_SYNC();
-            for (int i = tid; i < gh * GWS; i += NT) {
-                const int gyy = i / GWS, gxx = i - gyy * GWS;
-                if (gxx >= gw) continue;
-                const int r0 = 2 * (gy0 + gyy) - 2;
-                U2 q[5];
-                if (!border) {
+                DS_SYNC();
+                for (int i = tid; i < gh * HP; i += NT) {
+                    const int gyy = i / HP, pj = i - gyy * HP;
+                    const int rr = 2 * (gy0 + gyy) - 2 - py0;   // == 2 gyy
+                    uint32_t a[5][4];   // rows rr .. rr + 4: {br, g} of the pair's two columns
                     DS_UNROLL
-                    for (int t = 0; t < 5; t++) q[t] = s_h[(r0 - py0 + t) * GWS + gxx];
-                } else {
-                    DS_UNROLL
-                    for (int t = 0; t < 5; t++) q[t] = s_h[(refl101(r0 + t, rh) - py0) * GWS + gxx];
+                    for (int t = 0; t < 5; t++) lds_u4(a_h + 8 * ((rr + t) * GWS + 2 * pj), a[t][0], a[t][1], a[t][2], a[t][3]);
+                    const uint32_t o0br = ((tap5(a[0][0], a[1][0], a[2][0], a[3][0], a[4][0]) + 0x00800080u) >> 8) & 0x00FF00FFu;
+                    const uint32_t o0g = ((tap5(a[0][1], a[1][1], a[2][1], a[3][1], a[4][1]) + 0x00000080u) >> 8) & 0x000000FFu;
+                    const uint32_t o1br = ((tap5(a[0][2], a[1][2], a[2][2], a[3][2], a[4][2]) + 0x00800080u) >> 8) & 0x00FF00FFu;
+                    const uint32_t o1g = ((tap5(a[0][3], a[1][3], a[2][3], a[3][3], a[4][3]) + 0x00000080u) >> 8) & 0x000000FFu;
+#if DS_CUDA
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_g1 + 8 * (gyy * GWS + 2 * pj)), "r"(o0br), "r"(o0g), "r"(o1br), "r"(o1g) : "memory");
+#else
+                    U2 o0, o1; o0.br = o0br; o0.g = o0g; o1.br = o1br; o1.g = o1g;
+                    s_g1[gyy * GWS + 2 * pj] = o0; s_g1[gyy * GWS + 2 * pj + 1] = o1;
+#endif
+                    const int gx = gx0 + 2 * pj, gy = gy0 + gyy;
+                    if (gy >= jy0 && gy < jy1) {
+                        if (gx >= jx0 && gx < jx1 && 2 * pj < gw) G1out[(size_t)gy * op1 + gx] = byte_perm(o0br, o0g, 0x5240);
+                        if (gx + 1 >= jx0 && gx + 1 < jx1 && 2 * pj + 1 < gw) G1out[(size_t)gy * op1 + gx + 1] = byte_perm(o1br, o1g, 0x5240);
+                    }
                 }
-                U2 o;
-                o.br = ((tap5(q[0].br, q[1].br, q[2].br, q[3].br, q[4].br) + 0x00800080u) >> 8) & 0x00FF00FFu;
-                o.g = ((tap5(q[0].g, q[1].g, q[2].g, q[3].g, q[4].g) + 0x00000080u) >> 8) & 0x000000FFu;
-                s_g1[gyy * GWS + gxx] = o;
-                const int gx = gx0 + gxx, gy = gy0 + gyy;
-                if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1)
-                    G1out[(size_t)gy * op1 + gx] = byte_perm(o.br, o.g, 0x5240);
+                DS_SYNC();
+            } else {
+                for (int i = tid; i < ph * GWS; i += NT) {
+                    const int yy = i / GWS, gxx = i - yy * GWS;
+                    if (gxx >= gw) continue;
+                    const int c0 = 2 * (gx0 + gxx) - 2;
+                    uint32_t q[5];
+                    if (!border) {
+                        const uint32_t* s = s_g0 + yy * PWS + (c0 - px0);
+                        DS_UNROLL
+                        for (int t = 0; t < 5; t++) q[t] = s[t];
+                    } else {
+                        DS_UNROLL
+                        for (int t = 0; t < 5; t++) q[t] = s_g0[yy * PWS + (refl101(c0 + t, rw) - px0)];
+                    }
+                    U2 h;
+                    h.br = tap5(byte_perm(q[0], 0, 0x4240), byte_perm(q[1], 0, 0x4240), byte_perm(q[2], 0, 0x4240),
+                                byte_perm(q[3], 0, 0x4240), byte_perm(q[4], 0, 0x4240));
+                    h.g = tap5(byte_perm(q[0], 0, 0x4341), byte_perm(q[1], 0, 0x4341), byte_perm(q[2], 0, 0x4341),
+                               byte_perm(q[3], 0, 0x4341), byte_perm(q[4], 0, 0x4341));
+                    s_h[i] = h;
+                }
+                DS_SYNC();
+                for (int i = tid; i < gh * GWS; i += NT) {
+                    const int gyy = i / GWS, gxx = i - gyy * GWS;
+                    if (gxx >= gw) continue;
+                    const int r0 = 2 * (gy0 + gyy) - 2;
+                    U2 q[5];
+                    if (!border) {
+                        DS_UNROLL
+                        for (int t = 0; t < 5; t++) q[t] = s_h[(r0 - py0 + t) * GWS + gxx];
+                    } else {
+                        DS_UNROLL
+                        for (int t = 0; t < 5; t++) q[t] = s_h[(refl101(r0 + t, rh) - py0) * GWS + gxx];
+                    }
+                    U2 o;
+                    o.br = ((tap5(q[0].br, q[1].br, q[2].br, q[3].br, q[4].br) + 0x00800080u) >> 8) & 0x00FF00FFu;
+                    o.g = ((tap5(q[0].g, q[1].g, q[2].g, q[3].g, q[4].g) + 0x00000080u) >> 8) & 0x000000FFu;
+                    s_g1[gyy * GWS + gxx] = o;
+                    const int gx = gx0 + gxx, gy = gy0 + gyy;
+                    if (gx >= jx0 && gx < jx1 && gy >= jy0 && gy < jy1)
+                        G1out[(size_t)gy * op1 + gx] = byte_perm(o.br, o.g, 0x5240);
+                }
+                DS_SYNC();
             }
-            DS_SYNC();
             if (tid == 0) *s_vote = 0;   // read by everyone two barriers ago; next written after this frame's last barrier
 
             // ---- W_1 = pyrDownF32(W_0) over the own range
@@ -2208,12 +2257,17 @@ struct PyrParams {
     int txmax, R;         // CTAs per frame: txmax column blocks x R row blocks (first row block = the frame's first needed row)
     uint32_t m_per, m_tx; // floor(2^32 / (txmax * R)), floor(2^32 / txmax): block index decode without divisions
     int own_y0, own_y1;   // canvas rows of level l + 1 to produce
+    const void* lmaps; int lstride;   // tensor maps of the per-frame planes (MBParams::lmaps), or NULL
 };
 struct PyrDownBody {
     // One CTA = 32 x 64 outputs; one thread = a strip of 2 columns x 8 rows, marched down two output rows at a time: of
     // the seven input rows a 2 x 2 output block reads, three were filtered horizontally for the block above.
-    static constexpr int BW = 32, STRIP = 8, BH = 8 * STRIP, NTH = 128;
-    static int smem_bytes() { return 0; }
+    static constexpr int BW = 32, STRIP = 4, BH = 8 * STRIP, NTH = 128;
+    // CTAs whose input window lies inside the plane (no BORDER_REFLECT_101 index to resolve) bring it into shared memory
+    // with one TMA box per plane - (2 BW + 8) x (2 BH + 3) elements from a 16-byte aligned column - and filter from there.
+    static constexpr int XW = 2 * BW + 8, XH = 2 * BH + 3, XBOX = XW * XH * 4, XBOX_AL = (XBOX + 127) & ~127;
+    static constexpr int LM_PG = 3, LM_PW = 4, LM_N = 5;   // == AccumBody::LM_*
+    static int smem_bytes() { return 2 * XBOX_AL + 16; }
     struct HRow { uint32_t br[2], g[2]; float w[2]; };   // horizontally filtered input row at the thread's two output columns
     // q = i / d with m = floor(2^32 / d): the estimate is at most 2 short
     DS_DM int div_m(int i, int d, uint32_t m) {
@@ -2224,7 +2278,7 @@ struct PyrDownBody {
         return q;
     }
     template <int NT>
-    DS_DM void run(const PyrParams& p, int block, int tid, unsigned char*) {
+    DS_DM void run(const PyrParams& p, int block, int tid, unsigned char* smem) {
         const int per = p.txmax * p.R;
         const int fslot = div_m(block, per, p.m_per), rem = block - fslot * per;
         const int byr = div_m(rem, p.txmax, p.m_tx), bx = rem - byr * p.txmax;
@@ -2244,6 +2298,22 @@ struct PyrDownBody {
         // the CTA's outputs all have weight 1 by geometry: W_l is not even read
         const bool ones = weights_all_ones(F, l + 1, bx * BW, imin(bx * BW + BW, w_out) - 1, imax(by * BH, jlo), imin(by * BH + BH, jhi) - 1);
         const bool need_w = !ones || !DS_CUDA;   // (the emulator computes them anyway and checks the claim)
+        // input window of the CTA: columns 2 bx BW - 2 .. + 2 BW + 2, rows 2 by BH - 2 .. + 2 BH + 2
+        const int xs = 2 * bx * BW - 4, ys = 2 * by * BH - 2;   // box origin (column rounded down to 4 elements)
+        const bool boxed = (p.lmaps != nullptr || !DS_CUDA) && xs >= 0 && ys >= 0 && 2 * bx * BW + 2 * BW + 2 <= w_in - 1 && 2 * by * BH + 2 * BH + 2 <= h_in - 1;
+        unsigned long long* const s_bar = (unsigned long long*)(smem + 2 * XBOX_AL);
+        if (boxed) {
+            if (tid == 0) {
+                const char* lm = (const char*)((uintptr_t)p.lmaps + ((size_t)fslot * p.lstride + l) * (LM_N * 128));
+                mbar_init(s_bar, 1);
+                mbar_expect_tx(s_bar, (uint32_t)(need_w && DS_CUDA ? 2 * XBOX : XBOX));
+                box_load(smem, lm + LM_PG * 128, Gin, w_in, h_in, ip, xs, ys, XW, XH, s_bar);
+                if (need_w) box_load(smem + XBOX_AL, lm + LM_PW * 128, Win, w_in, h_in, ip, xs, ys, XW, XH, s_bar);
+            }
+            DS_SYNC();          // the barrier word is initialised for everyone
+            mbar_wait(s_bar, 0u);
+        }
+        const SAddr a_gbox = s_addr(smem), a_wbox = s_addr(smem + XBOX_AL);
         for (int t = tid; t < NTH; t += NT) {
             const int tx = t & 15, ty = t >> 4;
             const int jx = bx * BW + 2 * tx, jy0 = by * BH + ty * STRIP;   // the strip's first output
@@ -2262,7 +2332,18 @@ struct PyrDownBody {
                 const uint32_t* gr = Gin + (size_t)rr * ip;
                 const float* wr = Win + (size_t)rr * ip;
                 uint32_t q[7]; float w[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (xin) {
+                if (boxed) {
+                    // (inside the plane: rr == r) 8 + 16 + 4 bytes at 16-byte aligned shared addresses
+                    const int o = (r - ys) * XW + (c0 - xs);
+                    lds_u2(a_gbox + 4 * o, q[0], q[1]); lds_u4(a_gbox + 4 * o + 8, q[2], q[3], q[4], q[5]); q[6] = lds_u1(a_gbox + 4 * o + 24);
+                    if (need_w) {
+                        uint32_t u2, u3, u4, u5;
+                        lds_f2(a_wbox + 4 * o, w[0], w[1]);
+                        lds_u4(a_wbox + 4 * o + 8, u2, u3, u4, u5);
+                        w[2] = i2f_bits((int)u2); w[3] = i2f_bits((int)u3); w[4] = i2f_bits((int)u4); w[5] = i2f_bits((int)u5);
+                        w[6] = i2f_bits((int)lds_u1(a_wbox + 4 * o + 24));
+                    }
+                } else if (xin) {
                     // c0 = 2 mod 4 and rows are 16-byte aligned: 8 + 16 + 4 bytes
                     const uint2 a = ld_ro((const uint2*)(gr + c0)); const uint4 b = ld_ro((const uint4*)(gr + c0 + 2)); const uint32_t c = ld_ro(gr + c0 + 6);
                     q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = b.z; q[5] = b.w; q[6] = c;
@@ -2332,14 +2413,18 @@ struct PyrDownBody {
     }
 };
 
+#ifndef DS_ACC_TW
+#define DS_ACC_TW 32
+#define DS_ACC_TH 16
+#endif
 struct AccumBody {
-    static constexpr int TW = 32, TH = 16, NQ = 128;   // one thread = one 2 x 2 quad
+    static constexpr int TW = DS_ACC_TW, TH = DS_ACC_TH, NQ = TW * TH / 4, QW = TW / 2;   // one thread = one 2 x 2 quad
     static constexpr int GCH = 32;                     // frames whose geometry is staged at a time; also the span of the packed sums
     // Shared-memory ring (below the top level, when the tensor maps exist): the boxes of up to NST frames of the tile's list
     // are in flight at once - G_l and W_l of the tile (36 x 16: the innermost start of a TMA box must be 16-byte aligned, so
     // up to 3 extra columns on the left) and G_{l+1} of the tile / 2 + its pyrUp ring (24 x 10) - each stage completing on
     // its own mbarrier. Loads in flight no longer cost registers, and the taps become shared-memory reads at fixed offsets.
-    static constexpr int NST = 4, GBW = 36, GBH = TH, CBW = 24, CBH = TH / 2 + 2;
+    static constexpr int NST = 4, GBW = TW + 4, GBH = TH, CBW = (TW / 2 + 2 + 3 + 3) & ~3, CBH = TH / 2 + 2;
     static constexpr int GBOX = GBW * GBH * 4, CBOX = CBW * CBH * 4;
     static constexpr int STAGE_BYTES = 2 * GBOX + ds_al128(CBOX);
     static constexpr int LM_G = 0, LM_W = 1, LM_C = 2, LM_PG = 3, LM_PW = 4, LM_N = 5;   // tensor maps per frame and level (MBParams::lmaps)
@@ -2493,7 +2578,7 @@ struct AccumBody {
                 DS_UNROLL
                 for (int k = 0; k < K; k++) {
                     const int q = tid + k * NT;
-                    const int qx = q & 15, qy = q >> 4;
+                    const int qx = q % QW, qy = q / QW;
                     if (top) {
                         // the top level accumulates G_L itself; its ROI need not be even-aligned: per pixel
                         DS_UNROLL
@@ -2573,7 +2658,7 @@ struct AccumBody {
         DS_UNROLL
         for (int k = 0; k < K; k++) {
             const int q = tid + k * NT;
-            const int X = X0 + 2 * (q & 15), Y = Y0 + 2 * (q >> 4);
+            const int X = X0 + 2 * (q % QW), Y = Y0 + 2 * (q / QW);
             DS_UNROLL
             for (int dy = 0; dy < 2; dy++) {
                 const int Yp = Y + dy;
@@ -2927,7 +3012,7 @@ typedef MBFastBody<64, true> MBFastL0;
 typedef MBFastBody<64, true, true> MBFastL0A;
 DS_DEFINE_KERNEL(ds_mb_feed_l0, MBFastL0, 512, MBParams, 2)
 DS_DEFINE_KERNEL(ds_mb_feed_l0_affine, MBFastL0A, 512, MBParams, 2)
-DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 6)
+DS_DEFINE_KERNEL(ds_mb_pyrdown, PyrDownBody, 128, PyrParams, 5)
 DS_DEFINE_KERNEL(ds_mb_accum, AccumBody, 128, MBParams, 8)
 DS_DEFINE_KERNEL(ds_mb_collapse, CollapseBody, 256, CollapseParams, 4)
 DS_DEFINE_KERNEL(ds_mb_finalize_l0, FinalizeL0Body, 256, FinalizeL0Params, 1)

@@ -939,7 +939,9 @@ int build_lists(ds_canvas* c) {
                     CUtensorMap* m = &lm[(i * ls + l) * AccumBody::LM_N];
                     ok = encode_tile_map(m + AccumBody::LM_G, false, f.dev.G[l], w, h, f.dev.gp[l], AccumBody::GBW, AccumBody::GBH) &&
                          encode_tile_map(m + AccumBody::LM_W, true, f.dev.W[l], w, h, f.dev.gp[l], AccumBody::GBW, AccumBody::GBH) &&
-                         encode_tile_map(m + AccumBody::LM_C, false, f.dev.G[l], w, h, f.dev.gp[l], AccumBody::CBW, AccumBody::CBH);
+                         encode_tile_map(m + AccumBody::LM_C, false, f.dev.G[l], w, h, f.dev.gp[l], AccumBody::CBW, AccumBody::CBH) &&
+                         encode_tile_map(m + AccumBody::LM_PG, false, f.dev.G[l], w, h, f.dev.gp[l], PyrDownBody::XW, PyrDownBody::XH) &&
+                         encode_tile_map(m + AccumBody::LM_PW, true, f.dev.W[l], w, h, f.dev.gp[l], PyrDownBody::XW, PyrDownBody::XH);
                 }
             }
             if (ok) { lmaps_off = mbd.add(lm.data(), lm.size() * sizeof(CUtensorMap)); lmaps_ok = true; }
@@ -1099,11 +1101,13 @@ int launch_pyrdown(ds_canvas* c, stream_t st, int l, const SubBand& sb, const AB
     if (pp.txmax * pp.R == 1) pp.m_per = 0xffffffffu;
     if (pp.txmax == 1) pp.m_tx = 0xffffffffu;
     pp.own_y0 = rows.lo; pp.own_y1 = rows.hi;
+    static const bool pyr_box = !(getenv("DS_PYR_BOX") && atoi(getenv("DS_PYR_BOX")) == 0);   // DS_PYR_BOX=0: direct loads everywhere
+    pp.lmaps = pyr_box ? c->d_lmaps : nullptr; pp.lstride = c->L + 1;
     const double q = 1.0 / (double)(1ull << (2 * l));
     const Range all = c->plan[l + 1].own;
     const double ab = abm.A * q * 12.5 * (double)(rows.hi - rows.lo) / (double)std::max(all.hi - all.lo, 1);
     if ((rc = prof_mark(c, st, true, "mb_pyrdown", l, (int64_t)ab))) return rc;
-    if ((rc = launch<PyrDownBody, 128>(pp, (long long)pp.nframes * pp.txmax * pp.R, st, 0))) return rc;
+    if ((rc = launch<PyrDownBody, 128>(pp, (long long)pp.nframes * pp.txmax * pp.R, st, PyrDownBody::smem_bytes()))) return rc;
     if ((rc = prof_mark(c, st, false, nullptr, 0, 0))) return rc;
     c->launches++;
     return DS_OK;
