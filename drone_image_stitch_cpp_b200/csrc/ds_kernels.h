@@ -1059,6 +1059,9 @@ DS_D void fence_tensormap_acquire(const void* tmap) {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
 }
 DS_D void fence_proxy_async_smem() { fence_proxy_async(); }
+// 16 bytes global -> shared without a register round trip; complete (for the issuing thread) after cp_async_wait_all
+DS_D void cp_async16(void* dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
+DS_D void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // One bw x bh box of a pitched plane of 4-byte elements into shared memory (TMA tile load, completion on `bar`); elements
 // outside the plane arrive as zeros. The emulator copies.
 // (The descriptors were written by an earlier grid - ds_meta_copy - so no tensormap-proxy fence is needed here.)
@@ -1070,6 +1073,8 @@ DS_D void mbar_init(void*, int) {}
 DS_D void mbar_expect_tx(void*, uint32_t) {}
 DS_D void mbar_wait(void*, uint32_t) {}
 DS_D void fence_proxy_async_smem() {}
+DS_D void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+DS_D void cp_async_wait_all() {}
 DS_D void box_load(void* dst, const void*, const void* plane, int w, int h, int pitch, int x0, int y0, int bw, int bh, void*) {
     uint32_t* d = (uint32_t*)dst;
     const uint32_t* s = (const uint32_t*)plane;
@@ -1283,8 +1288,9 @@ struct MBFastBody {
         auto stage_frame_at = [&](int frame_idx, int fi_) {
             const uint4* srcw = (const uint4*)(p.frames + frame_idx);
             uint4* dstw = (uint4*)(smem + FDEV_OFF + (fi_ & 1) * FDEV_BYTES);
-            // the last warps copy: the first ones build the tile-frame geometry at the same time
-            for (int w = NT - 1 - tid; w < (int)(sizeof(FrameDev) / 16); w += NT) dstw[w] = srcw[w];
+            // the last warps copy: the first ones build the tile-frame geometry at the same time. Asynchronous copies
+            // (cp.async): the copying warp does not wait for the data; stage_wait() before the barrier the readers pass
+            for (int w = NT - 1 - tid; w < (int)(sizeof(FrameDev) / 16); w += NT) cp_async16(dstw + w, srcw + w);
         };
         auto stage_frame = [&](int fi_) { stage_frame_at(p.tile_frames[fi_], fi_); };
         if (f_begin < f_end) stage_frame_at(rec.w, f_begin);   // the first frame's index came with the tile record
@@ -1343,6 +1349,7 @@ struct MBFastBody {
             if constexpr (LEVEL0 && !AFF) classify_plane(F, g, p.flags);
             s_geo[j] = g;
         }
+        cp_async_wait_all();
         DS_SYNC();
 
         // ---- level-0 tables of one tile-frame: reflected bbox index + per-column / per-row map terms. Built for frame
@@ -1493,6 +1500,7 @@ struct MBFastBody {
             (void)jx0; (void)jx1; (void)jy0; (void)jy1; (void)gx0; (void)gy0; (void)px0; (void)py0; (void)pw; (void)ph; \
             (void)gw; (void)gh; (void)jw; (void)jh; (void)border;
             if (s_geo[fi - f_begin].skip) {       // block-uniform
+                cp_async_wait_all();
                 DS_SYNC();
                 if constexpr (LEVEL0) { prepare_next(fi); issue_box(fi + 1); DS_SYNC(); }
                 continue;
@@ -1971,6 +1979,7 @@ struct MBFastBody {
             const int op1 = F.gp[l + 1];   // row pitch of the level-(l+1) arrays
             const int all255 = (m_and == 255), all0 = (m_or == 0);
             int uni255, uni0;
+            cp_async_wait_all();   // the next frame's descriptor (requested at the top of the iteration) is read after this barrier
             if (known_votes >= 0) {
                 DS_SYNC();
                 uni255 = (known_votes & 1) && (c255 == 1.f); uni0 = (known_votes & 2) != 0;
@@ -2079,6 +2088,14 @@ struct MBFastBody {
             // ---- W_1 = pyrDownF32(W_0) over the own range
             if (uni255 || uni0) {
                 const float wv = uni255 ? 1.f : 0.f;
+                if (!((jx0 | jw) & 3)) {
+                    // rows of the level-1 plane are 16-byte aligned and so is the tile's part: four weights per store
+                    float4 w4; w4.x = w4.y = w4.z = w4.w = wv;
+                    for (int i = tid; i < jh * (JW / 4); i += NT) {
+                        const int jyy = i / (JW / 4), j4 = (i - jyy * (JW / 4)) * 4;
+                        if (j4 < jw) *(float4*)(W1out + (size_t)(jy0 + jyy) * op1 + (jx0 + j4)) = w4;
+                    }
+                } else
                 for (int i = tid; i < jh * JW; i += NT) {
                     const int jyy = i / JW, jj = i - jyy * JW;
                     if (jj < jw) W1out[(size_t)(jy0 + jyy) * op1 + (jx0 + jj)] = wv;
