@@ -1705,13 +1705,72 @@ struct MBFastBody {
                             }
                         }
                     };
+                    // The common tile-frame - mode 0, footprint in the box, the whole 71 x 71 region - with everything that is
+                    // known at compile time folded into the instructions: rows rg + 8 k live for k < 8 (no clamps, no per-pixel
+                    // predicates), row-table loads and stores at immediate offsets from one base register each, the four taps of
+                    // a pixel off one address register.
+                    auto run_full0 = [&]() {
+                        for (int vt = tid; vt < NTV; vt += NT) {
+                            const int col = vt & 63, rg = vt >> 6;
+                            uint32_t c0, c1, c2, c3;
+                            lds_u4(a_col + col * 16, c0, c1, c2, c3);
+                            const float ca0 = i2f_bits((int)c0), ca3 = i2f_bits((int)c1);
+                            const SAddr arow = a_row + rg * 16, d0 = a_g0 + (rg * PWS + col) * 4;
+                            auto taps = [&](float fa0, float fa3, float rb1, float rb4, PX& q) {
+                                const float x = f_add(f_add(fa0, rb1), k2), y = f_add(f_add(fa3, rb4), k5);
+                                q.bx = rnd32_bits(x); q.by = rnd32_bits(y);
+                                const uint32_t t = (uint32_t)(q.by >> 5) * (uint32_t)BOXW + (uint32_t)(q.bx >> 5);
+                                lds_tap4<BOXW * 4>(box_addr(t), q.p00, q.p01, q.p10, q.p11);
+                            };
+                            auto fetch_k = [&](auto ktag, PX& q) {
+                                float rb1, rb4;
+                                lds_f2_o<decltype(ktag)::value * RG * 16>(arow, rb1, rb4);
+                                taps(ca0, ca3, rb1, rb4, q);
+                            };
+                            auto value = [&](const PX& q) {
+                                const uint32_t ax = (uint32_t)q.bx & 31u, ay = (uint32_t)q.by & 31u;
+                                const uint32_t wxp = ax * 65535u + 32u;                     // (32 - ax) | ax << 16
+                                const uint32_t wbot = wxp * ay, wtop = wxp * 32u - wbot;    // rows weighted by ay / 32 - ay
+                                const uint32_t t0 = byte_perm(q.p00, q.p01, 0x5140), t0r = byte_perm(q.p00, q.p01, 0x6262);
+                                const uint32_t t1 = byte_perm(q.p10, q.p11, 0x5140), t1r = byte_perm(q.p10, q.p11, 0x6262);
+                                const uint32_t sb = dot2lo(wbot, t1, dot2lo(wtop, t0, 512u));
+                                const uint32_t sg = dot2hi(wbot, t1, dot2hi(wtop, t0, 512u));
+                                const uint32_t sr = dot2lo(wbot, t1r, dot2lo(wtop, t0r, 512u + (0xFFu << 18)));   // mask 255 rides in red
+                                return byte_perm(byte_perm(sb << 6, sg << 6, 0x0062), sr << 6, 0x7610);
+                            };
+                            auto fin_k = [&](auto ktag, const PX& q) { sts_u1_o<decltype(ktag)::value * RG * PWS * 4>(d0, value(q)); };
+                            PX A[2], B[2];
+                            fetch_k(IntTag<0>(), A[0]); fetch_k(IntTag<1>(), A[1]);
+                            fetch_k(IntTag<2>(), B[0]); fetch_k(IntTag<3>(), B[1]);
+                            fin_k(IntTag<0>(), A[0]); fin_k(IntTag<1>(), A[1]);
+                            fetch_k(IntTag<4>(), A[0]); fetch_k(IntTag<5>(), A[1]);
+                            fin_k(IntTag<2>(), B[0]); fin_k(IntTag<3>(), B[1]);
+                            fetch_k(IntTag<6>(), B[0]); fetch_k(IntTag<7>(), B[1]);
+                            fin_k(IntTag<4>(), A[0]); fin_k(IntTag<5>(), A[1]);
+                            // row rg + 64 (live for rg < 7) and the thread's one pixel of the columns beyond the 64th (497 items)
+                            {
+                                float rb1, rb4;
+                                lds_f2(a_row + imin(rg + RG * 8, PHM - 1) * 16, rb1, rb4);
+                                taps(ca0, ca3, rb1, rb4, A[0]);
+                                const int er_ = vt / 7, ec = 64 + (vt - er_ * 7), er = imin(er_, PHM - 1);
+                                uint32_t e0, e1, e2, e3;
+                                lds_u4(a_col + ec * 16, e0, e1, e2, e3);
+                                lds_f2(a_row + er * 16, rb1, rb4);
+                                taps(i2f_bits((int)e0), i2f_bits((int)e1), rb1, rb4, A[1]);
+                                fin_k(IntTag<6>(), B[0]); fin_k(IntTag<7>(), B[1]);
+                                if (rg < PHM - RG * 8) sts_u1_o<8 * RG * PWS * 4>(d0, value(A[0]));
+                                if (er_ < PHM) sts_u1(a_g0 + (er * PWS + ec) * 4, value(A[1]));
+                            }
+                        }
+                    };
 #if !DS_CUDA
                     ds_emu_count(interior ? 0 : (inbounds ? 1 : 2));
                     if (boxed) ds_emu_count(5);
 #endif
                     // tag = 4 * mode + (taps from the shared-memory box)
                     if (interior) {
-                        if (boxed) run_v2(IntTag<1>()); else run_v2(IntTag<0>());
+                        if (boxed && ph == PHM && pw == PHM) run_full0();
+                        else if (boxed) run_v2(IntTag<1>()); else run_v2(IntTag<0>());
                         m_or = 255; known_votes = 1;                 // uniform 255
                     } else if (inbounds) {
                         if (boxed) run_v2(IntTag<5>()); else run_v2(IntTag<4>());

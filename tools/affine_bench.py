@@ -3,6 +3,9 @@
   affine_seam the same with a soft blend mask and a channel gain per strip (stitch_global.cpp:644-658)
   plane_seam  PLANE_F32 with a seam mask and a block gain map per frame (composePanorama with DpSeamFinder and
               BlocksGainCompensator, stitch_robust.cpp:207-211)
+  plane_proj  PLANE_F32 with a slight perspective (the map divides by z per pixel: per-pixel loop of the fast kernel)
+  homography  HOMOGRAPHY_F64 transforms (cv::warpPerspective coordinates, double arithmetic per pixel): generic level-0 kernel
+  many        30 PLANE_F32 frames over the same ground (more than the 24 frames per tile the fast level-0 kernel stages): generic kernel
 usage: python tools/affine_bench.py [mode]"""
 import os, sys, json, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,6 +33,16 @@ if mode == "plane_proj":
         Rs.append(R)
     xfs = [CP.plane_transform(K, R, plan.scale, affine=False) for K, R in zip(plan.Ks, Rs)]
     rois = [CP.warp_roi(xf, fw, fh, lib) for xf in xfs]
+if mode == "homography":
+    xfs = []
+    for A, r in zip(plan.A, rois):
+        H = np.eye(3); H[:2] = A; H[0, 2] -= r[0]; H[1, 2] -= r[1]
+        H[2, 0] = 1e-7; H[2, 1] = -1e-7
+        xfs.append(CP.homography_transform(H, (r[0], r[1]), (r[2], r[3])))
+if mode == "many":
+    plan = synth.plan_grid(6, 5, 5472, 3648, overlap=0.93, seed=synth.MASTER_SEED)
+    xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
+    rois = [CP.warp_roi(xf, fw, fh, lib) for xf in xfs]
 if mode == "plane_seam":
     xfs = [CP.plane_transform(K, R, plan.scale) for K, R in zip(plan.Ks, plan.Rs)]
     rois = [CP.warp_roi(xf, fw, fh, lib) for xf in xfs]
@@ -39,7 +52,7 @@ cv = CP.Canvas(roi, "multiband", 5, lib=lib)
 rng = np.random.default_rng(3)
 for i, f in enumerate(frames):
     kw = {}
-    if mode not in ("affine", "plane_proj"):
+    if mode not in ("affine", "plane_proj", "homography", "many"):
         # a seam mask over the frame's bbox: everything but a diagonal band and the outer 40 px; soft edges for the global stage
         w, h = rois[i][2], rois[i][3]
         yy, xx = np.mgrid[0:h, 0:w]
@@ -61,5 +74,5 @@ kt = cv.kernel_times()
 agg = {}
 for k in kt:
     agg.setdefault((k["name"], k["level"]), []).append(k["ms"])
-print(json.dumps({"mode": mode, "canvas": [roi[2], roi[3]], "ms_composite": cv.info().ms_last_composite,
+print(json.dumps({"mode": mode, "canvas": [roi[2], roi[3]], "frames": len(frames), "MP_per_s": roi[2] * roi[3] / 1e3 / cv.info().ms_last_composite, "ms_composite": cv.info().ms_last_composite,
                   "kernels": {f"{n}[{l}]": round(float(np.mean(v)), 4) for (n, l), v in agg.items()}}))
