@@ -823,6 +823,7 @@ struct MBParams {
     const void* tmaps;            // CUtensorMap[frame][2] over the frame sources (level 0: L2 prefetch box, shared-memory box), or NULL
     int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI; bit 1: level-0 source boxes; bit 2: ds_mb_accum ring
     const void* lmaps; int lstride;   // CUtensorMap[frame][lstride][AccumBody::LM_N] over the per-frame G_l / W_l planes (levels 1 .. L), or NULL
+    int rnd_bias;                 // DS_RND_BIAS (a parameter on purpose: see the level-0 box addressing)
 };
 
 template <int T, bool LEVEL0>
@@ -1599,7 +1600,10 @@ struct MBFastBody {
                     // modes 0 / 1 with the footprint in the shared-memory box: the biased tap offset is taken against the
                     // box origin (all 32-bit, wrap-around is harmless: the final shared address is exact)
                     const bool boxed = HAS_BOX && g.box != 0;
-                    const uint32_t boxK = (uint32_t)(CB + g.by0) * (uint32_t)BOXW + (uint32_t)(CB + g.bx0);
+                    // (the bias comes in as a kernel parameter: as a compile-time constant ptxas carries its part of the address -
+                    // which does not fit a load's immediate field - to every single tap and adds it there, one instruction per tap)
+                    const int CBr = p.rnd_bias >> 5;
+                    const uint32_t boxK = (uint32_t)(CBr + g.by0) * (uint32_t)BOXW + (uint32_t)(CBr + g.bx0);
 #if DS_CUDA
                     const SAddr a_boxb = s_addr(smem + G0_BYTES + G1_BYTES) - 4u * boxK;   // shared addresses are 32-bit: the bias folds in
                     auto box_addr = [&](uint32_t t) { return a_boxb + 4u * t; };

@@ -1061,6 +1061,7 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     // bit 2: ds_mb_accum brings the planes in through its shared-memory ring of TMA boxes (DS_ACC_RING=0: direct loads)
     static const bool acc_ring = !(getenv("DS_ACC_RING") && atoi(getenv("DS_ACC_RING")) == 0);
     mp.lmaps = c->d_lmaps; mp.lstride = c->L + 1;
+    mp.rnd_bias = DS_RND_BIAS;
     if (acc_ring && mp.lmaps) mp.flags |= 4;
 #if !DS_CUDA
     if (src_box) mp.flags |= 2;   // the emulator stages the boxes with a plain copy loop
