@@ -2195,6 +2195,47 @@ struct MBFastBody {
             issue_box(fi + 1);
 
             // ---- phase 3: lap = G_0 - pyrUp(G_1), weighted accumulate, one 2x2 quad per item
+            // The common tile-frame - all weights 1, no ROI border, the whole tile inside the frame's part and the rows that
+            // accumulate - has every shared-memory address of a quad fixed per thread: the coarse 3 x 3 block starts at
+            // (qy, qx) of s_g1, the fine pixels at (2 qy + 4, 2 qx + 4) of the warped region. One base register each,
+            // immediate offsets, no window tests, no per-pixel predicates.
+            const bool full3 = LEVEL0 && uni255 && !border && ax0 == X0 && ax1 == X0 + T && ay0 == Y0 && ay1 == Y0 + T &&
+                               Y0 >= p.acc_y0 && Y0 + T <= p.acc_y1;
+            if (full3) {
+                const SAddr a_g1 = s_addr(s_g1), a_g0 = s_addr(s_g0), a_acc = s_addr(s_acc), a_ws = s_addr(s_ws);
+                for (int q = tid; q < NQ; q += NT) {
+                    const int qy = q / (T / 2), qx = q - qy * (T / 2);
+                    const SAddr ac = a_g1 + (qy * GWS + qx) * 8;
+                    U2 a0, a1, a2, b0, b1, b2, d0, d1, d2;
+                    lds_u2_o<0>(ac, a0.br, a0.g); lds_u2_o<8>(ac, a1.br, a1.g); lds_u2_o<16>(ac, a2.br, a2.g);
+                    lds_u2_o<GWS * 8>(ac, b0.br, b0.g); lds_u2_o<GWS * 8 + 8>(ac, b1.br, b1.g); lds_u2_o<GWS * 8 + 16>(ac, b2.br, b2.g);
+                    lds_u2_o<GWS * 16>(ac, d0.br, d0.g); lds_u2_o<GWS * 16 + 8>(ac, d1.br, d1.g); lds_u2_o<GWS * 16 + 16>(ac, d2.br, d2.g);
+                    const SAddr ag = a_g0 + ((2 * qy + 4) * PWS + 2 * qx + 4) * 4;
+                    const SAddr aa = a_acc + (2 * qy * T + 2 * qx) * 8, aw = a_ws + (2 * qy * T + 2 * qx) * 4;
+                    uint32_t g00, g01, g10, g11;
+                    lds_u2_o<0>(ag, g00, g01); lds_u2_o<PWS * 4>(ag, g10, g11);
+                    const uint32_t El_br = a0.br + 6u * a1.br + a2.br, Ol_br = 4u * (a1.br + a2.br);
+                    const uint32_t Ec_br = b0.br + 6u * b1.br + b2.br, Oc_br = 4u * (b1.br + b2.br);
+                    const uint32_t Er_br = d0.br + 6u * d1.br + d2.br, Or_br = 4u * (d1.br + d2.br);
+                    const uint32_t El_g = a0.g + 6u * a1.g + a2.g, Ol_g = 4u * (a1.g + a2.g);
+                    const uint32_t Ec_g = b0.g + 6u * b1.g + b2.g, Oc_g = 4u * (b1.g + b2.g);
+                    const uint32_t Er_g = d0.g + 6u * d1.g + d2.g, Or_g = 4u * (d1.g + d2.g);
+                    const uint32_t u00br = ((El_br + 6u * Ec_br + Er_br + 0x00200020u) >> 6) & 0x03FF03FFu, u01br = ((Ol_br + 6u * Oc_br + Or_br + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    const uint32_t u10br = ((4u * (Ec_br + Er_br) + 0x00200020u) >> 6) & 0x03FF03FFu, u11br = ((4u * (Oc_br + Or_br) + 0x00200020u) >> 6) & 0x03FF03FFu;
+                    const uint32_t u00g = ((El_g + 6u * Ec_g + Er_g + 0x20u) >> 6) & 0x3FFu, u01g = ((Ol_g + 6u * Oc_g + Or_g + 0x20u) >> 6) & 0x3FFu;
+                    const uint32_t u10g = ((4u * (Ec_g + Er_g) + 0x20u) >> 6) & 0x3FFu, u11g = ((4u * (Oc_g + Or_g) + 0x20u) >> 6) & 0x3FFu;
+                    uint32_t v0, v1, v2, v3; float w0, w1;
+                    // row 0 of the quad: lap_b + 65536 * lap_r == gbr - up_br as plain integers; trunc(lap * 1) == lap
+                    lds_u4_o<0>(aa, v0, v1, v2, v3); lds_f2_o<0>(aw, w0, w1);
+                    v0 += byte_perm(g00, 0, 0x4240) - u00br; v1 += ((g00 >> 8) & 255u) - u00g;
+                    v2 += byte_perm(g01, 0, 0x4240) - u01br; v3 += ((g01 >> 8) & 255u) - u01g;
+                    sts_u4_o<0>(aa, v0, v1, v2, v3); sts_f2_o<0>(aw, f_add(w0, 1.f), f_add(w1, 1.f));
+                    lds_u4_o<T * 8>(aa, v0, v1, v2, v3); lds_f2_o<T * 4>(aw, w0, w1);
+                    v0 += byte_perm(g10, 0, 0x4240) - u10br; v1 += ((g10 >> 8) & 255u) - u10g;
+                    v2 += byte_perm(g11, 0, 0x4240) - u11br; v3 += ((g11 >> 8) & 255u) - u11g;
+                    sts_u4_o<T * 8>(aa, v0, v1, v2, v3); sts_f2_o<T * 4>(aw, f_add(w0, 1.f), f_add(w1, 1.f));
+                }
+            } else
             if (!uni0) {
                 for (int q = tid; q < NQ; q += NT) {
                     const int qy = q / (T / 2), qx = q - qy * (T / 2);
