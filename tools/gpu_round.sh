@@ -11,6 +11,9 @@ timeout 300 python bench.py --workload cfg1 --steps 20 --warmup 3 --no-cpu-basel
 B="python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline --no-parity"
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $o/${tag}_launches_cfg2.csv $B > $o/${tag}_ncu_list.log 2>&1; echo "list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ds_mb_feed_l0 -s 4 -c 1 -f -o $o/${tag}_feed_l0 $B > $o/${tag}_ncu_l0.log 2>&1; echo "l0 rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ds_mb_feed_ln -s 16 -c 1 -f -o $o/${tag}_feed_l1 $B > $o/${tag}_ncu_l1.log 2>&1; echo "l1 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ds_mb_pyrdown -s 12 -c 1 -f -o $o/${tag}_pyrdown_l1 $B > $o/${tag}_ncu_p1.log 2>&1; echo "pyrdown rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ds_mb_accum -s 15 -c 1 -f -o $o/${tag}_accum_l1 $B > $o/${tag}_ncu_a1.log 2>&1; echo "accum rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ds_mb_collapse -s 19 -c 1 -f -o $o/${tag}_collapse_l0 $B > $o/${tag}_ncu_c0.log 2>&1; echo "collapse rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ds_feather_blend -s 4 -c 1 -f -o $o/${tag}_feather python bench.py --workload cfg1 --steps 3 --warmup 3 --no-cpu-baseline --no-parity > $o/${tag}_ncu_fe.log 2>&1; echo "feather rc=$?"
+for m in affine affine_seam plane_seam plane_proj homography many; do timeout 300 python tools/affine_bench.py $m 2>&1 | tail -1 >> $o/${tag}_slow_paths.jsonl; done
 tail -3 $o/${tag}_gputests.log
