@@ -373,10 +373,11 @@ def parity_windows(edges, rank, world, roi, bands, PH):
     """Windows (x, y, w, h) this rank checks and the canvas rows of its own it compares in each: one window straddling
     every band edge the rank touches (compared on its side of the edge), or the canvas centre on a single GPU."""
     m = 1 << bands
-    g = 8 << bands
-    ww = min(2048, (roi[2] // m) * m)
+    g = 8 << bands                      # margin of the windowed oracle (SURVEY 8(c) P17): 8 * 2^L px inside the window
+    ww = min(max(2048, 2 * g + 1024), (roi[2] // m) * m)
     wx = max(0, ((roi[2] - ww) // 2) // m * m)
-    half = 768 // m * m if PH >= 4 * 768 else max(g + m, (PH // 4) // m * m)
+    reach = max(768, g + 256)           # rows either side of an edge: the margin + at least 256 compared rows
+    half = -(-reach // m) * m if PH >= 4 * reach else max(g + m, (PH // 4) // m * m)
     out = []
 
     def win_at(e):
@@ -385,6 +386,12 @@ def parity_windows(edges, rank, world, roi, bands, PH):
         return (wx, y0, ww, y1 - y0)
     if world == 1:
         out.append((win_at((PH // 2) // m * m), None))
+    elif bands >= 7:
+        # deep pyramids: one 2 g + 1024 wide window costs the CPU oracle about a minute, so two ranks check one edge each
+        # (the band below the first edge and the one below the middle edge: both sides of a P2P hand-over are exercised
+        # by the pull of the rank that checks); the other ranks' rows are covered by tests/test_gpu_parity.py (cfg5 band)
+        if rank in (1, world // 2):
+            out.append((win_at(edges[rank]), "below"))
     else:
         if rank > 0:
             out.append((win_at(edges[rank]), "below"))          # my rows just below my upper edge
@@ -510,6 +517,13 @@ def run_native(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
 
+        def gather_rows(rows):
+            if world == 1:
+                return [rows]
+            out = [None] * world
+            dist.all_gather_object(out, rows)
+            return out
+
         def allsum(xs):
             t = torch.tensor([float(v) for v in xs], dtype=torch.float64, device=dev)
             if world > 1:
@@ -536,6 +550,11 @@ def run_native(args):
         if not args.no_parity and blend == "multiband":
             from oracle import windowed as W
             wins, g = parity_windows(edges, rank, world, roi, eff_bands, PH)
+            if world > 1:
+                # (torchrun pins OMP_NUM_THREADS to 1; the checker may use this rank's share of the host cores)
+                from oracle import ds_oracle as O
+                checkers = 2 if eff_bands >= 7 else world
+                O.set_threads(max(1, (os.cpu_count() or 1) // checkers))
             n_px = n_bad = mx = 0
             y_lo, y_hi = info.band_y0, min(info.band_y1, roi[3])
             checked_rows = []
@@ -559,9 +578,10 @@ def run_native(args):
             tot = allsum([n_px, n_bad])
             parity = {"checked": tot[0] > 0, "identical": tot[0] > 0 and tot[1] == 0, "pixels_compared": int(tot[0]),
                       "pixels_differing": int(tot[1]), "max_abs_diff": int(allmax(mx)),
-                      "how": ("every rank compares 2048-px-wide windows straddling its band edges (its own rows, >= 256 px inside the window) "
-                              "with the windowed CPU oracle (oracle/windowed.py, SURVEY 8(c) P17); bit-exact required"),
-                      "rank0_rows": checked_rows}
+                      "how": (("two ranks compare one" if (world > 1 and eff_bands >= 7) else "every rank compares") +
+                              f" {max(2048, 2 * g + 1024)}-px-wide windows straddling band edges (the rank's own rows, >= 8 * 2^L = {g} px inside the "
+                              "window) with the windowed CPU oracle (oracle/windowed.py, SURVEY 8(c) P17); bit-exact required"),
+                      "rows_checked": [r for rr in (gather_rows(checked_rows)) for r in rr]}
             note(f"parity {parity['identical']} over {parity['pixels_compared']} px")
 
         # ---------------- e2e: upload from pinned host + composite + download, every step

@@ -1177,6 +1177,7 @@ struct MBFastBody {
     };
     typedef typename std::conditional<(LEVEL0 && !AFF), TFGeo0, TFGeo>::type Geo;
     static_assert(sizeof(Geo) == GEO_BYTES, "TFGeo layout");
+    static_assert(LEVEL0 && T_ == 64, "level 0 only: the levels above are ds_mb_pyrdown / ds_mb_accum");
     // mirrored index interval [mn, mx] of [lo, hi] on an axis of length n (single reflection only)
     DS_DM bool fold_range(int lo, int hi, int n, int& mn, int& mx) {
         if (lo < -n || hi >= 2 * n) return false;
@@ -1269,15 +1270,8 @@ struct MBFastBody {
         uint32_t box_phase = 0u;                            // level 0: parity of the source-box barrier
         if (tid == 0) *s_vote = 0;
 #if DS_CUDA
-        unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);   // two barriers, one per box buffer
-        uint32_t tma_phase0 = 0u, tma_phase1 = 0u;
-        int tma_cur = 0;
-        const bool use_tma = !LEVEL0 && p.tmaps != nullptr;
-        if (use_tma && tid == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
-        if (HAS_BOX && (p.flags & 2) && tid == 0) mbar_init(s_bar, 1);   // level 0: one barrier, the source box
-        constexpr int W0A_OFF = G0_BYTES + G1_BYTES + H_BYTES + 3 * ACC_BYTES + TAB_BYTES;
-        auto g0_buf = [&](int b_) { return (uint32_t*)(smem + (b_ ? G0B_OFF : 0)); };
-        auto w_buf = [&](int b_) { return (float*)(smem + (b_ ? W0B_OFF : W0A_OFF)); };
+        unsigned long long* s_bar = (unsigned long long*)(smem + MBAR_OFF);
+        if (HAS_BOX && (p.flags & 2) && tid == 0) mbar_init(s_bar, 1);   // one barrier: the source box
 #endif
         // (no barrier: the accumulators are first touched after several more)
 
@@ -1316,37 +1310,6 @@ struct MBFastBody {
             g.border = !(2 * g.gx0 - 2 >= 0 && 2 * g.gx1 + 2 <= g.rw - 1 && 2 * g.gy0 - 2 >= 0 && 2 * g.gy1 + 2 <= g.rh - 1 &&
                          g.jx0 >= 1 && g.jx1 <= n1x - 1 && g.jy0 >= 1 && g.jy1 <= n1y - 1) ? 1 : 0;
             g.pad0 = g.pad1 = 0;
-            if constexpr (!LEVEL0) {
-                // pad0 = "every weight of the needed region is exactly 1", decided from geometry alone: a plane-mapped frame
-                // without per-pixel mask whose level-0 support of the region (radius 2^(l+1) - 2 after l pyrDowns) lies
-                // inside the bbox and maps into the source at its four corners - x(u, v) is monotone in u and in v even in
-                // float arithmetic (the level-0 kernel's interior test), so the corners bound every pixel; the nearest mask
-                // is then 255 throughout, W_0 = 255 * (1 / 255f) = 1 and every pyrDown of all-ones is exactly 1. Such
-                // tile-frames skip the load and the scan of their weight box.
-                if (!g.skip && F.kind == XF_PLANE && !F.seam && F.k[6] == 0.f && F.k[7] == 0.f && F.k8one == 1.f) {
-                    const int rl = (2 << l) - 2;
-                    const int u_lo = F.rx + (g.px0 << l) - rl - F.cx, u_hi = F.rx + ((g.px0 + g.pw - 1) << l) + rl - F.cx;
-                    const int v_lo = F.ry + (g.py0 << l) - rl - F.cy, v_hi = F.ry + ((g.py0 + g.ph - 1) << l) + rl - F.cy;
-                    if (u_lo >= 0 && u_hi <= F.w - 1 && v_lo >= 0 && v_hi <= F.h - 1) {
-                        float ca0[2], ca3[2], rb1[2], rb4[2];
-                        DS_UNROLL
-                        for (int e = 0; e < 2; e++) {
-                            float U = (float)(F.tlx + (e ? u_hi : u_lo)), V = (float)(F.tly + (e ? v_hi : v_lo));
-                            if (F.scale != 1.f) { U = f_div(U, F.scale); V = f_div(V, F.scale); }
-                            const float up = f_sub(U, F.t0), vp = f_sub(V, F.t1);
-                            ca0[e] = f_mul(F.k[0], up); ca3[e] = f_mul(F.k[3], up);
-                            rb1[e] = f_mul(F.k[1], vp); rb4[e] = f_mul(F.k[4], vp);
-                        }
-                        float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
-                        DS_UNROLL
-                        for (int e = 0; e < 4; e++) {
-                            const float xx_ = f_add(f_add(ca0[e & 1], rb1[e >> 1]), F.k2one), yy_ = f_add(f_add(ca3[e & 1], rb4[e >> 1]), F.k5one);
-                            xmn = fminf(xmn, xx_); xmx = fmaxf(xmx, xx_); ymn = fminf(ymn, yy_); ymx = fmaxf(ymx, yy_);
-                        }
-                        if (xmn >= 0.f && xmx <= (float)(F.src_w - 1) && ymn >= 0.f && ymx <= (float)(F.src_h - 1) && c255 == 1.f) g.pad0 = 1;
-                    }
-                }
-            }
             if constexpr (LEVEL0 && !AFF) classify_plane(F, g, p.flags);
             s_geo[j] = g;
         }
@@ -1460,22 +1423,6 @@ struct MBFastBody {
         if constexpr (LEVEL0) {
             if (f_begin < f_end) { build_tables(*(const FrameDev*)(smem + FDEV_OFF + (f_begin & 1) * FDEV_BYTES), f_begin); issue_box(f_begin); }
         }
-#if DS_CUDA
-        // TMA pipeline over the tile's frame list: the boxes of the next non-skipped frame are requested while
-        // the current one is processed (two buffers, two mbarriers)
-        auto next_live = [&](int from) { int j = from; while (j < f_end && s_geo[j - f_begin].skip) j++; return j; };
-        auto tma_issue = [&](int fi_, int buf) {
-            const Geo gg = s_geo[fi_ - f_begin];
-            const char* tm = (const char*)p.tmaps + ((size_t)p.tile_frames[fi_] * DS_MAXL + l) * 2 * 128;
-            fence_tensormap_acquire(tm);
-            fence_tensormap_acquire(tm + 128);
-            fence_proxy_async();   // generic-proxy reads of this buffer ended before the last barrier
-            mbar_expect_tx(s_bar + buf, gg.pad0 ? TMA_BYTES : 2 * TMA_BYTES);
-            tma_load_2d(g0_buf(buf), tm, gg.px0, gg.py0, s_bar + buf);
-            if (!gg.pad0) tma_load_2d(w_buf(buf), tm + 128, gg.px0, gg.py0, s_bar + buf);   // weights known to be 1: not loaded
-        };
-        if (use_tma && tid == 0) { const int j0 = next_live(f_begin); if (j0 < f_end) tma_issue(j0, 0); }
-#endif
         DS_SYNC();
 
         for (int fi = f_begin; fi < f_end; fi++) {
@@ -1972,59 +1919,6 @@ struct MBFastBody {
                     m_or |= m;
                 }
             }
-            } else {
-#if DS_CUDA
-                if (use_tma) {
-                    // box-shaped footprint: one TMA tile load each for G_l and W_l of the needed region
-                    // (PWS x PHM elements from (px0, py0); rows beyond the level are zero-filled and never read).
-                    // This frame's boxes were requested one iteration ago; request the next frame's now.
-                    s_g0 = g0_buf(tma_cur); s_w = w_buf(tma_cur);
-                    mbar_wait(s_bar + tma_cur, tma_cur ? tma_phase1 : tma_phase0);
-                    if (tma_cur) tma_phase1 ^= 1u; else tma_phase0 ^= 1u;
-                    if (tid == 0) { const int jn = next_live(fi + 1); if (jn < f_end) tma_issue(jn, tma_cur ^ 1); }
-                    tma_cur ^= 1;
-                    // weights lie in [0, 1]: all == 1 <=> min == 1, all == 0 <=> max == 0; four per 128-bit load
-                    float wmn = 1.f, wmx = 0.f;
-                    constexpr int Q = PWS / 4;
-                    static_assert(PWS % 4 == 0, "rows of the weight box are read as float4");
-                    if (g.pad0) { known_votes = 1; wmx = 1.f; }   // all ones by geometry: the box was not even loaded
-                    else
-                    for (int q = tid; q < Q * ph; q += NT) {
-                        const int yy = q / Q, x4 = (q - yy * Q) * 4;
-                        if (x4 >= pw) continue;
-                        const float4 v = *(const float4*)(s_w + yy * PWS + x4);
-                        wmn = fminf(wmn, v.x); wmx = fmaxf(wmx, v.x);
-                        if (x4 + 3 < pw) {
-                            wmn = fminf(fminf(wmn, v.y), fminf(v.z, v.w)); wmx = fmaxf(fmaxf(wmx, v.y), fmaxf(v.z, v.w));
-                        } else {
-                            if (x4 + 1 < pw) { wmn = fminf(wmn, v.y); wmx = fmaxf(wmx, v.y); }
-                            if (x4 + 2 < pw) { wmn = fminf(wmn, v.z); wmx = fmaxf(wmx, v.z); }
-                        }
-                    }
-                    m_and = (wmn == 1.f) ? 255 : 0;
-                    m_or = (wmx != 0.f) ? 255 : 0;
-                } else
-#endif
-                {
-                const uint32_t* const Gin = (const uint32_t*)F.G[l];
-                const float* const Win = F.W[l];
-                const int ip = F.gp[l];
-                for (int i = tid; i < PWS * ph; i += NT) {
-                    const int yy = i / PWS, xx = i - yy * PWS;
-                    if (xx >= pw) continue;
-                    const size_t gi = (size_t)(py0 + yy) * ip + (px0 + xx);
-                    const float w = Win[gi];
-                    s_g0[i] = Gin[gi];
-                    s_w[i] = w;
-                    m_and &= (w == 1.f) ? 255 : 0;
-                    m_or |= (w != 0.f) ? 255 : 0;
-                }
-#if !DS_CUDA
-                // emulation (tests): the geometric "all ones" claim the TMA path relies on is checked against the data
-                if (g.pad0 && m_and != 255) { fprintf(stderr, "ds emu: level %d tile %d frame %d: weights claimed 1 by geometry are not\n", l, tile, fi); abort(); }
-                if (g.pad0) known_votes = 1;
-#endif
-                }
             }
             }   // ======== end of the first half
             {   // ======== second half: votes, pyrDown, Laplacian + accumulate

@@ -275,3 +275,46 @@ def test_widened_api_errors_emu(emu_lib):
 @pytest.mark.gpu
 def test_widened_api_errors_gpu(cuda_lib):
     _widened_api_errors(cuda_lib)
+
+
+def _plan_rows(L, H, band):
+    """Python twin of plan_rows (csrc/ds_runtime.cu): rows of every level a band accumulates (acc) and the rows of the
+    per-frame planes it must hold (own); own[0] = the level-0 tile rows that run."""
+    lh = [H]
+    for _ in range(L):
+        lh.append((lh[-1] + 1) // 2)
+    clip = lambda a, b, n: (max(a, 0), min(b, n))
+    acc = [band]
+    for l in range(1, L + 1):
+        acc.append(clip((acc[l - 1][0] >> 1) - 1, ((acc[l - 1][1] - 1) >> 1) + 2, lh[l]))
+    own = [None] * (L + 1)
+    own[L] = acc[L]
+    for l in range(L - 1, 0, -1):
+        own[l] = clip(min(acc[l][0], 2 * own[l + 1][0] - 2), max(acc[l][1], 2 * own[l + 1][1] + 1), lh[l])
+    own[0] = clip(min(band[0], 2 * own[1][0]) & ~1, (max(band[1], 2 * own[1][1]) + 1) & ~1, lh[0])
+    return acc, own
+
+
+def test_band_halo_rows(emu_lib):
+    """Which frames a row band needs (ds_frame_touches_band). With every per-frame plane pixel computed once
+    (ds_mb_pyrdown) the level-0 rows a band recomputes beyond its edges stay below 4 * 2^L per edge (124 / 94 rows at
+    L = 5; the tile ring per level of round 1 needed ~290); a frame touches the band iff its feed ROI - bbox + the
+    blender's 3 * 2^L gap, aligned to 2^L - reaches into those rows."""
+    for L in (5, 8):
+        m = 1 << L
+        H = 64 * m
+        y0, y1 = 24 * m, 40 * m
+        _, own = _plan_rows(L, H, (y0, y1))
+        lo, hi = own[0]
+        assert 0 < y0 - lo <= 4 * m and 0 < hi - y1 <= 4 * m, (L, own[0])
+        band = CP.Canvas((0, 0, 4096, H), "multiband", L, band=(y0, y1), lib=emu_lib)
+        gap = 3 * m
+        # a frame whose bbox is rows [0, h): its feed ROI ends at h + gap rounded up to 2^L
+        e_out = (lo // m) * m                  # ROI end <= lo: outside
+        assert not band.touches((100, 0, 500, e_out - gap)), (L, lo, e_out)
+        assert band.touches((100, 0, 500, e_out - gap + m)), (L, lo, e_out)
+        # a frame starting at row s: its feed ROI starts at (s - gap) rounded down to 2^L
+        s_out = -(-hi // m) * m + gap          # ROI start >= hi: outside
+        assert not band.touches((100, s_out, 500, 300)), (L, hi, s_out)
+        assert band.touches((100, s_out - m, 500, 300)), (L, hi, s_out)
+        band.close()
