@@ -1858,7 +1858,13 @@ struct MBFastBody {
                     const L0Row r = s_row[yy];
                     bool okx = true, oky = true;
                     int ix, iy, nx, ny;
-                    if (affine) {
+                    if (AFF && F.kind == XF_HOMOGRAPHY) {
+                        // cv::warpPerspective coordinates (A7): double arithmetic per pixel, at the (mirrored) bbox position;
+                        // everything after the coordinates - taps, pyramids, accumulation - is the fast kernel's
+                        const Coord hc = eval_coord(F, c.u >= 0 ? c.u : ~c.u, r.v >= 0 ? r.v : ~r.v);
+                        ix = hc.sx * 32 + hc.ax; iy = hc.sy * 32 + hc.ay;   // sat16(ix >> 5) == hc.sx again below
+                        nx = hc.m ? 0 : -1; ny = 0;                          // the nearest mask comes with the coordinate
+                    } else if (affine) {
                         const int xr = f2i_bits(r.b1), yr = f2i_bits(r.b4), ad = f2i_bits(c.a0), bd = f2i_bits(c.a3);
                         ix = (xr + 16 + ad) >> 5; iy = (yr + 16 + bd) >> 5;
                         nx = sat16i((xr + 512 + ad) >> 10); ny = sat16i((yr + 512 + bd) >> 10);

@@ -858,11 +858,11 @@ int build_lists(ds_canvas* c) {
             int longest = 0;
             for (int t = 0; t < ntiles; t++) longest = std::max(longest, counts[(size_t)t + 1] - counts[t]);
             if (l == 0) {
-                bool all_plane = true;   // the fast level-0 kernel builds plane (float) and warpAffine (integer) coordinates
-                for (const Frame& f : c->frames) if (f.used && f.xf.kind != DS_XF_PLANE_F32 && f.xf.kind != DS_XF_AFFINE_F64) all_plane = false;
-                c->l0_fast_ok = all_plane && longest <= MBFastBody<64, true>::MAXF;
+                // the fast level-0 kernel builds plane (float) and warpAffine (integer) coordinates in its pipelined loops;
+                // warpPerspective (double) coordinates go through the per-pixel loop of its general variant
+                c->l0_fast_ok = longest <= MBFastBody<64, true>::MAXF;
                 c->l0_has_affine = false;
-                for (const Frame& f : c->frames) if (f.used && (f.xf.kind == DS_XF_AFFINE_F64 || f.d_seam || f.d_gainmap || f.dev.any_gain)) c->l0_has_affine = true;
+                for (const Frame& f : c->frames) if (f.used && (f.xf.kind != DS_XF_PLANE_F32 || f.d_seam || f.d_gainmap || f.dev.any_gain)) c->l0_has_affine = true;
             }
         }
         // tiles to run, per slice: every tile in the slice's tile rows (empty ones still write zeros), the ones with
