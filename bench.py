@@ -505,6 +505,13 @@ def run_native(args):
                 cv.p2p_disconnect()
                 halo = "recomputed per band (P2P unavailable: " + next(o[1] for o in oks if not o[0])[:120] + ")"
 
+        def gather_rows(rows):
+            if world == 1:
+                return [rows]
+            out = [None] * world
+            dist.all_gather_object(out, rows)
+            return out
+
         def barrier():
             torch.cuda.synchronize()
             if world > 1:
@@ -516,13 +523,6 @@ def run_native(args):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
-
-        def gather_rows(rows):
-            if world == 1:
-                return [rows]
-            out = [None] * world
-            dist.all_gather_object(out, rows)
-            return out
 
         def allsum(xs):
             t = torch.tensor([float(v) for v in xs], dtype=torch.float64, device=dev)
@@ -539,6 +539,7 @@ def run_native(args):
         ms_total, kt = resident_value(cv, args.steps, args.warmup, stream, barrier, flush)
         clk = clocks.stop()
         launches = int(cv.info().launches_last_composite) * args.steps
+        ms_rank = gather_rows(round(ms_total / args.steps, 4))   # every rank's own device time per composite
         ms_total = allmax(ms_total)
         canvas_mp = roi[2] * roi[3] / 1e6
         value = canvas_mp * args.steps / (ms_total / 1e3)
@@ -688,7 +689,7 @@ def run_native(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": DTYPE, "data": "synthetic", "config": cfg,
                 "run": {"halo": halo, "band_edges": [int(e) for e in edges], "frames_rank0": len(mine), "device_GB_rank0": info.device_bytes / 1e9,
-                        "host_frames": host_mode, "host_affinity": affinities,
+                        "host_frames": host_mode, "host_affinity": affinities, "ms_per_composite_by_rank": ms_rank,
                         "frames_from": "procedural orthophoto evaluated per frame (synth.procedural_frame)" if procedural else "stored procedural orthophoto (synth.orthophoto)"},
                 "clocks": clk, "parity": parity,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps,

@@ -759,12 +759,12 @@ struct FeatherBody {
             const int pidx = tid + k * NT;
             const float den = f_add(ws[k], 1e-5f);
             const int m = ws[k] > 1e-5f;
+            const float rden = rcp_refined(den);   // the three quotients share the reciprocal refinement (ds_device.h)
             int o[3];
             DS_UNROLL
             for (int ch = 0; ch < 3; ch++) {
                 const short a16 = (short)acc[k][ch];
-                // 0 / den == 0 exactly: skips the division for untouched pixels
-                const int v16 = a16 ? (int)(short)f2i_rz(f_div((float)a16, den)) : 0;
+                const int v16 = (int)(short)f2i_rz(div_by_rcp((float)a16, den, rden));
                 o[ch] = m ? sat8i(v16) : 0;
             }
             s_out[pidx] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | (m ? 0xff000000u : 0u);
