@@ -824,6 +824,7 @@ struct MBParams {
     int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI; bit 1: level-0 source boxes; bit 2: ds_mb_accum ring
     const void* lmaps; int lstride;   // CUtensorMap[frame][lstride][AccumBody::LM_N] over the per-frame G_l / W_l planes (levels 1 .. L), or NULL
     int rnd_bias;                 // DS_RND_BIAS (a parameter on purpose: see the level-0 box addressing)
+    uint32_t m_tiles_x;           // floor(2^32 / tiles_x): tile index decode without a division (ds_mb_accum)
 };
 
 template <int T, bool LEVEL0>
@@ -2542,7 +2543,7 @@ struct AccumBody {
         unsigned long long* const s_bar = (unsigned long long*)(s_ring + NST * STAGE_BYTES);
         const int4 rec = ld_ro(p.tile_rec + block);
         const int tile = rec.x, f_begin = rec.y, f_end = rec.z;
-        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int ty = PyrDownBody::div_m(tile, p.tiles_x, p.m_tiles_x), tx = tile - ty * p.tiles_x;
         const int X0 = tx * TW, Y0 = ty * TH;
         const bool top = p.level == p.L;
         const bool ring = !top && (p.flags & 4) && (p.lmaps != nullptr || !DS_CUDA);
@@ -2558,15 +2559,17 @@ struct AccumBody {
             if (base > f_begin) DS_SYNC();   // everyone is done with the previous chunk's entries
             for (int j = tid; j < n; j += NT) make_geo(p, (base + j == f_begin) ? rec.w : p.tile_frames[base + j], X0, Y0, top, s_geo[j]);
             DS_SYNC();
-            int jn = 0;   // next entry to look at for the ring
-            // every thread follows the ring's bookkeeping (block-uniform); thread 0 issues the loads
-            auto issue_next = [&]() {
-                while (jn < n && s_geo[jn].skip) jn++;
-                if (jn >= n) return false;
-                if (tid == 0) {
-                    const AGeo& g = s_geo[jn];
-                    const int s = m_issue % NST;
-                    unsigned char* st = s_ring + s * STAGE_BYTES;
+            if (ring) {
+                // ---- ring path. Thread 0 alone walks the list and issues the boxes; the others only need the number of live
+                // entries of the chunk to know - block-uniformly - when a consumed stage has to be handed back for a refill.
+                const SAddr a_geo = s_addr(s_geo);
+                int nl = 0;
+                for (int j = 0; j < n; j++) nl += (int)lds_u1(a_geo + j * (int)sizeof(AGeo) + 64) ? 0 : 1;
+                int jn = 0;   // thread 0: next entry to issue
+                auto issue_one = [&](int stage) {   // thread 0 only
+                    while (s_geo[jn].skip) jn++;
+                    const AGeo& g = s_geo[jn++];
+                    unsigned char* st = s_ring + stage * STAGE_BYTES;
                     const char* lm = (const char*)((uintptr_t)p.lmaps + ((size_t)g.frame * p.lstride + p.level) * (LM_N * 128));
                     const char* lc = (const char*)((uintptr_t)p.lmaps + ((size_t)g.frame * p.lstride + p.level + 1) * (LM_N * 128));
 #if DS_CUDA
@@ -2577,31 +2580,74 @@ struct AccumBody {
                     const void* pG = F.G[p.level]; const void* pW = F.W[p.level]; const void* pC = F.G[p.level + 1];
                     const int pw_ = F.rw >> p.level, ph_ = F.rh >> p.level;
 #endif
-                    if (m_issue >= NST) fence_proxy_async_smem();   // the stage's previous contents were read through the generic proxy
-                    mbar_expect_tx(s_bar + s, (uint32_t)(GBOX + CBOX + (g.ones ? 0 : GBOX)));
-                    box_load(st, lm + LM_G * 128, pG, pw_, ph_, g.gp, g.gbx, g.gby, GBW, GBH, s_bar + s);
-                    if (!g.ones || !DS_CUDA) box_load(st + GBOX, lm + LM_W * 128, pW, pw_, ph_, g.gp, g.gbx, g.gby, GBW, GBH, s_bar + s);
-                    box_load(st + 2 * GBOX, lc + LM_C * 128, pC, g.n1x, g.n1y, g.gp1, g.cbx, g.cby, CBW, CBH, s_bar + s);
+                    mbar_expect_tx(s_bar + stage, (uint32_t)(GBOX + CBOX + (g.ones ? 0 : GBOX)));
+                    box_load(st, lm + LM_G * 128, pG, pw_, ph_, g.gp, g.gbx, g.gby, GBW, GBH, s_bar + stage);
+                    if (!g.ones || !DS_CUDA) box_load(st + GBOX, lm + LM_W * 128, pW, pw_, ph_, g.gp, g.gbx, g.gby, GBW, GBH, s_bar + stage);
+                    box_load(st + 2 * GBOX, lc + LM_C * 128, pC, g.n1x, g.n1y, g.gp1, g.cbx, g.cby, CBW, CBH, s_bar + stage);
+                };
+                const int first = imin(nl, NST);
+                if (tid == 0) {
+                    if (m_issue > 0) fence_proxy_async_smem();   // the stages were read through the generic proxy in the previous chunk
+                    for (int i = 0; i < first; i++) issue_one((m_issue + i) % NST);
                 }
-                m_issue++; jn++;
-                return true;
-            };
-            if (ring) { for (int s = 0; s < NST; s++) if (!issue_next()) break; }
+                m_issue += first;
+                int lm_ = 0;   // live entries of this chunk consumed so far
+                for (int j = 0; j < n; j++) {
+                    uint32_t gx0_, gnx, gy0_, gny, gskip, gones, gborder, gframe, goff, coff;
+                    lds_u4(a_geo + j * (int)sizeof(AGeo) + 64, gskip, gones, gborder, gframe);
+                    if (gskip) continue;   // block-uniform
+                    lds_u4(a_geo + j * (int)sizeof(AGeo) + 32, gx0_, gnx, gy0_, gny);
+                    lds_u2(a_geo + j * (int)sizeof(AGeo) + 96, goff, coff);
+                    const int s = m_use % NST;
+                    const SAddr a_st = s_addr(s_ring + s * STAGE_BYTES);
+                    mbar_wait(s_bar + s, (uint32_t)((m_use / NST) & 1));
+                    DS_UNROLL
+                    for (int k = 0; k < K; k++) {
+                        const int q = tid + k * NT;
+                        const int qx = q % QW, qy = q / QW;
+                        if ((unsigned)(qx - (int)gx0_) >= gnx || (unsigned)(qy - (int)gy0_) >= gny) continue;
+                        uint32_t cw[9], g0v[4]; float wv4[4] = {1.f, 1.f, 1.f, 1.f};
+                        const SAddr ag = a_st + 4 * ((int)goff + 2 * qy * GBW + 2 * qx);
+                        const SAddr ac = a_st + 2 * GBOX + 4 * ((int)coff + qy * CBW + qx);
+                        if (!gborder) {
+                            cw[0] = lds_u1(ac - 4 * CBW - 4); cw[1] = lds_u1(ac - 4 * CBW); cw[2] = lds_u1(ac - 4 * CBW + 4);
+                            cw[3] = lds_u1(ac - 4); cw[4] = lds_u1(ac); cw[5] = lds_u1(ac + 4);
+                            cw[6] = lds_u1(ac + 4 * CBW - 4); cw[7] = lds_u1(ac + 4 * CBW); cw[8] = lds_u1(ac + 4 * CBW + 4);
+                        } else {
+                            uint32_t c1x0, c1y0, n1x, n1y;
+                            lds_u4(a_geo + j * (int)sizeof(AGeo) + 48, c1x0, c1y0, n1x, n1y);
+                            const int c1x = (int)c1x0 + qx, c1y = (int)c1y0 + qy;
+                            const int dxl = up_l(c1x, (int)n1x) - c1x, dxr = up_r(c1x, (int)n1x) - c1x;
+                            const SAddr aa = ac + 4 * CBW * (up_l(c1y, (int)n1y) - c1y), ad = ac + 4 * CBW * (up_r(c1y, (int)n1y) - c1y);
+                            cw[0] = lds_u1(aa + 4 * dxl); cw[1] = lds_u1(aa); cw[2] = lds_u1(aa + 4 * dxr);
+                            cw[3] = lds_u1(ac + 4 * dxl); cw[4] = lds_u1(ac); cw[5] = lds_u1(ac + 4 * dxr);
+                            cw[6] = lds_u1(ad + 4 * dxl); cw[7] = lds_u1(ad); cw[8] = lds_u1(ad + 4 * dxr);
+                        }
+                        lds_u2(ag, g0v[0], g0v[1]); lds_u2(ag + 4 * GBW, g0v[2], g0v[3]);
+                        if (!gones || !DS_CUDA) { lds_f2(ag + GBOX, wv4[0], wv4[1]); lds_f2(ag + GBOX + 4 * GBW, wv4[2], wv4[3]); }
+#if !DS_CUDA
+                        if (gones && (wv4[0] != 1.f || wv4[1] != 1.f || wv4[2] != 1.f || wv4[3] != 1.f)) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
+#endif
+                        quad(cw, g0v, wv4, gones != 0, pbr[k], pg[k], ws[k]);
+                    }
+                    m_use++; lm_++;
+                    if (lm_ + NST - 1 < nl) {   // live entry lm_ - 1 + NST exists: it goes into the stage just consumed
+                        DS_SYNC();
+                        if (tid == 0) { fence_proxy_async_smem(); issue_one(s); }
+                        m_issue++;
+                    }
+                }
+            } else {
+            // ---- the top level (accumulates G_L itself, per pixel: its ROI need not be even-aligned) and, without tensor
+            // maps, the levels below it with direct loads
             for (int j = 0; j < n; j++) {
                 const AGeo& g = s_geo[j];
                 if (g.skip) continue;   // block-uniform
-                const unsigned char* st = nullptr;
-                if (ring) {
-                    const int s = m_use % NST;
-                    st = s_ring + s * STAGE_BYTES;
-                    mbar_wait(s_bar + s, (uint32_t)((m_use / NST) & 1));
-                }
                 DS_UNROLL
                 for (int k = 0; k < K; k++) {
                     const int q = tid + k * NT;
                     const int qx = q % QW, qy = q / QW;
                     if (top) {
-                        // the top level accumulates G_L itself; its ROI need not be even-aligned: per pixel
                         DS_UNROLL
                         for (int i = 0; i < 4; i++) {
                             const int xp = 2 * qx + (i & 1), yp = 2 * qy + (i >> 1);
@@ -2626,43 +2672,26 @@ struct AccumBody {
                         const int c1x = g.c1x0 + qx, c1y = g.c1y0 + qy;
                         dxl = up_l(c1x, g.n1x) - c1x; dxr = up_r(c1x, g.n1x) - c1x; dyl = up_l(c1y, g.n1y) - c1y; dyr = up_r(c1y, g.n1y) - c1y;
                     }
-                    if (ring) {
-                        const SAddr ag = s_addr(st) + 4 * (g.goff + 2 * qy * GBW + 2 * qx);
-                        const SAddr ac = s_addr(st + 2 * GBOX) + 4 * (g.coff + qy * CBW + qx);
-                        const SAddr aa = ac + 4 * CBW * dyl, ad = ac + 4 * CBW * dyr;
-                        cw[0] = lds_u1(aa + 4 * dxl); cw[1] = lds_u1(aa); cw[2] = lds_u1(aa + 4 * dxr);
-                        cw[3] = lds_u1(ac + 4 * dxl); cw[4] = lds_u1(ac); cw[5] = lds_u1(ac + 4 * dxr);
-                        cw[6] = lds_u1(ad + 4 * dxl); cw[7] = lds_u1(ad); cw[8] = lds_u1(ad + 4 * dxr);
-                        lds_u2(ag, g0v[0], g0v[1]); lds_u2(ag + 4 * GBW, g0v[2], g0v[3]);
-                        if (!g.ones || !DS_CUDA) { lds_f2(ag + GBOX, wv4[0], wv4[1]); lds_f2(ag + GBOX + 4 * GBW, wv4[2], wv4[3]); }
-                    } else {
-                        const uint32_t* const g0p = g.G + (2 * qy * g.gp + 2 * qx);
-                        const uint32_t* const c = g.G1 + (qy * g.gp1 + qx);
-                        const uint32_t* const ca = c + dyl * g.gp1; const uint32_t* const cd = c + dyr * g.gp1;
-                        // every load of the quad is requested before the first use
-                        cw[0] = ld_ro(ca + dxl); cw[1] = ld_ro(ca); cw[2] = ld_ro(ca + dxr);
-                        cw[3] = ld_ro(c + dxl); cw[4] = ld_ro(c); cw[5] = ld_ro(c + dxr);
-                        cw[6] = ld_ro(cd + dxl); cw[7] = ld_ro(cd); cw[8] = ld_ro(cd + dxr);
-                        const uint2 gr0 = ld_ro((const uint2*)g0p), gr1 = ld_ro((const uint2*)(g0p + g.gp));
-                        g0v[0] = gr0.x; g0v[1] = gr0.y; g0v[2] = gr1.x; g0v[3] = gr1.y;
-                        if (!g.ones || !DS_CUDA) {
-                            const float* wp = g.W + (2 * qy * g.gp + 2 * qx);
-                            const float2 wr0 = ld_ro((const float2*)wp), wr1 = ld_ro((const float2*)(wp + g.gp));
-                            wv4[0] = wr0.x; wv4[1] = wr0.y; wv4[2] = wr1.x; wv4[3] = wr1.y;
-                        }
+                    const uint32_t* const g0p = g.G + (2 * qy * g.gp + 2 * qx);
+                    const uint32_t* const c = g.G1 + (qy * g.gp1 + qx);
+                    const uint32_t* const ca = c + dyl * g.gp1; const uint32_t* const cd = c + dyr * g.gp1;
+                    // every load of the quad is requested before the first use
+                    cw[0] = ld_ro(ca + dxl); cw[1] = ld_ro(ca); cw[2] = ld_ro(ca + dxr);
+                    cw[3] = ld_ro(c + dxl); cw[4] = ld_ro(c); cw[5] = ld_ro(c + dxr);
+                    cw[6] = ld_ro(cd + dxl); cw[7] = ld_ro(cd); cw[8] = ld_ro(cd + dxr);
+                    const uint2 gr0 = ld_ro((const uint2*)g0p), gr1 = ld_ro((const uint2*)(g0p + g.gp));
+                    g0v[0] = gr0.x; g0v[1] = gr0.y; g0v[2] = gr1.x; g0v[3] = gr1.y;
+                    if (!g.ones || !DS_CUDA) {
+                        const float* wp = g.W + (2 * qy * g.gp + 2 * qx);
+                        const float2 wr0 = ld_ro((const float2*)wp), wr1 = ld_ro((const float2*)(wp + g.gp));
+                        wv4[0] = wr0.x; wv4[1] = wr0.y; wv4[2] = wr1.x; wv4[3] = wr1.y;
                     }
 #if !DS_CUDA
                     if (g.ones && (wv4[0] != 1.f || wv4[1] != 1.f || wv4[2] != 1.f || wv4[3] != 1.f)) { fprintf(stderr, "ds emu: level %d tile %d: weights claimed 1 by geometry are not\n", p.level, tile); abort(); }
 #endif
                     quad(cw, g0v, wv4, g.ones != 0, pbr[k], pg[k], ws[k]);
                 }
-                if (ring) {
-                    m_use++;
-                    // refill the stage just consumed, if the chunk has more live entries (block-uniform decision)
-                    int jp = jn;
-                    while (jp < n && s_geo[jp].skip) jp++;
-                    if (jp < n) { DS_SYNC(); issue_next(); }
-                }
+            }
             }
             // fold the chunk's packed sums into the wide ones
             DS_UNROLL

@@ -1062,6 +1062,7 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     static const bool acc_ring = !(getenv("DS_ACC_RING") && atoi(getenv("DS_ACC_RING")) == 0);
     mp.lmaps = c->d_lmaps; mp.lstride = c->L + 1;
     mp.rnd_bias = DS_RND_BIAS;
+    mp.m_tiles_x = pl.tiles_x > 1 ? (uint32_t)(0x100000000ull / (uint32_t)pl.tiles_x) : 0xffffffffu;
     if (acc_ring && mp.lmaps) mp.flags |= 4;
 #if !DS_CUDA
     if (src_box) mp.flags |= 2;   // the emulator stages the boxes with a plain copy loop
