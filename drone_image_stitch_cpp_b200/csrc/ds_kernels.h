@@ -821,7 +821,7 @@ struct MBParams {
     int acc_y0, acc_y1;           // rows of this level whose dst the band's collapse reads (dst written only there)
     int own_y0, own_y1;           // even-aligned rows of this level the handle processes at all
     const void* tmaps;            // CUtensorMap[frame][2] over the frame sources (level 0: L2 prefetch box, shared-memory box), or NULL
-    int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI; bit 1: level-0 source boxes; bit 2: ds_mb_accum ring
+    int flags;                    // bit 0: fast warp loop also for in-bounds tile-frames in the gap of the feed ROI; bit 1: level-0 source boxes; bit 2: ds_mb_accum ring; bit 3: no specialised loop for gap tile-frames (A/B)
     const void* lmaps; int lstride;   // CUtensorMap[frame][lstride][AccumBody::LM_N] over the per-frame G_l / W_l planes (levels 1 .. L), or NULL
     int rnd_bias;                 // DS_RND_BIAS (a parameter on purpose: see the level-0 box addressing)
     uint32_t m_tiles_x;           // floor(2^32 / tiles_x): tile index decode without a division (ds_mb_accum)
@@ -1661,7 +1661,8 @@ struct MBFastBody {
                     // known at compile time folded into the instructions: rows rg + 8 k live for k < 8 (no clamps, no per-pixel
                     // predicates), row-table loads and stores at immediate offsets from one base register each, the four taps of
                     // a pixel off one address register.
-                    auto run_full0 = [&]() {
+                    auto run_full0 = [&](auto mask_tag) {   // mask 255 (inside the bbox) or 0 (wholly in the gap of the feed ROI)
+                        constexpr uint32_t MINIT = 512u + ((uint32_t)decltype(mask_tag)::value << 18);
                         for (int vt = tid; vt < NTV; vt += NT) {
                             const int col = vt & 63, rg = vt >> 6;
                             uint32_t c0, c1, c2, c3;
@@ -1687,7 +1688,7 @@ struct MBFastBody {
                                 const uint32_t t1 = byte_perm(q.p10, q.p11, 0x5140), t1r = byte_perm(q.p10, q.p11, 0x6262);
                                 const uint32_t sb = dot2lo(wbot, t1, dot2lo(wtop, t0, 512u));
                                 const uint32_t sg = dot2hi(wbot, t1, dot2hi(wtop, t0, 512u));
-                                const uint32_t sr = dot2lo(wbot, t1r, dot2lo(wtop, t0r, 512u + (0xFFu << 18)));   // mask 255 rides in red
+                                const uint32_t sr = dot2lo(wbot, t1r, dot2lo(wtop, t0r, MINIT));   // the mask byte rides in red
                                 return byte_perm(byte_perm(sb << 6, sg << 6, 0x0062), sr << 6, 0x7610);
                             };
                             auto fin_k = [&](auto ktag, const PX& q) { sts_u1_o<decltype(ktag)::value * RG * PWS * 4>(d0, value(q)); };
@@ -1721,11 +1722,12 @@ struct MBFastBody {
 #endif
                     // tag = 4 * mode + (taps from the shared-memory box)
                     if (interior) {
-                        if (boxed && ph == PHM && pw == PHM) run_full0();
+                        if (boxed && ph == PHM && pw == PHM) run_full0(IntTag<255>());
                         else if (boxed) run_v2(IntTag<1>()); else run_v2(IntTag<0>());
                         m_or = 255; known_votes = 1;                 // uniform 255
                     } else if (inbounds) {
-                        if (boxed) run_v2(IntTag<5>()); else run_v2(IntTag<4>());
+                        if (boxed && gap_all0 && ph == PHM && pw == PHM && !(p.flags & 8)) run_full0(IntTag<0>());   // mirror image, mask 0 throughout
+                        else if (boxed) run_v2(IntTag<5>()); else run_v2(IntTag<4>());
                         known_votes = gap_all0 ? 2 : 0;              // not inside the bbox: never uniform 255
                     } else {
                         run_v2(IntTag<8>());

@@ -1064,6 +1064,8 @@ int launch_feed(ds_canvas* c, stream_t st, int l, const SubBand& sb, const ABMod
     mp.rnd_bias = DS_RND_BIAS;
     mp.m_tiles_x = pl.tiles_x > 1 ? (uint32_t)(0x100000000ull / (uint32_t)pl.tiles_x) : 0xffffffffu;
     if (acc_ring && mp.lmaps) mp.flags |= 4;
+    static const bool gap_full = !(getenv("DS_GAP_FULL") && atoi(getenv("DS_GAP_FULL")) == 0);
+    if (!gap_full) mp.flags |= 8;
 #if !DS_CUDA
     if (src_box) mp.flags |= 2;   // the emulator stages the boxes with a plain copy loop
     if (acc_ring) mp.flags |= 4;
