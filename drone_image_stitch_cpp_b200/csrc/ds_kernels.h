@@ -1325,7 +1325,8 @@ struct MBFastBody {
             L0Col* const t_col = col_buf(fj);
             L0Row* const t_row = row_buf(fj);
             const bool aff = AFF && LEVEL0 && Fx.kind == XF_AFFINE;
-            for (int i = tid; i < PWS + gx.ph; i += NT) {
+            // (the last warps build the tables: the first ones have the extra items of the pyrDown pass that follows)
+            for (int i = NT - 1 - tid; i < PWS + gx.ph; i += NT) {
                 if (i < PWS) {
                     const int u = gx.rx + gx.px0 + imin(i, gx.pw - 1) - Fx.cx;   // padding columns repeat the last one
                     const int ur = refl(u, Fx.w, BORDER_REFL);
@@ -2057,7 +2058,7 @@ struct MBFastBody {
                 if (!((jx0 | jw) & 3)) {
                     // rows of the level-1 plane are 16-byte aligned and so is the tile's part: four weights per store
                     float4 w4; w4.x = w4.y = w4.z = w4.w = wv;
-                    for (int i = tid; i < jh * (JW / 4); i += NT) {
+                    for (int i = NT - 1 - tid; i < jh * (JW / 4); i += NT) {   // the last warps: the first ones had the tail of the pyrDown pass
                         const int jyy = i / (JW / 4), j4 = (i - jyy * (JW / 4)) * 4;
                         if (j4 < jw) *(float4*)(W1out + (size_t)(jy0 + jyy) * op1 + (jx0 + j4)) = w4;
                     }
@@ -2282,6 +2283,7 @@ struct PyrParams {
     uint32_t m_per, m_tx; // floor(2^32 / (txmax * R)), floor(2^32 / txmax): block index decode without divisions
     int own_y0, own_y1;   // canvas rows of level l + 1 to produce
     const void* lmaps; int lstride;   // tensor maps of the per-frame planes (MBParams::lmaps), or NULL
+    int boxes;            // input windows staged in shared memory (TMA; the emulator copies) where no border index is involved
 };
 struct PyrDownBody {
     // One CTA = 32 x 64 outputs; one thread = a strip of 2 columns x 8 rows, marched down two output rows at a time: of
@@ -2324,7 +2326,7 @@ struct PyrDownBody {
         const bool need_w = !ones || !DS_CUDA;   // (the emulator computes them anyway and checks the claim)
         // input window of the CTA: columns 2 bx BW - 2 .. + 2 BW + 2, rows 2 by BH - 2 .. + 2 BH + 2
         const int xs = 2 * bx * BW - 4, ys = 2 * by * BH - 2;   // box origin (column rounded down to 4 elements)
-        const bool boxed = (p.lmaps != nullptr || !DS_CUDA) && xs >= 0 && ys >= 0 && 2 * bx * BW + 2 * BW + 2 <= w_in - 1 && 2 * by * BH + 2 * BH + 2 <= h_in - 1;
+        const bool boxed = p.boxes && xs >= 0 && ys >= 0 && 2 * bx * BW + 2 * BW + 2 <= w_in - 1 && 2 * by * BH + 2 * BH + 2 <= h_in - 1;
         unsigned long long* const s_bar = (unsigned long long*)(smem + 2 * XBOX_AL);
         if (boxed) {
             if (tid == 0) {

@@ -1107,6 +1107,11 @@ int launch_pyrdown(ds_canvas* c, stream_t st, int l, const SubBand& sb, const AB
     pp.own_y0 = rows.lo; pp.own_y1 = rows.hi;
     static const bool pyr_box = !(getenv("DS_PYR_BOX") && atoi(getenv("DS_PYR_BOX")) == 0);   // DS_PYR_BOX=0: direct loads everywhere
     pp.lmaps = pyr_box ? c->d_lmaps : nullptr; pp.lstride = c->L + 1;
+#if DS_CUDA
+    pp.boxes = (pyr_box && pp.lmaps) ? 1 : 0;
+#else
+    pp.boxes = pyr_box ? 1 : 0;
+#endif
     const double q = 1.0 / (double)(1ull << (2 * l));
     const Range all = c->plan[l + 1].own;
     const double ab = abm.A * q * 12.5 * (double)(rows.hi - rows.lo) / (double)std::max(all.hi - all.lo, 1);
