@@ -668,7 +668,8 @@ def run_native(args):
         if rows:
             (name, level), ms, ab = rows[0]
             ach = ab / (ms / 1e3) / 1e9
-            traffic, traffic_src = dominant_traffic(args.workload, name, level)
+            # (the capture is of the single-GPU launch: a row band's launch moves its share of it, not measured separately)
+            traffic, traffic_src = dominant_traffic(args.workload, name, level) if world == 1 else (None, "captured at N = 1 only (profiles/dominant_kernel_traffic.json)")
             step_ms = ms_total / args.steps
             roof = {"bound": "hbm", "kernel": f"{name}[level {level}]", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
