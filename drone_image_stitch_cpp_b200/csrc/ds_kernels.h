@@ -800,7 +800,9 @@ struct FeatherBody {
 };
 
 // ---------------------------------------------------------------------------------------------
-// MULTIBAND feed, one pyramid level per launch, gather formulation (A11).
+// MULTIBAND feed, gather formulation (A11): the straightforward tile kernel. Instantiated for level 0 only
+// (ds_mb_feed_l0_generic: tiles with more frames than the fast kernel stages, and the zero-band blender whose level 0 is
+// the top level); the hot paths are MBFastBody (level 0) and PyrDownBody / AccumBody (levels >= 1) below.
 // A canvas tile of level l walks the frames whose feed ROI touches it, in feed order. Per frame:
 //   phase 1  G_l over the tile + halo into shared memory (level 0: inverse warp of the source,
 //            copyMakeBorder(REFLECT) and the warped mask folded in; l >= 1: read the frame's G_l, W_l)
@@ -1094,14 +1096,17 @@ DS_D void box_load(void* dst, const void*, const void* plane, int w, int h, int 
 //   * per tile-frame column / row tables hold the reflected bbox index and the per-column / per-row
 //     products of the plane map (k0*u', k3*u', k6*u' / k1*v', k4*v', k7*v'), so a pixel costs two adds
 //     per coordinate (each product and sum is still rounded separately, as OpenCV does);
-//   * bilinear taps as packed byte dot products (dp4a) on the BGRX words;
+//   * the source footprint of a tile-frame staged in shared memory by one TMA box load; bilinear taps as two-way dot
+//     products with 16-bit 2-D weights (dp2a) on the BGRX words, cvRound on the FMA pipe (biased mantissa);
 //   * G_0 / G_1 kept as packed 16-bit lanes (B|R<<16, G) so the separable 5-tap pyrDown and the 2x2
 //     pyrUp quads run two channels per integer op (all partial sums fit 16 bits: <= 255*256);
 //   * block-uniform shortcuts: a tile-frame whose mask is all 255 has W_1 == 1 exactly and
 //     trunc(lap * 1) == lap; all 0 contributes nothing but still produces G_1;
 //   * tile-frames that touch a ROI border use index-reflecting variants of the same phases.
-// acc lanes: B + 65536 * R in one int (exact while |sum| < 2^15, guaranteed by the host for tiles with
-// <= 64 frames; longer lists go to the generic kernel).
+//   * specialised straight-line variants of the warp loop and of the Laplacian phase for the common tile-frame (whole
+//     71 x 71 region, mask 255 or - wholly in the gap of the feed ROI - 0): immediate-offset shared accesses, no clamps.
+// acc lanes: B + 65536 * R in one int (exact while |sum| < 2^15; the host sends tiles with more than MAXF = 24 frames to
+// the generic kernel).
 
 // Normalised Laplacian pixel of a destination level (A11 blend): trunc(sum / (wsum + 1e-5)) per channel, flag = wsum >
 // 1e-5, as the two words of a px16 (b | g << 16, r | flag << 16). The three quotients share the reciprocal refinement

@@ -287,7 +287,7 @@ DS_API const char* ds_version(void);
 /* ---- per-kernel timing (measurement only) ---- */
 
 typedef struct ds_kernel_time {
-    char name[32];             /* "mb_feed", "mb_collapse", "feather_mask", "feather_blend", ... */
+    char name[32];             /* "mb_feed" (level 0), "mb_pyrdown", "mb_accum", "mb_collapse", "p2p_pull", "feather_mask", "feather_dist", "feather_blend" */
     int32_t level;             /* pyramid level the launch works on (-1 if not applicable) */
     float ms;                  /* device time of the launch (CUDA events on the canvas stream) */
     int64_t algorithmic_bytes; /* share of the SURVEY.md §8(d) model attributed to this launch */
