@@ -280,6 +280,14 @@ def bind_to_gpu_numa_node(idx):
             node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
         except Exception:
             pass
+        if node is None:
+            try:   # sysfs knows the node of the GPU's PCI function even where NVML does not report it
+                bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+                bus = bus.decode() if isinstance(bus, bytes) else bus
+                with open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node") as fh:
+                    node = int(fh.read().strip())
+            except Exception:
+                pass
         if cpus:
             os.sched_setaffinity(0, cpus)
             return {"gpu": idx, "cores": len(cpus), "first_core": min(cpus), "numa_node": node}
